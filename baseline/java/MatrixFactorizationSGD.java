@@ -1,0 +1,268 @@
+/*
+ * MatrixFactorizationSGD.java -- REFERENCE STAND-IN (not the upstream source).
+ *
+ * The mounted reference (/root/reference) holds only README.md:1-2 ("# MatrixFactorizationSGD.java",
+ * a concurrent-programming coursework at UFRN) and no Java source. BASELINE.json's north_star
+ * instructs: "If no Java SGD source is present, commit a plain sequential Java SGD with the
+ * identical update rule as the reference stand-in". This file is that stand-in. The class name
+ * comes from README.md:1. Everything the README leaves open is pinned in SURVEY.md section 8
+ * (rows a1-a6, 8d) and restated in DESIGN.md section 2.
+ *
+ * Zero dependencies, Java 17 source level. It cannot be compiled in this project's image (no JDK);
+ * its executable proxy is oracle/oracle.cpp, which restates it function by function and cites the
+ * line numbers of this file.
+ *
+ * Arithmetic contract: every float operation below is a separate IEEE-754 binary32 operation,
+ * rounded to nearest-even, in exactly the order written (Java never contracts a*b+c into an FMA
+ * unless Math.fma is called, and since JDK 17 all float arithmetic is strict).
+ */
+import java.util.Arrays;
+
+public final class MatrixFactorizationSGD {
+
+    /** Output of factorize: row-major P (nUsers x k) and Q (nItems x k). */
+    public static final class Factors {
+        public final float[] P;
+        public final float[] Q;
+        public final int nUsers, nItems, k;
+        Factors(float[] P, float[] Q, int nUsers, int nItems, int k) {
+            this.P = P; this.Q = Q; this.nUsers = nUsers; this.nItems = nItems; this.k = k;
+        }
+    }
+
+    /* hash streams (SURVEY.md 8a row a6) */
+    public static final long STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2,
+                             STREAM_USER = 3, STREAM_ITEM = 4, STREAM_NOISE = 5,
+                             STREAM_HELDOUT = 6, STREAM_PSTAR = 7, STREAM_QSTAR = 8;
+
+    /** a6: counter hash, SplitMix64 finaliser over (seed, stream, ctr); arithmetic mod 2^64. */
+    public static long hash64(long seed, long stream, long ctr) {
+        long z = seed + 0x9E3779B97F4A7C15L * (ctr + 1L) + 0xD1B54A32D192ED03L * stream;
+        z = (z ^ (z >>> 30)) * 0xBF58476D1CE4E5B9L;
+        z = (z ^ (z >>> 27)) * 0x94D049BB133111EBL;
+        z = z ^ (z >>> 31);
+        return z;
+    }
+
+    /** a6: uniform in [0,1) with 24 random bits; exact in binary32. */
+    public static float uniform(long seed, long stream, long ctr) {
+        return (float) (hash64(seed, stream, ctr) >>> 40) * 0x1.0p-24f;
+    }
+
+    /** a3: rows[r*k+f] = uniform(seed, stream, r*k+f) * scale. */
+    public static void initFactors(float[] rows, int nRows, int k, long seed, long stream, float scale) {
+        for (int r = 0; r < nRows; r++) {
+            for (int f = 0; f < k; f++) {
+                long ctr = (long) r * k + f;
+                rows[(int) ctr] = uniform(seed, stream, ctr) * scale;
+            }
+        }
+    }
+
+    /** Default init scale 1/sqrt(k), rounded once to binary32 (sqrt in double, divide in double). */
+    public static float defaultInitScale(int k) {
+        return (float) (1.0 / Math.sqrt((double) k));
+    }
+
+    /**
+     * a4: visiting order for one epoch. Record idx gets the 31-bit key hash64(seed,2,(epoch<<32)|idx)>>>33;
+     * the order is ascending (key, idx). Packing key and idx into one non-negative long makes that a
+     * plain primitive sort, identical in Java, C++ (sort of uint64) and CUDA (64-bit radix sort).
+     */
+    public static int[] shuffle(long seed, int epoch, int n) {
+        long[] packed = new long[n];
+        for (int idx = 0; idx < n; idx++) {
+            long key = hash64(seed, STREAM_SHUFFLE, ((long) epoch << 32) | (long) idx) >>> 33;
+            packed[idx] = (key << 32) | (long) idx;
+        }
+        Arrays.sort(packed);
+        int[] order = new int[n];
+        for (int j = 0; j < n; j++) order[j] = (int) (packed[j] & 0xFFFFFFFFL);
+        return order;
+    }
+
+    /**
+     * a2: one SGD update on (p_u, q_i) for rating r. Returns the error e = r - p.q used for it.
+     * Dot product: f ascending, binary32 accumulate starting from 0. Both rows are updated from the
+     * PRE-update values (simultaneous update).
+     */
+    public static float sgdUpdate(float[] P, int pOff, float[] Q, int qOff, int k,
+                                  float r, float lr, float lambda) {
+        float dot = 0.0f;
+        for (int f = 0; f < k; f++) {
+            dot = dot + P[pOff + f] * Q[qOff + f];
+        }
+        float e = r - dot;
+        for (int f = 0; f < k; f++) {
+            float pf = P[pOff + f];
+            float qf = Q[qOff + f];
+            P[pOff + f] = pf + lr * (e * qf - lambda * pf);
+            Q[qOff + f] = qf + lr * (e * pf - lambda * qf);
+        }
+        return e;
+    }
+
+    /**
+     * a1: the entry point. Ratings triplets, rank k, learning rate, lambda, epochs in; P and Q out.
+     * Sequential: epoch e visits the records in shuffle(seed, e, n) order.
+     */
+    public static Factors factorize(int[] users, int[] items, float[] ratings,
+                                    int nUsers, int nItems, int k,
+                                    float lr, float lambda, int epochs, long seed) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || nUsers <= 0 || nItems <= 0 || epochs < 0)
+            throw new IllegalArgumentException("bad shape");
+        final int n = ratings.length;
+        for (int t = 0; t < n; t++) {
+            if (users[t] < 0 || users[t] >= nUsers || items[t] < 0 || items[t] >= nItems)
+                throw new IllegalArgumentException("index out of range at record " + t);
+        }
+        float[] P = new float[nUsers * k];
+        float[] Q = new float[nItems * k];
+        float scale = defaultInitScale(k);
+        initFactors(P, nUsers, k, seed, STREAM_P_INIT, scale);
+        initFactors(Q, nItems, k, seed, STREAM_Q_INIT, scale);
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            int[] order = shuffle(seed, epoch, n);
+            for (int j = 0; j < n; j++) {
+                int t = order[j];
+                sgdUpdate(P, users[t] * k, Q, items[t] * k, k, ratings[t], lr, lambda);
+            }
+        }
+        return new Factors(P, Q, nUsers, nItems, k);
+    }
+
+    /**
+     * Thread-parallel (Hogwild) variant: T threads, thread w visits positions j = w, w+T, ... of the
+     * same per-epoch order, no locks; threads join at every epoch end. Nondeterministic by design.
+     */
+    public static Factors factorizeThreaded(int[] users, int[] items, float[] ratings,
+                                            int nUsers, int nItems, int k,
+                                            float lr, float lambda, int epochs, long seed,
+                                            int threads) throws InterruptedException {
+        final int n = ratings.length;
+        final float[] P = new float[nUsers * k];
+        final float[] Q = new float[nItems * k];
+        float scale = defaultInitScale(k);
+        initFactors(P, nUsers, k, seed, STREAM_P_INIT, scale);
+        initFactors(Q, nItems, k, seed, STREAM_Q_INIT, scale);
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            final int[] order = shuffle(seed, epoch, n);
+            Thread[] pool = new Thread[threads];
+            for (int w = 0; w < threads; w++) {
+                final int w0 = w;
+                pool[w] = new Thread(() -> {
+                    for (int j = w0; j < n; j += threads) {
+                        int t = order[j];
+                        sgdUpdate(P, users[t] * k, Q, items[t] * k, k, ratings[t], lr, lambda);
+                    }
+                });
+                pool[w].start();
+            }
+            for (Thread th : pool) th.join();
+        }
+        return new Factors(P, Q, nUsers, nItems, k);
+    }
+
+    /** a5: sqrt( sum (r - p_u.q_i)^2 / n ); dot in binary32 (f ascending), sum in double. */
+    public static double rmse(float[] P, float[] Q, int k, int[] users, int[] items, float[] ratings) {
+        double sse = 0.0;
+        final int n = ratings.length;
+        for (int t = 0; t < n; t++) {
+            int pOff = users[t] * k, qOff = items[t] * k;
+            float dot = 0.0f;
+            for (int f = 0; f < k; f++) dot = dot + P[pOff + f] * Q[qOff + f];
+            float e = ratings[t] - dot;
+            sse += (double) e * (double) e;
+        }
+        return n == 0 ? 0.0 : Math.sqrt(sse / (double) n);
+    }
+
+    /* ------------------------------------------------------------------------------------------
+     * Synthetic power-law ratings (SURVEY.md 8d). Every value is a pure function of (seed, n).
+     * ------------------------------------------------------------------------------------------ */
+
+    public static final int PLANTED_RANK = 16;
+    public static final float PLANTED_AMPLITUDE = 0.8660254f;   /* sqrt(0.75): planted dot has unit variance */
+    public static final long ID_MULT = 2654435761L;              /* prime > 2^31, so coprime to every id count */
+
+    /** 53-bit uniform double in [0,1). */
+    public static double uniform53(long seed, long stream, long ctr) {
+        return (double) (hash64(seed, stream, ctr) >>> 11) * 0x1.0p-53;
+    }
+
+    /**
+     * Shifted power-law rank in [0, count): y = c + (1-c)x, rank = floor(count * (y^a - c^a)/(1 - c^a)),
+     * a = 2^log2Alpha computed by repeated squaring (only + - * / in binary64: bit-identical anywhere).
+     */
+    public static int skewedRank(double x, int count, int log2Alpha, double c) {
+        double y = c + (1.0 - c) * x;
+        double ca = c;
+        for (int s = 0; s < log2Alpha; s++) { y = y * y; ca = ca * ca; }
+        double t = (y - ca) / (1.0 - ca);
+        long rank = (long) Math.floor((double) count * t);
+        if (rank < 0) rank = 0;
+        if (rank > count - 1) rank = count - 1;
+        return (int) rank;
+    }
+
+    /** Fixed bijection on [0,count) so hot ids are not contiguous: (rank*ID_MULT + count/2) mod count. */
+    public static int scatterId(int rank, int count) {
+        return (int) ((((long) rank * ID_MULT) + (long) (count / 2)) % (long) count);
+    }
+
+    public static float plantedEntry(long seed, long stream, int row, int f) {
+        return (uniform(seed, stream, (long) row * PLANTED_RANK + f) - 0.5f) * PLANTED_AMPLITUDE;
+    }
+
+    /** Record n of the synthetic data set: fills u[0], i[0], r[0]; returns true when n is held out. */
+    public static boolean syntheticRecord(long seed, long n, int nUsers, int nItems,
+                                          int log2AlphaU, double cU, int log2AlphaI, double cI,
+                                          int[] u, int[] i, float[] r) {
+        int uu = scatterId(skewedRank(uniform53(seed, STREAM_USER, n), nUsers, log2AlphaU, cU), nUsers);
+        int ii = scatterId(skewedRank(uniform53(seed, STREAM_ITEM, n), nItems, log2AlphaI, cI), nItems);
+        float dot = 0.0f;
+        for (int f = 0; f < PLANTED_RANK; f++) {
+            dot = dot + plantedEntry(seed, STREAM_PSTAR, uu, f) * plantedEntry(seed, STREAM_QSTAR, ii, f);
+        }
+        float noise = 0.0f;
+        for (int j = 0; j < 4; j++) noise = noise + uniform(seed, STREAM_NOISE, 4L * n + j);
+        noise = noise - 2.0f;
+        float rating = 3.5f + dot;
+        rating = rating + 0.5f * noise;
+        if (rating < 1.0f) rating = 1.0f;
+        if (rating > 5.0f) rating = 5.0f;
+        u[0] = uu; i[0] = ii; r[0] = rating;
+        return Long.remainderUnsigned(hash64(seed, STREAM_HELDOUT, n), 10L) == 0L;
+    }
+
+    /** ML-100K-shaped demo: sequential and threaded, updates/s and held-out RMSE. */
+    public static void main(String[] args) throws Exception {
+        final long seed = 20261018L;
+        final int nUsers = 943, nItems = 1682, total = 100_000, k = 32, epochs = 20;
+        final float lr = 0.01f, lambda = 0.05f;
+        int[] tu = new int[total], ti = new int[total]; float[] tr = new float[total];
+        int[] hu = new int[total], hi = new int[total]; float[] hr = new float[total];
+        int nt = 0, nh = 0;
+        int[] u = new int[1], i = new int[1]; float[] r = new float[1];
+        for (long n = 0; n < total; n++) {
+            boolean held = syntheticRecord(seed, n, nUsers, nItems, 2, 0.25, 3, 0.375, u, i, r);
+            if (held) { hu[nh] = u[0]; hi[nh] = i[0]; hr[nh] = r[0]; nh++; }
+            else      { tu[nt] = u[0]; ti[nt] = i[0]; tr[nt] = r[0]; nt++; }
+        }
+        tu = Arrays.copyOf(tu, nt); ti = Arrays.copyOf(ti, nt); tr = Arrays.copyOf(tr, nt);
+        hu = Arrays.copyOf(hu, nh); hi = Arrays.copyOf(hi, nh); hr = Arrays.copyOf(hr, nh);
+        long t0 = System.nanoTime();
+        Factors seq = factorize(tu, ti, tr, nUsers, nItems, k, lr, lambda, epochs, seed);
+        double sSeq = (System.nanoTime() - t0) * 1e-9;
+        System.out.printf("sequential: %.3e updates/s, held-out RMSE %.6f%n",
+                (double) nt * epochs / sSeq, rmse(seq.P, seq.Q, k, hu, hi, hr));
+        int threads = Runtime.getRuntime().availableProcessors();
+        t0 = System.nanoTime();
+        Factors par = factorizeThreaded(tu, ti, tr, nUsers, nItems, k, lr, lambda, epochs, seed, threads);
+        double sPar = (System.nanoTime() - t0) * 1e-9;
+        System.out.printf("threaded(%d): %.3e updates/s, held-out RMSE %.6f%n", threads,
+                (double) nt * epochs / sPar, rmse(par.P, par.Q, k, hu, hi, hr));
+    }
+}

@@ -1,0 +1,294 @@
+/*
+ * oracle.cpp -- CPU ORACLE for the factorization path. TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library. libmfsgd.so never links, loads or calls it.
+ *
+ * PARITY UNPINNED BY THE REFERENCE: /root/reference holds README.md:1-2 only (no source, no tests,
+ * no golden vectors). This file restates, function by function, the stand-in
+ * baseline/java/MatrixFactorizationSGD.java that BASELINE.json's north_star tells us to commit; each
+ * function cites the stand-in's line. The pins that exist are project-made: the hand-computed KAT
+ * (tests/golden/kat.json), SplitMix64 known answers, and an independent NumPy restatement
+ * (tests/np_restatement.py) whose outputs are committed under tests/golden/.
+ *
+ * Build: g++ -O2 -ffp-contract=off -fno-fast-math (Java float arithmetic is strict binary32, no FMA).
+ */
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+enum { ORC_ORDER_SEQ = 0, ORC_ORDER_WARP_TREE = 1 };
+
+static const uint64_t STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2, STREAM_USER = 3,
+                      STREAM_ITEM = 4, STREAM_NOISE = 5, STREAM_HELDOUT = 6, STREAM_PSTAR = 7,
+                      STREAM_QSTAR = 8;
+
+/* MatrixFactorizationSGD.java:39 hash64 */
+ORC_API uint64_t orc_hash64(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (ctr + 1ULL) + 0xD1B54A32D192ED03ULL * stream;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return z;
+}
+
+/* MatrixFactorizationSGD.java:48 uniform */
+ORC_API float orc_uniform(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    return (float)(orc_hash64(seed, stream, ctr) >> 40) * 0x1.0p-24f;
+}
+
+/* MatrixFactorizationSGD.java:63 defaultInitScale */
+ORC_API float orc_default_init_scale(int k) { return (float)(1.0 / std::sqrt((double)k)); }
+
+/* MatrixFactorizationSGD.java:53 initFactors */
+ORC_API void orc_init_factors(float* rows, int64_t n_rows, int k, uint64_t seed, uint64_t stream,
+                              float scale) {
+    for (int64_t r = 0; r < n_rows; r++)
+        for (int f = 0; f < k; f++) {
+            uint64_t ctr = (uint64_t)r * (uint64_t)k + (uint64_t)f;
+            rows[ctr] = orc_uniform(seed, stream, ctr) * scale;
+        }
+}
+
+/* MatrixFactorizationSGD.java:72 shuffle */
+ORC_API void orc_shuffle(uint64_t seed, int epoch, int n, int32_t* order) {
+    std::vector<uint64_t> packed((size_t)n);
+    for (int idx = 0; idx < n; idx++) {
+        uint64_t key = orc_hash64(seed, STREAM_SHUFFLE, ((uint64_t)(uint32_t)epoch << 32) | (uint64_t)idx) >> 33;
+        packed[idx] = (key << 32) | (uint64_t)idx;
+    }
+    std::sort(packed.begin(), packed.end());
+    for (int j = 0; j < n; j++) order[j] = (int32_t)(packed[j] & 0xFFFFFFFFULL);
+}
+
+/* The dot product of MatrixFactorizationSGD.java:91-94 (f ascending, binary32 accumulate). */
+static inline float dot_seq(const float* p, const float* q, int k) {
+    float dot = 0.0f;
+    for (int f = 0; f < k; f++) dot = dot + p[f] * q[f];
+    return dot;
+}
+
+/*
+ * ORC_ORDER_WARP_TREE: the same products summed in the order the CUDA kernels use:
+ * L = min(32, pow2ceil(k/4)) lanes; lane l adds, starting from 0, the 4 products of each chunk
+ * c = l, l+L, l+2L, ... (< k/4), ascending; then an xor butterfly over masks L/2 .. 1.
+ * Not in the stand-in: it exists so the GPU's deterministic mode can be checked bit for bit.
+ */
+static inline float dot_warp_tree(const float* p, const float* q, int k) {
+    int chunks = k / 4, L = 1;
+    while (L < chunks && L < 32) L <<= 1;
+    float s[32];
+    for (int l = 0; l < L; l++) {
+        float acc = 0.0f;
+        for (int c = l; c < chunks; c += L)
+            for (int j = 0; j < 4; j++) acc = acc + p[4 * c + j] * q[4 * c + j];
+        s[l] = acc;
+    }
+    for (int m = L >> 1; m >= 1; m >>= 1) {
+        float t[32];
+        for (int l = 0; l < L; l++) t[l] = s[l] + s[l ^ m];
+        for (int l = 0; l < L; l++) s[l] = t[l];
+    }
+    return s[0];
+}
+
+static inline float dot_ordered(const float* p, const float* q, int k, int order_mode) {
+    return order_mode == ORC_ORDER_WARP_TREE ? dot_warp_tree(p, q, k) : dot_seq(p, q, k);
+}
+
+/* MatrixFactorizationSGD.java:89 sgdUpdate */
+ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float lambda, int order_mode) {
+    float e = r - dot_ordered(p, q, k, order_mode);
+    for (int f = 0; f < k; f++) {
+        float pf = p[f], qf = q[f];
+        p[f] = pf + lr * (e * qf - lambda * pf);
+        q[f] = qf + lr * (e * pf - lambda * qf);
+    }
+    return e;
+}
+
+static int check_triplets(const int32_t* u, const int32_t* i, int64_t n, int nU, int nI) {
+    for (int64_t t = 0; t < n; t++)
+        if (u[t] < 0 || u[t] >= nU || i[t] < 0 || i[t] >= nI) return -1;
+    return 0;
+}
+
+/*
+ * Epochs [epoch_begin, epoch_end) of the loop in MatrixFactorizationSGD.java:127-133 on existing
+ * P, Q. shuffled=0 visits records in array order (used by tests that feed a pre-ordered list).
+ * trace_e (nullable): the error of every update, in visiting order.
+ */
+ORC_API int orc_train(const int32_t* u, const int32_t* i, const float* r, int64_t n, float* P, float* Q,
+                      int nU, int nI, int k, float lr, float lambda, int epoch_begin, int epoch_end,
+                      uint64_t seed, int order_mode, int shuffled, float* trace_e) {
+    if (n > 0x7fffffffLL || check_triplets(u, i, n, nU, nI)) return -1;
+    std::vector<int32_t> order((size_t)n);
+    int64_t w = 0;
+    for (int epoch = epoch_begin; epoch < epoch_end; epoch++) {
+        if (shuffled) orc_shuffle(seed, epoch, (int)n, order.data());
+        else for (int64_t j = 0; j < n; j++) order[j] = (int32_t)j;
+        for (int64_t j = 0; j < n; j++) {
+            int32_t t = order[j];
+            float e = orc_sgd_update(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, r[t], lr, lambda, order_mode);
+            if (trace_e) trace_e[w++] = e;
+        }
+    }
+    return 0;
+}
+
+/*
+ * One epoch like orc_train, additionally recording for every update (visiting order) the rows
+ * before and after it: pre_p, pre_q, post_p, post_q are [n*k]. This is the teacher-forcing tape
+ * for the per-update parity test.
+ */
+ORC_API int orc_train_tape(const int32_t* u, const int32_t* i, const float* r, int64_t n, float* P, float* Q,
+                           int nU, int nI, int k, float lr, float lambda, int epoch, uint64_t seed,
+                           int order_mode, int32_t* order_out, float* pre_p, float* pre_q,
+                           float* post_p, float* post_q, float* err) {
+    if (n > 0x7fffffffLL || check_triplets(u, i, n, nU, nI)) return -1;
+    orc_shuffle(seed, epoch, (int)n, order_out);
+    for (int64_t j = 0; j < n; j++) {
+        int32_t t = order_out[j];
+        float* p = P + (int64_t)u[t] * k;
+        float* q = Q + (int64_t)i[t] * k;
+        std::memcpy(pre_p + j * k, p, sizeof(float) * k);
+        std::memcpy(pre_q + j * k, q, sizeof(float) * k);
+        err[j] = orc_sgd_update(p, q, k, r[t], lr, lambda, order_mode);
+        std::memcpy(post_p + j * k, p, sizeof(float) * k);
+        std::memcpy(post_q + j * k, q, sizeof(float) * k);
+    }
+    return 0;
+}
+
+/* MatrixFactorizationSGD.java:109 factorize */
+ORC_API int orc_factorize(const int32_t* u, const int32_t* i, const float* r, int64_t n, int nU, int nI, int k,
+                          float lr, float lambda, int epochs, uint64_t seed, int order_mode,
+                          float* P_out, float* Q_out) {
+    if (k <= 0 || nU <= 0 || nI <= 0 || epochs < 0) return -1;
+    float scale = orc_default_init_scale(k);
+    orc_init_factors(P_out, nU, k, seed, STREAM_P_INIT, scale);
+    orc_init_factors(Q_out, nI, k, seed, STREAM_Q_INIT, scale);
+    return orc_train(u, i, r, n, P_out, Q_out, nU, nI, k, lr, lambda, 0, epochs, seed, order_mode, 1, nullptr);
+}
+
+/*
+ * MatrixFactorizationSGD.java:140 factorizeThreaded -- Hogwild, T threads, thread w takes positions
+ * w, w+T, ... of the epoch order; join per epoch. Races on P and Q are intended. shuffled=0 skips
+ * the per-epoch sort (for bounded timing samples of very large inputs). Returns seconds spent in
+ * the update loops (sort excluded) through *seconds.
+ */
+ORC_API int orc_train_hogwild(const int32_t* u, const int32_t* i, const float* r, int64_t n, float* P, float* Q,
+                              int nU, int nI, int k, float lr, float lambda, int epoch_begin, int epoch_end,
+                              uint64_t seed, int threads, int shuffled, double* seconds) {
+    if (n > 0x7fffffffLL || threads < 1 || check_triplets(u, i, n, nU, nI)) return -1;
+    std::vector<int32_t> order((size_t)n);
+    double total = 0.0;
+    for (int epoch = epoch_begin; epoch < epoch_end; epoch++) {
+        if (shuffled) orc_shuffle(seed, epoch, (int)n, order.data());
+        else for (int64_t j = 0; j < n; j++) order[j] = (int32_t)j;
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        const int32_t* ord = order.data();
+        for (int w = 0; w < threads; w++)
+            pool.emplace_back([=]() {
+                for (int64_t j = w; j < n; j += threads) {
+                    int32_t t = ord[j];
+                    orc_sgd_update(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, r[t], lr, lambda, ORC_ORDER_SEQ);
+                }
+            });
+        for (auto& th : pool) th.join();
+        total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (seconds) *seconds = total;
+    return 0;
+}
+
+/* MatrixFactorizationSGD.java:169 rmse */
+ORC_API double orc_rmse(const float* P, const float* Q, int k, const int32_t* u, const int32_t* i,
+                        const float* r, int64_t n, int order_mode) {
+    double sse = 0.0;
+    for (int64_t t = 0; t < n; t++) {
+        float e = r[t] - dot_ordered(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, order_mode);
+        sse += (double)e * (double)e;
+    }
+    return n == 0 ? 0.0 : std::sqrt(sse / (double)n);
+}
+
+/* ---- synthetic power-law ratings: MatrixFactorizationSGD.java:186-239 ---- */
+
+static const int PLANTED_RANK = 16;
+static const float PLANTED_AMPLITUDE = 0.8660254f;
+static const uint64_t ID_MULT = 2654435761ULL;
+
+/* MatrixFactorizationSGD.java:191 uniform53 */
+static inline double uniform53(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    return (double)(orc_hash64(seed, stream, ctr) >> 11) * 0x1.0p-53;
+}
+
+/* MatrixFactorizationSGD.java:199 skewedRank */
+ORC_API int32_t orc_skewed_rank(double x, int32_t count, int log2_alpha, double c) {
+    double y = c + (1.0 - c) * x;
+    double ca = c;
+    for (int s = 0; s < log2_alpha; s++) { y = y * y; ca = ca * ca; }
+    double t = (y - ca) / (1.0 - ca);
+    int64_t rank = (int64_t)std::floor((double)count * t);
+    if (rank < 0) rank = 0;
+    if (rank > count - 1) rank = count - 1;
+    return (int32_t)rank;
+}
+
+/* MatrixFactorizationSGD.java:211 scatterId */
+ORC_API int32_t orc_scatter_id(int32_t rank, int32_t count) {
+    return (int32_t)((((uint64_t)rank * ID_MULT) + (uint64_t)(count / 2)) % (uint64_t)count);
+}
+
+/* MatrixFactorizationSGD.java:215 plantedEntry */
+static inline float planted_entry(uint64_t seed, uint64_t stream, int32_t row, int f) {
+    return (orc_uniform(seed, stream, (uint64_t)row * PLANTED_RANK + (uint64_t)f) - 0.5f) * PLANTED_AMPLITUDE;
+}
+
+/* MatrixFactorizationSGD.java:220 syntheticRecord */
+static inline bool synthetic_record(uint64_t seed, uint64_t n, int nU, int nI, int l2au, double cu, int l2ai,
+                                    double ci, int32_t* u, int32_t* i, float* r) {
+    int32_t uu = orc_scatter_id(orc_skewed_rank(uniform53(seed, STREAM_USER, n), nU, l2au, cu), nU);
+    int32_t ii = orc_scatter_id(orc_skewed_rank(uniform53(seed, STREAM_ITEM, n), nI, l2ai, ci), nI);
+    float dot = 0.0f;
+    for (int f = 0; f < PLANTED_RANK; f++)
+        dot = dot + planted_entry(seed, STREAM_PSTAR, uu, f) * planted_entry(seed, STREAM_QSTAR, ii, f);
+    float noise = 0.0f;
+    for (int j = 0; j < 4; j++) noise = noise + orc_uniform(seed, STREAM_NOISE, 4ULL * n + (uint64_t)j);
+    noise = noise - 2.0f;
+    float rating = 3.5f + dot;
+    rating = rating + 0.5f * noise;
+    if (rating < 1.0f) rating = 1.0f;
+    if (rating > 5.0f) rating = 5.0f;
+    *u = uu; *i = ii; *r = rating;
+    return orc_hash64(seed, STREAM_HELDOUT, n) % 10ULL == 0ULL;
+}
+
+/*
+ * Records [start, start+count) of the synthetic set, in record order; held[t] = 1 when record
+ * start+t belongs to the held-out tenth. Split across `threads` host threads (pure function of n).
+ */
+ORC_API void orc_generate(uint64_t seed, int64_t start, int64_t count, int nU, int nI, int l2au, double cu,
+                          int l2ai, double ci, int32_t* u, int32_t* i, float* r, uint8_t* held, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; w++)
+        pool.emplace_back([=]() {
+            int64_t lo = count * w / threads, hi = count * (w + 1) / threads;
+            for (int64_t t = lo; t < hi; t++)
+                held[t] = synthetic_record(seed, (uint64_t)(start + t), nU, nI, l2au, cu, l2ai, ci,
+                                           u + t, i + t, r + t) ? 1 : 0;
+        });
+    for (auto& th : pool) th.join();
+}
+
+ORC_API int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }

@@ -1,0 +1,144 @@
+"""ctypes binding of liboracle.so (CPU oracle -- TEST INFRASTRUCTURE, see oracle.cpp header).
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
+The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_DIR, "liboracle.so")
+
+ORDER_SEQ, ORDER_WARP_TREE = 0, 1
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _DIR])
+
+
+def _load():
+    if not os.path.exists(_LIB):
+        build()
+    lib = C.CDLL(_LIB)
+    lib.orc_hash64.restype = C.c_uint64
+    lib.orc_hash64.argtypes = [C.c_uint64] * 3
+    lib.orc_uniform.restype = C.c_float
+    lib.orc_uniform.argtypes = [C.c_uint64] * 3
+    lib.orc_default_init_scale.restype = C.c_float
+    lib.orc_default_init_scale.argtypes = [C.c_int]
+    lib.orc_init_factors.restype = None
+    lib.orc_init_factors.argtypes = [_f32p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_float]
+    lib.orc_shuffle.restype = None
+    lib.orc_shuffle.argtypes = [C.c_uint64, C.c_int, C.c_int, _i32p]
+    lib.orc_sgd_update.restype = C.c_float
+    lib.orc_sgd_update.argtypes = [_f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+    lib.orc_train.restype = C.c_int
+    lib.orc_train.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+                              C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    lib.orc_train_tape.restype = C.c_int
+    lib.orc_train_tape.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, _i32p, _f32p, _f32p,
+                                   _f32p, _f32p, _f32p]
+    lib.orc_factorize.restype = C.c_int
+    lib.orc_factorize.argtypes = [_i32p, _i32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
+                                  C.c_float, C.c_int, C.c_uint64, C.c_int, _f32p, _f32p]
+    lib.orc_train_hogwild.restype = C.c_int
+    lib.orc_train_hogwild.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                      C.POINTER(C.c_double)]
+    lib.orc_rmse.restype = C.c_double
+    lib.orc_rmse.argtypes = [_f32p, _f32p, C.c_int, _i32p, _i32p, _f32p, C.c_int64, C.c_int]
+    lib.orc_skewed_rank.restype = C.c_int32
+    lib.orc_skewed_rank.argtypes = [C.c_double, C.c_int32, C.c_int, C.c_double]
+    lib.orc_scatter_id.restype = C.c_int32
+    lib.orc_scatter_id.argtypes = [C.c_int32, C.c_int32]
+    lib.orc_generate.restype = None
+    lib.orc_generate.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.c_int, C.c_double, _i32p, _i32p, _f32p, _u8p, C.c_int]
+    lib.orc_hardware_threads.restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+
+def hardware_threads():
+    return int(lib.orc_hardware_threads())
+
+
+def init_factors(n_rows, k, seed, stream, scale=None):
+    out = np.empty((n_rows, k), dtype=np.float32)
+    if scale is None:
+        scale = lib.orc_default_init_scale(k)
+    lib.orc_init_factors(out, n_rows, k, seed, stream, scale)
+    return out
+
+
+def shuffle(seed, epoch, n):
+    out = np.empty(n, dtype=np.int32)
+    lib.orc_shuffle(seed, epoch, n, out)
+    return out
+
+
+def generate(seed, start, count, n_users, n_items, l2au=2, cu=0.25, l2ai=3, ci=0.375, threads=None):
+    u = np.empty(count, dtype=np.int32)
+    i = np.empty(count, dtype=np.int32)
+    r = np.empty(count, dtype=np.float32)
+    held = np.empty(count, dtype=np.uint8)
+    lib.orc_generate(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci, u, i, r, held,
+                     threads or hardware_threads())
+    return u, i, r, held.astype(bool)
+
+
+def train(u, i, r, P, Q, lr, lam, epoch_begin, epoch_end, seed, order_mode=ORDER_SEQ, shuffled=True,
+          trace=False):
+    n_users, k = P.shape
+    n_items = Q.shape[0]
+    tr = np.empty((epoch_end - epoch_begin) * len(r), dtype=np.float32) if trace else None
+    rc = lib.orc_train(u, i, r, len(r), P, Q, n_users, n_items, k, lr, lam, epoch_begin, epoch_end, seed,
+                       order_mode, int(shuffled), tr.ctypes.data if trace else None)
+    if rc:
+        raise ValueError("oracle: bad triplets")
+    return tr
+
+
+def train_tape(u, i, r, P, Q, lr, lam, epoch, seed, order_mode=ORDER_SEQ):
+    n_users, k = P.shape
+    n = len(r)
+    order = np.empty(n, dtype=np.int32)
+    pre_p, pre_q, post_p, post_q = (np.empty((n, k), dtype=np.float32) for _ in range(4))
+    err = np.empty(n, dtype=np.float32)
+    rc = lib.orc_train_tape(u, i, r, n, P, Q, n_users, Q.shape[0], k, lr, lam, epoch, seed, order_mode,
+                            order, pre_p, pre_q, post_p, post_q, err)
+    if rc:
+        raise ValueError("oracle: bad triplets")
+    return order, pre_p, pre_q, post_p, post_q, err
+
+
+def factorize(u, i, r, n_users, n_items, k, lr, lam, epochs, seed, order_mode=ORDER_SEQ):
+    P = np.empty((n_users, k), dtype=np.float32)
+    Q = np.empty((n_items, k), dtype=np.float32)
+    rc = lib.orc_factorize(u, i, r, len(r), n_users, n_items, k, lr, lam, epochs, seed, order_mode, P, Q)
+    if rc:
+        raise ValueError("oracle: bad arguments")
+    return P, Q
+
+
+def train_hogwild(u, i, r, P, Q, lr, lam, epoch_begin, epoch_end, seed, threads, shuffled=True):
+    secs = C.c_double(0.0)
+    rc = lib.orc_train_hogwild(u, i, r, len(r), P, Q, P.shape[0], Q.shape[0], P.shape[1], lr, lam,
+                               epoch_begin, epoch_end, seed, threads, int(shuffled), C.byref(secs))
+    if rc:
+        raise ValueError("oracle: bad arguments")
+    return secs.value
+
+
+def rmse(P, Q, u, i, r, order_mode=ORDER_SEQ):
+    return float(lib.orc_rmse(P, Q, P.shape[1], u, i, r, len(r), order_mode))

@@ -1,0 +1,194 @@
+"""CPU tests of the oracle (oracle/oracle.cpp) against the committed pins.
+
+The reference has no tests or vectors (README.md:1-2 only); the pins are: published SplitMix64
+outputs, the hand-computed KAT, and tests/golden/golden_small.json produced by the independent
+NumPy restatement (tests/np_restatement.py, script tests/golden/make_golden.py).
+"""
+import numpy as np
+import pytest
+
+import np_restatement as npr
+import pyoracle as orc
+
+SEED = 20261018
+
+
+def f32(bits):
+    return np.array(bits, dtype=np.uint32).view(np.float32)
+
+
+def test_splitmix64_published_vectors(golden):
+    for n, want in enumerate(golden["splitmix64_seed0"]):
+        assert orc.lib.orc_hash64(0, 0, n) == want
+    for n, want in enumerate(golden["splitmix64_seed1234567"]):
+        assert orc.lib.orc_hash64(1234567, 0, n) == want
+
+
+def test_hash64_streams(golden):
+    for stream, ctr, want in golden["hash64"]:
+        assert orc.lib.orc_hash64(SEED, stream, ctr) == want
+
+
+def test_uniform_range_and_exactness():
+    for c in range(1000):
+        x = orc.lib.orc_uniform(SEED, 0, c)
+        assert 0.0 <= x < 1.0
+        assert float(np.float32(x)) * 2**24 == int(float(x) * 2**24)
+
+
+def test_kat_hand_computed(kat):
+    for mode in (orc.ORDER_SEQ, orc.ORDER_WARP_TREE):
+        # k=2 is padded to 4 with zeros for the tree order (k % 4 == 0 on the GPU path); zeros add exactly.
+        p = np.array(kat["p"] + [0, 0], dtype=np.float32)
+        q = np.array(kat["q"] + [0, 0], dtype=np.float32)
+        e = orc.lib.orc_sgd_update(p, q, 4, kat["r"], kat["lr"], kat["lambda"], mode)
+        assert abs(e - kat["e"]) < 1e-6
+        np.testing.assert_allclose(p[:2], kat["p_new"], rtol=1e-6)
+        np.testing.assert_allclose(q[:2], kat["q_new"], rtol=1e-6)
+        assert p[2] == 0 and q[3] == 0
+
+
+def test_kat_k2_sequential(kat):
+    p = np.array(kat["p"], dtype=np.float32)
+    q = np.array(kat["q"], dtype=np.float32)
+    e = orc.lib.orc_sgd_update(p, q, 2, kat["r"], kat["lr"], kat["lambda"], orc.ORDER_SEQ)
+    assert abs(e - kat["e"]) < 1e-6
+    np.testing.assert_allclose(p, kat["p_new"], rtol=1e-6)
+    np.testing.assert_allclose(q, kat["q_new"], rtol=1e-6)
+
+
+def test_init_factors_golden(golden):
+    np.testing.assert_array_equal(orc.init_factors(3, 8, SEED, 0).ravel(), f32(golden["init_p_k8_rows3"]))
+    np.testing.assert_array_equal(orc.init_factors(2, 32, SEED, 1).ravel(), f32(golden["init_q_k32_rows2"]))
+
+
+def test_shuffle_golden_and_permutation(golden):
+    assert orc.shuffle(SEED, 0, 64).tolist() == golden["shuffle_e0_n64"]
+    assert orc.shuffle(SEED, 3, 64).tolist() == golden["shuffle_e3_n64"]
+    big = orc.shuffle(SEED, 5, 100_000)
+    assert np.array_equal(np.sort(big), np.arange(100_000))
+    assert np.array_equal(big, npr.shuffle(SEED, 5, 100_000))
+    assert not np.array_equal(big, orc.shuffle(SEED, 6, 100_000))
+    assert orc.shuffle(SEED, 0, 0).size == 0
+
+
+@pytest.mark.parametrize("name,nu,ni,l2ai", [("ml100k", 943, 1682, 3), ("heavy", 10_000_000, 1_000_000, 4)])
+def test_generator_golden(golden, name, nu, ni, l2ai):
+    g = golden["gen_" + name]
+    u, i, r, held = orc.generate(SEED, 0, 256, nu, ni, 2, 0.25, l2ai, 0.375)
+    assert u.tolist() == g["u"] and i.tolist() == g["i"]
+    np.testing.assert_array_equal(r, f32(g["r"]))
+    assert held.astype(int).tolist() == g["held"]
+    u, i, r, held = orc.generate(SEED, 10**9, 64, nu, ni, 2, 0.25, l2ai, 0.375, threads=3)
+    assert u.tolist() == g["u_at_1e9"] and i.tolist() == g["i_at_1e9"]
+    np.testing.assert_array_equal(r, f32(g["r_at_1e9"]))
+    assert held.astype(int).tolist() == g["held_at_1e9"]
+
+
+def test_generator_shape_properties():
+    nu, ni, n = 480_000, 17_800, 2_000_000
+    u, i, r, held = orc.generate(SEED, 0, n, nu, ni)
+    assert u.min() >= 0 and u.max() < nu and i.min() >= 0 and i.max() < ni
+    assert 1.0 <= r.min() and r.max() <= 5.0
+    assert abs(held.mean() - 0.1) < 0.002
+    counts = np.sort(np.bincount(i, minlength=ni))[::-1]
+    top1 = counts[: ni // 100].sum() / n
+    assert 0.27 < top1 < 0.33                      # top 1 % of items ~ 30 % of ratings
+    assert counts[0] / n < 0.02                    # no single item dominates
+    assert 3.3 < r.mean() < 3.7
+
+
+def test_scatter_id_is_bijection():
+    for count in (1, 2, 943, 1682, 17_800, 65_536):
+        ids = np.array([orc.lib.orc_scatter_id(x, count) for x in range(count)])
+        assert np.array_equal(np.sort(ids), np.arange(count))
+
+
+def test_sgd_small_run_golden(golden):
+    s = golden["sgd_small_shape"]
+    u, i, r, _ = orc.generate(SEED, 0, s["n"], s["n_users"], s["n_items"])
+    for mode, key in ((orc.ORDER_SEQ, "sgd_small_seq"), (orc.ORDER_WARP_TREE, "sgd_small_tree")):
+        P, Q = orc.factorize(u, i, r, s["n_users"], s["n_items"], s["k"], s["lr"], s["lambda"], s["epochs"],
+                             SEED, mode)
+        np.testing.assert_array_equal(P.ravel(), f32(golden[key]["P"]))
+        np.testing.assert_array_equal(Q.ravel(), f32(golden[key]["Q"]))
+        assert abs(orc.rmse(P, Q, u, i, r) - golden[key]["rmse"]) < 1e-12
+
+
+def test_update_k20_golden(golden):
+    for mode, key in ((orc.ORDER_SEQ, "update_k20_seq"), (orc.ORDER_WARP_TREE, "update_k20_tree")):
+        p = orc.init_factors(1, 20, SEED, 0, 0.5)[0].copy()
+        q = orc.init_factors(1, 20, SEED, 1, 0.5)[0].copy()
+        e = orc.lib.orc_sgd_update(p, q, 20, 3.25, 0.05, 0.02, mode)
+        np.testing.assert_array_equal(p, f32(golden[key]["p"]))
+        np.testing.assert_array_equal(q, f32(golden[key]["q"]))
+        assert np.float32(e) == f32(golden[key]["e"])[0]
+
+
+def test_oracle_vs_numpy_1k_ratings_k8():
+    """SURVEY section 4 'oracle unit': C++ oracle vs NumPy float32 restatement, bit for bit."""
+    nu, ni, k = 50, 80, 8
+    u, i, r, _ = orc.generate(SEED + 1, 0, 1000, nu, ni)
+    Pn, Qn = npr.factorize(u, i, r, nu, ni, k, 0.03, 0.02, 1, SEED + 1)
+    Po, Qo = orc.factorize(u, i, r, nu, ni, k, 0.03, 0.02, 1, SEED + 1)
+    np.testing.assert_array_equal(Pn, Po)
+    np.testing.assert_array_equal(Qn, Qo)
+
+
+def test_tree_and_seq_orders_agree_per_update_1e5():
+    """Teacher-forced: from the same pre-update rows both summation orders land within 1e-5 relative."""
+    nu, ni, k = 943, 1682, 32
+    u, i, r, held = orc.generate(SEED, 0, 20_000, nu, ni)
+    P = orc.init_factors(nu, k, SEED, 0)
+    Q = orc.init_factors(ni, k, SEED, 1)
+    order, pre_p, pre_q, post_p, post_q, err = orc.train_tape(u, i, r, P, Q, 0.01, 0.05, 0, SEED)
+    for j in range(0, len(r), 7):
+        p, q = pre_p[j].copy(), pre_q[j].copy()
+        orc.lib.orc_sgd_update(p, q, k, r[order[j]], 0.01, 0.05, orc.ORDER_WARP_TREE)
+        np.testing.assert_allclose(p, post_p[j], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(q, post_q[j], rtol=1e-5, atol=1e-8)
+
+
+def test_trace_and_tape_consistent():
+    nu, ni, k = 30, 40, 8
+    u, i, r, _ = orc.generate(SEED, 0, 500, nu, ni)
+    P1, Q1 = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    P2, Q2 = P1.copy(), Q1.copy()
+    tr = orc.train(u, i, r, P1, Q1, 0.02, 0.05, 0, 1, SEED, trace=True)
+    order, pre_p, pre_q, post_p, post_q, err = orc.train_tape(u, i, r, P2, Q2, 0.02, 0.05, 0, SEED)
+    np.testing.assert_array_equal(tr, err)
+    np.testing.assert_array_equal(P1, P2)
+    assert np.array_equal(order, orc.shuffle(SEED, 0, 500))
+
+
+def test_rejects_out_of_range_ids():
+    u = np.array([0, 5], dtype=np.int32)
+    i = np.array([0, 0], dtype=np.int32)
+    r = np.ones(2, dtype=np.float32)
+    with pytest.raises(ValueError):
+        orc.factorize(u, i, r, 5, 3, 8, 0.1, 0.1, 1, 1)
+
+
+def test_empty_input_is_identity():
+    P, Q = orc.factorize(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32), 3, 4, 8,
+                         0.1, 0.1, 5, SEED)
+    np.testing.assert_array_equal(P, orc.init_factors(3, 8, SEED, 0))
+    np.testing.assert_array_equal(Q, orc.init_factors(4, 8, SEED, 1))
+    assert orc.rmse(P, Q, np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32)) == 0.0
+
+
+def test_ml100k_shaped_converges_and_hogwild_matches():
+    """configs[0]: 943 x 1682, 100K ratings, k=32, 20 epochs, sequential and threaded."""
+    nu, ni, k, lr, lam, epochs = 943, 1682, 32, 0.01, 0.05, 20
+    u, i, r, held = orc.generate(SEED, 0, 100_000, nu, ni)
+    tu, ti, tr = u[~held].copy(), i[~held].copy(), r[~held].copy()
+    hu, hi, hr = u[held].copy(), i[held].copy(), r[held].copy()
+    P, Q = orc.factorize(tu, ti, tr, nu, ni, k, lr, lam, epochs, SEED)
+    seq = orc.rmse(P, Q, hu, hi, hr)
+    assert seq < 0.45
+    P2, Q2 = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    orc.train_hogwild(tu, ti, tr, P2, Q2, lr, lam, 0, epochs, SEED, threads=4)
+    hog = orc.rmse(P2, Q2, hu, hi, hr)
+    assert abs(hog - seq) / seq < 0.005            # the 0.5 % bar the GPU Hogwild path must also meet
+    Pt, Qt = orc.factorize(tu, ti, tr, nu, ni, k, lr, lam, epochs, SEED, orc.ORDER_WARP_TREE)
+    assert abs(orc.rmse(Pt, Qt, hu, hi, hr) - seq) / seq < 1e-4
