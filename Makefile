@@ -1,0 +1,32 @@
+# Builds libmfsgd.so (sm_100a only), the CPU oracle (test infrastructure) and the C ABI harness.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
+PKG       := matrixfactorizationsgd.java_b200
+CSRC      := $(PKG)/csrc
+OBJDIR    := build/obj
+LIB       := $(PKG)/lib/libmfsgd.so
+OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
+
+all: $(LIB) oracle harness
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh include/mfsgd.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
+
+oracle:
+	$(MAKE) -s -C oracle
+
+harness: tests/c/abi_harness
+tests/c/abi_harness: tests/c/abi_harness.c include/mfsgd.h
+	gcc -O1 -Wall -Wextra -Iinclude -o $@ $< -ldl
+
+clean:
+	rm -rf build $(LIB) tests/c/abi_harness
+	$(MAKE) -s -C oracle clean
+
+.PHONY: all oracle harness clean

@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- SGD rating updates/sec on the Netflix-shaped workload (BASELINE.json configs[2]; the
+config the metric and the 40 %-of-roofline target are quoted on), 1/2/4/8 B200.
+
+  python bench.py --gpus N --steps K --warmup W            # N>1: launched by torch.distributed.run
+  python bench.py --impl reference ...                      # the CPU path (oracle port), host cores
+
+A step = one epoch = one pass of the hot path (reshuffle + update kernels [+ Q rotation]) over the
+training records of the workload. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sgd_rating_updates_per_sec"
+UNIT = "updates/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """dram bytes per update-kernel launch from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            try:
+                sm.append(float(row[1])); mx.append(float(row[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def host_training_set(mf, w, device, pinned):
+    """Host triplets of the workload's training records (generated on the GPU, held-out tenth removed)."""
+    sp = mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    us, is_, rs = [], [], []
+    step = 25_000_000
+    for start in range(0, w.n_ratings, step):
+        u, i, r, held = mf.generate_to_host(sp, w.n_users, w.n_items, start, min(step, w.n_ratings - start), device)
+        us.append(u[~held]); is_.append(i[~held]); rs.append(r[~held])
+    n = sum(len(x) for x in rs)
+    if not pinned:
+        return np.concatenate(us), np.concatenate(is_), np.concatenate(rs), None
+    ptrs, arrs = [], []
+    for parts, dt in ((us, np.int32), (is_, np.int32), (rs, np.float32)):
+        p = C.c_void_p()
+        mf.capi.check(mf.capi.lib.mfsgd_host_alloc(C.byref(p), n * 4))
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32 if dt == np.int32 else C.c_float)), shape=(n,))
+        np.concatenate(parts, out=a)
+        ptrs.append(p); arrs.append(a)
+    return arrs[0], arrs[1], arrs[2], ptrs
+
+
+def run_ours(args):
+    import matrixfactorizationsgd.java_b200 as mf
+    capi = mf.capi
+    w = mf.WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        # torch.distributed carries only bootstrap bytes and timing scalars (CPU tensors): gloo. The Q-shard
+        # rotation runs over NCCL inside libmfsgd.so.
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    elif args.gpus > 1:
+        raise SystemExit("N>1 runs one process per GPU: launch with python -m torch.distributed.run (see docstring)")
+
+    def barrier():
+        import torch
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(local_rank)
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def allsum(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t)
+        return t.item()
+
+    from matrixfactorizationsgd.java_b200 import ring
+    flags = capi.FLAG_TIME_KERNELS
+    common = dict(n_users=w.n_users, n_items=w.n_items, k=w.k, lr=w.lr, lambda_=w.lambda_, seed=mf.SEED,
+                  stripes_per_gpu=args.stripes, shards_per_gpu=args.shards, scatter=args.scatter, flags=flags,
+                  ctas_per_sm=args.ctas_per_sm)
+    if world > 1:
+        eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
+    else:
+        eng = mf.Engine(mf.make_config(mode=capi.MODE_HOGWILD, device=local_rank, **common))
+    sp = mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    t0 = time.time()
+    n_train_local, n_held_local = eng.generate_synthetic(sp)
+    setup_s = time.time() - t0
+    info = eng.layout_info()
+    eng.init_factors()
+    if args.warmup > 0:
+        eng.train(args.warmup)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    wall0 = time.time()
+    stats = eng.train(args.steps)
+    barrier()
+    wall = time.time() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(s.epoch_ms for s in stats)                       # CUDA events on the engine's stream
+    total_ms = allmax(dev_ms)
+    updates = allsum(float(sum(s.updates for s in stats)))
+    value = updates / (total_ms * 1e-3)
+    kernel_ms = sum(s.update_kernel_ms for s in stats)
+    n_launch = sum(s.update_launches for s in stats)
+    launches_all = allsum(float(sum(s.total_launches for s in stats)))
+    shuffle_ms = sum(s.shuffle_ms for s in stats) / max(1, len(stats))
+    # held-out RMSE after warmup+steps epochs (evidence that the timed work is real training)
+    _, sse, cnt = eng.rmse_heldout()
+    heldout_rmse = ring.reduce_rmse(dist, sse, cnt) if dist is not None else float(np.sqrt(sse / max(cnt, 1)))
+    eng.close()
+
+    # roofline of the dominant kernel (rank 0's launches): algorithmic bytes / measured launch time
+    peak, peak_src = peaks()
+    bpu = mf.bytes_per_update(w.k)
+    rank_updates = float(sum(s.updates for s in stats))
+    achieved = rank_updates * bpu / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic = recorded_traffic(args.workload) if world == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "sgd_update_hogwild_kernel",
+                "bytes_per_update": bpu, "updates_per_launch": rank_updates / max(1, n_launch),
+                "avg_launch_ms": kernel_ms / max(1, n_launch), "kernel_share_of_step": kernel_ms / max(dev_ms, 1e-9),
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # e2e: the reference-facing call with HOST buffers: H2D + bucketing + init + K epochs + D2H of P, Q
+    e2e = None
+    if not args.no_e2e:
+        hu, hi, hr, pins = host_training_set(mf, w, local_rank, pinned=True)
+        n_host = len(hr)
+        P = np.zeros((w.n_users, w.k), dtype=np.float32)
+        Q = np.zeros((w.n_items, w.k), dtype=np.float32)
+        if world > 1:
+            nid = ring.broadcast_unique_id(dist, rank)
+            cfg = mf.make_config(mode=capi.MODE_DSGD, n_gpus=world, world_size=world, rank=rank, device=local_rank,
+                                 nccl_id=nid, **dict(common, flags=0))
+        else:
+            cfg = mf.make_config(mode=capi.MODE_HOGWILD, device=local_rank, **dict(common, flags=0))
+        barrier()
+        t0 = time.time()
+        capi.check(capi.lib.mfsgd_factorize(capi.ptr(hu), capi.ptr(hi), capi.ptr(hr), n_host, C.byref(cfg), args.steps,
+                                            capi.ptr(P), capi.ptr(Q)))
+        barrier()
+        e2e_s = allmax(time.time() - t0)
+        for p in pins:
+            capi.lib.mfsgd_host_free(p)
+        e2e = {"value": float(n_host) * args.steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": 12.0 * n_host * world / args.steps,
+               "d2h_bytes_per_step": 4.0 * w.k * (w.n_users + w.n_items) / args.steps,
+               "seconds": e2e_s, "call": "mfsgd_factorize(host triplets -> host P,Q), pinned host buffers",
+               "epochs": args.steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(w, sample=args.cpu_sample, threads=1)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "%s: %d users x %d items, %d ratings (%d train), k=%d, lr=%g, lambda=%g" % (
+                              w.name, w.n_users, w.n_items, w.n_ratings, int(info.n_train_total), w.k, w.lr, w.lambda_),
+                          "parallelism": "hogwild-1gpu" if world == 1 else "dsgd-ring%d" % world,
+                          "stripes_per_gpu": int(info.stripes_per_gpu), "shards_per_gpu": int(info.shards_per_gpu),
+                          "scatter": "store" if args.scatter == 0 else "atomic",
+                          "l2": "inputs larger than L2: %.2f GB of records + %.0f MB of factors streamed per step" % (
+                              12e-9 * info.n_train_total, 4e-6 * w.k * (w.n_users + w.n_items)),
+                          "setup_seconds_excluded": setup_s},
+               "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches_all), "clocks": clocks,
+               "heldout_rmse": heldout_rmse, "epochs_trained": args.warmup + args.steps,
+               "shuffle_ms_per_step": shuffle_ms, "wall_ms_per_step": wall * 1e3 / args.steps}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(w, sample, threads):
+    """The reference's CPU path (the C++ oracle port of the Java stand-in: no JDK in this image) on a
+    bounded sample: the first `sample` records of the same synthetic set, full-size P and Q."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    import matrixfactorizationsgd.java_b200 as mf
+    n = min(sample, w.n_ratings)
+    u, i, r, held = orc.generate(mf.SEED, 0, n, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    u, i, r = u[~held].copy(), i[~held].copy(), r[~held].copy()
+    P = orc.init_factors(w.n_users, w.k, mf.SEED, 0)
+    Q = orc.init_factors(w.n_items, w.k, mf.SEED, 1)
+    if threads == 1:
+        t0 = time.time()
+        orc.train(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, mf.SEED, shuffled=False)
+        secs = time.time() - t0
+    else:
+        secs = orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, mf.SEED, threads, shuffled=False)
+    return {"value": len(r) / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "1 epoch over the first %d records (%d train) of %s, full-size P/Q, k=%d" % (n, len(r), w.name, w.k),
+            "host_cores_available": orc.hardware_threads(), "seconds": secs}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path, all host threads, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    import matrixfactorizationsgd.java_b200 as mf
+    w = mf.WORKLOADS[args.workload]
+    threads = orc.hardware_threads()
+    n = min(args.ref_sample, w.n_ratings)
+    u, i, r, held = orc.generate(mf.SEED, 0, n, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    u, i, r = u[~held].copy(), i[~held].copy(), r[~held].copy()
+    P = orc.init_factors(w.n_users, w.k, mf.SEED, 0)
+    Q = orc.init_factors(w.n_items, w.k, mf.SEED, 1)
+    for s in range(args.warmup):
+        orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, mf.SEED, threads, shuffled=False)
+    secs = 0.0
+    for s in range(args.steps):
+        secs += orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, mf.SEED, threads, shuffled=False)
+    value = len(r) * args.steps / secs
+    sample = "each step = 1 Hogwild epoch, %d host threads, over the first %d records (%d train) of %s, full-size P/Q" % (
+        threads, n, len(r), w.name)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s: %d users x %d items, k=%d, lr=%g, lambda=%g (bounded sample)" % (
+               w.name, w.n_users, w.n_items, w.k, w.lr, w.lambda_), "parallelism": "cpu-hogwild-%dthreads" % threads},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference = C++ oracle port of the Java stand-in (no JDK in the image; /root/reference has no source)"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="netflix")
+    ap.add_argument("--stripes", type=int, default=0)
+    ap.add_argument("--shards", type=int, default=0)
+    ap.add_argument("--scatter", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=12_000_000)
+    ap.add_argument("--ref-sample", type=int, default=20_000_000)
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

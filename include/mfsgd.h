@@ -1,0 +1,185 @@
+/*
+ * mfsgd.h -- C ABI of libmfsgd.so, the B200-native matrix-factorization SGD engine.
+ *
+ * This is the drop-in boundary for the factorization path of MatrixFactorizationSGD.java
+ * (/root/reference/README.md:1 names the class; the reference ships no source, so the interface
+ * replaced is that of the committed stand-in baseline/java/MatrixFactorizationSGD.java). A Java host
+ * binds these symbols with Panama FFM (java/MatrixFactorizationSGDGpu.java); see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every pointer argument is caller-owned, read or written only during the
+ *    call, never retained or freed by the library (the opaque handle excepted);
+ *  - return value 0 = MFSGD_OK, negative = error code; text via mfsgd_last_error() (thread-local);
+ *  - no exceptions, no abort, no CPU fallback: without a usable sm_100 device every compute entry
+ *    point fails with MFSGD_E_CUDA;
+ *  - a handle is used by one caller thread at a time; distinct handles are independent.
+ */
+#ifndef MFSGD_H
+#define MFSGD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFSGD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MFSGD_API __attribute__((visibility("default")))
+#else
+#define MFSGD_API
+#endif
+
+#define MFSGD_OK             0
+#define MFSGD_E_INVALID_ARG -1
+#define MFSGD_E_CUDA        -2
+#define MFSGD_E_NCCL        -3
+#define MFSGD_E_OOM         -4
+#define MFSGD_E_STATE       -5
+
+/* mfsgd_config.mode */
+#define MFSGD_MODE_DETERMINISTIC 0 /* one warp, records strictly in stand-in shuffle order (parity mode) */
+#define MFSGD_MODE_HOGWILD       1 /* one GPU, lock-free, full grid                                     */
+#define MFSGD_MODE_DSGD          2 /* n_gpus ring members: P striped, Q shard groups rotate             */
+
+/* mfsgd_config.scatter */
+#define MFSGD_SCATTER_STORE  0 /* st.global of the updated rows (Hogwild, last writer wins)  */
+#define MFSGD_SCATTER_ATOMIC 1 /* red.global.add.v4.f32 of the row deltas (no lost updates)  */
+
+/* mfsgd_config.flags */
+#define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
+#define MFSGD_FLAG_VIRTUAL_RING   2u /* place all n_gpus ring members on one device (scheduler test mode) */
+#define MFSGD_FLAG_NO_SHUFFLE     4u /* skip the per-epoch reshuffle (measurement aid)                    */
+
+typedef struct mfsgd_handle mfsgd_handle;
+
+/* POD, caller-owned, copied by mfsgd_create. Zero-fill then set; mfsgd_config_default() does that. */
+typedef struct mfsgd_config {
+    int32_t  n_users;          /* rows of P                                                        */
+    int32_t  n_items;          /* rows of Q                                                        */
+    int32_t  k;                /* rank; k % 4 == 0, 4 <= k <= 512                                   */
+    float    lr;               /* learning rate (constant)                                         */
+    float    lambda;           /* L2 regularisation                                                */
+    float    init_scale;       /* <= 0 -> 1/sqrt(k) (MatrixFactorizationSGD.java:63)                */
+    uint64_t seed;             /* init + shuffle seed (MatrixFactorizationSGD.java:109 `seed`)      */
+    int32_t  mode;             /* MFSGD_MODE_*                                                     */
+    int32_t  n_gpus;           /* ring size G: 1 for DETERMINISTIC/HOGWILD; 1,2,4,8 for DSGD        */
+    int32_t  stripes_per_gpu;  /* P sub-stripes per ring member, 0 = auto (sized to stay L2-resident) */
+    int32_t  shards_per_gpu;   /* Q sub-shards per ring member, 0 = auto (1)                         */
+    int32_t  scatter;          /* MFSGD_SCATTER_*                                                  */
+    uint32_t flags;            /* MFSGD_FLAG_*                                                     */
+    int32_t  device;           /* first CUDA ordinal to use; single-process ring uses device..device+G-1 */
+    int32_t  world_size;       /* 1 = this process drives all ring members; G = one process per member */
+    int32_t  rank;             /* ring member driven by this process when world_size == n_gpus       */
+    uint8_t  nccl_id[128];     /* world_size > 1: ncclUniqueId from mfsgd_nccl_unique_id() of rank 0 */
+    int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
+    int32_t  reserved[7];
+} mfsgd_config;
+
+/* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
+ * events on the engine's own streams), max over the ring members this process drives. */
+typedef struct mfsgd_epoch_stats {
+    int64_t updates;            /* rating updates applied by this process's ring members             */
+    double  epoch_ms;           /* shuffle + all sub-epochs + rotations                              */
+    double  shuffle_ms;         /* the reshuffle kernel alone                                        */
+    double  update_kernel_ms;   /* sum over update launches (MFSGD_FLAG_TIME_KERNELS), else 0         */
+    int32_t update_launches;    /* update-kernel launches in the epoch                               */
+    int32_t total_launches;     /* every kernel this library launched in the epoch                   */
+    double  heldout_rmse;       /* NaN unless a held-out set is loaded and eval_every_epoch is on     */
+} mfsgd_epoch_stats;
+
+/* Synthetic power-law ratings (MatrixFactorizationSGD.java:220 syntheticRecord). Record n in
+ * [0, n_total) is a pure function of (seed, n); those with hash64(seed,6,n) % 10 == 0 are held out. */
+typedef struct mfsgd_synth_params {
+    int64_t  n_total;
+    uint64_t seed;
+    int32_t  log2_alpha_user;   /* 2  (alpha 4)                                                      */
+    int32_t  log2_alpha_item;   /* 3  (alpha 8; top 1 % of items ~30 %), 4 = heavy (alpha 16; ~60 %)  */
+    double   c_user;            /* 0.25                                                              */
+    double   c_item;            /* 0.375                                                             */
+} mfsgd_synth_params;
+
+/* Layout report for tests and tools (all counts are for this process's ring members). */
+typedef struct mfsgd_layout_info {
+    int32_t n_gpus, stripes_per_gpu, shards_per_gpu;
+    int32_t user_blocks;        /* n_gpus * stripes_per_gpu                                          */
+    int32_t item_blocks;        /* n_gpus * shards_per_gpu                                           */
+    int64_t n_train_local;      /* records held by this process                                      */
+    int64_t n_heldout_local;
+    int64_t n_train_total;      /* records in the whole data set (all processes)                     */
+} mfsgd_layout_info;
+
+MFSGD_API int  mfsgd_abi_version(void);
+MFSGD_API const char* mfsgd_last_error(void);   /* library-owned, valid until this thread's next mfsgd call */
+MFSGD_API int  mfsgd_device_count(int32_t* count);
+MFSGD_API int  mfsgd_config_default(mfsgd_config* cfg);
+
+MFSGD_API int  mfsgd_create(const mfsgd_config* cfg, mfsgd_handle** out);
+MFSGD_API void mfsgd_destroy(mfsgd_handle* h);
+
+/* Training triplets (MatrixFactorizationSGD.java:109 users/items/ratings). Host pointers. In a
+ * multi-process ring every rank passes the same full arrays; each keeps its own user stripe. */
+MFSGD_API int  mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings,
+                        int64_t n);
+/* Optional held-out triplets kept on the device for mfsgd_rmse_heldout / per-epoch evaluation. */
+MFSGD_API int  mfsgd_load_heldout(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings,
+                        int64_t n);
+/* Extension: generate, split and bucket the synthetic data set on the device (no host arrays). */
+MFSGD_API int  mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout);
+
+MFSGD_API int  mfsgd_init_factors(mfsgd_handle* h);                        /* MatrixFactorizationSGD.java:53 */
+MFSGD_API int  mfsgd_set_factors(mfsgd_handle* h, const float* P, const float* Q);  /* full nU*k, nI*k host arrays */
+MFSGD_API int  mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q);     /* multi-process: only this rank's rows are written */
+/* Row ranges this process owns (users [u_lo,u_hi), items [i_lo,i_hi)) -- whole matrices when world_size==1. */
+MFSGD_API int  mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi);
+
+/* `epochs` more epochs of MatrixFactorizationSGD.java:127-133; stats nullable, length epochs. */
+MFSGD_API int  mfsgd_train(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats);
+/* DETERMINISTIC mode only: also returns the error e of every update in visiting order
+ * (err_trace length = epochs * n_train). */
+MFSGD_API int  mfsgd_train_traced(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace);
+MFSGD_API int  mfsgd_set_eval_every_epoch(mfsgd_handle* h, int32_t on);
+
+/* MatrixFactorizationSGD.java:169 rmse. Multi-process: sse_out and n_out receive this rank's partial
+ * sums (nullable); rmse_out is the rank-local value -- reduce the partials across ranks for the total. */
+MFSGD_API int  mfsgd_rmse(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                double* rmse_out);
+MFSGD_API int  mfsgd_rmse_heldout(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out);
+MFSGD_API int  mfsgd_rmse_train(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out);
+
+/* One-shot form = the Java entry point 1:1 (init from cfg->seed, train `epochs`, copy P and Q out). */
+MFSGD_API int  mfsgd_factorize(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                     const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out);
+
+/* Introspection for tests and tools. */
+MFSGD_API int  mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out);
+/* user_bounds[user_blocks+1], item_bounds[item_blocks+1] (global row ids). */
+MFSGD_API int  mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds);
+/* Ring member `member`'s current record layout: recs = 3*n int32 words (u,i,r-bits per record);
+ * block_offsets[stripes_per_gpu*item_blocks+1]. Pass recs=NULL to query *n only. */
+MFSGD_API int  mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n);
+/* Runs the reshuffle kernel once for `epoch` (HOGWILD/DSGD) or the stand-in order sort (DETERMINISTIC). */
+MFSGD_API int  mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch);
+
+/* Teacher-forced per-update check: applies the update rule to n independent
+ * (pre_p[j], pre_q[j], r[j]) row pairs on the device, returns post rows and errors. Host pointers. */
+MFSGD_API int  mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,
+                                const float* pre_q, const float* r, float* post_p, float* post_q, float* err);
+/* Device twin of MatrixFactorizationSGD.java:220 for records [start,start+count): host output arrays. */
+MFSGD_API int  mfsgd_generate_to_host(int32_t device, const mfsgd_synth_params* sp, int32_t n_users, int32_t n_items,
+                            int64_t start, int64_t count, int32_t* users, int32_t* items, float* ratings,
+                            uint8_t* held);
+
+/* Multi-process ring bootstrap: rank 0 calls this, ships the 128 bytes to every rank (any channel),
+ * every rank puts them in mfsgd_config.nccl_id. */
+MFSGD_API int  mfsgd_nccl_unique_id(uint8_t out[128]);
+
+/* Pinned host staging helpers (optional; plain host memory works too, at lower H2D bandwidth). */
+MFSGD_API int  mfsgd_host_alloc(void** out, int64_t bytes);
+MFSGD_API int  mfsgd_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFSGD_H */

@@ -1,0 +1,121 @@
+"""ctypes binding of libmfsgd.so -- the same symbols, in the same way, that the Java host binds with
+Panama FFM (java/MatrixFactorizationSGDGpu.java). Declarations mirror include/mfsgd.h one to one.
+
+There is no fallback: if the CUDA library is missing, importing this module raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmfsgd.so")
+
+OK, E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
+MODE_DETERMINISTIC, MODE_HOGWILD, MODE_DSGD = 0, 1, 2
+SCATTER_STORE, SCATTER_ATOMIC = 0, 1
+FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE = 1, 2, 4
+ABI_VERSION = 1
+
+
+class Config(C.Structure):
+    _fields_ = [("n_users", C.c_int32), ("n_items", C.c_int32), ("k", C.c_int32), ("lr", C.c_float),
+                ("lambda_", C.c_float), ("init_scale", C.c_float), ("seed", C.c_uint64), ("mode", C.c_int32),
+                ("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
+                ("scatter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32), ("world_size", C.c_int32),
+                ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
+
+
+class EpochStats(C.Structure):
+    _fields_ = [("updates", C.c_int64), ("epoch_ms", C.c_double), ("shuffle_ms", C.c_double),
+                ("update_kernel_ms", C.c_double), ("update_launches", C.c_int32), ("total_launches", C.c_int32),
+                ("heldout_rmse", C.c_double)]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("n_total", C.c_int64), ("seed", C.c_uint64), ("log2_alpha_user", C.c_int32),
+                ("log2_alpha_item", C.c_int32), ("c_user", C.c_double), ("c_item", C.c_double)]
+
+
+class LayoutInfo(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
+                ("user_blocks", C.c_int32), ("item_blocks", C.c_int32), ("n_train_local", C.c_int64),
+                ("n_heldout_local", C.c_int64), ("n_train_total", C.c_int64)]
+
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes): every symbol include/mfsgd.h declares
+SIGNATURES = {
+    "mfsgd_abi_version": (C.c_int, []),
+    "mfsgd_last_error": (C.c_char_p, []),
+    "mfsgd_device_count": (C.c_int, [C.POINTER(_i32)]),
+    "mfsgd_config_default": (C.c_int, [C.POINTER(Config)]),
+    "mfsgd_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
+    "mfsgd_destroy": (None, [_vp]),
+    "mfsgd_load_ratings": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "mfsgd_load_heldout": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "mfsgd_generate_synthetic": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_i64), C.POINTER(_i64)]),
+    "mfsgd_init_factors": (C.c_int, [_vp]),
+    "mfsgd_set_factors": (C.c_int, [_vp, _vp, _vp]),
+    "mfsgd_get_factors": (C.c_int, [_vp, _vp, _vp]),
+    "mfsgd_get_partition": (C.c_int, [_vp] + [C.POINTER(_i32)] * 4),
+    "mfsgd_train": (C.c_int, [_vp, _i32, C.POINTER(EpochStats)]),
+    "mfsgd_train_traced": (C.c_int, [_vp, _i32, C.POINTER(EpochStats), _vp]),
+    "mfsgd_set_eval_every_epoch": (C.c_int, [_vp, _i32]),
+    "mfsgd_rmse": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(C.c_double)]),
+    "mfsgd_rmse_heldout": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "mfsgd_rmse_train": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "mfsgd_factorize": (C.c_int, [_vp, _vp, _vp, _i64, C.POINTER(Config), _i32, _vp, _vp]),
+    "mfsgd_get_layout_info": (C.c_int, [_vp, C.POINTER(LayoutInfo)]),
+    "mfsgd_get_bounds": (C.c_int, [_vp, _vp, _vp]),
+    "mfsgd_get_records": (C.c_int, [_vp, _i32, _vp, _vp, C.POINTER(_i64)]),
+    "mfsgd_shuffle_once": (C.c_int, [_vp, _i32]),
+    "mfsgd_apply_updates_forced": (C.c_int, [_i32, _i32, _f32, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mfsgd_generate_to_host": (C.c_int, [_i32, C.POINTER(SynthParams), _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mfsgd_nccl_unique_id": (C.c_int, [_vp]),
+    "mfsgd_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
+    "mfsgd_host_free": (C.c_int, [_vp]),
+}
+
+
+class MfsgdError(RuntimeError):
+    """Non-zero return of an mfsgd_* call (the Java host raises IllegalStateException here)."""
+
+    def __init__(self, code, message):
+        super().__init__("mfsgd error %d: %s" % (code, message))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmfsgd.so is not built (%s missing): run `make` or __graft_entry__.build(); "
+                          "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mfsgd_abi_version() != ABI_VERSION:
+        raise ImportError("libmfsgd.so ABI %d != binding ABI %d" % (lib.mfsgd_abi_version(), ABI_VERSION))
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != OK:
+        raise MfsgdError(rc, (lib.mfsgd_last_error() or b"").decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def as_f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)

@@ -1,0 +1,100 @@
+// common.cuh -- shared device helpers of libmfsgd.so (sm_100a only).
+//
+// Arithmetic contract: every float op of the update rule is an explicit round-to-
+// nearest intrinsic (__fmul_rn/__fadd_rn/__fsub_rn), so nvcc can never contract a*b+c into an FMA;
+// this mirrors the strict binary32 semantics of baseline/java/MatrixFactorizationSGD.java:89-105.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mfsgd {
+
+// 12-byte rating record (BASELINE.json north_star: "12-byte (u, i, r) records").
+struct Rec {
+    int32_t u;
+    int32_t i;
+    float   r;
+};
+static_assert(sizeof(Rec) == 12, "Rec must be 12 bytes");
+
+enum : uint64_t {
+    STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2, STREAM_USER = 3, STREAM_ITEM = 4,
+    STREAM_NOISE = 5, STREAM_HELDOUT = 6, STREAM_PSTAR = 7, STREAM_QSTAR = 8,
+    STREAM_BLOCK_SHUFFLE = 9   // Hogwild/DSGD in-block reshuffle keys (not in the stand-in)
+};
+
+// MatrixFactorizationSGD.java:39 hash64 (SplitMix64 finaliser over seed, stream, counter).
+__host__ __device__ __forceinline__ uint64_t hash64(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (ctr + 1ULL) + 0xD1B54A32D192ED03ULL * stream;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return z;
+}
+
+// MatrixFactorizationSGD.java:48 uniform: 24 random bits -> [0,1), exact in binary32.
+__device__ __forceinline__ float uniform24(uint64_t seed, uint64_t stream, uint64_t ctr) {
+    return __fmul_rn((float)(uint32_t)(hash64(seed, stream, ctr) >> 40), 0x1.0p-24f);
+}
+
+// ---- cache-policy loads/stores -------------------------------------------------------------
+// Factor rows are read and written by every SM: keep them out of the (incoherent) L1 and resident
+// in L2 (ld/st .cg). Records are streamed once per epoch: no L1 allocation, evict-first in L2.
+__device__ __forceinline__ float4 ld_row4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_row4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ void red_add_row4(float* p, float4 d) {
+    // sm_90+: vectorised fire-and-forget float atomic add, resolved in L2.
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                 : "memory");
+}
+
+// L2 eviction policy (createpolicy): records are read once per epoch -> evict-first.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// ---- the update rule -----------------------------------------------------------------------
+// Partial dot of one float4 chunk, continuing a running binary32 sum, element order x,y,z,w.
+__device__ __forceinline__ float dot4_acc(float acc, float4 a, float4 b) {
+    acc = __fadd_rn(acc, __fmul_rn(a.x, b.x));
+    acc = __fadd_rn(acc, __fmul_rn(a.y, b.y));
+    acc = __fadd_rn(acc, __fmul_rn(a.z, b.z));
+    acc = __fadd_rn(acc, __fmul_rn(a.w, b.w));
+    return acc;
+}
+
+// xor butterfly over a LANES-wide sub-warp, masks LANES/2 .. 1 (oracle.cpp
+// dot_warp_tree reproduces this order bit for bit). All 32 lanes of the warp must call it.
+template <int LANES>
+__device__ __forceinline__ float group_sum(float s) {
+#pragma unroll
+    for (int m = LANES >> 1; m >= 1; m >>= 1) s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, m));
+    return s;
+}
+
+// new = old + lr * (e * other - lambda * old)      MatrixFactorizationSGD.java:100-101
+__device__ __forceinline__ float upd1(float old_, float other, float e, float lr, float lambda) {
+    return __fadd_rn(old_, __fmul_rn(lr, __fsub_rn(__fmul_rn(e, other), __fmul_rn(lambda, old_))));
+}
+// the increment alone (for the atomic scatter): lr * (e * other - lambda * old)
+__device__ __forceinline__ float delta1(float old_, float other, float e, float lr, float lambda) {
+    return __fmul_rn(lr, __fsub_rn(__fmul_rn(e, other), __fmul_rn(lambda, old_)));
+}
+__device__ __forceinline__ float4 upd4(float4 o, float4 x, float e, float lr, float lambda) {
+    return make_float4(upd1(o.x, x.x, e, lr, lambda), upd1(o.y, x.y, e, lr, lambda),
+                       upd1(o.z, x.z, e, lr, lambda), upd1(o.w, x.w, e, lr, lambda));
+}
+__device__ __forceinline__ float4 delta4(float4 o, float4 x, float e, float lr, float lambda) {
+    return make_float4(delta1(o.x, x.x, e, lr, lambda), delta1(o.y, x.y, e, lr, lambda),
+                       delta1(o.z, x.z, e, lr, lambda), delta1(o.w, x.w, e, lr, lambda));
+}
+
+}  // namespace mfsgd

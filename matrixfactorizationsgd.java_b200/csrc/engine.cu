@@ -1,0 +1,1293 @@
+// engine.cu -- host side of libmfsgd.so: handle lifecycle, data staging/bucketing, and subsystem (4),
+// the single-box DSGD scheduler (P row stripes stay put, Q shard groups rotate round the ring).
+//
+// Replaces the loop of baseline/java/MatrixFactorizationSGD.java:109-135 (factorize). C ABI in
+// include/mfsgd.h. No CPU fallback: every compute entry point needs an sm_100 device.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/mfsgd.h"
+#include "kernels.cuh"
+
+using namespace mfsgd;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(e__ == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e__));                          \
+    } while (0)
+
+#define CKRC(call)               \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != MFSGD_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (only a multi-process ring needs it; libmfsgd.so has no link-time dependency)
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return MFSGD_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) {
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(MFSGD_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                                \
+    if (!g_nccl.field) return fail(MFSGD_E_NCCL, "libnccl lacks symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return MFSGD_OK;
+}
+
+#define CKN(call)                                                                                          \
+    do {                                                                                                   \
+        ncclResult_t r__ = (call);                                                                         \
+        if (r__ != ncclSuccess)                                                                            \
+            return fail(MFSGD_E_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+struct EvalSet {            // held-out records of one ring member, bucketed per Q shard group
+    Rec* recs = nullptr;
+    int64_t n = 0;
+    std::vector<int64_t> group_off;  // [G + 1]
+};
+
+struct Member {              // one ring member ("GPU g")
+    int g = 0;               // ring index
+    int device = 0;          // CUDA ordinal
+    int n_sms = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    int32_t u_lo = 0, u_hi = 0;      // owned P rows
+    float* P = nullptr;
+    float* Q[2] = {nullptr, nullptr};
+    int64_t q_cap_rows = 0;
+    int cur = 0;             // Q buffer holding the current shard group
+    int held_group = 0;      // which shard group that is
+    Rec* recs[2] = {nullptr, nullptr};
+    int rcur = 0;
+    int64_t n_recs = 0;
+    std::vector<int64_t> block_off;  // host copy, [mu * IB + 1]
+    int64_t* d_block_off = nullptr;
+    uint16_t* d_owner_u = nullptr;
+    uint16_t* d_owner_i = nullptr;
+    EvalSet heldout;
+    double* d_scratch = nullptr;     // rmse partials + 1 accumulator at the end
+    double* d_sse = nullptr;
+    // deterministic mode
+    Rec* recs_orig = nullptr;
+    uint64_t* keys_a = nullptr;
+    uint64_t* keys_b = nullptr;
+    void* sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
+    // events
+    cudaEvent_t ev_compute = nullptr, ev_sent = nullptr;
+    std::vector<cudaEvent_t> evpool; // timing events, handed out per train call
+    int ev_used = 0;
+    struct EpochRec {                // one per epoch of the running train call, resolved after a sync
+        cudaEvent_t start, shuffled, end;
+        int kbeg, kend;              // range in kev of (begin, end) pairs bracketing update launches
+        int launches, update_launches;
+    };
+    std::vector<EpochRec> pending;
+    std::vector<cudaEvent_t> kev;
+    int grid = 148;
+    int launches = 0, update_launches = 0;
+};
+
+struct mfsgd_handle {
+    mfsgd_config cfg;
+    int G = 1, mu = 1, mi = 1, UB = 1, IB = 1;
+    float scale = 0.f;
+    std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
+    std::vector<Member> members;                    // the ring members this process drives
+    bool loaded = false, factors_ready = false;
+    int epoch = 0;
+    int eval_every = 0;
+    int64_t n_train_total = 0;
+    ncclComm_t comm = nullptr;
+    bool multi_process = false;
+    int min_windows = 128;   // MFSGD_MIN_WINDOWS overrides (tuning aid)
+};
+
+static inline int group_lo(const mfsgd_handle* h, int grp) { return h->item_bounds[(size_t)grp * h->mi]; }
+static inline int group_hi(const mfsgd_handle* h, int grp) { return h->item_bounds[(size_t)(grp + 1) * h->mi]; }
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+template <typename T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static void free_eval(EvalSet& e) {
+    dev_free(e.recs);
+    e.n = 0;
+    e.group_off.clear();
+}
+
+static void free_member_data(Member& m) {
+    cudaSetDevice(m.device);
+    dev_free(m.P);
+    dev_free(m.Q[0]);
+    dev_free(m.Q[1]);
+    dev_free(m.recs[0]);
+    dev_free(m.recs[1]);
+    dev_free(m.d_block_off);
+    dev_free(m.d_owner_u);
+    dev_free(m.d_owner_i);
+    dev_free(m.recs_orig);
+    dev_free(m.keys_a);
+    dev_free(m.keys_b);
+    dev_free(m.sort_temp);
+    free_eval(m.heldout);
+    m.n_recs = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// record sources: device SoA chunks of the input (host arrays or the synthetic generator)
+// ------------------------------------------------------------------------------------------------
+struct Source {
+    const int32_t* hu = nullptr;   // host arrays (training set, or explicit held-out set)
+    const int32_t* hi = nullptr;
+    const float* hr = nullptr;
+    bool synthetic = false;
+    SynthArgs synth{};
+    int64_t total = 0;
+    bool all_held = false;         // host arrays are a held-out set
+};
+
+struct Chunk {                     // per-device staging buffers
+    int32_t* u = nullptr;
+    int32_t* i = nullptr;
+    float* r = nullptr;
+    uint8_t* held = nullptr;       // only for synthetic sources
+    int64_t cap = 0;
+    int64_t start = -1, count = 0; // what is currently staged
+};
+
+static const int64_t CHUNK_MAX = 256LL << 20;  // records per staging chunk (3.3 GB of device buffers)
+
+static int chunk_alloc(Chunk& c, int64_t cap, bool with_held) {
+    c.cap = cap;
+    CK(dev_alloc(&c.u, (size_t)cap));
+    CK(dev_alloc(&c.i, (size_t)cap));
+    CK(dev_alloc(&c.r, (size_t)cap));
+    if (with_held) CK(dev_alloc(&c.held, (size_t)cap));
+    return MFSGD_OK;
+}
+static void chunk_free(Chunk& c) {
+    dev_free(c.u);
+    dev_free(c.i);
+    dev_free(c.r);
+    dev_free(c.held);
+    c.start = -1;
+}
+// Stage records [start, start+count) on the current device (no-op when already staged).
+static int chunk_stage(Chunk& c, const Source& s, int64_t start, int64_t count, cudaStream_t stream, int* launches) {
+    if (c.start == start && c.count == count) return MFSGD_OK;
+    if (s.synthetic) {
+        CK(launch_generate(s.synth, start, count, c.u, c.i, c.r, c.held, stream, launches));
+    } else {
+        CK(cudaMemcpyAsync(c.u, s.hu + start, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(c.i, s.hi + start, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(c.r, s.hr + start, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+    }
+    c.start = start;
+    c.count = count;
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int mfsgd_abi_version(void) { return MFSGD_ABI_VERSION; }
+extern "C" const char* mfsgd_last_error(void) { return g_err; }
+
+extern "C" int mfsgd_device_count(int32_t* count) {
+    if (!count) return fail(MFSGD_E_INVALID_ARG, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(MFSGD_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_config_default(mfsgd_config* cfg) {
+    if (!cfg) return fail(MFSGD_E_INVALID_ARG, "cfg is null");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->k = 128;
+    cfg->lr = 0.005f;
+    cfg->lambda = 0.05f;
+    cfg->seed = 20261018ULL;
+    cfg->mode = MFSGD_MODE_HOGWILD;
+    cfg->n_gpus = 1;
+    cfg->world_size = 1;
+    return MFSGD_OK;
+}
+
+static int validate_config(const mfsgd_config* c) {
+    if (!c) return fail(MFSGD_E_INVALID_ARG, "cfg is null");
+    if (c->n_users <= 0 || c->n_items <= 0) return fail(MFSGD_E_INVALID_ARG, "n_users and n_items must be positive");
+    if (!rank_supported(c->k)) return fail(MFSGD_E_INVALID_ARG, "k=%d unsupported: need k %% 4 == 0 and 4 <= k <= 512", c->k);
+    if (!(c->lr > 0.f) || !(c->lambda >= 0.f)) return fail(MFSGD_E_INVALID_ARG, "need lr > 0 and lambda >= 0");
+    if (c->mode < MFSGD_MODE_DETERMINISTIC || c->mode > MFSGD_MODE_DSGD) return fail(MFSGD_E_INVALID_ARG, "bad mode %d", c->mode);
+    if (c->n_gpus < 1 || c->n_gpus > 64) return fail(MFSGD_E_INVALID_ARG, "n_gpus=%d out of range", c->n_gpus);
+    if (c->mode != MFSGD_MODE_DSGD && c->n_gpus != 1) return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC/HOGWILD modes need n_gpus == 1");
+    if (c->scatter != MFSGD_SCATTER_STORE && c->scatter != MFSGD_SCATTER_ATOMIC) return fail(MFSGD_E_INVALID_ARG, "bad scatter %d", c->scatter);
+    if (c->stripes_per_gpu < 0 || c->stripes_per_gpu > 256 || c->shards_per_gpu < 0 || c->shards_per_gpu > 64)
+        return fail(MFSGD_E_INVALID_ARG, "stripes_per_gpu/shards_per_gpu out of range");
+    if (c->world_size != 1 && c->world_size != c->n_gpus) return fail(MFSGD_E_INVALID_ARG, "world_size must be 1 or n_gpus");
+    if (c->world_size > 1 && (c->rank < 0 || c->rank >= c->world_size)) return fail(MFSGD_E_INVALID_ARG, "bad rank %d", c->rank);
+    if (c->world_size > 1 && (c->flags & MFSGD_FLAG_VIRTUAL_RING)) return fail(MFSGD_E_INVALID_ARG, "virtual ring is single-process only");
+    if (c->mode == MFSGD_MODE_DETERMINISTIC && (c->stripes_per_gpu > 1 || c->shards_per_gpu > 1))
+        return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode keeps the caller's record order: no blocking");
+    if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
+    return MFSGD_OK;
+}
+
+static int member_setup(mfsgd_handle* h, Member& m) {
+    CK(cudaSetDevice(m.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, m.device));
+    if (prop.major < 10) return fail(MFSGD_E_CUDA, "device %d is sm_%d%d; libmfsgd.so carries sm_100a code only", m.device, prop.major, prop.minor);
+    m.n_sms = prop.multiProcessorCount;
+    m.l2_bytes = (size_t)prop.l2CacheSize;
+    CK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&m.ev_compute, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_sent, cudaEventDisableTiming));
+    CK(dev_alloc(&m.d_scratch, (size_t)rmse_scratch_doubles() + 1));
+    m.d_sse = m.d_scratch + rmse_scratch_doubles();
+    int ctas = 0;
+    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter == MFSGD_SCATTER_ATOMIC, &ctas));
+    if (ctas < 1) ctas = 1;
+    if (h->cfg.ctas_per_sm > 0 && h->cfg.ctas_per_sm < ctas) ctas = h->cfg.ctas_per_sm;
+    m.grid = m.n_sms * ctas;
+    return MFSGD_OK;
+}
+
+extern "C" void mfsgd_destroy(mfsgd_handle* h) {
+    if (!h) return;
+    for (Member& m : h->members) {
+        cudaSetDevice(m.device);
+        if (m.stream) cudaStreamSynchronize(m.stream);
+        if (m.copy_stream) cudaStreamSynchronize(m.copy_stream);
+    }
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (Member& m : h->members) {
+        free_member_data(m);
+        dev_free(m.d_scratch);
+        for (cudaEvent_t e : m.evpool) cudaEventDestroy(e);
+        cudaEvent_t evs[] = {m.ev_compute, m.ev_sent};
+        for (cudaEvent_t e : evs)
+            if (e) cudaEventDestroy(e);
+        if (m.stream) cudaStreamDestroy(m.stream);
+        if (m.copy_stream) cudaStreamDestroy(m.copy_stream);
+    }
+    delete h;
+}
+
+extern "C" int mfsgd_create(const mfsgd_config* cfg, mfsgd_handle** out) {
+    if (!out) return fail(MFSGD_E_INVALID_ARG, "out is null");
+    *out = nullptr;
+    CKRC(validate_config(cfg));
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail(MFSGD_E_CUDA, "no CUDA device: %s (libmfsgd.so has no CPU fallback)",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    mfsgd_handle* h = new mfsgd_handle();
+    h->cfg = *cfg;
+    h->G = cfg->n_gpus;
+    h->multi_process = cfg->world_size > 1;
+    if (const char* mw = getenv("MFSGD_MIN_WINDOWS")) h->min_windows = std::max(1, atoi(mw));
+    h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
+    const bool virtual_ring = (cfg->flags & MFSGD_FLAG_VIRTUAL_RING) != 0;
+    const int n_local = h->multi_process ? 1 : h->G;
+    if (!virtual_ring && !h->multi_process && cfg->device + h->G > ndev) {
+        delete h;
+        return fail(MFSGD_E_INVALID_ARG, "need devices %d..%d but only %d visible", cfg->device, cfg->device + h->G - 1, ndev);
+    }
+    if (cfg->device >= ndev) {
+        delete h;
+        return fail(MFSGD_E_INVALID_ARG, "device %d not visible (%d devices)", cfg->device, ndev);
+    }
+    h->members.resize((size_t)n_local);
+    for (int j = 0; j < n_local; j++) {
+        Member& m = h->members[(size_t)j];
+        m.g = h->multi_process ? cfg->rank : j;
+        m.device = (virtual_ring || h->multi_process) ? cfg->device : cfg->device + j;
+        m.held_group = m.g;
+        int rc = member_setup(h, m);
+        if (rc != MFSGD_OK) {
+            mfsgd_destroy(h);
+            return rc;
+        }
+    }
+    if (!h->multi_process && !virtual_ring && h->G > 1) {
+        for (Member& a : h->members)
+            for (Member& b : h->members)
+                if (a.device != b.device) {
+                    cudaSetDevice(a.device);
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, a.device, b.device);
+                    if (can) {
+                        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                        if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
+                    }
+                }
+    }
+    if (h->multi_process) {
+        int rc = nccl_load();
+        if (rc != MFSGD_OK) {
+            mfsgd_destroy(h);
+            return rc;
+        }
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        memcpy(&id, cfg->nccl_id, sizeof(id));
+        cudaSetDevice(h->members[0].device);
+        ncclResult_t r = g_nccl.CommInitRank(&h->comm, cfg->world_size, id, cfg->rank);
+        if (r != ncclSuccess) {
+            int rc2 = fail(MFSGD_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+            h->comm = nullptr;
+            mfsgd_destroy(h);
+            return rc2;
+        }
+    }
+    *out = h;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_nccl_unique_id(uint8_t out[128]) {
+    if (!out) return fail(MFSGD_E_INVALID_ARG, "out is null");
+    CKRC(nccl_load());
+    ncclUniqueId id;
+    CKN(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, 128);
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return fail(MFSGD_E_INVALID_ARG, "bad arguments");
+    CK(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return MFSGD_OK;
+}
+extern "C" int mfsgd_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout: bounds, owner tables, bucketing
+// ------------------------------------------------------------------------------------------------
+static void choose_blocking(mfsgd_handle* h) {
+    const mfsgd_config& c = h->cfg;
+    h->mi = c.shards_per_gpu > 0 ? c.shards_per_gpu : 1;
+    if (c.mode == MFSGD_MODE_DETERMINISTIC) {
+        h->mu = 1;
+    } else if (c.stripes_per_gpu > 0) {
+        h->mu = c.stripes_per_gpu;
+    } else {
+        // auto: keep one P sub-stripe plus the held Q shard group resident in L2
+        const double l2 = (double)h->members[0].l2_bytes;
+        const double p_bytes = (double)c.n_users * c.k * 4.0 / h->G;
+        const double q_bytes = (double)c.n_items * c.k * 4.0 / h->G;
+        int mu = 1;
+        if (l2 > 0 && p_bytes + q_bytes > 0.6 * l2) {
+            const double budget = std::max(0.35 * l2 - q_bytes, 0.1 * l2);
+            mu = (int)std::ceil(p_bytes / budget);
+        }
+        h->mu = std::min(std::max(mu, 1), 256);
+    }
+    h->UB = h->G * h->mu;
+    h->IB = h->G * h->mi;
+}
+
+// Balanced (by rating count) bounds from the source, computed on member 0's device.
+static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
+    Member& m = h->members[0];
+    const mfsgd_config& c = h->cfg;
+    CK(cudaSetDevice(m.device));
+    uint32_t *ucnt = nullptr, *icnt = nullptr;
+    uint64_t *ucum = nullptr, *icum = nullptr;
+    int32_t *ub = nullptr, *ib = nullptr;
+    int* bad = nullptr;
+    void* temp = nullptr;
+    int rc = MFSGD_OK;
+    auto cleanup = [&]() {
+        dev_free(ucnt); dev_free(icnt); dev_free(ucum); dev_free(icum); dev_free(ub); dev_free(ib); dev_free(bad);
+        if (temp) cudaFree(temp);
+    };
+#define CKC(call)                                                                                           \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            rc = fail(e__ == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "%s:%d %s: %s", __FILE__, \
+                      __LINE__, #call, cudaGetErrorString(e__));                                            \
+            cleanup();                                                                                      \
+            return rc;                                                                                      \
+        }                                                                                                   \
+    } while (0)
+    CKC(dev_alloc(&ucnt, (size_t)c.n_users + 1));
+    CKC(dev_alloc(&icnt, (size_t)c.n_items + 1));
+    CKC(dev_alloc(&ucum, (size_t)c.n_users + 1));
+    CKC(dev_alloc(&icum, (size_t)c.n_items + 1));
+    CKC(dev_alloc(&ub, (size_t)h->UB + 1));
+    CKC(dev_alloc(&ib, (size_t)h->IB + 1));
+    CKC(dev_alloc(&bad, 1));
+    CKC(cudaMemsetAsync(ucnt, 0, ((size_t)c.n_users + 1) * 4, m.stream));
+    CKC(cudaMemsetAsync(icnt, 0, ((size_t)c.n_items + 1) * 4, m.stream));
+    CKC(cudaMemsetAsync(bad, 0, sizeof(int), m.stream));
+    for (int64_t start = 0; start < src.total; start += ch.cap) {
+        const int64_t count = std::min(ch.cap, src.total - start);
+        rc = chunk_stage(ch, src, start, count, m.stream, &m.launches);
+        if (rc != MFSGD_OK) { cleanup(); return rc; }
+        CKC(launch_count_rows(ch.u, ch.i, src.synthetic ? ch.held : nullptr, count, ucnt, icnt, c.n_users, c.n_items, bad,
+                              m.stream, &m.launches));
+    }
+    size_t tb_u = 0, tb_i = 0;
+    CKC(exclusive_cumsum_u32(ucnt, ucum, c.n_users, nullptr, &tb_u, m.stream, nullptr));
+    CKC(exclusive_cumsum_u32(icnt, icum, c.n_items, nullptr, &tb_i, m.stream, nullptr));
+    size_t tb = std::max(tb_u, tb_i);
+    CKC(cudaMalloc(&temp, tb ? tb : 1));
+    CKC(exclusive_cumsum_u32(ucnt, ucum, c.n_users, temp, &tb, m.stream, &m.launches));
+    CKC(launch_balanced_bounds(ucum, c.n_users, h->UB, ub, m.stream, &m.launches));
+    CKC(exclusive_cumsum_u32(icnt, icum, c.n_items, temp, &tb, m.stream, &m.launches));
+    CKC(launch_balanced_bounds(icum, c.n_items, h->IB, ib, m.stream, &m.launches));
+    h->user_bounds.assign((size_t)h->UB + 1, 0);
+    h->item_bounds.assign((size_t)h->IB + 1, 0);
+    int bad_host = 0;
+    uint64_t total_train = 0;
+    CKC(cudaMemcpyAsync(h->user_bounds.data(), ub, ((size_t)h->UB + 1) * 4, cudaMemcpyDeviceToHost, m.stream));
+    CKC(cudaMemcpyAsync(h->item_bounds.data(), ib, ((size_t)h->IB + 1) * 4, cudaMemcpyDeviceToHost, m.stream));
+    CKC(cudaMemcpyAsync(&bad_host, bad, sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+    CKC(cudaMemcpyAsync(&total_train, ucum + c.n_users, sizeof(uint64_t), cudaMemcpyDeviceToHost, m.stream));
+    CKC(cudaStreamSynchronize(m.stream));
+#undef CKC
+    cleanup();
+    if (bad_host) return fail(MFSGD_E_INVALID_ARG, "a rating has a user or item id outside [0,n_users) x [0,n_items)");
+    h->n_train_total = (int64_t)total_train;
+    return MFSGD_OK;
+}
+
+static void uniform_bounds(mfsgd_handle* h) {
+    h->user_bounds.resize((size_t)h->UB + 1);
+    h->item_bounds.resize((size_t)h->IB + 1);
+    for (int b = 0; b <= h->UB; b++) h->user_bounds[(size_t)b] = (int32_t)((int64_t)h->cfg.n_users * b / h->UB);
+    for (int b = 0; b <= h->IB; b++) h->item_bounds[(size_t)b] = (int32_t)((int64_t)h->cfg.n_items * b / h->IB);
+}
+
+// Allocate factors + owner tables of a member for the current bounds.
+static int member_alloc_factors(mfsgd_handle* h, Member& m) {
+    const mfsgd_config& c = h->cfg;
+    CK(cudaSetDevice(m.device));
+    m.u_lo = h->user_bounds[(size_t)m.g * h->mu];
+    m.u_hi = h->user_bounds[(size_t)(m.g + 1) * h->mu];
+    int64_t cap = 0;
+    for (int grp = 0; grp < h->G; grp++) cap = std::max<int64_t>(cap, group_hi(h, grp) - group_lo(h, grp));
+    m.q_cap_rows = cap;
+    dev_free(m.P); dev_free(m.Q[0]); dev_free(m.Q[1]); dev_free(m.d_owner_u); dev_free(m.d_owner_i);
+    CK(dev_alloc(&m.P, (size_t)(m.u_hi - m.u_lo) * c.k));
+    CK(dev_alloc(&m.Q[0], (size_t)cap * c.k));
+    if (h->G > 1) CK(dev_alloc(&m.Q[1], (size_t)cap * c.k));
+    m.cur = 0;
+    m.held_group = m.g;
+    CK(dev_alloc(&m.d_owner_u, (size_t)c.n_users));
+    CK(dev_alloc(&m.d_owner_i, (size_t)c.n_items));
+    int32_t* d_b = nullptr;
+    CK(dev_alloc(&d_b, (size_t)std::max(h->UB, h->IB) + 1));
+    cudaError_t e = cudaMemcpyAsync(d_b, h->user_bounds.data(), ((size_t)h->UB + 1) * 4, cudaMemcpyHostToDevice, m.stream);
+    if (e == cudaSuccess) e = launch_fill_owner(d_b, h->UB, c.n_users, m.d_owner_u, m.stream, &m.launches);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, h->item_bounds.data(), ((size_t)h->IB + 1) * 4, cudaMemcpyHostToDevice, m.stream);
+    if (e == cudaSuccess) e = launch_fill_owner(d_b, h->IB, c.n_items, m.d_owner_i, m.stream, &m.launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+    cudaFree(d_b);
+    CK(e);
+    return MFSGD_OK;
+}
+
+// Bucket the member's share of the source into `nblk` blocks. On success *out_recs (device, owned by the
+// caller) holds the records sorted by block and off[nblk+1] the offsets.
+static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& ch, int want_held, int row_div, int col_div,
+                         int n_cols, Rec** out_recs, std::vector<int64_t>& off) {
+    CK(cudaSetDevice(m.device));
+    BucketArgs b{};
+    b.owner_u = m.d_owner_u;
+    b.owner_i = m.d_owner_i;
+    b.ub_lo = m.g * h->mu;
+    b.ub_hi = (m.g + 1) * h->mu;
+    b.row_div = row_div;
+    b.col_div = col_div;
+    b.n_cols = n_cols;
+    b.want_held = want_held;
+    const int nblk = bucket_block_count(b);
+    if (nblk > 4096) return fail(MFSGD_E_INVALID_ARG, "%d blocks per ring member exceed the 4096 limit", nblk);
+    unsigned long long* d_cnt = nullptr;
+    CK(dev_alloc(&d_cnt, (size_t)nblk));
+    int rc = MFSGD_OK;
+    Rec* recs = nullptr;
+    std::vector<unsigned long long> cnt((size_t)nblk, 0ULL);
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, (size_t)nblk * 8, m.stream);
+    for (int64_t start = 0; e == cudaSuccess && start < src.total; start += ch.cap) {
+        const int64_t count = std::min(ch.cap, src.total - start);
+        rc = chunk_stage(ch, src, start, count, m.stream, &m.launches);
+        if (rc != MFSGD_OK) break;
+        b.u = ch.u; b.i = ch.i; b.r = ch.r; b.n = count;
+        b.held = src.synthetic ? ch.held : nullptr;
+        if (src.all_held) { b.held = nullptr; b.want_held = 0; }   // explicit held-out arrays: take every record
+        e = launch_block_histogram(b, d_cnt, m.stream, &m.launches);
+    }
+    if (rc == MFSGD_OK && e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nblk * 8, cudaMemcpyDeviceToHost, m.stream);
+    if (rc == MFSGD_OK && e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+    if (rc == MFSGD_OK && e == cudaSuccess) {
+        off.assign((size_t)nblk + 1, 0);
+        for (int j = 0; j < nblk; j++) off[(size_t)j + 1] = off[(size_t)j] + (int64_t)cnt[(size_t)j];
+        std::vector<unsigned long long> cursors((size_t)nblk);
+        for (int j = 0; j < nblk; j++) cursors[(size_t)j] = (unsigned long long)off[(size_t)j];
+        e = dev_alloc(&recs, (size_t)off[(size_t)nblk]);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, cursors.data(), (size_t)nblk * 8, cudaMemcpyHostToDevice, m.stream);
+        for (int64_t start = 0; e == cudaSuccess && start < src.total; start += ch.cap) {
+            const int64_t count = std::min(ch.cap, src.total - start);
+            rc = chunk_stage(ch, src, start, count, m.stream, &m.launches);
+            if (rc != MFSGD_OK) break;
+            b.u = ch.u; b.i = ch.i; b.r = ch.r; b.n = count;
+            b.held = src.synthetic ? ch.held : nullptr;
+            if (src.all_held) { b.held = nullptr; b.want_held = 0; }
+            e = launch_block_scatter(b, d_cnt, recs, m.stream, &m.launches);
+        }
+        if (rc == MFSGD_OK && e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+    }
+    cudaFree(d_cnt);
+    if (rc != MFSGD_OK || e != cudaSuccess) {
+        if (recs) cudaFree(recs);
+        if (rc != MFSGD_OK) return rc;
+        CK(e);
+    }
+    *out_recs = recs;
+    return MFSGD_OK;
+}
+
+static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) {
+    const mfsgd_config& c = h->cfg;
+    for (Member& m : h->members) free_member_data(m);
+    h->loaded = false;
+    h->factors_ready = false;
+    h->epoch = 0;
+    choose_blocking(h);
+    if (h->UB > 65535 || h->IB > 65535) return fail(MFSGD_E_INVALID_ARG, "too many blocks");
+    if (c.mode == MFSGD_MODE_DETERMINISTIC && src.total > 0x7fffffffLL)
+        return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode takes at most 2^31-1 records");
+    const int64_t cap = std::max<int64_t>(1, std::min(src.total, CHUNK_MAX));
+    int rc = MFSGD_OK;
+    for (size_t mi_ = 0; mi_ < h->members.size() && rc == MFSGD_OK; mi_++) {
+        Member& m = h->members[mi_];
+        cudaSetDevice(m.device);
+        Chunk ch;
+        rc = chunk_alloc(ch, cap, src.synthetic);
+        if (rc == MFSGD_OK && mi_ == 0) {
+            if (src.total > 0) rc = compute_bounds(h, src, ch);
+            else { uniform_bounds(h); h->n_train_total = 0; }
+        }
+        if (rc == MFSGD_OK) rc = member_alloc_factors(h, m);
+        if (rc == MFSGD_OK && c.mode == MFSGD_MODE_DETERMINISTIC) {
+            // keep the caller's order; validate ids happened in compute_bounds; synthetic sources drop held records
+            if (src.synthetic) rc = fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode takes host triplets (use mfsgd_generate_to_host)");
+            if (rc == MFSGD_OK && src.total > 0) {
+                rc = chunk_stage(ch, src, 0, src.total, m.stream, &m.launches);
+                cudaError_t e = cudaSuccess;
+                if (rc == MFSGD_OK) e = dev_alloc(&m.recs_orig, (size_t)src.total);
+                if (e == cudaSuccess) e = dev_alloc(&m.recs[0], (size_t)src.total);
+                if (e == cudaSuccess) e = dev_alloc(&m.keys_a, (size_t)src.total);
+                if (e == cudaSuccess) e = dev_alloc(&m.keys_b, (size_t)src.total);
+                if (e == cudaSuccess) e = launch_pack_records(ch.u, ch.i, ch.r, src.total, m.recs_orig, m.stream, &m.launches);
+                if (e == cudaSuccess) e = deterministic_order_gather(nullptr, nullptr, (int32_t)src.total, 0, 0, m.keys_a, m.keys_b, nullptr, &m.sort_temp_bytes, m.stream, nullptr);
+                if (e == cudaSuccess) e = cudaMalloc(&m.sort_temp, m.sort_temp_bytes ? m.sort_temp_bytes : 1);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+                if (rc == MFSGD_OK && e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "deterministic staging: %s", cudaGetErrorString(e));
+            }
+            m.n_recs = src.total;
+            m.block_off.assign(2, 0);
+            m.block_off[1] = src.total;
+        } else if (rc == MFSGD_OK) {
+            rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, &m.recs[0], m.block_off);
+            if (rc == MFSGD_OK) {
+                m.n_recs = m.block_off.back();
+                m.rcur = 0;
+                cudaError_t e = dev_alloc(&m.recs[1], (size_t)m.n_recs);
+                if (e == cudaSuccess) e = dev_alloc(&m.d_block_off, m.block_off.size());
+                if (e == cudaSuccess) e = cudaMemcpy(m.d_block_off, m.block_off.data(), m.block_off.size() * 8, cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "record buffers: %s", cudaGetErrorString(e));
+            }
+            if (rc == MFSGD_OK && with_heldout) {
+                free_eval(m.heldout);
+                rc = bucket_member(h, m, src, ch, 1, h->mu, h->mi, h->G, &m.heldout.recs, m.heldout.group_off);
+                if (rc == MFSGD_OK) m.heldout.n = m.heldout.group_off.back();
+            }
+        }
+        chunk_free(ch);
+    }
+    if (rc != MFSGD_OK) {
+        for (Member& m : h->members) free_member_data(m);
+        return rc;
+    }
+    h->loaded = true;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
+    Source s;
+    s.hu = users; s.hi = items; s.hr = ratings; s.total = n;
+    return load_training(h, s, false);
+}
+
+extern "C" int mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout) {
+    if (!h || !sp) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (sp->n_total < 0 || sp->log2_alpha_user < 0 || sp->log2_alpha_user > 6 || sp->log2_alpha_item < 0 || sp->log2_alpha_item > 6 ||
+        !(sp->c_user >= 0.0 && sp->c_user < 1.0) || !(sp->c_item >= 0.0 && sp->c_item < 1.0))
+        return fail(MFSGD_E_INVALID_ARG, "bad synthetic parameters");
+    Source s;
+    s.synthetic = true;
+    s.total = sp->n_total;
+    s.synth.seed = sp->seed;
+    s.synth.n_users = h->cfg.n_users;
+    s.synth.n_items = h->cfg.n_items;
+    s.synth.l2au = sp->log2_alpha_user;
+    s.synth.l2ai = sp->log2_alpha_item;
+    s.synth.cu = sp->c_user;
+    s.synth.ci = sp->c_item;
+    CKRC(load_training(h, s, true));
+    int64_t nt = 0, nh = 0;
+    for (Member& m : h->members) { nt += m.n_recs; nh += m.heldout.n; }
+    if (n_train) *n_train = nt;
+    if (n_heldout) *n_heldout = nh;
+    return MFSGD_OK;
+}
+
+static int build_eval_set(mfsgd_handle* h, Member& m, const int32_t* users, const int32_t* items, const float* ratings,
+                          int64_t n, EvalSet& out) {
+    Source s;
+    s.hu = users; s.hi = items; s.hr = ratings; s.total = n; s.all_held = true;
+    CK(cudaSetDevice(m.device));
+    // validate ids on the device first (count kernel with throw-away counters would cost memory: do it on the host)
+    for (int64_t t = 0; t < n; t++)
+        if (users[t] < 0 || users[t] >= h->cfg.n_users || items[t] < 0 || items[t] >= h->cfg.n_items)
+            return fail(MFSGD_E_INVALID_ARG, "record %lld has an id outside [0,n_users) x [0,n_items)", (long long)t);
+    Chunk ch;
+    int rc = chunk_alloc(ch, std::max<int64_t>(1, std::min(n, CHUNK_MAX)), false);
+    if (rc == MFSGD_OK) {
+        free_eval(out);
+        rc = bucket_member(h, m, s, ch, 0, h->mu, h->mi, h->G, &out.recs, out.group_off);
+        if (rc == MFSGD_OK) out.n = out.group_off.back();
+    }
+    chunk_free(ch);
+    return rc;
+}
+
+extern "C" int mfsgd_load_heldout(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "call mfsgd_load_ratings first (it fixes the stripe bounds)");
+    if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
+    for (Member& m : h->members) CKRC(build_eval_set(h, m, users, items, ratings, n, m.heldout));
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// factors
+// ------------------------------------------------------------------------------------------------
+extern "C" int mfsgd_init_factors(mfsgd_handle* h) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before initialising factors");
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        CK(launch_init_factors(m.P, m.u_hi - m.u_lo, h->cfg.k, m.u_lo, h->cfg.seed, STREAM_P_INIT, h->scale, m.stream, &m.launches));
+        const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
+        CK(launch_init_factors(m.Q[m.cur], hi - lo, h->cfg.k, lo, h->cfg.seed, STREAM_Q_INIT, h->scale, m.stream, &m.launches));
+    }
+    for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
+    h->factors_ready = true;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_set_factors(mfsgd_handle* h, const float* P, const float* Q) {
+    if (!h || !P || !Q) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before setting factors");
+    const int k = h->cfg.k;
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemcpyAsync(m.P, P + (size_t)m.u_lo * k, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
+        const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
+        CK(cudaMemcpyAsync(m.Q[m.cur], Q + (size_t)lo * k, (size_t)(hi - lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
+    }
+    for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
+    h->factors_ready = true;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q) {
+    if (!h || !P || !Q) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
+    const int k = h->cfg.k;
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemcpyAsync(P + (size_t)m.u_lo * k, m.P, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
+        const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
+        CK(cudaMemcpyAsync(Q + (size_t)lo * k, m.Q[m.cur], (size_t)(hi - lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
+    }
+    for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    int32_t ul = h->cfg.n_users, uh = 0, il = h->cfg.n_items, ih = 0;
+    for (Member& m : h->members) {
+        ul = std::min(ul, m.u_lo); uh = std::max(uh, m.u_hi);
+        il = std::min(il, (int32_t)group_lo(h, m.held_group)); ih = std::max(ih, (int32_t)group_hi(h, m.held_group));
+    }
+    if (u_lo) *u_lo = ul;
+    if (u_hi) *u_hi = uh;
+    if (i_lo) *i_lo = il;
+    if (i_hi) *i_hi = ih;
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// subsystem (4): ring rotation of the Q shard groups
+// ------------------------------------------------------------------------------------------------
+// After the kernels of a sub-epoch: member g hands the group it holds to member g-1 and takes the next
+// one from member g+1. Everything is stream/event ordered; the host never blocks inside an epoch.
+static int rotate_q(mfsgd_handle* h) {
+    const int G = h->G, k = h->cfg.k;
+    if (G == 1) return MFSGD_OK;
+    if (h->multi_process) {
+        Member& m = h->members[0];
+        const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
+        const int send_grp = m.held_group, recv_grp = (m.held_group + 1) % G;
+        const size_t send_n = (size_t)(group_hi(h, send_grp) - group_lo(h, send_grp)) * k;
+        const size_t recv_n = (size_t)(group_hi(h, recv_grp) - group_lo(h, recv_grp)) * k;
+        CK(cudaSetDevice(m.device));
+        CKN(g_nccl.GroupStart());
+        CKN(g_nccl.Send(m.Q[m.cur], send_n, ncclFloat, to, h->comm, m.stream));
+        CKN(g_nccl.Recv(m.Q[m.cur ^ 1], recv_n, ncclFloat, from, h->comm, m.stream));
+        CKN(g_nccl.GroupEnd());
+        m.launches += 1;
+        m.cur ^= 1;
+        m.held_group = recv_grp;
+        return MFSGD_OK;
+    }
+    // single process: peer copies on the copy streams
+    for (Member& m : h->members) {
+        Member& dst = h->members[(size_t)((m.g - 1 + G) % G)];
+        CK(cudaSetDevice(m.device));
+        CK(cudaEventRecord(m.ev_compute, m.stream));
+        CK(cudaStreamWaitEvent(m.copy_stream, m.ev_compute, 0));
+        CK(cudaStreamWaitEvent(m.copy_stream, dst.ev_sent, 0));   // dst's previous send out of the buffer we overwrite
+    }
+    for (Member& m : h->members) {
+        Member& dst = h->members[(size_t)((m.g - 1 + G) % G)];
+        const size_t bytes = (size_t)(group_hi(h, m.held_group) - group_lo(h, m.held_group)) * k * 4;
+        CK(cudaSetDevice(m.device));
+        if (dst.device == m.device)
+            CK(cudaMemcpyAsync(dst.Q[dst.cur ^ 1], m.Q[m.cur], bytes, cudaMemcpyDeviceToDevice, m.copy_stream));
+        else
+            CK(cudaMemcpyPeerAsync(dst.Q[dst.cur ^ 1], dst.device, m.Q[m.cur], m.device, bytes, m.copy_stream));
+        CK(cudaEventRecord(m.ev_sent, m.copy_stream));   // also the receiver's "data arrived" signal
+    }
+    for (Member& m : h->members) {
+        Member& src = h->members[(size_t)((m.g + 1) % G)];
+        CK(cudaSetDevice(m.device));
+        CK(cudaStreamWaitEvent(m.stream, src.ev_sent, 0));        // cross-device waits are legal; records are not
+        m.cur ^= 1;
+        m.held_group = (m.held_group + 1) % G;
+    }
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training
+// ------------------------------------------------------------------------------------------------
+static int timing_event(Member& m, cudaEvent_t* out) {
+    if (m.ev_used == (int)m.evpool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        m.evpool.push_back(e);
+    }
+    *out = m.evpool[(size_t)m.ev_used++];
+    return MFSGD_OK;
+}
+
+static int shuffle_member(mfsgd_handle* h, Member& m, int epoch) {
+    CK(cudaSetDevice(m.device));
+    if (h->cfg.mode == MFSGD_MODE_DETERMINISTIC) {
+        if (m.n_recs > 0)
+            CK(deterministic_order_gather(m.recs_orig, m.recs[0], (int32_t)m.n_recs, h->cfg.seed, (uint32_t)epoch, m.keys_a,
+                                          m.keys_b, m.sort_temp, &m.sort_temp_bytes, m.stream, &m.launches));
+        m.rcur = 0;
+        return MFSGD_OK;
+    }
+    const int nblk = h->mu * h->IB;
+    CK(launch_block_shuffle(m.recs[m.rcur], m.recs[m.rcur ^ 1], m.d_block_off, nblk, m.n_recs, h->cfg.seed, (uint32_t)epoch,
+                            (uint32_t)(m.g * nblk), m.stream, &m.launches));
+    m.rcur ^= 1;
+    return MFSGD_OK;
+}
+
+static int rmse_pass(mfsgd_handle* h, bool heldout, double* sse_out, int64_t* n_out);
+
+static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (epochs < 0) return fail(MFSGD_E_INVALID_ARG, "epochs < 0");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
+    const mfsgd_config& c = h->cfg;
+    if (err_trace && c.mode != MFSGD_MODE_DETERMINISTIC) return fail(MFSGD_E_STATE, "error traces exist in DETERMINISTIC mode only");
+    const bool time_kernels = (c.flags & MFSGD_FLAG_TIME_KERNELS) != 0;
+    const bool atomic_scatter = c.scatter == MFSGD_SCATTER_ATOMIC;
+    float* d_trace = nullptr;
+    if (err_trace && h->members[0].n_recs > 0) {
+        CK(cudaSetDevice(h->members[0].device));
+        CK(dev_alloc(&d_trace, (size_t)h->members[0].n_recs));
+    }
+    int rc = MFSGD_OK;
+    for (Member& m : h->members) {
+        m.ev_used = 0;
+        m.pending.clear();
+        m.kev.clear();
+    }
+    int resolved = 0;   // epochs of this call whose stats are final
+    // Epochs are enqueued back to back (no host sync in between) unless per-epoch evaluation is on;
+    // their event records are resolved after the next synchronisation point.
+    auto resolve = [&](int upto) -> int {
+        for (Member& m : h->members) {
+            CK(cudaSetDevice(m.device));
+            CK(cudaStreamSynchronize(m.stream));
+            CK(cudaStreamSynchronize(m.copy_stream));
+        }
+        for (int ep = resolved; ep < upto; ep++) {
+            mfsgd_epoch_stats st{};
+            st.heldout_rmse = std::numeric_limits<double>::quiet_NaN();
+            for (Member& m : h->members) {
+                const Member::EpochRec& er = m.pending[(size_t)ep];
+                float ms = 0.f, sms = 0.f;
+                CK(cudaEventElapsedTime(&ms, er.start, er.end));
+                CK(cudaEventElapsedTime(&sms, er.start, er.shuffled));
+                double kms = 0.0;
+                for (int j = er.kbeg; j + 1 < er.kend; j += 2) {
+                    float t = 0.f;
+                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 1]));
+                    kms += t;
+                }
+                st.updates += m.n_recs;
+                st.epoch_ms = std::max(st.epoch_ms, (double)ms);
+                st.shuffle_ms = std::max(st.shuffle_ms, (double)sms);
+                st.update_kernel_ms = std::max(st.update_kernel_ms, kms);
+                st.update_launches = std::max(st.update_launches, er.update_launches);
+                st.total_launches += er.launches;
+            }
+            if (stats) stats[ep] = st;
+        }
+        resolved = upto;
+        return MFSGD_OK;
+    };
+    const bool want_eval = h->eval_every && !h->members[0].heldout.group_off.empty();
+    for (int ep = 0; ep < epochs && rc == MFSGD_OK; ep++) {
+        for (Member& m : h->members) {
+            m.launches = 0;
+            m.update_launches = 0;
+            Member::EpochRec er{};
+            CK(cudaSetDevice(m.device));
+            CKRC(timing_event(m, &er.start));
+            CKRC(timing_event(m, &er.shuffled));
+            CKRC(timing_event(m, &er.end));
+            er.kbeg = er.kend = (int)m.kev.size();
+            m.pending.push_back(er);
+            CK(cudaEventRecord(er.start, m.stream));
+            if (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) || c.mode == MFSGD_MODE_DETERMINISTIC) CKRC(shuffle_member(h, m, h->epoch));
+            CK(cudaEventRecord(er.shuffled, m.stream));
+        }
+        for (int s = 0; s < h->G; s++) {
+            for (Member& m : h->members) {
+                CK(cudaSetDevice(m.device));
+                const int grp = m.held_group;
+                UpdateArgs a{};
+                a.P = m.P;
+                a.Q = m.Q[m.cur];
+                a.k = c.k;
+                a.u_base = m.u_lo;
+                a.i_base = group_lo(h, grp);
+                a.lr = c.lr;
+                a.lambda = c.lambda;
+                if (c.mode == MFSGD_MODE_DETERMINISTIC) {
+                    a.recs = m.recs[0];
+                    a.n = m.n_recs;
+                    CK(launch_sgd_update_deterministic(a, d_trace, m.stream, &m.launches));
+                    m.update_launches++;
+                    if (d_trace)
+                        CK(cudaMemcpyAsync(err_trace + (size_t)ep * m.n_recs, d_trace, (size_t)m.n_recs * 4, cudaMemcpyDeviceToHost, m.stream));
+                    continue;
+                }
+                for (int sa = 0; sa < h->mu; sa++) {
+                    const int64_t lo = m.block_off[(size_t)sa * h->IB + (size_t)grp * h->mi];
+                    const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
+                    if (hi == lo) continue;
+                    a.recs = m.recs[m.rcur] + lo;
+                    a.n = hi - lo;
+                    cudaEvent_t e0 = nullptr, e1 = nullptr;
+                    if (time_kernels) {
+                        CKRC(timing_event(m, &e0));
+                        CKRC(timing_event(m, &e1));
+                        CK(cudaEventRecord(e0, m.stream));
+                    }
+                    CK(launch_sgd_update_hogwild(a, atomic_scatter, m.grid, h->min_windows, m.stream, &m.launches));
+                    m.update_launches++;
+                    if (time_kernels) {
+                        CK(cudaEventRecord(e1, m.stream));
+                        m.kev.push_back(e0);
+                        m.kev.push_back(e1);
+                    }
+                }
+            }
+            CKRC(rotate_q(h));
+        }
+        for (Member& m : h->members) {
+            Member::EpochRec& er = m.pending.back();
+            CK(cudaSetDevice(m.device));
+            CK(cudaEventRecord(er.end, m.stream));
+            er.kend = (int)m.kev.size();
+            er.launches = m.launches;
+            er.update_launches = m.update_launches;
+        }
+        h->epoch++;
+        if (want_eval) {
+            CKRC(resolve(ep + 1));
+            double sse = 0.0;
+            int64_t n = 0;
+            rc = rmse_pass(h, true, &sse, &n);
+            if (rc == MFSGD_OK && stats) stats[ep].heldout_rmse = n > 0 ? std::sqrt(sse / (double)n) : 0.0;
+        }
+    }
+    if (rc == MFSGD_OK) rc = resolve(epochs);
+    if (d_trace) {
+        cudaSetDevice(h->members[0].device);
+        cudaFree(d_trace);
+    }
+    return rc;
+}
+
+extern "C" int mfsgd_train(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats) { return train_impl(h, epochs, stats, nullptr); }
+extern "C" int mfsgd_train_traced(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace) {
+    if (!err_trace) return fail(MFSGD_E_INVALID_ARG, "err_trace is null");
+    return train_impl(h, epochs, stats, err_trace);
+}
+extern "C" int mfsgd_set_eval_every_epoch(mfsgd_handle* h, int32_t on) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    h->eval_every = on ? 1 : 0;
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// subsystem (3) driver: RMSE over bucketed record sets, Q groups rotating once round the ring
+// ------------------------------------------------------------------------------------------------
+static int rmse_sets(mfsgd_handle* h, std::vector<EvalSet*>& sets, bool train_set, double* sse_out, int64_t* n_out) {
+    const int k = h->cfg.k;
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemsetAsync(m.d_sse, 0, sizeof(double), m.stream));
+    }
+    for (int s = 0; s < h->G; s++) {
+        for (size_t j = 0; j < h->members.size(); j++) {
+            Member& m = h->members[j];
+            CK(cudaSetDevice(m.device));
+            const int grp = m.held_group;
+            if (train_set) {
+                for (int sa = 0; sa < h->mu; sa++) {
+                    const int64_t lo = m.block_off[(size_t)sa * h->IB + (size_t)grp * h->mi];
+                    const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
+                    CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                                       m.d_sse, m.n_sms, m.stream, &m.launches));
+                }
+            } else {
+                EvalSet* e = sets[j];
+                const int64_t lo = e->group_off[(size_t)grp], hi = e->group_off[(size_t)grp + 1];
+                CK(launch_rmse_sse(e->recs + lo, hi - lo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch, m.d_sse,
+                                   m.n_sms, m.stream, &m.launches));
+            }
+        }
+        CKRC(rotate_q(h));
+    }
+    double sse = 0.0;
+    int64_t n = 0;
+    for (size_t j = 0; j < h->members.size(); j++) {
+        Member& m = h->members[j];
+        double part = 0.0;
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemcpyAsync(&part, m.d_sse, sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+        CK(cudaStreamSynchronize(m.stream));
+        CK(cudaStreamSynchronize(m.copy_stream));
+        sse += part;
+        n += train_set ? m.n_recs : sets[j]->n;
+    }
+    *sse_out = sse;
+    *n_out = n;
+    return MFSGD_OK;
+}
+
+static int rmse_pass(mfsgd_handle* h, bool heldout, double* sse_out, int64_t* n_out) {
+    std::vector<EvalSet*> sets;
+    if (heldout)
+        for (Member& m : h->members) sets.push_back(&m.heldout);
+    return rmse_sets(h, sets, !heldout, sse_out, n_out);
+}
+
+static int finish_rmse(double sse, int64_t n, double* rmse_out, double* sse_out, int64_t* n_out) {
+    if (rmse_out) *rmse_out = n > 0 ? std::sqrt(sse / (double)n) : 0.0;
+    if (sse_out) *sse_out = sse;
+    if (n_out) *n_out = n;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_rmse_heldout(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
+    for (Member& m : h->members)
+        if (m.heldout.group_off.empty()) return fail(MFSGD_E_STATE, "no held-out set loaded");
+    double sse = 0.0;
+    int64_t n = 0;
+    CKRC(rmse_pass(h, true, &sse, &n));
+    return finish_rmse(sse, n, rmse_out, sse_out, n_out);
+}
+
+extern "C" int mfsgd_rmse_train(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->factors_ready || !h->loaded) return fail(MFSGD_E_STATE, "need loaded ratings and factors");
+    if (h->cfg.mode == MFSGD_MODE_DETERMINISTIC) {
+        // records live in caller order (recs_orig); evaluate them as one block
+        Member& m = h->members[0];
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemsetAsync(m.d_sse, 0, sizeof(double), m.stream));
+        CK(launch_rmse_sse(m.recs_orig, m.n_recs, m.P, m.Q[m.cur], h->cfg.k, m.u_lo, 0, m.d_scratch, m.d_sse, m.n_sms, m.stream, &m.launches));
+        double sse = 0.0;
+        CK(cudaMemcpyAsync(&sse, m.d_sse, sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+        CK(cudaStreamSynchronize(m.stream));
+        return finish_rmse(sse, m.n_recs, rmse_out, sse_out, n_out);
+    }
+    double sse = 0.0;
+    int64_t n = 0;
+    CKRC(rmse_pass(h, false, &sse, &n));
+    return finish_rmse(sse, n, rmse_out, sse_out, n_out);
+}
+
+extern "C" int mfsgd_rmse(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n, double* rmse_out) {
+    if (!h || !rmse_out) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
+    if (!h->loaded || !h->factors_ready) return fail(MFSGD_E_STATE, "need loaded ratings and factors");
+    std::vector<EvalSet> tmp(h->members.size());
+    std::vector<EvalSet*> sets;
+    int rc = MFSGD_OK;
+    for (size_t j = 0; j < h->members.size() && rc == MFSGD_OK; j++) {
+        rc = build_eval_set(h, h->members[j], users, items, ratings, n, tmp[j]);
+        sets.push_back(&tmp[j]);
+    }
+    double sse = 0.0;
+    int64_t cnt = 0;
+    if (rc == MFSGD_OK) rc = rmse_sets(h, sets, false, &sse, &cnt);
+    for (size_t j = 0; j < tmp.size(); j++) {
+        cudaSetDevice(h->members[j].device);
+        free_eval(tmp[j]);
+    }
+    if (rc != MFSGD_OK) return rc;
+    *rmse_out = cnt > 0 ? std::sqrt(sse / (double)cnt) : 0.0;
+    return MFSGD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot entry point (MatrixFactorizationSGD.java:109 factorize)
+// ------------------------------------------------------------------------------------------------
+extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                               const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out) {
+    if (!P_out || !Q_out) return fail(MFSGD_E_INVALID_ARG, "output arrays are null");
+    if (epochs < 0) return fail(MFSGD_E_INVALID_ARG, "epochs < 0");
+    mfsgd_handle* h = nullptr;
+    CKRC(mfsgd_create(cfg, &h));
+    int rc = mfsgd_load_ratings(h, users, items, ratings, n);
+    if (rc == MFSGD_OK) rc = mfsgd_init_factors(h);
+    if (rc == MFSGD_OK) rc = mfsgd_train(h, epochs, nullptr);
+    if (rc == MFSGD_OK) rc = mfsgd_get_factors(h, P_out, Q_out);
+    mfsgd_destroy(h);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection + test hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out) {
+    if (!h || !out) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    memset(out, 0, sizeof(*out));
+    out->n_gpus = h->G;
+    out->stripes_per_gpu = h->mu;
+    out->shards_per_gpu = h->mi;
+    out->user_blocks = h->UB;
+    out->item_blocks = h->IB;
+    for (Member& m : h->members) {
+        out->n_train_local += m.n_recs;
+        out->n_heldout_local += m.heldout.n;
+    }
+    out->n_train_total = h->n_train_total;
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds) {
+    if (!h || !user_bounds || !item_bounds) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    memcpy(user_bounds, h->user_bounds.data(), h->user_bounds.size() * 4);
+    memcpy(item_bounds, h->item_bounds.data(), h->item_bounds.size() * 4);
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n) {
+    if (!h || !n) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    if (member < 0 || member >= (int)h->members.size()) return fail(MFSGD_E_INVALID_ARG, "bad member index");
+    Member& m = h->members[(size_t)member];
+    *n = m.n_recs;
+    if (block_offsets) memcpy(block_offsets, m.block_off.data(), m.block_off.size() * 8);
+    if (recs && m.n_recs > 0) {
+        CK(cudaSetDevice(m.device));
+        CK(cudaStreamSynchronize(m.stream));
+        CK(cudaMemcpy(recs, m.recs[m.rcur], (size_t)m.n_recs * sizeof(Rec), cudaMemcpyDeviceToHost));
+    }
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
+    for (Member& m : h->members) {
+        CKRC(shuffle_member(h, m, epoch));
+        CK(cudaStreamSynchronize(m.stream));
+    }
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,
+                                          const float* pre_q, const float* r, float* post_p, float* post_q, float* err) {
+    if (!rank_supported(k)) return fail(MFSGD_E_INVALID_ARG, "k=%d unsupported", k);
+    if (n < 0 || (n > 0 && (!pre_p || !pre_q || !r || !post_p || !post_q || !err))) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (n == 0) return MFSGD_OK;
+    CK(cudaSetDevice(device));
+    float *dp = nullptr, *dq = nullptr, *dr = nullptr, *op = nullptr, *oq = nullptr, *de = nullptr;
+    const size_t rows = (size_t)n * k;
+    cudaError_t e = dev_alloc(&dp, rows);
+    if (e == cudaSuccess) e = dev_alloc(&dq, rows);
+    if (e == cudaSuccess) e = dev_alloc(&dr, (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(&op, rows);
+    if (e == cudaSuccess) e = dev_alloc(&oq, rows);
+    if (e == cudaSuccess) e = dev_alloc(&de, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(dp, pre_p, rows * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dq, pre_q, rows * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dr, r, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_sgd_update_forced(k, lr, lambda, n, dp, dq, dr, op, oq, de, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(post_p, op, rows * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(post_q, oq, rows * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(err, de, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dp); cudaFree(dq); cudaFree(dr); cudaFree(op); cudaFree(oq); cudaFree(de);
+    CK(e);
+    return MFSGD_OK;
+}
+
+extern "C" int mfsgd_generate_to_host(int32_t device, const mfsgd_synth_params* sp, int32_t n_users, int32_t n_items,
+                                      int64_t start, int64_t count, int32_t* users, int32_t* items, float* ratings, uint8_t* held) {
+    if (!sp || count < 0 || start < 0 || n_users <= 0 || n_items <= 0) return fail(MFSGD_E_INVALID_ARG, "bad arguments");
+    if (count > 0 && (!users || !items || !ratings || !held)) return fail(MFSGD_E_INVALID_ARG, "null output arrays");
+    if (count == 0) return MFSGD_OK;
+    CK(cudaSetDevice(device));
+    SynthArgs s{};
+    s.seed = sp->seed; s.n_users = n_users; s.n_items = n_items;
+    s.l2au = sp->log2_alpha_user; s.l2ai = sp->log2_alpha_item; s.cu = sp->c_user; s.ci = sp->c_item;
+    int32_t *du = nullptr, *di = nullptr;
+    float* dr = nullptr;
+    uint8_t* dh = nullptr;
+    cudaError_t e = dev_alloc(&du, (size_t)count);
+    if (e == cudaSuccess) e = dev_alloc(&di, (size_t)count);
+    if (e == cudaSuccess) e = dev_alloc(&dr, (size_t)count);
+    if (e == cudaSuccess) e = dev_alloc(&dh, (size_t)count);
+    if (e == cudaSuccess) e = launch_generate(s, start, count, du, di, dr, dh, nullptr, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(users, du, (size_t)count * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(items, di, (size_t)count * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ratings, dr, (size_t)count * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(held, dh, (size_t)count, cudaMemcpyDeviceToHost);
+    cudaFree(du); cudaFree(di); cudaFree(dr); cudaFree(dh);
+    CK(e);
+    return MFSGD_OK;
+}

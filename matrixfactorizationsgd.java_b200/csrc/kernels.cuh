@@ -1,0 +1,136 @@
+// kernels.cuh -- host-callable launchers of the sm_100a kernels (definitions in kernels_*.cu).
+// Every launcher enqueues on `stream`, returns cudaGetLastError(), and adds the number of kernels it
+// launched to *launches (nullable) -- that count feeds mfsgd_epoch_stats.total_launches.
+#pragma once
+#include "common.cuh"
+
+namespace mfsgd {
+
+// Sub-warp geometry for rank k: `lanes` lanes cooperate on one rating, each holding
+// `vec` float4 chunks of the row; chunk c belongs to lane c % lanes.
+struct Geometry {
+    int lanes, vec;
+    bool full;  // lanes * vec == k/4 -> no tail predicate
+};
+inline Geometry geometry_for(int k) {
+    int chunks = k / 4, lanes = 1;
+    while (lanes < chunks && lanes < 32) lanes <<= 1;
+    Geometry g;
+    g.lanes = lanes;
+    g.vec = (chunks + lanes - 1) / lanes;
+    g.full = (lanes * g.vec == chunks);
+    return g;
+}
+inline bool rank_supported(int k) { return k >= 4 && k <= 512 && (k % 4) == 0; }
+
+// Expands CALL(LANES, VEC, FULL) for the geometry g (compile-time sub-warp shapes).
+#define MFSGD_DISPATCH_GEOMETRY(g, CALL)                                   \
+    do {                                                                   \
+        if ((g).vec == 1) {                                                \
+            switch ((g).lanes) {                                           \
+                case 1:  if ((g).full) { CALL(1, 1, true); }  else { CALL(1, 1, false); }  break;  \
+                case 2:  if ((g).full) { CALL(2, 1, true); }  else { CALL(2, 1, false); }  break;  \
+                case 4:  if ((g).full) { CALL(4, 1, true); }  else { CALL(4, 1, false); }  break;  \
+                case 8:  if ((g).full) { CALL(8, 1, true); }  else { CALL(8, 1, false); }  break;  \
+                case 16: if ((g).full) { CALL(16, 1, true); } else { CALL(16, 1, false); } break;  \
+                default: if ((g).full) { CALL(32, 1, true); } else { CALL(32, 1, false); } break;  \
+            }                                                              \
+        } else if ((g).vec == 2) {                                         \
+            if ((g).full) { CALL(32, 2, true); } else { CALL(32, 2, false); }  \
+        } else if ((g).vec == 3) {                                         \
+            if ((g).full) { CALL(32, 3, true); } else { CALL(32, 3, false); }  \
+        } else {                                                           \
+            if ((g).full) { CALL(32, 4, true); } else { CALL(32, 4, false); }  \
+        }                                                                  \
+    } while (0)
+
+struct UpdateArgs {
+    const Rec* recs;   // records of one block range
+    int64_t n;
+    float* P;          // row (u - u_base) of the local P stripe
+    float* Q;          // row (i - i_base) of the held Q shard group
+    int32_t k, u_base, i_base;
+    float lr, lambda;
+};
+
+// (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
+// min_windows: lower bound on (records in the launch) / (ratings in flight at once), see kernels_update.cu.
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, bool atomic_scatter, int grid, int min_windows,
+                                      cudaStream_t stream, int* launches);
+// Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
+cudaError_t hogwild_max_ctas_per_sm(int k, bool atomic_scatter, int* ctas);
+// Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
+cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches);
+// Teacher-forced check: n independent row pairs.
+cudaError_t launch_sgd_update_forced(int k, float lr, float lambda, int64_t n, const float* pre_p, const float* pre_q,
+                                     const float* r, float* post_p, float* post_q, float* err, cudaStream_t stream);
+
+// (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
+// scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
+int rmse_scratch_doubles();
+cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, int32_t k, int32_t u_base,
+                            int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
+                            int* launches);
+
+// factor init (MatrixFactorizationSGD.java:53) for local rows [row_lo, row_lo + n_rows).
+cudaError_t launch_init_factors(float* rows, int64_t n_rows, int32_t k, int64_t row_lo, uint64_t seed, uint64_t stream_id,
+                                float scale, cudaStream_t stream, int* launches);
+
+// synthetic records [start, start+count) -> SoA + held flag (MatrixFactorizationSGD.java:220).
+struct SynthArgs {
+    uint64_t seed;
+    int32_t n_users, n_items, l2au, l2ai;
+    double cu, ci;
+};
+cudaError_t launch_generate(const SynthArgs& s, int64_t start, int64_t count, int32_t* u, int32_t* i, float* r,
+                            uint8_t* held, cudaStream_t stream, int* launches);
+
+// (1) bucketing + shuffle
+// per-row rating counts of the training records (held != 0 records are skipped when held != nullptr)
+cudaError_t launch_count_rows(const int32_t* u, const int32_t* i, const uint8_t* held, int64_t n, uint32_t* user_cnt,
+                              uint32_t* item_cnt, int32_t n_users, int32_t n_items, int* bad_flag, cudaStream_t stream,
+                              int* launches);
+// bounds[b] = first row whose exclusive cumulative count reaches b * total / nblocks; bounds[nblocks] = n_rows.
+// cum = exclusive prefix sums of the counts (n_rows + 1 entries, cum[n_rows] = total).
+cudaError_t launch_balanced_bounds(const uint64_t* cum, int32_t n_rows, int32_t nblocks, int32_t* bounds,
+                                   cudaStream_t stream, int* launches);
+// owner[row] = block b with bounds[b] <= row < bounds[b+1]
+cudaError_t launch_fill_owner(const int32_t* bounds, int32_t nblocks, int32_t n_rows, uint16_t* owner,
+                              cudaStream_t stream, int* launches);
+// Block of a record for the ring member owning user blocks [ub_lo, ub_hi):
+//   row = (owner_u[u] - ub_lo) / row_div, col = owner_i[i] / col_div, block = row * n_cols + col.
+// Records of other members, or whose held flag differs from want_held, are skipped.
+// Training layout: row_div = col_div = 1, n_cols = item_blocks. Held-out sets: row_div = stripes_per_gpu
+// (one row), col_div = shards_per_gpu, n_cols = n_gpus (one block per Q shard group).
+struct BucketArgs {
+    const int32_t* u;
+    const int32_t* i;
+    const float* r;
+    const uint8_t* held;   // nullable
+    int64_t n;
+    const uint16_t* owner_u;
+    const uint16_t* owner_i;
+    int32_t ub_lo, ub_hi, row_div, col_div, n_cols;
+    int32_t want_held;     // 0: training records, 1: held-out records
+};
+inline int bucket_block_count(const BucketArgs& b) { return ((b.ub_hi - b.ub_lo + b.row_div - 1) / b.row_div) * b.n_cols; }
+cudaError_t launch_block_histogram(const BucketArgs& b, unsigned long long* block_cnt, cudaStream_t stream, int* launches);
+// cursors start as the exclusive offsets; each record claims a slot with atomicAdd.
+cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursors, Rec* out, cudaStream_t stream,
+                                 int* launches);
+// out[off[b] + j] = in[off[b] + perm_b(j)], perm_b = keyed Feistel bijection on [0, n_b) (epoch, block).
+cudaError_t launch_block_shuffle(const Rec* in, Rec* out, const int64_t* block_off, int32_t nblocks, int64_t n,
+                                 uint64_t seed, uint32_t epoch, uint32_t block_id_base, cudaStream_t stream, int* launches);
+// SoA -> AoS in input order (deterministic mode keeps the caller's record order).
+cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, Rec* out,
+                                cudaStream_t stream, int* launches);
+// Stand-in visiting order (MatrixFactorizationSGD.java:72): out[j] = in[order_j]; device radix sort of the
+// packed (key31<<32 | idx) words. temp/temp_bytes: caller-owned scratch, query with temp == nullptr.
+cudaError_t deterministic_order_gather(const Rec* in, Rec* out, int32_t n, uint64_t seed, uint32_t epoch,
+                                       uint64_t* keys_a, uint64_t* keys_b, void* temp, size_t* temp_bytes,
+                                       cudaStream_t stream, int* launches);
+// exclusive prefix sum of uint32 counts into uint64 cum[n+1] (cub::DeviceScan); query with temp == nullptr.
+cudaError_t exclusive_cumsum_u32(const uint32_t* cnt, uint64_t* cum, int32_t n, void* temp, size_t* temp_bytes,
+                                 cudaStream_t stream, int* launches);
+
+}  // namespace mfsgd

@@ -1,0 +1,246 @@
+// kernels_update.cu -- subsystem (2): the per-rating SGD update kernels (sm_100a).
+//
+// Update rule = baseline/java/MatrixFactorizationSGD.java:89-105 (sgdUpdate). One LANES-wide sub-warp
+// per rating (LANES = 32 at k = 128: "one warp per rating"), float4 gathers of p_u and q_i, xor-
+// butterfly dot product, lock-free scatter. Bound by L2/HBM bandwidth (12 + 16k algorithmic bytes per
+// update); tensor cores are deliberately unused (gather-dot-scatter, not a contraction).
+#include "kernels.cuh"
+
+namespace mfsgd {
+
+namespace {
+
+template <int LANES, int VEC>
+struct RowPair {
+    float4 p[VEC];
+    float4 q[VEC];
+};
+
+template <int LANES, int VEC, bool FULL>
+__device__ __forceinline__ void load_rows(RowPair<LANES, VEC>& rp, const float* __restrict__ prow,
+                                          const float* __restrict__ qrow, int gl, int chunks, bool active) {
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        const int c = gl + v * LANES;
+        if (active && (FULL || c < chunks)) {
+            rp.p[v] = ld_row4(prow + 4 * c);
+            rp.q[v] = ld_row4(qrow + 4 * c);
+        } else {
+            rp.p[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rp.q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+template <int LANES, int VEC>
+__device__ __forceinline__ float row_dot(const RowPair<LANES, VEC>& rp) {
+    float s = 0.0f;
+#pragma unroll
+    for (int v = 0; v < VEC; v++) s = dot4_acc(s, rp.p[v], rp.q[v]);
+    return group_sum<LANES>(s);
+}
+
+template <int LANES, int VEC, bool FULL, bool ATOMIC>
+__device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, float* prow, float* qrow, int gl,
+                                             int chunks, float e, float lr, float lambda) {
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        const int c = gl + v * LANES;
+        if (FULL || c < chunks) {
+            if (ATOMIC) {
+                red_add_row4(prow + 4 * c, delta4(rp.p[v], rp.q[v], e, lr, lambda));
+                red_add_row4(qrow + 4 * c, delta4(rp.q[v], rp.p[v], e, lr, lambda));
+            } else {
+                st_row4(prow + 4 * c, upd4(rp.p[v], rp.q[v], e, lr, lambda));
+                st_row4(qrow + 4 * c, upd4(rp.q[v], rp.p[v], e, lr, lambda));
+            }
+        }
+    }
+}
+
+// Hogwild kernel. Work unit = tile of 32 consecutive records per warp (lane l loads record l, 12 B
+// each, streamed past L1); the warp's 32/LANES sub-warps walk the tile, each step gathering the rows
+// of the NEXT rating before reducing the current one (2 ratings in flight per sub-warp), and the
+// next tile's records are fetched a whole tile ahead.
+template <int LANES, int VEC, bool FULL, bool ATOMIC>
+__global__ void __launch_bounds__(256) sgd_update_hogwild_kernel(UpdateArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const int grp = lane / LANES;
+    const int chunks = a.k >> 2;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_tiles = (a.n + 31) >> 5;
+    const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
+    const uint64_t pol = l2_policy_evict_first();
+
+    int32_t ru = 0, ri = 0, rr = 0;  // this lane's record of the current tile (r as bits)
+    int64_t tile = warp;
+    if (tile < n_tiles) {
+        const int64_t idx = tile * 32 + lane;
+        if (idx < a.n) {
+            ru = ld_stream_i32(words + 3 * idx, pol);
+            ri = ld_stream_i32(words + 3 * idx + 1, pol);
+            rr = ld_stream_i32(words + 3 * idx + 2, pol);
+        }
+    }
+    for (; tile < n_tiles; tile += n_warps) {
+        const int64_t base = tile * 32;
+        const int cnt = (a.n - base) < 32 ? (int)(a.n - base) : 32;
+        const int steps = (cnt + GPW - 1) / GPW;
+        // records of the warp's next tile, one tile ahead
+        int32_t nu = 0, ni = 0, nr = 0;
+        {
+            const int64_t idx = (tile + n_warps) * 32 + lane;
+            if (idx < a.n) {
+                nu = ld_stream_i32(words + 3 * idx, pol);
+                ni = ld_stream_i32(words + 3 * idx + 1, pol);
+                nr = ld_stream_i32(words + 3 * idx + 2, pol);
+            }
+        }
+        RowPair<LANES, VEC> nxt;
+        int32_t xu = __shfl_sync(0xffffffffu, ru, grp);
+        int32_t xi = __shfl_sync(0xffffffffu, ri, grp);
+        int32_t xr = __shfl_sync(0xffffffffu, rr, grp);
+        bool xact = grp < cnt;
+        float* xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+        float* xq = a.Q + (int64_t)(xi - a.i_base) * a.k;
+        load_rows<LANES, VEC, FULL>(nxt, xp, xq, gl, chunks, xact);
+#pragma unroll 2
+        for (int t = 0; t < steps; t++) {
+            const RowPair<LANES, VEC> cur = nxt;
+            float* const cp = xp;
+            float* const cq = xq;
+            const float cr = __int_as_float(xr);
+            const bool cact = xact;
+            if (t + 1 < steps) {
+                const int j = (t + 1) * GPW + grp;
+                xu = __shfl_sync(0xffffffffu, ru, j);
+                xi = __shfl_sync(0xffffffffu, ri, j);
+                xr = __shfl_sync(0xffffffffu, rr, j);
+                xact = j < cnt;
+                xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+                xq = a.Q + (int64_t)(xi - a.i_base) * a.k;
+                load_rows<LANES, VEC, FULL>(nxt, xp, xq, gl, chunks, xact);
+            }
+            const float e = __fsub_rn(cr, row_dot<LANES, VEC>(cur));
+            if (cact) scatter_rows<LANES, VEC, FULL, ATOMIC>(cur, cp, cq, gl, chunks, e, a.lr, a.lambda);
+        }
+        ru = nu; ri = ni; rr = nr;
+    }
+}
+
+// Deterministic parity mode: a single warp applies the records strictly in array order; sub-warp 0
+// holds the rows (the other lanes carry zeros through the shuffles). Each lane re-reads only
+// addresses it wrote itself, so program order makes every update see its predecessor's result.
+template <int LANES, int VEC, bool FULL>
+__global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs a, float* __restrict__ err_trace) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const bool act = lane < LANES;
+    const int chunks = a.k >> 2;
+    for (int64_t j = 0; j < a.n; j++) {
+        const Rec rec = a.recs[j];
+        float* prow = a.P + (int64_t)(rec.u - a.u_base) * a.k;
+        float* qrow = a.Q + (int64_t)(rec.i - a.i_base) * a.k;
+        RowPair<LANES, VEC> rp;
+        load_rows<LANES, VEC, FULL>(rp, prow, qrow, gl, chunks, act);
+        const float e = __fsub_rn(rec.r, row_dot<LANES, VEC>(rp));
+        if (act) scatter_rows<LANES, VEC, FULL, false>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
+        if (err_trace != nullptr && lane == 0) err_trace[j] = e;
+    }
+}
+
+// Teacher-forced: update j reads pre_p[j], pre_q[j] (dense [n,k]) and writes post rows; one sub-warp each.
+template <int LANES, int VEC, bool FULL>
+__global__ void __launch_bounds__(256) sgd_update_forced_kernel(int k, float lr, float lambda, int64_t n,
+                                                                const float* __restrict__ pre_p,
+                                                                const float* __restrict__ pre_q,
+                                                                const float* __restrict__ r, float* __restrict__ post_p,
+                                                                float* __restrict__ post_q, float* __restrict__ err) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const int grp = lane / LANES;
+    const int chunks = k >> 2;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * GPW; base < n; base += n_warps * GPW) {   // warp-uniform trip count
+        const int64_t j = base + grp;
+        const bool act = j < n;
+        const int64_t jj = act ? j : 0;
+        RowPair<LANES, VEC> rp;
+        load_rows<LANES, VEC, FULL>(rp, pre_p + jj * k, pre_q + jj * k, gl, chunks, act);
+        const float e = __fsub_rn(act ? r[jj] : 0.f, row_dot<LANES, VEC>(rp));
+        if (act) {
+            scatter_rows<LANES, VEC, FULL, false>(rp, post_p + jj * k, post_q + jj * k, gl, chunks, e, lr, lambda);
+            if (gl == 0) err[jj] = e;
+        }
+    }
+}
+
+
+}  // namespace
+
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, bool atomic_scatter, int grid, int min_windows,
+                                      cudaStream_t stream, int* launches) {
+    if (min_windows < 1) min_windows = 1;
+    if (a.n <= 0) return cudaSuccess;
+    const Geometry g = geometry_for(a.k);
+    // Concurrency cap for small blocks: every resident sub-warp has ~2 ratings in flight that all read
+    // the same stale snapshot, so a launch should still span >= min_windows such snapshots, or the
+    // last-writer-wins scatter throws most of the block's updates away (tools/staleness_sim.py).
+    const int gpw = 32 / g.lanes;
+    const int64_t max_warps = a.n / ((int64_t)min_windows * 2 * gpw);
+    int64_t max_grid = (max_warps + 7) / 8;   // 8 warps per CTA
+    if (max_grid < 1) max_grid = 1;
+    if (grid > max_grid) grid = (int)max_grid;
+    if (grid < 1) grid = 1;
+#define CALL(L, V, F)                                                                              \
+    if (atomic_scatter) sgd_update_hogwild_kernel<L, V, F, true><<<grid, 256, 0, stream>>>(a);     \
+    else sgd_update_hogwild_kernel<L, V, F, false><<<grid, 256, 0, stream>>>(a)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t hogwild_max_ctas_per_sm(int k, bool atomic_scatter, int* ctas) {
+    const Geometry g = geometry_for(k);
+    cudaError_t err = cudaSuccess;
+#define CALL(L, V, F)                                                                                             \
+    err = atomic_scatter                                                                                          \
+              ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, true>, 256, 0)  \
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, false>, 256, 0)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    return err;
+}
+
+cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches) {
+    if (a.n <= 0) return cudaSuccess;
+    const Geometry g = geometry_for(a.k);
+#define CALL(L, V, F) sgd_update_deterministic_kernel<L, V, F><<<1, 32, 0, stream>>>(a, err_trace)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sgd_update_forced(int k, float lr, float lambda, int64_t n, const float* pre_p, const float* pre_q,
+                                     const float* r, float* post_p, float* post_q, float* err, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const Geometry g = geometry_for(k);
+    const int gpw = 32 / g.lanes;
+    int64_t ctas = (n + (int64_t)gpw * 8 - 1) / ((int64_t)gpw * 8);
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    const int grid = (int)ctas;
+#define CALL(L, V, F) \
+    sgd_update_forced_kernel<L, V, F><<<grid, 256, 0, stream>>>(k, lr, lambda, n, pre_p, pre_q, r, post_p, post_q, err)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    return cudaGetLastError();
+}
+
+}  // namespace mfsgd

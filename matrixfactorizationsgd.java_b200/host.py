@@ -1,0 +1,59 @@
+"""Host-side mirror of the reference's entry point.
+
+The reference's class is ``MatrixFactorizationSGD`` (/root/reference/README.md:1); its stand-in
+(baseline/java/MatrixFactorizationSGD.java:109) exposes
+``factorize(users, items, ratings, nUsers, nItems, k, lr, lambda, epochs, seed) -> Factors{P, Q}``.
+The production host is Java over Panama FFM (java/MatrixFactorizationSGDGpu.java); no JDK exists in
+this image, so this module is the same thin layer in Python over ctypes -- same names, argument
+order, error behaviour (bad arguments raise before any GPU work, like the stand-in's
+IllegalArgumentException) -- and is what the parity tests and bench.py call.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _capi as capi
+from .engine import Engine, make_config
+
+Factors = namedtuple("Factors", ["P", "Q", "nUsers", "nItems", "k"])
+
+
+class MatrixFactorizationSGD:
+    """Drop-in for the factorization path; every call runs on the GPU through libmfsgd.so."""
+
+    #: execution modes of the GPU path (mfsgd_config.mode)
+    DETERMINISTIC, HOGWILD, DSGD = capi.MODE_DETERMINISTIC, capi.MODE_HOGWILD, capi.MODE_DSGD
+
+    @staticmethod
+    def _check(users, items, ratings, nUsers, nItems, k, epochs):
+        if not (len(users) == len(items) == len(ratings)):
+            raise ValueError("triplet arrays differ in length")          # stand-in line 112-113
+        if k <= 0 or nUsers <= 0 or nItems <= 0 or epochs < 0:
+            raise ValueError("bad shape")                                # stand-in line 114-115
+
+    @staticmethod
+    def factorize(users, items, ratings, nUsers, nItems, k, lr, lambda_, epochs, seed,
+                  mode=capi.MODE_HOGWILD, n_gpus=1, device=0, **cfg_kw):
+        """One-shot form: maps 1:1 onto mfsgd_factorize (host arrays in, host P and Q out)."""
+        MatrixFactorizationSGD._check(users, items, ratings, nUsers, nItems, k, epochs)
+        u, i, r = capi.as_i32(users), capi.as_i32(items), capi.as_f32(ratings)
+        cfg = make_config(nUsers, nItems, k, lr, lambda_, seed=seed, mode=mode, n_gpus=n_gpus, device=device, **cfg_kw)
+        P = np.zeros((nUsers, k), dtype=np.float32)
+        Q = np.zeros((nItems, k), dtype=np.float32)
+        capi.check(capi.lib.mfsgd_factorize(capi.ptr(u), capi.ptr(i), capi.ptr(r), len(r), C.byref(cfg), int(epochs),
+                                            capi.ptr(P), capi.ptr(Q)))
+        return Factors(P, Q, nUsers, nItems, k)
+
+    @staticmethod
+    def rmse(P, Q, k, users, items, ratings, device=0):
+        """Stand-in line 169: sqrt(mean (r - p_u.q_i)^2), evaluated by the RMSE kernel."""
+        P, Q = capi.as_f32(P), capi.as_f32(Q)
+        if P.ndim != 2 or Q.ndim != 2 or P.shape[1] != k or Q.shape[1] != k:
+            raise ValueError("P and Q must be [rows, k]")
+        cfg = make_config(P.shape[0], Q.shape[0], k, 1e-3, 0.0, mode=capi.MODE_HOGWILD, device=device,
+                          stripes_per_gpu=1)
+        with Engine(cfg) as eng:
+            eng.load_ratings(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32))
+            eng.set_factors(P, Q)
+            return eng.rmse(users, items, ratings)

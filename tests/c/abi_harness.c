@@ -1,0 +1,92 @@
+/*
+ * abi_harness.c -- binds libmfsgd.so exactly the way Panama FFM's Linker.downcallHandle does:
+ * dlopen + dlsym only, no link-time dependency, plain C types. Checks that every symbol of
+ * include/mfsgd.h resolves and that the argument-validation paths return the documented codes.
+ * With a GPU present (argv[2] == "gpu") it also runs a tiny factorize through the one-shot entry.
+ */
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mfsgd.h"
+
+static const char* SYMBOLS[] = {
+    "mfsgd_abi_version", "mfsgd_last_error", "mfsgd_device_count", "mfsgd_config_default", "mfsgd_create",
+    "mfsgd_destroy", "mfsgd_load_ratings", "mfsgd_load_heldout", "mfsgd_generate_synthetic", "mfsgd_init_factors",
+    "mfsgd_set_factors", "mfsgd_get_factors", "mfsgd_get_partition", "mfsgd_train", "mfsgd_train_traced",
+    "mfsgd_set_eval_every_epoch", "mfsgd_rmse", "mfsgd_rmse_heldout", "mfsgd_rmse_train", "mfsgd_factorize",
+    "mfsgd_get_layout_info", "mfsgd_get_bounds", "mfsgd_get_records", "mfsgd_shuffle_once",
+    "mfsgd_apply_updates_forced", "mfsgd_generate_to_host", "mfsgd_nccl_unique_id", "mfsgd_host_alloc",
+    "mfsgd_host_free"};
+
+#define EXPECT(cond, msg)                                 \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            fprintf(stderr, "FAIL: %s (%s)\n", msg, #cond); \
+            return 1;                                     \
+        }                                                 \
+    } while (0)
+
+int main(int argc, char** argv) {
+    const char* path = argc > 1 ? argv[1] : "matrixfactorizationsgd.java_b200/lib/libmfsgd.so";
+    int want_gpu = argc > 2 && strcmp(argv[2], "gpu") == 0;
+    void* lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) { fprintf(stderr, "dlopen failed: %s\n", dlerror()); return 1; }
+    for (size_t s = 0; s < sizeof(SYMBOLS) / sizeof(SYMBOLS[0]); s++)
+        if (!dlsym(lib, SYMBOLS[s])) { fprintf(stderr, "missing symbol %s\n", SYMBOLS[s]); return 1; }
+
+    int (*abi)(void) = (int (*)(void))dlsym(lib, "mfsgd_abi_version");
+    const char* (*last_error)(void) = (const char* (*)(void))dlsym(lib, "mfsgd_last_error");
+    int (*config_default)(mfsgd_config*) = (int (*)(mfsgd_config*))dlsym(lib, "mfsgd_config_default");
+    int (*create)(const mfsgd_config*, mfsgd_handle**) = (int (*)(const mfsgd_config*, mfsgd_handle**))dlsym(lib, "mfsgd_create");
+    int (*factorize)(const int32_t*, const int32_t*, const float*, int64_t, const mfsgd_config*, int32_t, float*, float*) =
+        (int (*)(const int32_t*, const int32_t*, const float*, int64_t, const mfsgd_config*, int32_t, float*, float*))dlsym(lib, "mfsgd_factorize");
+
+    EXPECT(abi() == MFSGD_ABI_VERSION, "ABI version");
+    mfsgd_config cfg;
+    EXPECT(config_default(NULL) == MFSGD_E_INVALID_ARG, "null cfg rejected");
+    EXPECT(config_default(&cfg) == MFSGD_OK, "config_default");
+    mfsgd_handle* h = NULL;
+    cfg.n_users = 10; cfg.n_items = 10;
+    cfg.k = 6;
+    EXPECT(create(&cfg, &h) == MFSGD_E_INVALID_ARG && h == NULL, "k not multiple of 4 rejected");
+    EXPECT(strstr(last_error(), "k=6") != NULL, "error text names the bad rank");
+    cfg.k = 8; cfg.n_users = 0;
+    EXPECT(create(&cfg, &h) == MFSGD_E_INVALID_ARG, "n_users = 0 rejected");
+    cfg.n_users = 10; cfg.mode = MFSGD_MODE_HOGWILD; cfg.n_gpus = 2;
+    EXPECT(create(&cfg, &h) == MFSGD_E_INVALID_ARG, "HOGWILD with 2 GPUs rejected");
+    cfg.n_gpus = 1;
+    EXPECT(create(&cfg, NULL) == MFSGD_E_INVALID_ARG, "null out rejected");
+    EXPECT(factorize(NULL, NULL, NULL, 0, &cfg, 1, NULL, NULL) == MFSGD_E_INVALID_ARG, "null outputs rejected");
+
+    if (!want_gpu) {
+        int rc = create(&cfg, &h);
+        /* on a box without a GPU the product must fail loudly, not fall back */
+        if (rc == MFSGD_OK) { void (*destroy)(mfsgd_handle*) = (void (*)(mfsgd_handle*))dlsym(lib, "mfsgd_destroy"); destroy(h); }
+        else EXPECT(rc == MFSGD_E_CUDA, "no GPU -> MFSGD_E_CUDA");
+        printf("abi_harness: OK (%zu symbols, validation paths)\n", sizeof(SYMBOLS) / sizeof(SYMBOLS[0]));
+        return 0;
+    }
+
+    /* GPU: KAT through the one-shot entry in deterministic mode. k=4 (2 real dims + 2 zero pads). */
+    int32_t u[1] = {0}, i[1] = {0};
+    float r[1] = {1.0f};
+    float P[4], Q[4];
+    cfg.n_users = 1; cfg.n_items = 1; cfg.k = 4; cfg.lr = 0.1f; cfg.lambda = 0.01f; cfg.mode = MFSGD_MODE_DETERMINISTIC;
+    /* init is hash-based, so run 0 epochs to fetch it, then verify one epoch against the rule in C */
+    EXPECT(factorize(u, i, r, 1, &cfg, 0, P, Q) == MFSGD_OK, last_error());
+    float p0[4], q0[4];
+    memcpy(p0, P, sizeof(P)); memcpy(q0, Q, sizeof(Q));
+    EXPECT(factorize(u, i, r, 1, &cfg, 1, P, Q) == MFSGD_OK, last_error());
+    float dot = ((p0[0] * q0[0] + p0[1] * q0[1]) + p0[2] * q0[2]) + p0[3] * q0[3];
+    float e = 1.0f - dot;
+    for (int f = 0; f < 4; f++) {
+        float pe = p0[f] + 0.1f * (e * q0[f] - 0.01f * p0[f]);
+        float qe = q0[f] + 0.1f * (e * p0[f] - 0.01f * q0[f]);
+        EXPECT(fabsf(P[f] - pe) <= 1e-6f * fabsf(pe) && fabsf(Q[f] - qe) <= 1e-6f * fabsf(qe), "one update matches the rule");
+    }
+    printf("abi_harness: OK (GPU one-shot factorize)\n");
+    return 0;
+}

@@ -1,0 +1,380 @@
+"""GPU parity tests (run with -m gpu on a B200). Every call goes through the C ABI of libmfsgd.so
+(ctypes, the same symbols FFM binds); the CPU oracle (oracle/) is only the checker.
+
+Bars (BASELINE.json north_star):
+  * deterministic single-warp mode vs the reference's per-update results: <= 1e-5 relative fp32
+    (and bit-exact against the oracle's warp-tree summation order);
+  * integer/index work (generator ids, shuffle order, bucketing) bit-exact;
+  * Hogwild / DSGD held-out RMSE within 0.5 % of the oracle's at equal epochs on the same data.
+"""
+import numpy as np
+import pytest
+
+import matrixfactorizationsgd.java_b200 as mf
+from matrixfactorizationsgd.java_b200 import _capi as capi
+import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261018
+REL_TOL = 1e-5      # north_star: "within 1e-5 relative fp32"
+RMSE_TOL = 0.005    # north_star: "held-out RMSE within 0.5 %"
+
+
+def split(u, i, r, held):
+    return (u[~held].copy(), i[~held].copy(), r[~held].copy()), (u[held].copy(), i[held].copy(), r[held].copy())
+
+
+@pytest.fixture(scope="module")
+def ml100k():
+    w = mf.WORKLOADS["ml100k"]
+    u, i, r, held = orc.generate(SEED, 0, w.n_ratings, w.n_users, w.n_items)
+    return w, split(u, i, r, held)
+
+
+# ------------------------------------------------------------------------------------------------
+# integer / index paths: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nu,ni,l2ai,start", [(943, 1682, 3, 0), (480_000, 17_800, 3, 0),
+                                              (10_000_000, 1_000_000, 4, 0), (10_000_000, 1_000_000, 4, 1_999_000_000)])
+def test_generator_bit_exact(nu, ni, l2ai, start):
+    n = 200_000
+    sp = mf.synth_params(2_000_000_000, SEED, 2, 0.25, l2ai, 0.375)
+    gu, gi, gr, gh = mf.generate_to_host(sp, nu, ni, start, n)
+    ou, oi, or_, oh = orc.generate(SEED, start, n, nu, ni, 2, 0.25, l2ai, 0.375)
+    assert np.array_equal(gu, ou) and np.array_equal(gi, oi)
+    assert np.array_equal(gr.view(np.uint32), or_.view(np.uint32))
+    assert np.array_equal(gh, oh)
+
+
+def test_generator_golden(golden):
+    g = golden["gen_ml100k"]
+    sp = mf.synth_params(100_000, SEED)
+    u, i, r, h = mf.generate_to_host(sp, 943, 1682, 0, 256)
+    assert u.tolist() == g["u"] and i.tolist() == g["i"] and r.view(np.uint32).tolist() == g["r"]
+    assert h.astype(int).tolist() == g["held"]
+
+
+@pytest.mark.parametrize("k", [8, 32, 128])
+def test_init_factors_bit_exact(k):
+    nu, ni = 1000, 700
+    with mf.Engine(mf.make_config(nu, ni, k, 0.01, 0.05, seed=SEED)) as eng:
+        eng.load_ratings(np.zeros(1, np.int32), np.zeros(1, np.int32), np.ones(1, np.float32))
+        eng.init_factors()
+        P, Q = eng.get_factors()
+    assert np.array_equal(P, orc.init_factors(nu, k, SEED, 0))
+    assert np.array_equal(Q, orc.init_factors(ni, k, SEED, 1))
+
+
+def test_deterministic_shuffle_order_is_the_stand_ins(ml100k):
+    w, ((u, i, r), _) = ml100k
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_DETERMINISTIC)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)
+        for epoch in (0, 7):
+            eng.shuffle_once(epoch)
+            gu, gi, gr, _ = eng.records()
+            order = orc.shuffle(SEED, epoch, len(r))
+            assert np.array_equal(gu, u[order]) and np.array_equal(gi, i[order])
+            assert np.array_equal(gr.view(np.uint32), r[order].view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# the update rule
+# ------------------------------------------------------------------------------------------------
+def test_kat_hand_computed(kat):
+    """k=2 hand KAT, padded to k=4 with zeros (they add exactly)."""
+    p = np.array([kat["p"] + [0, 0]], dtype=np.float32)
+    q = np.array([kat["q"] + [0, 0]], dtype=np.float32)
+    pp, qq, e = mf.apply_updates_forced(4, kat["lr"], kat["lambda"], p, q, np.array([kat["r"]], np.float32))
+    assert abs(e[0] - kat["e"]) < 1e-6
+    np.testing.assert_allclose(pp[0, :2], kat["p_new"], rtol=1e-6)
+    np.testing.assert_allclose(qq[0, :2], kat["q_new"], rtol=1e-6)
+    assert pp[0, 2] == 0 and qq[0, 3] == 0
+
+
+@pytest.mark.parametrize("epoch", [0, 19])
+def test_per_update_parity_teacher_forced(ml100k, epoch):
+    """Every update of an epoch, both sides starting from the ORACLE's pre-update rows (sequential
+    summation = the stand-in's order): GPU result within 1e-5 relative; and bit-identical to the
+    oracle when it sums in the kernel's warp-tree order."""
+    w, ((u, i, r), _) = ml100k
+    P = orc.init_factors(w.n_users, w.k, SEED, 0)
+    Q = orc.init_factors(w.n_items, w.k, SEED, 1)
+    if epoch:
+        orc.train(u, i, r, P, Q, w.lr, w.lambda_, 0, epoch, SEED)
+    order, pre_p, pre_q, post_p, post_q, err = orc.train_tape(u, i, r, P, Q, w.lr, w.lambda_, epoch, SEED)
+    gp, gq, ge = mf.apply_updates_forced(w.k, w.lr, w.lambda_, pre_p, pre_q, r[order])
+    for got, want in ((gp, post_p), (gq, post_q)):
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+        assert rel.max() <= REL_TOL, rel.max()
+    assert np.abs(ge - err).max() <= 1e-5 * np.maximum(np.abs(err), 1.0).max()
+    # stronger: the tree-order oracle is reproduced bit for bit
+    tp, tq = pre_p.copy(), pre_q.copy()
+    te = np.empty_like(err)
+    for j in range(0, len(err), 11):
+        te[j] = orc.lib.orc_sgd_update(tp[j], tq[j], w.k, r[order[j]], w.lr, w.lambda_, orc.ORDER_WARP_TREE)
+        assert np.array_equal(tp[j], gp[j]) and np.array_equal(tq[j], gq[j]) and te[j] == ge[j]
+
+
+def test_deterministic_mode_free_running_ml100k(ml100k):
+    """configs[0] on the GPU in deterministic single-warp mode, 20 epochs free-running."""
+    w, ((u, i, r), (hu, hi, hr)) = ml100k
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_DETERMINISTIC)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)
+        eng.init_factors()
+        stats, trace = eng.train_traced(w.epochs, len(r))
+        P, Q = eng.get_factors()
+        gpu_rmse = eng.rmse(hu, hi, hr)
+    assert all(s.updates == len(r) for s in stats)
+    # bit-exact against the oracle summing in the kernel's order, including every per-update error
+    Pt = orc.init_factors(w.n_users, w.k, SEED, 0)
+    Qt = orc.init_factors(w.n_items, w.k, SEED, 1)
+    tt = orc.train(u, i, r, Pt, Qt, w.lr, w.lambda_, 0, w.epochs, SEED, orc.ORDER_WARP_TREE, trace=True)
+    assert np.array_equal(trace, tt)
+    assert np.array_equal(P, Pt) and np.array_equal(Q, Qt)
+    # against the stand-in's sequential order: trajectories drift in the last ulps only
+    Ps, Qs = orc.factorize(u, i, r, w.n_users, w.n_items, w.k, w.lr, w.lambda_, w.epochs, SEED)
+    seq_rmse = orc.rmse(Ps, Qs, hu, hi, hr)
+    assert abs(gpu_rmse - seq_rmse) / seq_rmse < 1e-4
+    assert np.abs(P - Ps).max() < 1e-3 and np.abs(Q - Qs).max() < 1e-3
+
+
+@pytest.mark.parametrize("k", [4, 8, 20, 64, 100, 128, 256, 320, 512])
+def test_deterministic_mode_all_ranks_bit_exact(k):
+    nu, ni, n = 300, 200, 6000
+    u, i, r, _ = orc.generate(SEED + k, 0, n, nu, ni)
+    got = mf.MatrixFactorizationSGD.factorize(u, i, r, nu, ni, k, 0.02, 0.03, 2, SEED, mode=capi.MODE_DETERMINISTIC)
+    P, Q = orc.factorize(u, i, r, nu, ni, k, 0.02, 0.03, 2, SEED, orc.ORDER_WARP_TREE)
+    assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
+    Ps, Qs = orc.factorize(u, i, r, nu, ni, k, 0.02, 0.03, 2, SEED, orc.ORDER_SEQ)
+    assert np.abs(got.P - Ps).max() < 1e-4 and np.abs(got.Q - Qs).max() < 1e-4
+
+
+def test_sgd_small_run_golden(golden):
+    s = golden["sgd_small_shape"]
+    u, i, r, _ = orc.generate(SEED, 0, s["n"], s["n_users"], s["n_items"])
+    got = mf.MatrixFactorizationSGD.factorize(u, i, r, s["n_users"], s["n_items"], s["k"], s["lr"], s["lambda"],
+                                              s["epochs"], SEED, mode=capi.MODE_DETERMINISTIC)
+    assert got.P.view(np.uint32).ravel().tolist() == golden["sgd_small_tree"]["P"]
+    assert got.Q.view(np.uint32).ravel().tolist() == golden["sgd_small_tree"]["Q"]
+
+
+def test_empty_and_single_record():
+    e = np.empty(0, np.int32)
+    got = mf.MatrixFactorizationSGD.factorize(e, e, np.empty(0, np.float32), 5, 7, 8, 0.1, 0.1, 3, SEED,
+                                              mode=capi.MODE_DETERMINISTIC)
+    assert np.array_equal(got.P, orc.init_factors(5, 8, SEED, 0)) and np.array_equal(got.Q, orc.init_factors(7, 8, SEED, 1))
+    got = mf.MatrixFactorizationSGD.factorize(e, e, np.empty(0, np.float32), 5, 7, 8, 0.1, 0.1, 3, SEED)   # hogwild
+    assert np.array_equal(got.P, orc.init_factors(5, 8, SEED, 0))
+    one = mf.MatrixFactorizationSGD.factorize(np.array([4], np.int32), np.array([6], np.int32), np.array([2.5], np.float32),
+                                              5, 7, 8, 0.1, 0.1, 3, SEED)   # hogwild, one record: order is forced
+    P, Q = orc.factorize(np.array([4], np.int32), np.array([6], np.int32), np.array([2.5], np.float32), 5, 7, 8,
+                         0.1, 0.1, 3, SEED, orc.ORDER_WARP_TREE)
+    assert np.array_equal(one.P, P) and np.array_equal(one.Q, Q)
+
+
+def test_out_of_range_ids_rejected():
+    with pytest.raises(mf.MfsgdError) as ei:
+        mf.MatrixFactorizationSGD.factorize(np.array([0, 5], np.int32), np.array([0, 0], np.int32),
+                                            np.ones(2, np.float32), 5, 3, 8, 0.1, 0.1, 1, SEED)
+    assert ei.value.code == capi.E_INVALID_ARG
+
+
+# ------------------------------------------------------------------------------------------------
+# subsystem (3): RMSE kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [32, 64, 128])
+def test_rmse_kernel_vs_float64(k):
+    nu, ni, n = 20_000, 5_000, 1_000_000
+    u, i, r, _ = orc.generate(SEED + 3, 0, n, nu, ni)
+    P = orc.init_factors(nu, k, SEED, 0, 0.3)
+    Q = orc.init_factors(ni, k, SEED, 1, 0.3)
+    got = mf.MatrixFactorizationSGD.rmse(P, Q, k, u, i, r)
+    pred = np.einsum("ij,ij->i", P[u].astype(np.float64), Q[i].astype(np.float64))
+    want = float(np.sqrt(np.mean((r.astype(np.float64) - pred) ** 2)))
+    assert abs(got - want) / want <= 1e-6
+    assert abs(got - orc.rmse(P, Q, u, i, r)) / want <= 1e-6
+    assert mf.MatrixFactorizationSGD.rmse(P, Q, k, u[:0], i[:0], r[:0]) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# subsystem (1): bucketing + shuffle
+# ------------------------------------------------------------------------------------------------
+def rec_keys(u, i, r):
+    return np.sort((u.astype(np.uint64) << np.uint64(40)) ^ (i.astype(np.uint64) << np.uint64(20)) ^
+                   r.view(np.uint32).astype(np.uint64))
+
+
+@pytest.mark.parametrize("mode,G,mu,mi", [(capi.MODE_HOGWILD, 1, 1, 1), (capi.MODE_HOGWILD, 1, 5, 3),
+                                          (capi.MODE_DSGD, 4, 2, 2), (capi.MODE_DSGD, 8, 1, 1)])
+def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
+    nu, ni, n = 30_000, 4_000, 1_500_000
+    u, i, r, held = orc.generate(SEED + 5, 0, n, nu, ni)
+    cfg = mf.make_config(nu, ni, 32, 0.01, 0.05, seed=SEED, mode=mode, n_gpus=G, stripes_per_gpu=mu, shards_per_gpu=mi,
+                         flags=capi.FLAG_VIRTUAL_RING if G > 1 else 0)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)
+        info = eng.layout_info()
+        assert (info.user_blocks, info.item_blocks, info.n_train_local, info.n_train_total) == (G * mu, G * mi, n, n)
+        ub, ib = eng.bounds()
+        assert ub[0] == 0 and ub[-1] == nu and ib[0] == 0 and ib[-1] == ni
+        assert np.all(np.diff(ub) >= 0) and np.all(np.diff(ib) >= 0)
+        # stripes balanced by rating count (not by row count)
+        ucnt = np.add.reduceat(np.bincount(u, minlength=nu), ub[:-1])
+        assert ucnt.max() <= 1.1 * n / (G * mu) + np.bincount(u).max()
+        IB = G * mi
+        all_keys = []
+        for g in range(G):
+            gu, gi, gr, off = eng.records(g)
+            assert off[0] == 0 and off[-1] == len(gu) and np.all(np.diff(off) >= 0)
+            for b in range(mu * IB):
+                a, c = divmod(b, IB)
+                su, si = gu[off[b]:off[b + 1]], gi[off[b]:off[b + 1]]
+                if len(su):
+                    assert su.min() >= ub[g * mu + a] and su.max() < ub[g * mu + a + 1]
+                    assert si.min() >= ib[c] and si.max() < ib[c + 1]
+            all_keys.append(rec_keys(gu, gi, gr))
+        assert np.array_equal(np.sort(np.concatenate(all_keys)), rec_keys(u, i, r))     # multiset preserved
+        # shuffle: a permutation inside every block, different per epoch
+        before = eng.records(0)
+        eng.shuffle_once(0)
+        e0 = eng.records(0)
+        eng.shuffle_once(1)
+        e1 = eng.records(0)
+        off = before[3]
+        assert np.array_equal(off, e0[3])
+        moved = 0
+        for b in range(mu * IB):
+            s = slice(off[b], off[b + 1])
+            kb = rec_keys(before[0][s], before[1][s], before[2][s])
+            assert np.array_equal(kb, rec_keys(e0[0][s], e0[1][s], e0[2][s]))
+            assert np.array_equal(kb, rec_keys(e1[0][s], e1[1][s], e1[2][s]))
+            moved += int(np.sum(before[0][s] != e0[0][s]))
+        assert moved > 0.5 * len(before[0])
+        assert not np.array_equal(e0[0], e1[0])
+
+
+def test_synthetic_on_device_matches_oracle_split():
+    nu, ni, n = 20_000, 3_000, 1_000_000
+    ou, oi, or_, oh = orc.generate(SEED, 0, n, nu, ni)
+    with mf.Engine(mf.make_config(nu, ni, 32, 0.01, 0.05, seed=SEED, stripes_per_gpu=2)) as eng:
+        nt, nh = eng.generate_synthetic(mf.synth_params(n, SEED))
+        assert (nt, nh) == (int((~oh).sum()), int(oh.sum()))
+        gu, gi, gr, _ = eng.records(0)
+        assert np.array_equal(rec_keys(gu, gi, gr), rec_keys(ou[~oh], oi[~oh], or_[~oh]))
+        eng.init_factors()
+        rm, sse, cnt = eng.rmse_heldout()
+        assert cnt == nh
+        P, Q = eng.get_factors()
+        assert abs(rm - orc.rmse(P, Q, ou[oh].copy(), oi[oh].copy(), or_[oh].copy())) / rm < 1e-6
+        rt, _, ct = eng.rmse_train()
+        assert ct == nt and abs(rt - orc.rmse(P, Q, ou[~oh].copy(), oi[~oh].copy(), or_[~oh].copy())) / rt < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# Hogwild and DSGD: convergence parity (held-out RMSE within 0.5 % of the oracle at equal epochs)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def midsize():
+    """ML-20M-shaped scaled 1:10 (13.8K x 2.7K, 2M ratings), k=32, 8 epochs: oracle runs in seconds."""
+    nu, ni, n, k, lr, lam, epochs = 13_800, 2_700, 2_000_000, 32, 0.005, 0.05, 8
+    u, i, r, held = orc.generate(SEED, 0, n, nu, ni)
+    tr, ho = split(u, i, r, held)
+    P, Q = orc.factorize(*tr, nu, ni, k, lr, lam, epochs, SEED)
+    return dict(nu=nu, ni=ni, k=k, lr=lr, lam=lam, epochs=epochs, train=tr, held=ho, oracle_rmse=orc.rmse(P, Q, *ho))
+
+
+@pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256])
+@pytest.mark.parametrize("scatter", [capi.SCATTER_STORE, capi.SCATTER_ATOMIC])
+def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, scatter):
+    """Records with pairwise distinct users and items commute exactly, so the full-grid Hogwild kernel
+    (tiles, sub-warps, prefetch, tails, blocking) must reproduce the oracle bit for bit in any order."""
+    n = 5003                                           # not a multiple of 32
+    rng = np.random.default_rng(k)
+    u = rng.permutation(n).astype(np.int32)
+    i = rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    P, Q = orc.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE)
+    for mu, mi in ((1, 1), (3, 2)):
+        got = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, mode=capi.MODE_HOGWILD,
+                                                  stripes_per_gpu=mu, shards_per_gpu=mi, scatter=scatter)
+        assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
+    ring = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, mode=capi.MODE_DSGD, n_gpus=4,
+                                               stripes_per_gpu=2, scatter=scatter, flags=capi.FLAG_VIRTUAL_RING)
+    assert np.array_equal(ring.P, P) and np.array_equal(ring.Q, Q)
+
+
+@pytest.mark.parametrize("mu", [1, 4])
+def test_hogwild_rmse_parity(midsize, mu):
+    m = midsize
+    cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_HOGWILD,
+                         stripes_per_gpu=mu)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(*m["train"])
+        eng.load_heldout(*m["held"])
+        eng.init_factors()
+        eng.set_eval_every_epoch(True)
+        stats = eng.train(m["epochs"])
+        got = eng.rmse(*m["held"])
+    assert abs(stats[-1].heldout_rmse - got) < 1e-9
+    assert stats[0].heldout_rmse > stats[-1].heldout_rmse
+    assert abs(got - m["oracle_rmse"]) / m["oracle_rmse"] < RMSE_TOL, (got, m["oracle_rmse"])
+
+
+@pytest.mark.parametrize("G,mu,mi", [(2, 1, 1), (4, 2, 2), (8, 1, 1)])
+def test_dsgd_virtual_ring_rmse_parity(midsize, G, mu, mi):
+    """The DSGD scheduler with G ring members placed on one GPU (streams instead of devices)."""
+    m = midsize
+    cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_DSGD, n_gpus=G,
+                         stripes_per_gpu=mu, shards_per_gpu=mi, flags=capi.FLAG_VIRTUAL_RING | capi.FLAG_TIME_KERNELS)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(*m["train"])
+        eng.init_factors()
+        P0, Q0 = eng.get_factors()
+        assert np.array_equal(P0, orc.init_factors(m["nu"], m["k"], SEED, 0))      # stripes reassemble the whole
+        assert np.array_equal(Q0, orc.init_factors(m["ni"], m["k"], SEED, 1))
+        stats = eng.train(m["epochs"])
+        assert all(s.updates == len(m["train"][2]) for s in stats)
+        assert all(s.update_launches <= G * mu and s.update_kernel_ms > 0 for s in stats)
+        got = eng.rmse(*m["held"])
+        P, Q = eng.get_factors()
+    assert abs(got - orc.rmse(P, Q, *m["held"])) / got < 1e-6                         # factors came home intact
+    assert abs(got - m["oracle_rmse"]) / m["oracle_rmse"] < RMSE_TOL, (got, m["oracle_rmse"])
+
+
+def test_set_get_factors_roundtrip_and_resume(midsize):
+    m = midsize
+    rng = np.random.default_rng(0)
+    P = rng.random((m["nu"], m["k"]), dtype=np.float32)
+    Q = rng.random((m["ni"], m["k"]), dtype=np.float32)
+    cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_DSGD, n_gpus=4,
+                         stripes_per_gpu=2, flags=capi.FLAG_VIRTUAL_RING)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(*m["train"])
+        eng.set_factors(P, Q)
+        P2, Q2 = eng.get_factors()
+        assert np.array_equal(P, P2) and np.array_equal(Q, Q2)
+        with pytest.raises(ValueError):
+            eng.set_factors(P[:, :8], Q)
+
+
+def test_state_errors():
+    with mf.Engine(mf.make_config(10, 10, 8, 0.1, 0.1)) as eng:
+        for fn in (eng.init_factors, lambda: eng.train(1), eng.get_factors, eng.layout_info):
+            with pytest.raises(mf.MfsgdError) as ei:
+                fn()
+            assert ei.value.code == capi.E_STATE
+        eng.load_ratings(np.zeros(3, np.int32), np.zeros(3, np.int32), np.ones(3, np.float32))
+        with pytest.raises(mf.MfsgdError) as ei:
+            eng.train(1)
+        assert ei.value.code == capi.E_STATE
+
+
+def test_c_harness_gpu_one_shot():
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([os.path.join(root, "tests", "c", "abi_harness"), capi.LIB_PATH, "gpu"], text=True)
+    assert "GPU one-shot factorize" in out
