@@ -46,6 +46,8 @@ extern "C" {
 /* mfsgd_config.scatter */
 #define MFSGD_SCATTER_STORE  0 /* st.global of the updated rows (Hogwild, last writer wins)  */
 #define MFSGD_SCATTER_ATOMIC 1 /* red.global.add.v4.f32 of the row deltas (no lost updates)  */
+#define MFSGD_SCATTER_ATOMIC_Q 2 /* store p_u, red q_i */
+#define MFSGD_SCATTER_ATOMIC_P 3 /* red p_u, store q_i */
 
 /* mfsgd_config.flags */
 #define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
@@ -74,7 +76,11 @@ typedef struct mfsgd_config {
     int32_t  rank;             /* ring member driven by this process when world_size == n_gpus       */
     uint8_t  nccl_id[128];     /* world_size > 1: ncclUniqueId from mfsgd_nccl_unique_id() of rank 0 */
     int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
-    int32_t  reserved[7];
+    int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
+    float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
+                                  (q_i register-resident, model-averaged); 0 = default 2e-4, < 0 = off   */
+    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 1024             */
+    int32_t  reserved[4];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
@@ -108,6 +114,8 @@ typedef struct mfsgd_layout_info {
     int64_t n_train_local;      /* records held by this process                                      */
     int64_t n_heldout_local;
     int64_t n_train_total;      /* records in the whole data set (all processes)                     */
+    int32_t rounds;             /* interleaved passes per sub-epoch (see mfsgd_config.rounds)        */
+    int32_t n_hot_items;        /* items on the hot-item path (whole data set)                       */
 } mfsgd_layout_info;
 
 MFSGD_API int  mfsgd_abi_version(void);
@@ -157,7 +165,8 @@ MFSGD_API int  mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out);
 /* user_bounds[user_blocks+1], item_bounds[item_blocks+1] (global row ids). */
 MFSGD_API int  mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds);
 /* Ring member `member`'s current record layout: recs = 3*n int32 words (u,i,r-bits per record);
- * block_offsets[stripes_per_gpu*item_blocks+1]. Pass recs=NULL to query *n only. */
+ * block_offsets[stripes_per_gpu*(item_blocks+n_hot_items)+1]: the cold blocks (stripe-major), then one
+ * bucket per (stripe, hot item). Pass recs=NULL to query *n only. */
 MFSGD_API int  mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n);
 /* Runs the reshuffle kernel once for `epoch` (HOGWILD/DSGD) or the stand-in order sort (DETERMINISTIC). */
 MFSGD_API int  mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch);

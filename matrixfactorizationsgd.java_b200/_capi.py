@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmfsgd.so")
 
 OK, E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
 MODE_DETERMINISTIC, MODE_HOGWILD, MODE_DSGD = 0, 1, 2
-SCATTER_STORE, SCATTER_ATOMIC = 0, 1
+SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
 FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE = 1, 2, 4
 ABI_VERSION = 1
 
@@ -23,7 +23,7 @@ class Config(C.Structure):
                 ("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
                 ("scatter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32), ("world_size", C.c_int32),
                 ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class EpochStats(C.Structure):
@@ -40,7 +40,8 @@ class SynthParams(C.Structure):
 class LayoutInfo(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
                 ("user_blocks", C.c_int32), ("item_blocks", C.c_int32), ("n_train_local", C.c_int64),
-                ("n_heldout_local", C.c_int64), ("n_train_total", C.c_int64)]
+                ("n_heldout_local", C.c_int64), ("n_train_total", C.c_int64), ("rounds", C.c_int32),
+                ("n_hot_items", C.c_int32)]
 
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float

@@ -43,6 +43,11 @@ __device__ __forceinline__ float uniform24(uint64_t seed, uint64_t stream, uint6
 __device__ __forceinline__ float4 ld_row4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_row4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
 
+// experiment variants of the row store (selected by scatter codes 4..6, see kernels_update.cu)
+__device__ __forceinline__ void st_row4_wb(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_row4_wt(float* p, float4 v) { __stwt(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st_row4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 __device__ __forceinline__ void red_add_row4(float* p, float4 d) {
     // sm_90+: vectorised fire-and-forget float atomic add, resolved in L2.
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)

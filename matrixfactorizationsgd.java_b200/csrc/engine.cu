@@ -124,6 +124,12 @@ struct Member {              // one ring member ("GPU g")
     int64_t* d_block_off = nullptr;
     uint16_t* d_owner_u = nullptr;
     uint16_t* d_owner_i = nullptr;
+    int32_t* d_hot_index = nullptr;  // item -> index into handle.hot_items, or -1
+    HotUnit* d_units = nullptr;      // hot-item units of all visits, grouped by visit
+    std::vector<int> visit_units;    // [(a * G + grp) * rounds + rnd] -> first unit; one extra entry at the end
+    unsigned int* d_counters = nullptr;   // one unit-claim counter per hot launch of an epoch
+    int n_counters = 0, counter_next = 0;
+    int hot_grid = 148;
     EvalSet heldout;
     double* d_scratch = nullptr;     // rmse partials + 1 accumulator at the end
     double* d_sse = nullptr;
@@ -151,6 +157,10 @@ struct Member {              // one ring member ("GPU g")
 struct mfsgd_handle {
     mfsgd_config cfg;
     int G = 1, mu = 1, mi = 1, UB = 1, IB = 1;
+    int rounds = 1;          // interleaved passes over the P sub-stripes per sub-epoch
+    std::vector<int32_t> hot_items;     // global ids of the hot items, ascending (so grouped by item block)
+    std::vector<int32_t> hot_group_lo;  // [G + 1]: hot_items[hot_group_lo[g] .. hot_group_lo[g+1]) lie in Q shard group g
+    int H = 0;
     float scale = 0.f;
     std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
     std::vector<Member> members;                    // the ring members this process drives
@@ -194,6 +204,10 @@ static void free_member_data(Member& m) {
     dev_free(m.d_block_off);
     dev_free(m.d_owner_u);
     dev_free(m.d_owner_i);
+    dev_free(m.d_hot_index);
+    dev_free(m.d_units);
+    dev_free(m.d_counters);
+    m.visit_units.clear();
     dev_free(m.recs_orig);
     dev_free(m.keys_a);
     dev_free(m.keys_b);
@@ -295,7 +309,7 @@ static int validate_config(const mfsgd_config* c) {
     if (c->mode < MFSGD_MODE_DETERMINISTIC || c->mode > MFSGD_MODE_DSGD) return fail(MFSGD_E_INVALID_ARG, "bad mode %d", c->mode);
     if (c->n_gpus < 1 || c->n_gpus > 64) return fail(MFSGD_E_INVALID_ARG, "n_gpus=%d out of range", c->n_gpus);
     if (c->mode != MFSGD_MODE_DSGD && c->n_gpus != 1) return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC/HOGWILD modes need n_gpus == 1");
-    if (c->scatter != MFSGD_SCATTER_STORE && c->scatter != MFSGD_SCATTER_ATOMIC) return fail(MFSGD_E_INVALID_ARG, "bad scatter %d", c->scatter);
+    if (c->scatter < MFSGD_SCATTER_STORE || c->scatter > 6) return fail(MFSGD_E_INVALID_ARG, "bad scatter %d", c->scatter);
     if (c->stripes_per_gpu < 0 || c->stripes_per_gpu > 256 || c->shards_per_gpu < 0 || c->shards_per_gpu > 64)
         return fail(MFSGD_E_INVALID_ARG, "stripes_per_gpu/shards_per_gpu out of range");
     if (c->world_size != 1 && c->world_size != c->n_gpus) return fail(MFSGD_E_INVALID_ARG, "world_size must be 1 or n_gpus");
@@ -304,6 +318,8 @@ static int validate_config(const mfsgd_config* c) {
     if (c->mode == MFSGD_MODE_DETERMINISTIC && (c->stripes_per_gpu > 1 || c->shards_per_gpu > 1))
         return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode keeps the caller's record order: no blocking");
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
+    if (c->hot_chunk < 0) return fail(MFSGD_E_INVALID_ARG, "hot_chunk < 0");
+    if (c->rounds < 0 || c->rounds > 256) return fail(MFSGD_E_INVALID_ARG, "rounds=%d out of range", c->rounds);
     return MFSGD_OK;
 }
 
@@ -321,10 +337,11 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     CK(dev_alloc(&m.d_scratch, (size_t)rmse_scratch_doubles() + 1));
     m.d_sse = m.d_scratch + rmse_scratch_doubles();
     int ctas = 0;
-    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter == MFSGD_SCATTER_ATOMIC, &ctas));
+    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter, &ctas));
     if (ctas < 1) ctas = 1;
     if (h->cfg.ctas_per_sm > 0 && h->cfg.ctas_per_sm < ctas) ctas = h->cfg.ctas_per_sm;
     m.grid = m.n_sms * ctas;
+    m.hot_grid = m.n_sms * 4;
     return MFSGD_OK;
 }
 
@@ -529,6 +546,26 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     CKC(cudaMemcpyAsync(&total_train, ucum + c.n_users, sizeof(uint64_t), cudaMemcpyDeviceToHost, m.stream));
     CKC(cudaStreamSynchronize(m.stream));
 #undef CKC
+    // hot items: rated by at least hot_share of the training set (and often enough to fill a warp's run)
+    h->hot_items.clear();
+    const float share = c.hot_share == 0.f ? 2e-4f : c.hot_share;
+    if (bad_host == 0 && share > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0) {
+        std::vector<uint32_t> icnt_host((size_t)c.n_items);
+        cudaError_t e = cudaMemcpy(icnt_host.data(), icnt, (size_t)c.n_items * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { cleanup(); return fail(MFSGD_E_CUDA, "copying item counts: %s", cudaGetErrorString(e)); }
+        const double thr = std::max((double)share * (double)total_train, 512.0);
+        std::vector<std::pair<uint32_t, int32_t>> cand;
+        for (int32_t it = 0; it < c.n_items; it++)
+            if ((double)icnt_host[(size_t)it] >= thr) cand.push_back({icnt_host[(size_t)it], it});
+        const size_t hmax = (size_t)std::max(0, MAX_BUCKETS / h->mu - h->IB - 1);
+        if (cand.size() > hmax) {
+            std::sort(cand.begin(), cand.end(), [](const std::pair<uint32_t, int32_t>& x, const std::pair<uint32_t, int32_t>& y) { return x.first > y.first; });
+            cand.resize(hmax);
+        }
+        for (auto& pr : cand) h->hot_items.push_back(pr.second);
+        std::sort(h->hot_items.begin(), h->hot_items.end());
+    }
+    h->H = (int)h->hot_items.size();
     cleanup();
     if (bad_host) return fail(MFSGD_E_INVALID_ARG, "a rating has a user or item id outside [0,n_users) x [0,n_items)");
     h->n_train_total = (int64_t)total_train;
@@ -536,6 +573,8 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 }
 
 static void uniform_bounds(mfsgd_handle* h) {
+    h->hot_items.clear();
+    h->H = 0;
     h->user_bounds.resize((size_t)h->UB + 1);
     h->item_bounds.resize((size_t)h->IB + 1);
     for (int b = 0; b <= h->UB; b++) h->user_bounds[(size_t)b] = (int32_t)((int64_t)h->cfg.n_users * b / h->UB);
@@ -568,13 +607,26 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
     cudaFree(d_b);
     CK(e);
+    // hot-item lookup table and the per-group ranges of the (ascending) hot list
+    h->hot_group_lo.assign((size_t)h->G + 1, 0);
+    for (int grp = 0; grp <= h->G; grp++) {
+        const int32_t bound = grp == h->G ? c.n_items : group_lo(h, grp);
+        h->hot_group_lo[(size_t)grp] = (int32_t)(std::lower_bound(h->hot_items.begin(), h->hot_items.end(), bound) - h->hot_items.begin());
+    }
+    dev_free(m.d_hot_index);
+    if (h->H > 0) {
+        std::vector<int32_t> idx((size_t)c.n_items, -1);
+        for (int j = 0; j < h->H; j++) idx[(size_t)h->hot_items[(size_t)j]] = j;
+        CK(dev_alloc(&m.d_hot_index, (size_t)c.n_items));
+        CK(cudaMemcpy(m.d_hot_index, idx.data(), (size_t)c.n_items * 4, cudaMemcpyHostToDevice));
+    }
     return MFSGD_OK;
 }
 
 // Bucket the member's share of the source into `nblk` blocks. On success *out_recs (device, owned by the
 // caller) holds the records sorted by block and off[nblk+1] the offsets.
 static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& ch, int want_held, int row_div, int col_div,
-                         int n_cols, Rec** out_recs, std::vector<int64_t>& off) {
+                         int n_cols, bool split_hot, Rec** out_recs, std::vector<int64_t>& off) {
     CK(cudaSetDevice(m.device));
     BucketArgs b{};
     b.owner_u = m.d_owner_u;
@@ -585,8 +637,13 @@ static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& c
     b.col_div = col_div;
     b.n_cols = n_cols;
     b.want_held = want_held;
+    if (split_hot && h->H > 0) {
+        b.hot_index = m.d_hot_index;
+        b.n_hot = h->H;
+        b.hot_base = bucket_rows(b) * n_cols;
+    }
     const int nblk = bucket_block_count(b);
-    if (nblk > 4096) return fail(MFSGD_E_INVALID_ARG, "%d blocks per ring member exceed the 4096 limit", nblk);
+    if (nblk > MAX_BUCKETS) return fail(MFSGD_E_INVALID_ARG, "%d blocks per ring member exceed the %d limit", nblk, MAX_BUCKETS);
     unsigned long long* d_cnt = nullptr;
     CK(dev_alloc(&d_cnt, (size_t)nblk));
     int rc = MFSGD_OK;
@@ -632,6 +689,54 @@ static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& c
     return MFSGD_OK;
 }
 
+// Record range of visit (sub-stripe sa, round rnd) inside bucket `blk` (cold block or hot bucket).
+static inline void slice_of(const Member& m, size_t blk_lo, size_t blk_hi, int rnd, int rounds, int64_t* lo, int64_t* hi) {
+    const int64_t blo = m.block_off[blk_lo], bhi = m.block_off[blk_hi];
+    *lo = blo + (bhi - blo) * rnd / rounds;
+    *hi = blo + (bhi - blo) * (rnd + 1) / rounds;
+}
+
+// Hot-item units of every visit (sa, grp, rnd): the round's slice of each (sa, hot item) bucket, cut into
+// runs of <= hot_chunk records. Bucket sizes never change, so this is built once per load.
+static int build_hot_units(mfsgd_handle* h, Member& m) {
+    dev_free(m.d_units);
+    dev_free(m.d_counters);
+    m.visit_units.assign((size_t)h->mu * h->G * h->rounds + 1, 0);
+    if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
+    CK(cudaSetDevice(m.device));
+    const int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 1024;
+    const int gpw = 32 / geometry_for(h->cfg.k).lanes;
+    const size_t hot_base = (size_t)h->mu * h->IB;
+    std::vector<HotUnit> units;
+    for (int sa = 0; sa < h->mu; sa++)
+        for (int grp = 0; grp < h->G; grp++)
+            for (int rnd = 0; rnd < h->rounds; rnd++) {
+                m.visit_units[((size_t)sa * h->G + grp) * h->rounds + rnd] = (int)units.size();
+                for (int hx = h->hot_group_lo[(size_t)grp]; hx < h->hot_group_lo[(size_t)grp + 1]; hx++) {
+                    const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
+                    int64_t lo, hi;
+                    slice_of(m, blk, blk + 1, rnd, h->rounds, &lo, &hi);
+                    const int64_t n = hi - lo;
+                    if (n <= 0) continue;
+                    const int64_t pieces = (n + chunk - 1) / chunk;
+                    for (int64_t pc = 0; pc < pieces; pc++) {
+                        HotUnit u{};
+                        u.start = lo + n * pc / pieces;
+                        u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
+                        u.item = h->hot_items[(size_t)hx];
+                        u.weight = 1.0f / (float)(pieces * gpw);
+                        units.push_back(u);
+                    }
+                }
+            }
+    m.visit_units.back() = (int)units.size();
+    m.n_counters = h->mu * h->G * h->rounds;
+    CK(dev_alloc(&m.d_units, units.size()));
+    CK(dev_alloc(&m.d_counters, (size_t)m.n_counters));
+    if (!units.empty()) CK(cudaMemcpy(m.d_units, units.data(), units.size() * sizeof(HotUnit), cudaMemcpyHostToDevice));
+    return MFSGD_OK;
+}
+
 static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) {
     const mfsgd_config& c = h->cfg;
     for (Member& m : h->members) free_member_data(m);
@@ -674,7 +779,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
             m.block_off.assign(2, 0);
             m.block_off[1] = src.total;
         } else if (rc == MFSGD_OK) {
-            rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, &m.recs[0], m.block_off);
+            rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off);
             if (rc == MFSGD_OK) {
                 m.n_recs = m.block_off.back();
                 m.rcur = 0;
@@ -685,7 +790,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
             }
             if (rc == MFSGD_OK && with_heldout) {
                 free_eval(m.heldout);
-                rc = bucket_member(h, m, src, ch, 1, h->mu, h->mi, h->G, &m.heldout.recs, m.heldout.group_off);
+                rc = bucket_member(h, m, src, ch, 1, h->mu, h->mi, h->G, false, &m.heldout.recs, m.heldout.group_off);
                 if (rc == MFSGD_OK) m.heldout.n = m.heldout.group_off.back();
             }
         }
@@ -694,6 +799,25 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
     if (rc != MFSGD_OK) {
         for (Member& m : h->members) free_member_data(m);
         return rc;
+    }
+    // Interleaving: a sub-epoch sweeps its mu sub-stripes `rounds` times, a 1/rounds slice of each block per
+    // visit, so Q sees every user stripe many times per epoch (a plain stripe-after-stripe order biases the
+    // item factors toward the last stripe and costs ~1 % RMSE at equal epochs) while each visit is still long
+    // enough (>= ~16 touches per P row) to keep the sub-stripe L2-resident.
+    if (c.rounds > 0) h->rounds = c.rounds;
+    else if (h->mu <= 1 || c.mode == MFSGD_MODE_DETERMINISTIC) h->rounds = 1;
+    else {
+        const Member& m0 = h->members[0];
+        const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
+        const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
+        h->rounds = (int)std::min(32.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+    }
+    for (Member& m : h->members) {
+        rc = build_hot_units(h, m);
+        if (rc != MFSGD_OK) {
+            for (Member& mm : h->members) free_member_data(mm);
+            return rc;
+        }
     }
     h->loaded = true;
     return MFSGD_OK;
@@ -743,7 +867,7 @@ static int build_eval_set(mfsgd_handle* h, Member& m, const int32_t* users, cons
     int rc = chunk_alloc(ch, std::max<int64_t>(1, std::min(n, CHUNK_MAX)), false);
     if (rc == MFSGD_OK) {
         free_eval(out);
-        rc = bucket_member(h, m, s, ch, 0, h->mu, h->mi, h->G, &out.recs, out.group_off);
+        rc = bucket_member(h, m, s, ch, 0, h->mu, h->mi, h->G, false, &out.recs, out.group_off);
         if (rc == MFSGD_OK) out.n = out.group_off.back();
     }
     chunk_free(ch);
@@ -893,7 +1017,7 @@ static int shuffle_member(mfsgd_handle* h, Member& m, int epoch) {
         m.rcur = 0;
         return MFSGD_OK;
     }
-    const int nblk = h->mu * h->IB;
+    const int nblk = (int)m.block_off.size() - 1;   // cold blocks + hot (stripe, item) buckets
     CK(launch_block_shuffle(m.recs[m.rcur], m.recs[m.rcur ^ 1], m.d_block_off, nblk, m.n_recs, h->cfg.seed, (uint32_t)epoch,
                             (uint32_t)(m.g * nblk), m.stream, &m.launches));
     m.rcur ^= 1;
@@ -910,7 +1034,6 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
     const mfsgd_config& c = h->cfg;
     if (err_trace && c.mode != MFSGD_MODE_DETERMINISTIC) return fail(MFSGD_E_STATE, "error traces exist in DETERMINISTIC mode only");
     const bool time_kernels = (c.flags & MFSGD_FLAG_TIME_KERNELS) != 0;
-    const bool atomic_scatter = c.scatter == MFSGD_SCATTER_ATOMIC;
     float* d_trace = nullptr;
     if (err_trace && h->members[0].n_recs > 0) {
         CK(cudaSetDevice(h->members[0].device));
@@ -970,6 +1093,10 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             er.kbeg = er.kend = (int)m.kev.size();
             m.pending.push_back(er);
             CK(cudaEventRecord(er.start, m.stream));
+            if (m.d_counters) {
+                CK(cudaMemsetAsync(m.d_counters, 0, (size_t)m.n_counters * sizeof(unsigned int), m.stream));
+                m.counter_next = 0;
+            }
             if (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) || c.mode == MFSGD_MODE_DETERMINISTIC) CKRC(shuffle_member(h, m, h->epoch));
             CK(cudaEventRecord(er.shuffled, m.stream));
         }
@@ -994,20 +1121,37 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         CK(cudaMemcpyAsync(err_trace + (size_t)ep * m.n_recs, d_trace, (size_t)m.n_recs * 4, cudaMemcpyDeviceToHost, m.stream));
                     continue;
                 }
-                for (int sa = 0; sa < h->mu; sa++) {
-                    const int64_t lo = m.block_off[(size_t)sa * h->IB + (size_t)grp * h->mi];
-                    const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
-                    if (hi == lo) continue;
-                    a.recs = m.recs[m.rcur] + lo;
-                    a.n = hi - lo;
+                for (int vis = 0; vis < h->mu * h->rounds; vis++) {
+                    const int rnd = vis / h->mu;
+                    // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
+                    const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
+                    const int pos = vis % h->mu;
+                    const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
+                    int64_t lo, hi;
+                    slice_of(m, (size_t)sa * h->IB + (size_t)grp * h->mi, (size_t)sa * h->IB + (size_t)(grp + 1) * h->mi, rnd, h->rounds, &lo, &hi);
+                    const size_t vkey = ((size_t)sa * h->G + grp) * h->rounds + rnd;
+                    const int unit_lo = m.visit_units[vkey], unit_hi = m.visit_units[vkey + 1];
+                    if (hi == lo && unit_hi == unit_lo) continue;
                     cudaEvent_t e0 = nullptr, e1 = nullptr;
                     if (time_kernels) {
                         CKRC(timing_event(m, &e0));
                         CKRC(timing_event(m, &e1));
                         CK(cudaEventRecord(e0, m.stream));
                     }
-                    CK(launch_sgd_update_hogwild(a, atomic_scatter, m.grid, h->min_windows, m.stream, &m.launches));
-                    m.update_launches++;
+                    if (hi > lo) {      // cold records: full-grid Hogwild kernel
+                        a.recs = m.recs[m.rcur] + lo;
+                        a.n = hi - lo;
+                        CK(launch_sgd_update_hogwild(a, c.scatter, m.grid, h->min_windows, m.stream, &m.launches));
+                        m.update_launches++;
+                    }
+                    if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
+                        a.recs = m.recs[m.rcur];
+                        a.n = m.n_recs;
+                        if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
+                        CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, m.hot_grid,
+                                                 m.stream, &m.launches));
+                        m.update_launches++;
+                    }
                     if (time_kernels) {
                         CK(cudaEventRecord(e1, m.stream));
                         m.kev.push_back(e0);
@@ -1073,6 +1217,13 @@ static int rmse_sets(mfsgd_handle* h, std::vector<EvalSet*>& sets, bool train_se
                     const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
                     CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                        m.d_sse, m.n_sms, m.stream, &m.launches));
+                    if (h->H > 0) {   // the hot buckets of (sa, grp) are contiguous too
+                        const size_t hb = (size_t)h->mu * h->IB + (size_t)sa * h->H;
+                        const int64_t hlo = m.block_off[hb + (size_t)h->hot_group_lo[(size_t)grp]];
+                        const int64_t hhi = m.block_off[hb + (size_t)h->hot_group_lo[(size_t)grp + 1]];
+                        CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                                           m.d_sse, m.n_sms, m.stream, &m.launches));
+                    }
                 }
             } else {
                 EvalSet* e = sets[j];
@@ -1202,6 +1353,8 @@ extern "C" int mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out) {
         out->n_heldout_local += m.heldout.n;
     }
     out->n_train_total = h->n_train_total;
+    out->rounds = h->rounds;
+    out->n_hot_items = h->H;
     return MFSGD_OK;
 }
 

@@ -55,15 +55,28 @@ struct UpdateArgs {
 
 // (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
 // min_windows: lower bound on (records in the launch) / (ratings in flight at once), see kernels_update.cu.
-cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, bool atomic_scatter, int grid, int min_windows,
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid, int min_windows,
                                       cudaStream_t stream, int* launches);
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
-cudaError_t hogwild_max_ctas_per_sm(int k, bool atomic_scatter, int* ctas);
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, int* ctas);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
 cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches);
 // Teacher-forced check: n independent row pairs.
 cudaError_t launch_sgd_update_forced(int k, float lr, float lambda, int64_t n, const float* pre_p, const float* pre_q,
                                      const float* r, float* post_p, float* post_q, float* err, cudaStream_t stream);
+
+// (2b) hot-item path: one warp per unit = a run of records that all rate the same (hot) item. q_i lives in
+// the warp's registers for the whole run (no L2 round trips, no contention on the hot row); the run's net
+// change is merged into Q at the end, scaled by `weight` (model averaging across the units of one item).
+struct HotUnit {
+    int64_t start;     // first record (index into the launch's record array)
+    int32_t count;
+    int32_t item;      // global item id
+    float   weight;    // 1 / (units of this item in the launch * sub-warps per warp)
+    int32_t pad;
+};
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter,
+                                  int grid, cudaStream_t stream, int* launches);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
@@ -112,8 +125,16 @@ struct BucketArgs {
     const uint16_t* owner_i;
     int32_t ub_lo, ub_hi, row_div, col_div, n_cols;
     int32_t want_held;     // 0: training records, 1: held-out records
+    // hot items (training layout only; hot_index == nullptr disables): a record whose item has
+    // hot_index[i] >= 0 goes to bucket hot_base + row * n_hot + hot_index[i] instead of its cold block.
+    const int32_t* hot_index;
+    int32_t hot_base, n_hot;
 };
-inline int bucket_block_count(const BucketArgs& b) { return ((b.ub_hi - b.ub_lo + b.row_div - 1) / b.row_div) * b.n_cols; }
+inline int bucket_rows(const BucketArgs& b) { return (b.ub_hi - b.ub_lo + b.row_div - 1) / b.row_div; }
+inline int bucket_block_count(const BucketArgs& b) {
+    return bucket_rows(b) * b.n_cols + (b.hot_index ? bucket_rows(b) * b.n_hot : 0);
+}
+constexpr int MAX_BUCKETS = 16384;   // per ring member: cold blocks + hot (stripe, item) buckets
 cudaError_t launch_block_histogram(const BucketArgs& b, unsigned long long* block_cnt, cudaStream_t stream, int* launches);
 // cursors start as the exclusive offsets; each record claims a slot with atomicAdd.
 cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursors, Rec* out, cudaStream_t stream,

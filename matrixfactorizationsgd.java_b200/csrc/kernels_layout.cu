@@ -15,7 +15,7 @@ namespace mfsgd {
 
 namespace {
 
-constexpr int MAX_SMEM_BLOCKS = 4096;
+constexpr int SHUFFLE_SMEM_BLOCKS = 4096;   // offsets above this count are read from global memory
 
 inline int grid_for(int64_t n, int threads, int max_ctas) {
     int64_t g = (n + threads - 1) / threads;
@@ -88,7 +88,13 @@ __device__ __forceinline__ int record_block(const BucketArgs& b, int64_t t) {
     }
     const int ou = (int)b.owner_u[b.u[t]];
     if (ou < b.ub_lo || ou >= b.ub_hi) return -1;
-    return ((ou - b.ub_lo) / b.row_div) * b.n_cols + (int)b.owner_i[b.i[t]] / b.col_div;
+    const int row = (ou - b.ub_lo) / b.row_div;
+    const int32_t item = b.i[t];
+    if (b.hot_index != nullptr) {
+        const int32_t hx = b.hot_index[item];
+        if (hx >= 0) return b.hot_base + row * b.n_hot + hx;
+    }
+    return row * b.n_cols + (int)b.owner_i[item] / b.col_div;
 }
 
 constexpr int BUCKET_THREADS = 256;
@@ -180,9 +186,13 @@ __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restric
                                                             const int64_t* __restrict__ block_off, int nblocks,
                                                             int64_t n, uint64_t seed, uint32_t epoch,
                                                             uint32_t block_id_base) {
-    extern __shared__ int64_t soff[];
-    for (int j = threadIdx.x; j <= nblocks; j += blockDim.x) soff[j] = block_off[j];
-    __syncthreads();
+    extern __shared__ int64_t soff_smem[];
+    const int64_t* __restrict__ soff = block_off;
+    if (nblocks <= SHUFFLE_SMEM_BLOCKS) {
+        for (int j = threadIdx.x; j <= nblocks; j += blockDim.x) soff_smem[j] = block_off[j];
+        __syncthreads();
+        soff = soff_smem;
+    }
     const int32_t* __restrict__ win = reinterpret_cast<const int32_t*>(in);
     int32_t* __restrict__ wout = reinterpret_cast<int32_t*>(out);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -276,9 +286,13 @@ cudaError_t launch_fill_owner(const int32_t* bounds, int32_t nblocks, int32_t n_
 cudaError_t launch_block_histogram(const BucketArgs& b, unsigned long long* block_cnt, cudaStream_t stream, int* launches) {
     if (b.n <= 0) return cudaSuccess;
     const int nblk = bucket_block_count(b);
-    if (nblk > MAX_SMEM_BLOCKS) return cudaErrorInvalidValue;
-    block_histogram_kernel<<<grid_for(b.n, BUCKET_THREADS * 16, 148 * 8), BUCKET_THREADS, nblk * sizeof(uint32_t), stream>>>(
-        b, nblk, block_cnt);
+    if (nblk > MAX_BUCKETS) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)nblk * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(block_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    block_histogram_kernel<<<grid_for(b.n, BUCKET_THREADS * 16, 148 * 4), BUCKET_THREADS, smem, stream>>>(b, nblk, block_cnt);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -287,9 +301,13 @@ cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursor
                                  int* launches) {
     if (b.n <= 0) return cudaSuccess;
     const int nblk = bucket_block_count(b);
-    if (nblk > MAX_SMEM_BLOCKS) return cudaErrorInvalidValue;
+    if (nblk > MAX_BUCKETS) return cudaErrorInvalidValue;
     const size_t smem = (size_t)((nblk + 1) & ~1) * sizeof(uint32_t) + (size_t)nblk * sizeof(unsigned long long);
-    block_scatter_kernel<<<grid_for(b.n, BUCKET_CHUNK, 148 * 8), BUCKET_THREADS, smem, stream>>>(b, nblk, cursors, out);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(block_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    block_scatter_kernel<<<grid_for(b.n, BUCKET_CHUNK, 148 * 4), BUCKET_THREADS, smem, stream>>>(b, nblk, cursors, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -297,8 +315,8 @@ cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursor
 cudaError_t launch_block_shuffle(const Rec* in, Rec* out, const int64_t* block_off, int32_t nblocks, int64_t n,
                                  uint64_t seed, uint32_t epoch, uint32_t block_id_base, cudaStream_t stream, int* launches) {
     if (n <= 0) return cudaSuccess;
-    if (nblocks > MAX_SMEM_BLOCKS) return cudaErrorInvalidValue;
-    block_shuffle_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, (nblocks + 1) * sizeof(int64_t), stream>>>(
+    const size_t smem = nblocks <= SHUFFLE_SMEM_BLOCKS ? (size_t)(nblocks + 1) * sizeof(int64_t) : 0;
+    block_shuffle_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, smem, stream>>>(
         in, out, block_off, nblocks, n, seed, epoch, block_id_base);
     if (launches) *launches += 1;
     return cudaGetLastError();

@@ -40,20 +40,25 @@ __device__ __forceinline__ float row_dot(const RowPair<LANES, VEC>& rp) {
     return group_sum<LANES>(s);
 }
 
-template <int LANES, int VEC, bool FULL, bool ATOMIC>
+// SC: 0 = st/st, 1 = red/red, 2 = st P + red Q, 3 = red P + st Q  (mfsgd.h MFSGD_SCATTER_*)
+template <int LANES, int VEC, bool FULL, int SC>
 __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, float* prow, float* qrow, int gl,
                                              int chunks, float e, float lr, float lambda) {
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
         const int c = gl + v * LANES;
         if (FULL || c < chunks) {
-            if (ATOMIC) {
-                red_add_row4(prow + 4 * c, delta4(rp.p[v], rp.q[v], e, lr, lambda));
-                red_add_row4(qrow + 4 * c, delta4(rp.q[v], rp.p[v], e, lr, lambda));
-            } else {
-                st_row4(prow + 4 * c, upd4(rp.p[v], rp.q[v], e, lr, lambda));
-                st_row4(qrow + 4 * c, upd4(rp.q[v], rp.p[v], e, lr, lambda));
+            if (SC >= 4) {   // store cache-operator experiments: 4 = default (wb), 5 = wt, 6 = cs
+                const float4 np_ = upd4(rp.p[v], rp.q[v], e, lr, lambda), nq_ = upd4(rp.q[v], rp.p[v], e, lr, lambda);
+                if (SC == 4) { st_row4_wb(prow + 4 * c, np_); st_row4_wb(qrow + 4 * c, nq_); }
+                else if (SC == 5) { st_row4_wt(prow + 4 * c, np_); st_row4_wt(qrow + 4 * c, nq_); }
+                else { st_row4_cs(prow + 4 * c, np_); st_row4_cs(qrow + 4 * c, nq_); }
+                continue;
             }
+            if (SC == 1 || SC == 3) red_add_row4(prow + 4 * c, delta4(rp.p[v], rp.q[v], e, lr, lambda));
+            else st_row4(prow + 4 * c, upd4(rp.p[v], rp.q[v], e, lr, lambda));
+            if (SC == 1 || SC == 2) red_add_row4(qrow + 4 * c, delta4(rp.q[v], rp.p[v], e, lr, lambda));
+            else st_row4(qrow + 4 * c, upd4(rp.q[v], rp.p[v], e, lr, lambda));
         }
     }
 }
@@ -62,7 +67,7 @@ __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, floa
 // each, streamed past L1); the warp's 32/LANES sub-warps walk the tile, each step gathering the rows
 // of the NEXT rating before reducing the current one (2 ratings in flight per sub-warp), and the
 // next tile's records are fetched a whole tile ahead.
-template <int LANES, int VEC, bool FULL, bool ATOMIC>
+template <int LANES, int VEC, bool FULL, int SC>
 __global__ void __launch_bounds__(256) sgd_update_hogwild_kernel(UpdateArgs a) {
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
@@ -125,9 +130,113 @@ __global__ void __launch_bounds__(256) sgd_update_hogwild_kernel(UpdateArgs a) {
                 load_rows<LANES, VEC, FULL>(nxt, xp, xq, gl, chunks, xact);
             }
             const float e = __fsub_rn(cr, row_dot<LANES, VEC>(cur));
-            if (cact) scatter_rows<LANES, VEC, FULL, ATOMIC>(cur, cp, cq, gl, chunks, e, a.lr, a.lambda);
+            if (cact) scatter_rows<LANES, VEC, FULL, SC>(cur, cp, cq, gl, chunks, e, a.lr, a.lambda);
         }
         ru = nu; ri = ni; rr = nr;
+    }
+}
+
+// (2b) Hot-item kernel. A unit is a run of records that all rate one hot item. The warp keeps q_i in
+// registers (each of its 32/LANES sub-warps a private copy, taking alternate records), streams the
+// run's users: gather p_u, dot, scatter p_u, update q_i in registers -- the item row costs no L2
+// traffic and sees no concurrent writer. At the end the run's net change is merged into Q scaled by
+// unit.weight (model averaging over the item's concurrent units); a unit that is alone on its item
+// (weight 1) stores q_i outright, which makes the path exactly sequential. Units are claimed from a
+// per-launch counter so uneven runs balance themselves.
+template <int LANES, int VEC, bool FULL>
+__global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
+                                                             unsigned int* __restrict__ counter) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const int grp = lane / LANES;
+    const int chunks = a.k >> 2;
+    const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
+    const uint64_t pol = l2_policy_evict_first();
+    for (;;) {
+        unsigned int unit = 0;
+        if (lane == 0) unit = atomicAdd(counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= (unsigned int)n_units) break;
+        const HotUnit hu = units[unit];
+        float* const qrow = a.Q + (int64_t)(hu.item - a.i_base) * a.k;
+        float4 q0[VEC], q[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const int c = gl + v * LANES;
+            q0[v] = (FULL || c < chunks) ? ld_row4(qrow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[v] = q0[v];
+        }
+        for (int base = 0; base < hu.count; base += 32) {
+            const int cnt = (hu.count - base) < 32 ? (hu.count - base) : 32;
+            int32_t ru = 0, rr = 0;
+            if (lane < cnt) {
+                const int64_t idx = hu.start + base + lane;
+                ru = ld_stream_i32(words + 3 * idx, pol);
+                rr = ld_stream_i32(words + 3 * idx + 2, pol);
+            }
+            const int steps = (cnt + GPW - 1) / GPW;
+            float4 pn[VEC];
+            int32_t xu = __shfl_sync(0xffffffffu, ru, grp);
+            int32_t xr = __shfl_sync(0xffffffffu, rr, grp);
+            bool xact = grp < cnt;
+            float* xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const int c = gl + v * LANES;
+                pn[v] = (xact && (FULL || c < chunks)) ? ld_row4(xp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll 2
+            for (int t = 0; t < steps; t++) {
+                float4 p[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) p[v] = pn[v];
+                float* const cp = xp;
+                const float cr = __int_as_float(xr);
+                const bool cact = xact;
+                if (t + 1 < steps) {
+                    const int j = (t + 1) * GPW + grp;
+                    xu = __shfl_sync(0xffffffffu, ru, j);
+                    xr = __shfl_sync(0xffffffffu, rr, j);
+                    xact = j < cnt;
+                    xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        const int c = gl + v * LANES;
+                        pn[v] = (xact && (FULL || c < chunks)) ? ld_row4(xp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                float s = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) s = dot4_acc(s, p[v], q[v]);
+                s = group_sum<LANES>(s);
+                const float e = __fsub_rn(cr, s);
+                if (cact) {
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        const int c = gl + v * LANES;
+                        if (FULL || c < chunks) {
+                            st_row4(cp + 4 * c, upd4(p[v], q[v], e, a.lr, a.lambda));
+                            q[v] = upd4(q[v], p[v], e, a.lr, a.lambda);
+                        }
+                    }
+                }
+            }
+        }
+        // merge the run's result into Q
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const int c = gl + v * LANES;
+            if (FULL || c < chunks) {
+                if (GPW == 1 && hu.weight == 1.0f) {
+                    st_row4(qrow + 4 * c, q[v]);
+                } else {
+                    const float w = hu.weight;
+                    red_add_row4(qrow + 4 * c, make_float4(__fmul_rn(__fsub_rn(q[v].x, q0[v].x), w), __fmul_rn(__fsub_rn(q[v].y, q0[v].y), w),
+                                                           __fmul_rn(__fsub_rn(q[v].z, q0[v].z), w), __fmul_rn(__fsub_rn(q[v].w, q0[v].w), w)));
+                }
+            }
+        }
     }
 }
 
@@ -147,7 +256,7 @@ __global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs
         RowPair<LANES, VEC> rp;
         load_rows<LANES, VEC, FULL>(rp, prow, qrow, gl, chunks, act);
         const float e = __fsub_rn(rec.r, row_dot<LANES, VEC>(rp));
-        if (act) scatter_rows<LANES, VEC, FULL, false>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
+        if (act) scatter_rows<LANES, VEC, FULL, 0>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
         if (err_trace != nullptr && lane == 0) err_trace[j] = e;
     }
 }
@@ -174,7 +283,7 @@ __global__ void __launch_bounds__(256) sgd_update_forced_kernel(int k, float lr,
         load_rows<LANES, VEC, FULL>(rp, pre_p + jj * k, pre_q + jj * k, gl, chunks, act);
         const float e = __fsub_rn(act ? r[jj] : 0.f, row_dot<LANES, VEC>(rp));
         if (act) {
-            scatter_rows<LANES, VEC, FULL, false>(rp, post_p + jj * k, post_q + jj * k, gl, chunks, e, lr, lambda);
+            scatter_rows<LANES, VEC, FULL, 0>(rp, post_p + jj * k, post_q + jj * k, gl, chunks, e, lr, lambda);
             if (gl == 0) err[jj] = e;
         }
     }
@@ -183,7 +292,7 @@ __global__ void __launch_bounds__(256) sgd_update_forced_kernel(int k, float lr,
 
 }  // namespace
 
-cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, bool atomic_scatter, int grid, int min_windows,
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid, int min_windows,
                                       cudaStream_t stream, int* launches) {
     if (min_windows < 1) min_windows = 1;
     if (a.n <= 0) return cudaSuccess;
@@ -197,22 +306,43 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, bool atomic_scatter, 
     if (max_grid < 1) max_grid = 1;
     if (grid > max_grid) grid = (int)max_grid;
     if (grid < 1) grid = 1;
-#define CALL(L, V, F)                                                                              \
-    if (atomic_scatter) sgd_update_hogwild_kernel<L, V, F, true><<<grid, 256, 0, stream>>>(a);     \
-    else sgd_update_hogwild_kernel<L, V, F, false><<<grid, 256, 0, stream>>>(a)
+#define CALL(L, V, F)                                                                         \
+    switch (scatter) {                                                                        \
+        case 1: sgd_update_hogwild_kernel<L, V, F, 1><<<grid, 256, 0, stream>>>(a); break;    \
+        case 2: sgd_update_hogwild_kernel<L, V, F, 2><<<grid, 256, 0, stream>>>(a); break;    \
+        case 3: sgd_update_hogwild_kernel<L, V, F, 3><<<grid, 256, 0, stream>>>(a); break;    \
+        case 4: sgd_update_hogwild_kernel<L, V, F, 4><<<grid, 256, 0, stream>>>(a); break;    \
+        case 5: sgd_update_hogwild_kernel<L, V, F, 5><<<grid, 256, 0, stream>>>(a); break;    \
+        case 6: sgd_update_hogwild_kernel<L, V, F, 6><<<grid, 256, 0, stream>>>(a); break;    \
+        default: sgd_update_hogwild_kernel<L, V, F, 0><<<grid, 256, 0, stream>>>(a); break;   \
+    }
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t hogwild_max_ctas_per_sm(int k, bool atomic_scatter, int* ctas) {
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter,
+                                  int grid, cudaStream_t stream, int* launches) {
+    if (n_units <= 0) return cudaSuccess;
+    const Geometry g = geometry_for(a.k);
+    const int max_grid = (n_units + 7) / 8;   // 8 warps per CTA, one unit per warp at a time
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+#define CALL(L, V, F) sgd_update_hot_kernel<L, V, F><<<grid, 256, 0, stream>>>(a, units, n_units, counter)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, int* ctas) {
     const Geometry g = geometry_for(k);
     cudaError_t err = cudaSuccess;
-#define CALL(L, V, F)                                                                                             \
-    err = atomic_scatter                                                                                          \
-              ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, true>, 256, 0)  \
-              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, false>, 256, 0)
+#define CALL(L, V, F)                                                                                          \
+    err = (scatter == 1)                                                                                       \
+              ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 1>, 256, 0) \
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0>, 256, 0)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     return err;

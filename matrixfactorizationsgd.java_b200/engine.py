@@ -11,7 +11,7 @@ from ._capi import Config, EpochStats, LayoutInfo, SynthParams, check, lib, ptr,
 
 def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_HOGWILD, n_gpus=1,
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
-                world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0):
+                world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -19,7 +19,8 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.seed, cfg.mode, cfg.n_gpus = int(seed), int(mode), int(n_gpus)
     cfg.stripes_per_gpu, cfg.shards_per_gpu = int(stripes_per_gpu), int(shards_per_gpu)
     cfg.scatter, cfg.flags, cfg.device = int(scatter), int(flags), int(device)
-    cfg.world_size, cfg.rank, cfg.ctas_per_sm = int(world_size), int(rank), int(ctas_per_sm)
+    cfg.world_size, cfg.rank, cfg.ctas_per_sm, cfg.rounds = int(world_size), int(rank), int(ctas_per_sm), int(rounds)
+    cfg.hot_share, cfg.hot_chunk = float(hot_share), int(hot_chunk)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg
@@ -157,7 +158,7 @@ class Engine:
         n = C.c_int64(0)
         check(lib.mfsgd_get_records(self._h, member, None, None, C.byref(n)))
         recs = np.zeros((n.value, 3), dtype=np.int32)
-        off = np.zeros(info.stripes_per_gpu * info.item_blocks + 1, dtype=np.int64)
+        off = np.zeros(info.stripes_per_gpu * (info.item_blocks + info.n_hot_items) + 1, dtype=np.int64)
         check(lib.mfsgd_get_records(self._h, member, ptr(recs), ptr(off), C.byref(n)))
         return recs[:, 0].copy(), recs[:, 1].copy(), recs[:, 2].copy().view(np.float32), off
 

@@ -41,7 +41,7 @@ def test_struct_sizes_match_c_layout():
     assert capi.Config.seed.offset == 24 and capi.Config.nccl_id.offset == 68 and capi.Config.ctas_per_sm.offset == 196
     assert C.sizeof(capi.EpochStats) == 48
     assert C.sizeof(capi.SynthParams) == 40
-    assert C.sizeof(capi.LayoutInfo) == 48
+    assert C.sizeof(capi.LayoutInfo) == 56
 
 
 def test_c_harness_dlopen_dlsym():
@@ -56,8 +56,9 @@ def test_c_harness_dlopen_dlsym():
     (dict(k=6), "k=6"), (dict(k=0), "k=0"), (dict(k=516), "k=516"), (dict(n_users=0), "n_users"),
     (dict(lr=0.0), "lr"), (dict(lambda_=-1.0), "lambda"), (dict(mode=7), "mode"),
     (dict(n_gpus=2), "n_gpus == 1"), (dict(mode=capi.MODE_DSGD, n_gpus=0), "n_gpus"),
-    (dict(scatter=5), "scatter"), (dict(mode=capi.MODE_DSGD, n_gpus=4, world_size=2), "world_size"),
+    (dict(scatter=9), "scatter"), (dict(mode=capi.MODE_DSGD, n_gpus=4, world_size=2), "world_size"),
     (dict(mode=capi.MODE_DETERMINISTIC, stripes_per_gpu=2), "DETERMINISTIC"), (dict(device=-1), "device"),
+    (dict(rounds=-1), "rounds"), (dict(hot_chunk=-5), "hot_chunk"),
 ])
 def test_invalid_config_rejected_before_gpu(kw, needle):
     base = dict(n_users=10, n_items=10, k=8, lr=0.1, lambda_=0.1)

@@ -1,0 +1,18 @@
+"""Short single-GPU run for ncu: Netflix-shaped (or other) workload, a few epochs, chosen scatter mode.
+usage: python tools/profile_target.py [workload] [scatter] [stripes] [epochs]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import matrixfactorizationsgd.java_b200 as mf
+wname = sys.argv[1] if len(sys.argv) > 1 else "netflix"
+scatter = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+stripes = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+epochs = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+w = mf.WORKLOADS[wname]
+cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=mf.capi.MODE_HOGWILD,
+                     stripes_per_gpu=stripes, scatter=scatter, rounds=1)
+with mf.Engine(cfg) as eng:
+    eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
+    eng.init_factors()
+    st = eng.train(epochs)
+    print("epoch_ms", [round(s.epoch_ms, 2) for s in st], "launches/epoch", st[-1].update_launches)
