@@ -154,7 +154,7 @@ def run_ours(args):
     flags = capi.FLAG_TIME_KERNELS
     common = dict(n_users=w.n_users, n_items=w.n_items, k=w.k, lr=w.lr, lambda_=w.lambda_, seed=mf.SEED,
                   stripes_per_gpu=args.stripes, shards_per_gpu=args.shards, scatter=args.scatter, flags=flags,
-                  ctas_per_sm=args.ctas_per_sm)
+                  ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share)
     if world > 1:
         eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
     else:
@@ -165,12 +165,13 @@ def run_ours(args):
     setup_s = time.time() - t0
     info = eng.layout_info()
     eng.init_factors()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs a moment to produce its first sample: start before the warm-up
     if args.warmup > 0:
         eng.train(args.warmup)
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.rows.clear()          # keep only samples taken during the timed region
     wall0 = time.time()
     stats = eng.train(args.steps)
     barrier()
@@ -189,17 +190,24 @@ def run_ours(args):
     heldout_rmse = ring.reduce_rmse(dist, sse, cnt) if dist is not None else float(np.sqrt(sse / max(cnt, 1)))
     eng.close()
 
-    # roofline of the dominant kernel (rank 0's launches): algorithmic bytes / measured launch time
+    # Roofline of the update phase on rank 0: the cold (sgd_update_hogwild_kernel) and hot-item
+    # (sgd_update_hot_kernel) launches of an epoch run concurrently on two streams, so they are timed together:
+    # one CUDA-event span per sub-epoch on the launching stream, fork to join. Algorithmic bytes = 12 + 16k per
+    # update x the updates in the span.
     peak, peak_src = peaks()
     bpu = mf.bytes_per_update(w.k)
     rank_updates = float(sum(s.updates for s in stats))
     achieved = rank_updates * bpu / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic = recorded_traffic(args.workload) if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "sgd_update_hogwild_kernel",
-                "bytes_per_update": bpu, "updates_per_launch": rank_updates / max(1, n_launch),
-                "avg_launch_ms": kernel_ms / max(1, n_launch), "kernel_share_of_step": kernel_ms / max(dev_ms, 1e-9),
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "sgd_update_hogwild_kernel + sgd_update_hot_kernel (concurrent streams, timed as one span per sub-epoch)",
+                "bytes_per_update": bpu, "updates_per_step": rank_updates / args.steps,
+                "algorithmic_bytes_per_step": rank_updates * bpu / args.steps,
+                "update_phase_ms_per_step": kernel_ms / args.steps, "update_launches_per_step": n_launch / args.steps,
+                "kernel_share_of_step": kernel_ms / max(dev_ms, 1e-9), "frac_of_nominal_8TBs": achieved / 8000.0,
+                "note": "frac > 1 is expected: the P sub-stripe and Q stay L2-resident (stratified blocks) and hot q_i rows "
+                        "live in registers, so DRAM traffic (see traffic) is a small fraction of the algorithmic bytes"}
 
     # e2e: the reference-facing call with HOST buffers: H2D + bucketing + init + K epochs + D2H of P, Q
     e2e = None
@@ -240,6 +248,7 @@ def run_ours(args):
                               w.name, w.n_users, w.n_items, w.n_ratings, int(info.n_train_total), w.k, w.lr, w.lambda_),
                           "parallelism": "hogwild-1gpu" if world == 1 else "dsgd-ring%d" % world,
                           "stripes_per_gpu": int(info.stripes_per_gpu), "shards_per_gpu": int(info.shards_per_gpu),
+                          "rounds": int(info.rounds), "hot_items": int(info.n_hot_items),
                           "scatter": "store" if args.scatter == 0 else "atomic",
                           "l2": "inputs larger than L2: %.2f GB of records + %.0f MB of factors streamed per step" % (
                               12e-9 * info.n_train_total, 4e-6 * w.k * (w.n_users + w.n_items)),
@@ -314,7 +323,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="netflix")
@@ -322,6 +331,8 @@ def main():
     ap.add_argument("--shards", type=int, default=0)
     ap.add_argument("--scatter", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--rounds", type=int, default=0)
+    ap.add_argument("--hot-share", type=float, default=0.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=12_000_000)

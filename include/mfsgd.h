@@ -78,8 +78,8 @@ typedef struct mfsgd_config {
     int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
     int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
     float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
-                                  (q_i register-resident, model-averaged); 0 = default 2e-4, < 0 = off   */
-    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 1024             */
+                                  (q_i register-resident, model-averaged); 0 = default 1e-4, < 0 = off   */
+    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 256              */
     int32_t  reserved[4];
 } mfsgd_config;
 
@@ -89,7 +89,8 @@ typedef struct mfsgd_epoch_stats {
     int64_t updates;            /* rating updates applied by this process's ring members             */
     double  epoch_ms;           /* shuffle + all sub-epochs + rotations                              */
     double  shuffle_ms;         /* the reshuffle kernel alone                                        */
-    double  update_kernel_ms;   /* sum over update launches (MFSGD_FLAG_TIME_KERNELS), else 0         */
+    double  update_kernel_ms;   /* MFSGD_FLAG_TIME_KERNELS: time inside the update kernels (per sub-epoch span
+                                   of the concurrent cold + hot-item launches), else 0                */
     int32_t update_launches;    /* update-kernel launches in the epoch                               */
     int32_t total_launches;     /* every kernel this library launched in the epoch                   */
     double  heldout_rmse;       /* NaN unless a held-out set is loaded and eval_every_epoch is on     */

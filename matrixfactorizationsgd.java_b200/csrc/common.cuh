@@ -66,6 +66,10 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t* p, uint64_t pol)
     return v;
 }
 
+__device__ __forceinline__ void st_stream_i32(int32_t* p, int32_t v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // ---- the update rule -----------------------------------------------------------------------
 // Partial dot of one float4 chunk, continuing a running binary32 sum, element order x,y,z,w.
 __device__ __forceinline__ float dot4_acc(float acc, float4 a, float4 b) {

@@ -110,7 +110,8 @@ struct Member {              // one ring member ("GPU g")
     int device = 0;          // CUDA ordinal
     int n_sms = 148;
     size_t l2_bytes = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, hot_stream = nullptr, shuffle_stream = nullptr;
+    int ahead_epoch = -1;    // epoch whose layout the background reshuffle has written (is writing) into recs[rcur ^ 1]
     int32_t u_lo = 0, u_hi = 0;      // owned P rows
     float* P = nullptr;
     float* Q[2] = {nullptr, nullptr};
@@ -140,7 +141,7 @@ struct Member {              // one ring member ("GPU g")
     void* sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
     // events
-    cudaEvent_t ev_compute = nullptr, ev_sent = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_sent = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_shuffle_go = nullptr, ev_shuffle_done = nullptr;
     std::vector<cudaEvent_t> evpool; // timing events, handed out per train call
     int ev_used = 0;
     struct EpochRec {                // one per epoch of the running train call, resolved after a sync
@@ -196,6 +197,8 @@ static void free_eval(EvalSet& e) {
 
 static void free_member_data(Member& m) {
     cudaSetDevice(m.device);
+    if (m.shuffle_stream) cudaStreamSynchronize(m.shuffle_stream);
+    m.ahead_epoch = -1;
     dev_free(m.P);
     dev_free(m.Q[0]);
     dev_free(m.Q[1]);
@@ -332,8 +335,18 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     m.l2_bytes = (size_t)prop.l2CacheSize;
     CK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m.hot_stream, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;   // the background reshuffle yields to the update kernels
+        CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CK(cudaStreamCreateWithPriority(&m.shuffle_stream, cudaStreamNonBlocking, lo_prio));
+    }
     CK(cudaEventCreateWithFlags(&m.ev_compute, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m.ev_sent, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_shuffle_go, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_shuffle_done, cudaEventDisableTiming));
     CK(dev_alloc(&m.d_scratch, (size_t)rmse_scratch_doubles() + 1));
     m.d_sse = m.d_scratch + rmse_scratch_doubles();
     int ctas = 0;
@@ -351,17 +364,21 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         cudaSetDevice(m.device);
         if (m.stream) cudaStreamSynchronize(m.stream);
         if (m.copy_stream) cudaStreamSynchronize(m.copy_stream);
+        if (m.hot_stream) cudaStreamSynchronize(m.hot_stream);
+        if (m.shuffle_stream) cudaStreamSynchronize(m.shuffle_stream);
     }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (Member& m : h->members) {
         free_member_data(m);
         dev_free(m.d_scratch);
         for (cudaEvent_t e : m.evpool) cudaEventDestroy(e);
-        cudaEvent_t evs[] = {m.ev_compute, m.ev_sent};
+        cudaEvent_t evs[] = {m.ev_compute, m.ev_sent, m.ev_fork, m.ev_join, m.ev_shuffle_go, m.ev_shuffle_done};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
         if (m.stream) cudaStreamDestroy(m.stream);
         if (m.copy_stream) cudaStreamDestroy(m.copy_stream);
+        if (m.hot_stream) cudaStreamDestroy(m.hot_stream);
+        if (m.shuffle_stream) cudaStreamDestroy(m.shuffle_stream);
     }
     delete h;
 }
@@ -548,7 +565,7 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 #undef CKC
     // hot items: rated by at least hot_share of the training set (and often enough to fill a warp's run)
     h->hot_items.clear();
-    const float share = c.hot_share == 0.f ? 2e-4f : c.hot_share;
+    const float share = c.hot_share == 0.f ? 1e-4f : c.hot_share;
     if (bad_host == 0 && share > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0) {
         std::vector<uint32_t> icnt_host((size_t)c.n_items);
         cudaError_t e = cudaMemcpy(icnt_host.data(), icnt, (size_t)c.n_items * 4, cudaMemcpyDeviceToHost);
@@ -704,7 +721,7 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     m.visit_units.assign((size_t)h->mu * h->G * h->rounds + 1, 0);
     if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
     CK(cudaSetDevice(m.device));
-    const int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 1024;
+    const int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 256;
     const int gpw = 32 / geometry_for(h->cfg.k).lanes;
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
@@ -810,7 +827,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
         const Member& m0 = h->members[0];
         const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
         const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
-        h->rounds = (int)std::min(32.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+        h->rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
     }
     for (Member& m : h->members) {
         rc = build_hot_units(h, m);
@@ -1008,7 +1025,10 @@ static int timing_event(Member& m, cudaEvent_t* out) {
     return MFSGD_OK;
 }
 
-static int shuffle_member(mfsgd_handle* h, Member& m, int epoch) {
+// Lay out the records for `epoch` (subsystem 1). Deterministic mode: the stand-in's visiting order. Otherwise an
+// in-block reshuffle into the spare buffer; with prefetch_next the layout of epoch + 1 is then produced in the
+// background (low-priority stream, DRAM-bound) while the update kernels (L2-bound) consume this one.
+static int shuffle_member(mfsgd_handle* h, Member& m, int epoch, bool prefetch_next) {
     CK(cudaSetDevice(m.device));
     if (h->cfg.mode == MFSGD_MODE_DETERMINISTIC) {
         if (m.n_recs > 0)
@@ -1018,9 +1038,24 @@ static int shuffle_member(mfsgd_handle* h, Member& m, int epoch) {
         return MFSGD_OK;
     }
     const int nblk = (int)m.block_off.size() - 1;   // cold blocks + hot (stripe, item) buckets
-    CK(launch_block_shuffle(m.recs[m.rcur], m.recs[m.rcur ^ 1], m.d_block_off, nblk, m.n_recs, h->cfg.seed, (uint32_t)epoch,
-                            (uint32_t)(m.g * nblk), m.stream, &m.launches));
+    if (m.ahead_epoch == epoch) {
+        CK(cudaStreamWaitEvent(m.stream, m.ev_shuffle_done, 0));      // prepared during the previous epoch
+    } else {
+        if (m.ahead_epoch >= 0) CK(cudaStreamWaitEvent(m.stream, m.ev_shuffle_done, 0));   // a stale prefetch owns the spare buffer
+        CK(launch_block_shuffle(m.recs[m.rcur], m.recs[m.rcur ^ 1], m.d_block_off, nblk, m.n_recs, h->cfg.seed, (uint32_t)epoch,
+                                (uint32_t)(m.g * nblk), m.stream, &m.launches));
+    }
     m.rcur ^= 1;
+    m.ahead_epoch = -1;
+    if (prefetch_next) {
+        // recs[rcur] is read-only until the next reshuffle; recs[rcur ^ 1] is free once everything enqueued so far is done
+        CK(cudaEventRecord(m.ev_shuffle_go, m.stream));
+        CK(cudaStreamWaitEvent(m.shuffle_stream, m.ev_shuffle_go, 0));
+        CK(launch_block_shuffle(m.recs[m.rcur], m.recs[m.rcur ^ 1], m.d_block_off, nblk, m.n_recs, h->cfg.seed, (uint32_t)(epoch + 1),
+                                (uint32_t)(m.g * nblk), m.shuffle_stream, &m.launches));
+        CK(cudaEventRecord(m.ev_shuffle_done, m.shuffle_stream));
+        m.ahead_epoch = epoch + 1;
+    }
     return MFSGD_OK;
 }
 
@@ -1097,7 +1132,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 CK(cudaMemsetAsync(m.d_counters, 0, (size_t)m.n_counters * sizeof(unsigned int), m.stream));
                 m.counter_next = 0;
             }
-            if (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) || c.mode == MFSGD_MODE_DETERMINISTIC) CKRC(shuffle_member(h, m, h->epoch));
+            if (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) || c.mode == MFSGD_MODE_DETERMINISTIC) CKRC(shuffle_member(h, m, h->epoch, true));
             CK(cudaEventRecord(er.shuffled, m.stream));
         }
         for (int s = 0; s < h->G; s++) {
@@ -1121,6 +1156,20 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         CK(cudaMemcpyAsync(err_trace + (size_t)ep * m.n_recs, d_trace, (size_t)m.n_recs * 4, cudaMemcpyDeviceToHost, m.stream));
                     continue;
                 }
+                // The cold (full-grid Hogwild) launches go to m.stream, the hot-item launches to m.hot_stream:
+                // they touch the same P sub-stripes Hogwild-style and fill each other's tails. Fork here, join
+                // before the Q rotation.
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (time_kernels) {
+                    CKRC(timing_event(m, &e0));
+                    CKRC(timing_event(m, &e1));
+                    CK(cudaEventRecord(e0, m.stream));
+                }
+                const bool has_hot = m.d_units != nullptr && m.visit_units.back() > 0;
+                if (has_hot) {
+                    CK(cudaEventRecord(m.ev_fork, m.stream));
+                    CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
+                }
                 for (int vis = 0; vis < h->mu * h->rounds; vis++) {
                     const int rnd = vis / h->mu;
                     // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
@@ -1131,13 +1180,6 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     slice_of(m, (size_t)sa * h->IB + (size_t)grp * h->mi, (size_t)sa * h->IB + (size_t)(grp + 1) * h->mi, rnd, h->rounds, &lo, &hi);
                     const size_t vkey = ((size_t)sa * h->G + grp) * h->rounds + rnd;
                     const int unit_lo = m.visit_units[vkey], unit_hi = m.visit_units[vkey + 1];
-                    if (hi == lo && unit_hi == unit_lo) continue;
-                    cudaEvent_t e0 = nullptr, e1 = nullptr;
-                    if (time_kernels) {
-                        CKRC(timing_event(m, &e0));
-                        CKRC(timing_event(m, &e1));
-                        CK(cudaEventRecord(e0, m.stream));
-                    }
                     if (hi > lo) {      // cold records: full-grid Hogwild kernel
                         a.recs = m.recs[m.rcur] + lo;
                         a.n = hi - lo;
@@ -1149,14 +1191,18 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         a.n = m.n_recs;
                         if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
                         CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, m.hot_grid,
-                                                 m.stream, &m.launches));
+                                                 m.hot_stream, &m.launches));
                         m.update_launches++;
                     }
-                    if (time_kernels) {
-                        CK(cudaEventRecord(e1, m.stream));
-                        m.kev.push_back(e0);
-                        m.kev.push_back(e1);
-                    }
+                }
+                if (has_hot) {
+                    CK(cudaEventRecord(m.ev_join, m.hot_stream));
+                    CK(cudaStreamWaitEvent(m.stream, m.ev_join, 0));
+                }
+                if (time_kernels) {
+                    CK(cudaEventRecord(e1, m.stream));
+                    m.kev.push_back(e0);
+                    m.kev.push_back(e1);
                 }
             }
             CKRC(rotate_q(h));
@@ -1385,7 +1431,7 @@ extern "C" int mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     for (Member& m : h->members) {
-        CKRC(shuffle_member(h, m, epoch));
+        CKRC(shuffle_member(h, m, epoch, false));
         CK(cudaStreamSynchronize(m.stream));
     }
     return MFSGD_OK;

@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restric
     }
     const int32_t* __restrict__ win = reinterpret_cast<const int32_t*>(in);
     int32_t* __restrict__ wout = reinterpret_cast<int32_t*>(out);
+    // The reshuffle runs in the background of the update kernels, whose factors live in L2: stream the
+    // records past it (evict-first both ways) so 2 x 12 B x N of one-touch data does not displace them.
+    const uint64_t pol = l2_policy_evict_first();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         int lo = 0, hi = nblocks;  // largest b with soff[b] <= j
@@ -213,10 +216,10 @@ __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restric
             src = block_perm(src, nb, hb, key);
         }
         const int64_t s3 = 3 * (off + (int64_t)src);
-        const int32_t a = win[s3], bb = win[s3 + 1], c = win[s3 + 2];
-        wout[3 * j] = a;
-        wout[3 * j + 1] = bb;
-        wout[3 * j + 2] = c;
+        const int32_t a = ld_stream_i32(win + s3, pol), bb = ld_stream_i32(win + s3 + 1, pol), c = ld_stream_i32(win + s3 + 2, pol);
+        st_stream_i32(wout + 3 * j, a, pol);
+        st_stream_i32(wout + 3 * j + 1, bb, pol);
+        st_stream_i32(wout + 3 * j + 2, c, pol);
     }
 }
 

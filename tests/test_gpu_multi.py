@@ -1,0 +1,52 @@
+"""Multi-GPU DSGD tests (need >= 2 B200s; skipped otherwise): real peer copies in one process, and the
+one-process-per-GPU ring over NCCL launched with torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import matrixfactorizationsgd.java_b200 as mf
+from matrixfactorizationsgd.java_b200 import _capi as capi
+import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = 20261018
+
+
+def n_gpus():
+    return mf.device_count()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_single_process_ring_real_devices(G):
+    if n_gpus() < G:
+        pytest.skip("needs %d GPUs" % G)
+    n = 5003
+    rng = np.random.default_rng(5)
+    u, i = rng.permutation(n).astype(np.int32), rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    got = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, 128, 0.02, 0.03, 3, SEED, mode=capi.MODE_DSGD, n_gpus=G)
+    P, Q = orc.factorize(u, i, r, n, n, 128, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE)
+    assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_multi_process_ring_nccl(G):
+    if n_gpus() < G:
+        pytest.skip("needs %d GPUs" % G)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(G), "--master-addr",
+           "127.0.0.1", "--master-port", str(29500 + G), os.path.join(ROOT, "tests", "mp", "ring_parity.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RING_PARITY ")][-1]
+    res = json.loads(line[len("RING_PARITY "):])
+    assert res["conflict_free_bit_exact"]
+    assert res["gpu_rmse"] <= res["oracle_rmse"] * 1.005 and res["gpu_rmse"] >= res["oracle_rmse"] * 0.98
+    assert abs(res["assembled_rmse"] - res["gpu_rmse"]) / res["gpu_rmse"] < 1e-6
+    lo = [p[0] for p in res["partitions"]]
+    hi = [p[1] for p in res["partitions"]]
+    assert lo[0] == 0 and hi[-1] == 13_800 and lo[1:] == hi[:-1]            # user stripes tile [0, nU)

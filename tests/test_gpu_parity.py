@@ -235,7 +235,7 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         IB = G * mi
         H = info.n_hot_items
         icount = np.bincount(i, minlength=ni)
-        hot_ids = np.flatnonzero(icount >= max(2e-4 * n, 512))        # the default hot_share rule
+        hot_ids = np.flatnonzero(icount >= max(np.float32(1e-4) * np.float64(n), 512))        # the default hot_share rule
         assert H == len(hot_ids) and H > 0
         all_keys = []
         for g in range(G):

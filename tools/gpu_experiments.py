@@ -51,10 +51,10 @@ def sweep(wname):
             print(json.dumps({"workload": wname, "scatter": scatter, "stripes": stripes, "rounds": rr, "epoch_ms": ms, "kernel_ms": kms,
                               "shuffle_ms": st[-1].shuffle_ms, "gupdates_s": st[0].updates / ms / 1e6, "rmse_after4": rm}), flush=True)
 
-def curve(wname, stripes=0, rounds=0, scatter=0, hot=0.0):
+def curve(wname, stripes=0, rounds=0, scatter=0, hot=0.0, chunk=0):
     w = mf.WORKLOADS[wname]
     sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
-    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=stripes, rounds=rounds, scatter=scatter, hot_share=hot)
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=stripes, rounds=rounds, scatter=scatter, hot_share=hot, hot_chunk=chunk)
     with mf.Engine(cfg) as eng:
         eng.generate_synthetic(sp); eng.init_factors(); eng.set_eval_every_epoch(True)
         st = eng.train(w.epochs)
@@ -64,9 +64,9 @@ def curve(wname, stripes=0, rounds=0, scatter=0, hot=0.0):
 
 def skew(wname):
     w = mf.WORKLOADS[wname]
-    for l2ai, ci in ((0, 0.0), (3, 0.375), (3, 0.0), (4, 0.375)):
+    for l2ai, ci in ((3, 0.375), (4, 0.375)):
         sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, l2ai, ci)
-        for scatter, hot, chunk, rounds in ((0, -1.0, 0, 1), (0, 0.0, 0, 1), (0, 0.0, 256, 1), (0, 0.0, 4096, 1), (0, 5e-5, 0, 1), (0, 0.0, 0, 0), (0, 0.0, 256, 0), (0, 5e-5, 512, 0)):
+        for scatter, hot, chunk, rounds in ((0, 0.0, 0, 1), (0, 0.0, 0, 0), (0, 0.0, 128, 0), (0, 0.0, 64, 0), (0, 0.0, 1024, 0), (0, 5e-5, 0, 0), (0, 1e-4, 0, 0), (0, 1e-4, 128, 0), (0, 0.0, 0, 4)):
             cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD,
                                  stripes_per_gpu=7, scatter=scatter, rounds=rounds, hot_share=hot, hot_chunk=chunk, flags=capi.FLAG_TIME_KERNELS)
             with mf.Engine(cfg) as eng:

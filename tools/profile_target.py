@@ -10,7 +10,7 @@ stripes = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 epochs = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 w = mf.WORKLOADS[wname]
 cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=mf.capi.MODE_HOGWILD,
-                     stripes_per_gpu=stripes, scatter=scatter, rounds=1)
+                     stripes_per_gpu=stripes, scatter=scatter)
 with mf.Engine(cfg) as eng:
     eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
     eng.init_factors()
