@@ -8,7 +8,7 @@ OBJDIR    := build/obj
 LIB       := $(PKG)/lib/libmfsgd.so
 OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
 
-all: $(LIB) oracle harness
+all: $(LIB) oracle harness host
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh include/mfsgd.h
 	@mkdir -p $(OBJDIR)
@@ -25,8 +25,12 @@ harness: tests/c/abi_harness
 tests/c/abi_harness: tests/c/abi_harness.c include/mfsgd.h
 	gcc -O1 -Wall -Wextra -Iinclude -o $@ $< -ldl
 
+host: host/factorize_demo
+host/factorize_demo: host/factorize_demo.cpp host/MatrixFactorizationSGD.hpp include/mfsgd.h
+	g++ -O1 -std=c++17 -Wall -Wextra -o $@ $< -ldl
+
 clean:
-	rm -rf build $(LIB) tests/c/abi_harness
+	rm -rf build $(LIB) tests/c/abi_harness host/factorize_demo
 	$(MAKE) -s -C oracle clean
 
-.PHONY: all oracle harness clean
+.PHONY: all oracle harness host clean

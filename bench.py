@@ -214,8 +214,15 @@ def run_ours(args):
     if not args.no_e2e:
         hu, hi, hr, pins = host_training_set(mf, w, local_rank, pinned=True)
         n_host = len(hr)
-        P = np.zeros((w.n_users, w.k), dtype=np.float32)
-        Q = np.zeros((w.n_items, w.k), dtype=np.float32)
+        # pinned output buffers too (a Java caller would hand in off-heap segments from mfsgd_host_alloc)
+        out_ptrs = []
+        def pinned_f32(rows, cols):
+            p = C.c_void_p()
+            capi.check(capi.lib.mfsgd_host_alloc(C.byref(p), rows * cols * 4))
+            out_ptrs.append(p)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(rows, cols))
+        P = pinned_f32(w.n_users, w.k)
+        Q = pinned_f32(w.n_items, w.k)
         if world > 1:
             nid = ring.broadcast_unique_id(dist, rank)
             cfg = mf.make_config(mode=capi.MODE_DSGD, n_gpus=world, world_size=world, rank=rank, device=local_rank,
@@ -228,12 +235,14 @@ def run_ours(args):
                                             capi.ptr(P), capi.ptr(Q)))
         barrier()
         e2e_s = allmax(time.time() - t0)
-        for p in pins:
+        e2e_check = float(np.abs(P[:1000]).sum() + np.abs(Q[:1000]).sum())   # the result was really read back
+        for p in pins + out_ptrs:
             capi.lib.mfsgd_host_free(p)
         e2e = {"value": float(n_host) * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": 12.0 * n_host * world / args.steps,
                "d2h_bytes_per_step": 4.0 * w.k * (w.n_users + w.n_items) / args.steps,
                "seconds": e2e_s, "call": "mfsgd_factorize(host triplets -> host P,Q), pinned host buffers",
+               "result_checksum": e2e_check,
                "epochs": args.steps}
 
     cpu = None

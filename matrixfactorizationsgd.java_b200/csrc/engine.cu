@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1372,12 +1373,20 @@ extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const
                                const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out) {
     if (!P_out || !Q_out) return fail(MFSGD_E_INVALID_ARG, "output arrays are null");
     if (epochs < 0) return fail(MFSGD_E_INVALID_ARG, "epochs < 0");
+    const bool trace = getenv("MFSGD_TRACE") != nullptr;   // phase timings on stderr (diagnostic aid)
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t1;
     mfsgd_handle* h = nullptr;
     CKRC(mfsgd_create(cfg, &h));
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] create %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     int rc = mfsgd_load_ratings(h, users, items, ratings, n);
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] load_ratings %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     if (rc == MFSGD_OK) rc = mfsgd_init_factors(h);
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] init_factors %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     if (rc == MFSGD_OK) rc = mfsgd_train(h, epochs, nullptr);
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] train %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     if (rc == MFSGD_OK) rc = mfsgd_get_factors(h, P_out, Q_out);
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] get_factors %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     mfsgd_destroy(h);
     return rc;
 }
