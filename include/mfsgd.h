@@ -53,6 +53,9 @@ extern "C" {
 #define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
 #define MFSGD_FLAG_VIRTUAL_RING   2u /* place all n_gpus ring members on one device (scheduler test mode) */
 #define MFSGD_FLAG_NO_SHUFFLE     4u /* skip the per-epoch reshuffle (measurement aid)                    */
+#define MFSGD_FLAG_EXACT_ARITH    8u /* HOGWILD/DSGD kernels apply the reference rule operation by operation
+                                        (no FMA) instead of the FFMA2 arrangement (a few ulp apart, 3x the issue slots);
+                                        DETERMINISTIC mode is always exact                                   */
 
 typedef struct mfsgd_handle mfsgd_handle;
 
@@ -78,7 +81,7 @@ typedef struct mfsgd_config {
     int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
     int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
     float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
-                                  (q_i register-resident, model-averaged); 0 = default 1e-4, < 0 = off   */
+                                  (q_i register-resident, model-averaged); 0 = default 3e-5, < 0 = off   */
     int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 256              */
     int32_t  reserved[4];
 } mfsgd_config;
@@ -94,6 +97,10 @@ typedef struct mfsgd_epoch_stats {
     int32_t update_launches;    /* update-kernel launches in the epoch                               */
     int32_t total_launches;     /* every kernel this library launched in the epoch                   */
     double  heldout_rmse;       /* NaN unless a held-out set is loaded and eval_every_epoch is on     */
+    /* MFSGD_FLAG_TIME_KERNELS breakdown, summed over the epoch's sub-epochs (the two kernels overlap): */
+    double  cold_ms;            /* fork -> last cold (full-grid) launch done                          */
+    double  hot_ms;             /* fork -> last hot-item launch done                                  */
+    double  exchange_ms;        /* join -> Q rotation enqueued on the compute stream done (NCCL path) */
 } mfsgd_epoch_stats;
 
 /* Synthetic power-law ratings (MatrixFactorizationSGD.java:220 syntheticRecord). Record n in

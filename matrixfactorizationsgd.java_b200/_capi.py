@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmfsgd.so")
 OK, E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
 MODE_DETERMINISTIC, MODE_HOGWILD, MODE_DSGD = 0, 1, 2
 SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
-FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE = 1, 2, 4
+FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE, FLAG_EXACT_ARITH = 1, 2, 4, 8
 ABI_VERSION = 1
 
 
@@ -29,7 +29,8 @@ class Config(C.Structure):
 class EpochStats(C.Structure):
     _fields_ = [("updates", C.c_int64), ("epoch_ms", C.c_double), ("shuffle_ms", C.c_double),
                 ("update_kernel_ms", C.c_double), ("update_launches", C.c_int32), ("total_launches", C.c_int32),
-                ("heldout_rmse", C.c_double)]
+                ("heldout_rmse", C.c_double), ("cold_ms", C.c_double), ("hot_ms", C.c_double),
+                ("exchange_ms", C.c_double)]
 
 
 class SynthParams(C.Structure):

@@ -49,6 +49,22 @@ static int fail(int code, const char* fmt, ...) {
         if (rc__ != MFSGD_OK) return rc__; \
     } while (0)
 
+// MFSGD_TRACE=1: phase timings on stderr (diagnostic aid)
+static inline bool trace_on() {
+    static int on = -1;
+    if (on < 0) on = getenv("MFSGD_TRACE") != nullptr ? 1 : 0;
+    return on == 1;
+}
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct PhaseTimer {
+    const char* what;
+    double t0;
+    explicit PhaseTimer(const char* w) : what(w), t0(trace_on() ? now_s() : 0.0) {}
+    ~PhaseTimer() {
+        if (trace_on()) fprintf(stderr, "[mfsgd]   %s %.1f ms\n", what, (now_s() - t0) * 1e3);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // NCCL, loaded lazily (only a multi-process ring needs it; libmfsgd.so has no link-time dependency)
 // ------------------------------------------------------------------------------------------------
@@ -147,7 +163,7 @@ struct Member {              // one ring member ("GPU g")
     int ev_used = 0;
     struct EpochRec {                // one per epoch of the running train call, resolved after a sync
         cudaEvent_t start, shuffled, end;
-        int kbeg, kend;              // range in kev of (begin, end) pairs bracketing update launches
+        int kbeg, kend;              // range in kev of (fork, join, cold_end, hot_end, exchange_end) 5-tuples, one per sub-epoch
         int launches, update_launches;
     };
     std::vector<EpochRec> pending;
@@ -351,11 +367,14 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     CK(dev_alloc(&m.d_scratch, (size_t)rmse_scratch_doubles() + 1));
     m.d_sse = m.d_scratch + rmse_scratch_doubles();
     int ctas = 0;
-    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter, &ctas));
+    const bool fast = !(h->cfg.flags & MFSGD_FLAG_EXACT_ARITH);
+    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter, fast, &ctas));
     if (ctas < 1) ctas = 1;
     if (h->cfg.ctas_per_sm > 0 && h->cfg.ctas_per_sm < ctas) ctas = h->cfg.ctas_per_sm;
     m.grid = m.n_sms * ctas;
-    m.hot_grid = m.n_sms * 4;
+    int hot_ctas = 0;
+    CK(hot_max_ctas_per_sm(h->cfg.k, fast, &hot_ctas));
+    m.hot_grid = m.n_sms * std::max(1, hot_ctas);
     return MFSGD_OK;
 }
 
@@ -566,7 +585,7 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 #undef CKC
     // hot items: rated by at least hot_share of the training set (and often enough to fill a warp's run)
     h->hot_items.clear();
-    const float share = c.hot_share == 0.f ? 1e-4f : c.hot_share;
+    const float share = c.hot_share == 0.f ? 3e-5f : c.hot_share;
     if (bad_host == 0 && share > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0) {
         std::vector<uint32_t> icnt_host((size_t)c.n_items);
         cudaError_t e = cudaMemcpy(icnt_host.data(), icnt, (size_t)c.n_items * 4, cudaMemcpyDeviceToHost);
@@ -722,6 +741,9 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     m.visit_units.assign((size_t)h->mu * h->G * h->rounds + 1, 0);
     if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
     CK(cudaSetDevice(m.device));
+    // Run length: a run is walked by one warp, one rating after another (only the p_u gathers are pipelined), so a
+    // launch lasts at least one run; shorter runs mean more parallelism but each makes less progress on q_i before
+    // the item's runs are averaged (128 already costs ~1 % RMSE on small inputs; 256 does not -- profiles/r01_experiments.md).
     const int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 256;
     const int gpw = 32 / geometry_for(h->cfg.k).lanes;
     const size_t hot_base = (size_t)h->mu * h->IB;
@@ -771,12 +793,13 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
         Member& m = h->members[mi_];
         cudaSetDevice(m.device);
         Chunk ch;
-        rc = chunk_alloc(ch, cap, src.synthetic);
+        { PhaseTimer pt("load: staging buffers"); rc = chunk_alloc(ch, cap, src.synthetic); }
         if (rc == MFSGD_OK && mi_ == 0) {
+            PhaseTimer pt("load: H2D/generate + row counts + balanced bounds");
             if (src.total > 0) rc = compute_bounds(h, src, ch);
             else { uniform_bounds(h); h->n_train_total = 0; }
         }
-        if (rc == MFSGD_OK) rc = member_alloc_factors(h, m);
+        if (rc == MFSGD_OK) { PhaseTimer pt("load: factor + owner tables"); rc = member_alloc_factors(h, m); }
         if (rc == MFSGD_OK && c.mode == MFSGD_MODE_DETERMINISTIC) {
             // keep the caller's order; validate ids happened in compute_bounds; synthetic sources drop held records
             if (src.synthetic) rc = fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode takes host triplets (use mfsgd_generate_to_host)");
@@ -797,7 +820,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
             m.block_off.assign(2, 0);
             m.block_off[1] = src.total;
         } else if (rc == MFSGD_OK) {
-            rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off);
+            { PhaseTimer pt("load: bucketing (histogram + scatter)"); rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off); }
             if (rc == MFSGD_OK) {
                 m.n_recs = m.block_off.back();
                 m.rcur = 0;
@@ -831,6 +854,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
         h->rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
     }
     for (Member& m : h->members) {
+        PhaseTimer pt("load: hot-unit lists");
         rc = build_hot_units(h, m);
         if (rc != MFSGD_OK) {
             for (Member& mm : h->members) free_member_data(mm);
@@ -1070,6 +1094,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
     const mfsgd_config& c = h->cfg;
     if (err_trace && c.mode != MFSGD_MODE_DETERMINISTIC) return fail(MFSGD_E_STATE, "error traces exist in DETERMINISTIC mode only");
     const bool time_kernels = (c.flags & MFSGD_FLAG_TIME_KERNELS) != 0;
+    const bool fast_arith = !(c.flags & MFSGD_FLAG_EXACT_ARITH);
     float* d_trace = nullptr;
     if (err_trace && h->members[0].n_recs > 0) {
         CK(cudaSetDevice(h->members[0].device));
@@ -1098,12 +1123,21 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 float ms = 0.f, sms = 0.f;
                 CK(cudaEventElapsedTime(&ms, er.start, er.end));
                 CK(cudaEventElapsedTime(&sms, er.start, er.shuffled));
-                double kms = 0.0;
-                for (int j = er.kbeg; j + 1 < er.kend; j += 2) {
+                double kms = 0.0, cms = 0.0, hms = 0.0, xms = 0.0;
+                for (int j = er.kbeg; j + 4 < er.kend; j += 5) {
                     float t = 0.f;
                     CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 1]));
                     kms += t;
+                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 2]));
+                    cms += t;
+                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 3]));
+                    hms += t;
+                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j + 1], m.kev[(size_t)j + 4]));
+                    xms += t;
                 }
+                st.cold_ms = std::max(st.cold_ms, cms);
+                st.hot_ms = std::max(st.hot_ms, hms);
+                st.exchange_ms = std::max(st.exchange_ms, xms);
                 st.updates += m.n_recs;
                 st.epoch_ms = std::max(st.epoch_ms, (double)ms);
                 st.shuffle_ms = std::max(st.shuffle_ms, (double)sms);
@@ -1160,10 +1194,13 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 // The cold (full-grid Hogwild) launches go to m.stream, the hot-item launches to m.hot_stream:
                 // they touch the same P sub-stripes Hogwild-style and fill each other's tails. Fork here, join
                 // before the Q rotation.
-                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                cudaEvent_t e0 = nullptr, e1 = nullptr, e_cold = nullptr, e_hot = nullptr, e_xchg = nullptr;
                 if (time_kernels) {
                     CKRC(timing_event(m, &e0));
                     CKRC(timing_event(m, &e1));
+                    CKRC(timing_event(m, &e_cold));
+                    CKRC(timing_event(m, &e_hot));
+                    CKRC(timing_event(m, &e_xchg));
                     CK(cudaEventRecord(e0, m.stream));
                 }
                 const bool has_hot = m.d_units != nullptr && m.visit_units.back() > 0;
@@ -1184,17 +1221,21 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     if (hi > lo) {      // cold records: full-grid Hogwild kernel
                         a.recs = m.recs[m.rcur] + lo;
                         a.n = hi - lo;
-                        CK(launch_sgd_update_hogwild(a, c.scatter, m.grid, h->min_windows, m.stream, &m.launches));
+                        CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, m.stream, &m.launches));
                         m.update_launches++;
                     }
                     if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
                         a.recs = m.recs[m.rcur];
                         a.n = m.n_recs;
                         if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
-                        CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, m.hot_grid,
+                        CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith, m.hot_grid,
                                                  m.hot_stream, &m.launches));
                         m.update_launches++;
                     }
+                }
+                if (time_kernels) {
+                    CK(cudaEventRecord(e_cold, m.stream));
+                    CK(cudaEventRecord(e_hot, has_hot ? m.hot_stream : m.stream));
                 }
                 if (has_hot) {
                     CK(cudaEventRecord(m.ev_join, m.hot_stream));
@@ -1204,9 +1245,17 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     CK(cudaEventRecord(e1, m.stream));
                     m.kev.push_back(e0);
                     m.kev.push_back(e1);
+                    m.kev.push_back(e_cold);
+                    m.kev.push_back(e_hot);
+                    m.kev.push_back(e_xchg);
                 }
             }
             CKRC(rotate_q(h));
+            if (time_kernels && c.mode != MFSGD_MODE_DETERMINISTIC)
+                for (Member& m : h->members) {
+                    CK(cudaSetDevice(m.device));
+                    CK(cudaEventRecord(m.kev.back(), m.stream));     // e_xchg of this sub-epoch
+                }
         }
         for (Member& m : h->members) {
             Member::EpochRec& er = m.pending.back();

@@ -55,10 +55,12 @@ struct UpdateArgs {
 
 // (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
 // min_windows: lower bound on (records in the launch) / (ratings in flight at once), see kernels_update.cu.
-cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid, int min_windows,
+// fast: FMA2 arithmetic (kernels_update.cu); false = the reference rule op by op.
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fast, int grid, int min_windows,
                                       cudaStream_t stream, int* launches);
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
-cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, int* ctas);
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas);
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
 cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches);
 // Teacher-forced check: n independent row pairs.
@@ -75,7 +77,7 @@ struct HotUnit {
     float   weight;    // 1 / (units of this item in the launch * sub-warps per warp)
     int32_t pad;
 };
-cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter,
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
                                   int grid, cudaStream_t stream, int* launches);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).

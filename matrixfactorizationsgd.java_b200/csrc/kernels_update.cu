@@ -4,6 +4,8 @@
 // per rating (LANES = 32 at k = 128: "one warp per rating"), float4 gathers of p_u and q_i, xor-
 // butterfly dot product, lock-free scatter. Bound by L2/HBM bandwidth (12 + 16k algorithmic bytes per
 // update); tensor cores are deliberately unused (gather-dot-scatter, not a contraction).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace mfsgd {
@@ -48,13 +50,6 @@ __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, floa
     for (int v = 0; v < VEC; v++) {
         const int c = gl + v * LANES;
         if (FULL || c < chunks) {
-            if (SC >= 4) {   // store cache-operator experiments: 4 = default (wb), 5 = wt, 6 = cs
-                const float4 np_ = upd4(rp.p[v], rp.q[v], e, lr, lambda), nq_ = upd4(rp.q[v], rp.p[v], e, lr, lambda);
-                if (SC == 4) { st_row4_wb(prow + 4 * c, np_); st_row4_wb(qrow + 4 * c, nq_); }
-                else if (SC == 5) { st_row4_wt(prow + 4 * c, np_); st_row4_wt(qrow + 4 * c, nq_); }
-                else { st_row4_cs(prow + 4 * c, np_); st_row4_cs(qrow + 4 * c, nq_); }
-                continue;
-            }
             if (SC == 1 || SC == 3) red_add_row4(prow + 4 * c, delta4(rp.p[v], rp.q[v], e, lr, lambda));
             else st_row4(prow + 4 * c, upd4(rp.p[v], rp.q[v], e, lr, lambda));
             if (SC == 1 || SC == 2) red_add_row4(qrow + 4 * c, delta4(rp.q[v], rp.p[v], e, lr, lambda));
@@ -63,76 +58,189 @@ __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, floa
     }
 }
 
-// Hogwild kernel. Work unit = tile of 32 consecutive records per warp (lane l loads record l, 12 B
-// each, streamed past L1); the warp's 32/LANES sub-warps walk the tile, each step gathering the rows
-// of the NEXT rating before reducing the current one (2 ratings in flight per sub-warp), and the
-// next tile's records are fetched a whole tile ahead.
-template <int LANES, int VEC, bool FULL, int SC>
-__global__ void __launch_bounds__(256) sgd_update_hogwild_kernel(UpdateArgs a) {
+// ---- arithmetic of the full-grid modes -------------------------------------------------------------
+// EXACT (FAST = false): the reference rule operation by operation, no FMA -- identical to the
+// deterministic kernel and to oracle.cpp ORC_ORDER_WARP_TREE.
+// FAST (FAST = true): the same algebra arranged for Blackwell's packed FP32 pipe (FFMA2):
+//     lane partial : (lo, hi) = fma2((p.z,p.w),(q.z,q.w), (p.x*q.x, p.y*q.y)), ... ; s = lo + hi
+//     update       : p' = fma(b, q, a*p),  q' = fma(b, p, a*q),  a = 1 - lr*lambda,  b = lr*e
+// A per-update deviation of a few ulp from the reference rule (<< the 1e-5 bar); oracle.cpp
+// ORC_ORDER_WARP_TREE_FMA reproduces it bit for bit with fmaf. 3.3x fewer issue slots per update.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int LANES, int VEC, bool FAST>
+__device__ __forceinline__ float rows_dot(const float4 (&p)[VEC], const float4 (&q)[VEC]) {
+    float s;
+    if (FAST) {
+        uint64_t acc = mul2(pk2(p[0].x, p[0].y), pk2(q[0].x, q[0].y));
+        acc = fma2(pk2(p[0].z, p[0].w), pk2(q[0].z, q[0].w), acc);
+#pragma unroll
+        for (int v = 1; v < VEC; v++) {
+            acc = fma2(pk2(p[v].x, p[v].y), pk2(q[v].x, q[v].y), acc);
+            acc = fma2(pk2(p[v].z, p[v].w), pk2(q[v].z, q[v].w), acc);
+        }
+        float lo, hi;
+        upk2(acc, lo, hi);
+        s = __fadd_rn(lo, hi);
+    } else {
+        s = 0.0f;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) s = dot4_acc(s, p[v], q[v]);
+    }
+    return group_sum<LANES>(s);
+}
+
+// new value of row chunk `o` given the other row's chunk `x`
+template <bool FAST>
+__device__ __forceinline__ float4 new_chunk(float4 o, float4 x, float e, float lr, float lambda, float acoef, float b) {
+    if (FAST) {
+        const uint64_t a2 = pk2(acoef, acoef), b2 = pk2(b, b);
+        const uint64_t lo = fma2(b2, pk2(x.x, x.y), mul2(a2, pk2(o.x, o.y)));
+        const uint64_t hi = fma2(b2, pk2(x.z, x.w), mul2(a2, pk2(o.z, o.w)));
+        float4 r;
+        upk2(lo, r.x, r.y);
+        upk2(hi, r.z, r.w);
+        return r;
+    }
+    return upd4(o, x, e, lr, lambda);
+}
+
+struct Coef {
+    float lr, lambda, acoef;   // acoef = 1 - lr * lambda (FAST arithmetic)
+};
+
+// One tile (<= 32 records, staged in shared memory as (u, i, r-bits, -) quads) walked by the warp's 32/LANES
+// sub-warps with a DEPTH-deep software pipeline: the row gathers of the next DEPTH-1 ratings are in flight while
+// the current one is reduced and scattered. FULLTILE: all 32 records present -> no activity predicates.
+// SC: 0 = st/st, 1 = red/red, 2 = st P + red Q, 3 = red P + st Q  (mfsgd.h MFSGD_SCATTER_*; FAST needs SC == 0)
+template <int VEC>
+struct Slot {          // only the gathered rows live in registers; ids and rating are re-read from the tile (one LDS)
+    float4 p[VEC], q[VEC];
+};
+
+template <int LANES, int VEC, bool FULL, bool FULLTILE>
+__device__ __forceinline__ void slot_load(Slot<VEC>& sl, const int4* __restrict__ tile, int j, int cnt, const float* __restrict__ Pl,
+                                          const float* __restrict__ Ql, int64_t k, int lane_chunk, int chunks) {
+    const int4 rec = tile[j & 31];
+    const bool act = FULLTILE || j < cnt;
+    const float* pp = Pl + (int64_t)rec.x * k;
+    const float* qq = Ql + (int64_t)rec.y * k;
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        const bool on = act && (FULL || lane_chunk + v * LANES < chunks);
+        sl.p[v] = on ? ld_row4(pp + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sl.q[v] = on ? ld_row4(qq + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, bool FULLTILE, int DEPTH>
+__device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt, float* __restrict__ Pl,
+                                          float* __restrict__ Ql, int64_t k, int grp, int lane_chunk, int chunks, Coef cf) {
     constexpr int GPW = 32 / LANES;
+    constexpr int FULL_STEPS = 32 / GPW;
+    const int steps = FULLTILE ? FULL_STEPS : (cnt + GPW - 1) / GPW;
+    Slot<VEC> ring[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; d++)
+        slot_load<LANES, VEC, FULL, FULLTILE>(ring[d], tile, d * GPW + grp, cnt, Pl, Ql, k, lane_chunk, chunks);
+    for (int t0 = 0; t0 < steps; t0 += DEPTH) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; d++) {
+            const int t = t0 + d;
+            if ((!FULLTILE || FULL_STEPS % DEPTH != 0) && t >= steps) break;   // warp-uniform; compiled out for full tiles
+            // keep DEPTH-1 gathers ahead: step t + DEPTH - 1 goes into the slot that step t - 1 just freed
+            // (past the end of a partial tile slot_load sees j >= cnt and loads nothing)
+            slot_load<LANES, VEC, FULL, FULLTILE>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp,
+                                                  (FULLTILE && t + DEPTH - 1 >= FULL_STEPS) ? 0 : cnt, Pl, Ql, k, lane_chunk, chunks);
+            const int j = t * GPW + grp;
+            const int4 rec = tile[j & 31];
+            const bool act = FULLTILE ? true : j < cnt;
+            float* const cp = Pl + (int64_t)rec.x * k;
+            float* const cq = Ql + (int64_t)rec.y * k;
+            const Slot<VEC>& c = ring[d];
+            const float e = __fsub_rn(__int_as_float(rec.z), rows_dot<LANES, VEC, FAST>(c.p, c.q));
+            const float b = __fmul_rn(cf.lr, e);
+            if (act) {
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    if (FULL || lane_chunk + v * LANES < chunks) {
+                        if (SC == 1 || SC == 3) red_add_row4(cp + 4 * v * LANES, delta4(c.p[v], c.q[v], e, cf.lr, cf.lambda));
+                        else st_row4(cp + 4 * v * LANES, new_chunk<FAST>(c.p[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                        if (SC == 1 || SC == 2) red_add_row4(cq + 4 * v * LANES, delta4(c.q[v], c.p[v], e, cf.lr, cf.lambda));
+                        else st_row4(cq + 4 * v * LANES, new_chunk<FAST>(c.q[v], c.p[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Hogwild kernel (cold records). Work unit = tile of 32 consecutive records per warp: lane l streams record l
+// (12 B, past L1, evict-first) one tile ahead and parks it in the warp's shared-memory slot, from where every
+// step reads its (u, i, r) with one broadcast LDS.128 instead of three shuffles.
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, int DEPTH>
+__global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_update_hogwild_kernel(UpdateArgs a) {
+    __shared__ int4 srec[8][2][32];
     const int lane = threadIdx.x & 31;
+    const int wic = threadIdx.x >> 5;
     const int gl = lane & (LANES - 1);
     const int grp = lane / LANES;
-    const int chunks = a.k >> 2;
+    const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;   // compile-time row length for the common ranks
+    const int chunks = (int)(k >> 2);
+    float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;               // lane-adjusted bases, indexed by global ids
+    float* const Ql = a.Q - (int64_t)a.i_base * k + 4 * gl;
+    const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_tiles = (a.n + 31) >> 5;
     const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
     const uint64_t pol = l2_policy_evict_first();
 
-    int32_t ru = 0, ri = 0, rr = 0;  // this lane's record of the current tile (r as bits)
     int64_t tile = warp;
+    int buf = 0;
     if (tile < n_tiles) {
         const int64_t idx = tile * 32 + lane;
+        int4 rec = make_int4(0, 0, 0, 0);
         if (idx < a.n) {
-            ru = ld_stream_i32(words + 3 * idx, pol);
-            ri = ld_stream_i32(words + 3 * idx + 1, pol);
-            rr = ld_stream_i32(words + 3 * idx + 2, pol);
+            rec.x = ld_stream_i32(words + 3 * idx, pol);
+            rec.y = ld_stream_i32(words + 3 * idx + 1, pol);
+            rec.z = ld_stream_i32(words + 3 * idx + 2, pol);
         }
+        srec[wic][0][lane] = rec;
     }
+    __syncwarp();
     for (; tile < n_tiles; tile += n_warps) {
         const int64_t base = tile * 32;
         const int cnt = (a.n - base) < 32 ? (int)(a.n - base) : 32;
-        const int steps = (cnt + GPW - 1) / GPW;
-        // records of the warp's next tile, one tile ahead
-        int32_t nu = 0, ni = 0, nr = 0;
+        int4 nrec = make_int4(0, 0, 0, 0);            // the warp's next tile, fetched now, parked after this tile
         {
             const int64_t idx = (tile + n_warps) * 32 + lane;
             if (idx < a.n) {
-                nu = ld_stream_i32(words + 3 * idx, pol);
-                ni = ld_stream_i32(words + 3 * idx + 1, pol);
-                nr = ld_stream_i32(words + 3 * idx + 2, pol);
+                nrec.x = ld_stream_i32(words + 3 * idx, pol);
+                nrec.y = ld_stream_i32(words + 3 * idx + 1, pol);
+                nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
             }
         }
-        RowPair<LANES, VEC> nxt;
-        int32_t xu = __shfl_sync(0xffffffffu, ru, grp);
-        int32_t xi = __shfl_sync(0xffffffffu, ri, grp);
-        int32_t xr = __shfl_sync(0xffffffffu, rr, grp);
-        bool xact = grp < cnt;
-        float* xp = a.P + (int64_t)(xu - a.u_base) * a.k;
-        float* xq = a.Q + (int64_t)(xi - a.i_base) * a.k;
-        load_rows<LANES, VEC, FULL>(nxt, xp, xq, gl, chunks, xact);
-#pragma unroll 2
-        for (int t = 0; t < steps; t++) {
-            const RowPair<LANES, VEC> cur = nxt;
-            float* const cp = xp;
-            float* const cq = xq;
-            const float cr = __int_as_float(xr);
-            const bool cact = xact;
-            if (t + 1 < steps) {
-                const int j = (t + 1) * GPW + grp;
-                xu = __shfl_sync(0xffffffffu, ru, j);
-                xi = __shfl_sync(0xffffffffu, ri, j);
-                xr = __shfl_sync(0xffffffffu, rr, j);
-                xact = j < cnt;
-                xp = a.P + (int64_t)(xu - a.u_base) * a.k;
-                xq = a.Q + (int64_t)(xi - a.i_base) * a.k;
-                load_rows<LANES, VEC, FULL>(nxt, xp, xq, gl, chunks, xact);
-            }
-            const float e = __fsub_rn(cr, row_dot<LANES, VEC>(cur));
-            if (cact) scatter_rows<LANES, VEC, FULL, SC>(cur, cp, cq, gl, chunks, e, a.lr, a.lambda);
-        }
-        ru = nu; ri = ni; rr = nr;
+        if (cnt == 32) walk_tile<LANES, VEC, FULL, SC, FAST, true, DEPTH>(srec[wic][buf], 32, Pl, Ql, k, grp, gl, chunks, cf);
+        else walk_tile<LANES, VEC, FULL, SC, FAST, false, DEPTH>(srec[wic][buf], cnt, Pl, Ql, k, grp, gl, chunks, cf);
+        buf ^= 1;
+        srec[wic][buf][lane] = nrec;
+        __syncwarp();
     }
 }
 
@@ -143,14 +251,20 @@ __global__ void __launch_bounds__(256) sgd_update_hogwild_kernel(UpdateArgs a) {
 // unit.weight (model averaging over the item's concurrent units); a unit that is alone on its item
 // (weight 1) stores q_i outright, which makes the path exactly sequential. Units are claimed from a
 // per-launch counter so uneven runs balance themselves.
-template <int LANES, int VEC, bool FULL>
+template <int LANES, int VEC, bool FULL, bool FAST>
 __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
                                                              unsigned int* __restrict__ counter) {
     constexpr int GPW = 32 / LANES;
+    constexpr int HDEPTH = VEC == 1 ? 4 : 2;
+    __shared__ int2 srec[8][32];
     const int lane = threadIdx.x & 31;
+    const int wic = threadIdx.x >> 5;
     const int gl = lane & (LANES - 1);
     const int grp = lane / LANES;
-    const int chunks = a.k >> 2;
+    const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;
+    const int chunks = (int)(k >> 2);
+    float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;
+    const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
     const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
     const uint64_t pol = l2_policy_evict_first();
     for (;;) {
@@ -159,65 +273,64 @@ __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= (unsigned int)n_units) break;
         const HotUnit hu = units[unit];
-        float* const qrow = a.Q + (int64_t)(hu.item - a.i_base) * a.k;
+        float* const qrow = a.Q + (int64_t)(hu.item - a.i_base) * k + 4 * gl;
         float4 q0[VEC], q[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
-            const int c = gl + v * LANES;
-            q0[v] = (FULL || c < chunks) ? ld_row4(qrow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q0[v] = (FULL || gl + v * LANES < chunks) ? ld_row4(qrow + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
             q[v] = q0[v];
         }
         for (int base = 0; base < hu.count; base += 32) {
             const int cnt = (hu.count - base) < 32 ? (hu.count - base) : 32;
-            int32_t ru = 0, rr = 0;
+            __syncwarp();                                   // the previous tile's readers are done with the slot
             if (lane < cnt) {
                 const int64_t idx = hu.start + base + lane;
-                ru = ld_stream_i32(words + 3 * idx, pol);
-                rr = ld_stream_i32(words + 3 * idx + 2, pol);
+                srec[wic][lane] = make_int2(ld_stream_i32(words + 3 * idx, pol), ld_stream_i32(words + 3 * idx + 2, pol));
             }
+            __syncwarp();
             const int steps = (cnt + GPW - 1) / GPW;
-            float4 pn[VEC];
-            int32_t xu = __shfl_sync(0xffffffffu, ru, grp);
-            int32_t xr = __shfl_sync(0xffffffffu, rr, grp);
-            bool xact = grp < cnt;
-            float* xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+            // HDEPTH-deep ring of gathered p rows: the gathers do not depend on q_i, so several ratings' rows are
+            // in flight while the (serial, q_i-dependent) dot -> update chain walks the run.
+            float4 ring[HDEPTH][VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                const int c = gl + v * LANES;
-                pn[v] = (xact && (FULL || c < chunks)) ? ld_row4(xp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int d = 0; d < HDEPTH - 1; d++) {
+                const int j = d * GPW + grp;
+                const int2 rec = srec[wic][j & 31];
+                const float* xp = Pl + (int64_t)rec.x * k;
+#pragma unroll
+                for (int v = 0; v < VEC; v++)
+                    ring[d][v] = (j < cnt && (FULL || gl + v * LANES < chunks)) ? ld_row4(xp + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-#pragma unroll 2
-            for (int t = 0; t < steps; t++) {
-                float4 p[VEC];
+            for (int t0 = 0; t0 < steps; t0 += HDEPTH) {
 #pragma unroll
-                for (int v = 0; v < VEC; v++) p[v] = pn[v];
-                float* const cp = xp;
-                const float cr = __int_as_float(xr);
-                const bool cact = xact;
-                if (t + 1 < steps) {
-                    const int j = (t + 1) * GPW + grp;
-                    xu = __shfl_sync(0xffffffffu, ru, j);
-                    xr = __shfl_sync(0xffffffffu, rr, j);
-                    xact = j < cnt;
-                    xp = a.P + (int64_t)(xu - a.u_base) * a.k;
+                for (int d = 0; d < HDEPTH; d++) {
+                    const int t = t0 + d;
+                    if (t >= steps) break;                                   // warp-uniform
+                    {
+                        const int j = (t + HDEPTH - 1) * GPW + grp;
+                        const int2 rec = srec[wic][j & 31];
+                        const float* xp = Pl + (int64_t)rec.x * k;
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) {
-                        const int c = gl + v * LANES;
-                        pn[v] = (xact && (FULL || c < chunks)) ? ld_row4(xp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int v = 0; v < VEC; v++)
+                            ring[(d + HDEPTH - 1) % HDEPTH][v] =
+                                (j < cnt && (FULL || gl + v * LANES < chunks)) ? ld_row4(xp + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                }
-                float s = 0.0f;
+                    const int j = t * GPW + grp;
+                    const int2 rec = srec[wic][j & 31];
+                    float* const cp = Pl + (int64_t)rec.x * k;
+                    const bool cact = j < cnt;
+                    float4 p[VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; v++) s = dot4_acc(s, p[v], q[v]);
-                s = group_sum<LANES>(s);
-                const float e = __fsub_rn(cr, s);
-                if (cact) {
+                    for (int v = 0; v < VEC; v++) p[v] = ring[d][v];
+                    const float e = __fsub_rn(__int_as_float(rec.y), rows_dot<LANES, VEC, FAST>(p, q));
+                    const float b = __fmul_rn(cf.lr, e);
+                    if (cact) {
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) {
-                        const int c = gl + v * LANES;
-                        if (FULL || c < chunks) {
-                            st_row4(cp + 4 * c, upd4(p[v], q[v], e, a.lr, a.lambda));
-                            q[v] = upd4(q[v], p[v], e, a.lr, a.lambda);
+                        for (int v = 0; v < VEC; v++) {
+                            if (FULL || gl + v * LANES < chunks) {
+                                st_row4(cp + 4 * v * LANES, new_chunk<FAST>(p[v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                                q[v] = new_chunk<FAST>(q[v], p[v], e, cf.lr, cf.lambda, cf.acoef, b);
+                            }
                         }
                     }
                 }
@@ -226,14 +339,14 @@ __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const
         // merge the run's result into Q
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
-            const int c = gl + v * LANES;
-            if (FULL || c < chunks) {
+            if (FULL || gl + v * LANES < chunks) {
                 if (GPW == 1 && hu.weight == 1.0f) {
-                    st_row4(qrow + 4 * c, q[v]);
+                    st_row4(qrow + 4 * v * LANES, q[v]);
                 } else {
                     const float w = hu.weight;
-                    red_add_row4(qrow + 4 * c, make_float4(__fmul_rn(__fsub_rn(q[v].x, q0[v].x), w), __fmul_rn(__fsub_rn(q[v].y, q0[v].y), w),
-                                                           __fmul_rn(__fsub_rn(q[v].z, q0[v].z), w), __fmul_rn(__fsub_rn(q[v].w, q0[v].w), w)));
+                    red_add_row4(qrow + 4 * v * LANES,
+                                 make_float4(__fmul_rn(__fsub_rn(q[v].x, q0[v].x), w), __fmul_rn(__fsub_rn(q[v].y, q0[v].y), w),
+                                             __fmul_rn(__fsub_rn(q[v].z, q0[v].z), w), __fmul_rn(__fsub_rn(q[v].w, q0[v].w), w)));
                 }
             }
         }
@@ -292,7 +405,16 @@ __global__ void __launch_bounds__(256) sgd_update_forced_kernel(int k, float lr,
 
 }  // namespace
 
-cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid, int min_windows,
+static int pipeline_depth() {   // MFSGD_DEPTH = 2 | 4 (tuning aid); gathers in flight per sub-warp = depth - 1
+    static int depth = 0;
+    if (depth == 0) {
+        const char* e = getenv("MFSGD_DEPTH");
+        depth = (e && atoi(e) == 4) ? 4 : 2;
+    }
+    return depth;
+}
+
+cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fast, int grid, int min_windows,
                                       cudaStream_t stream, int* launches) {
     if (min_windows < 1) min_windows = 1;
     if (a.n <= 0) return cudaSuccess;
@@ -306,15 +428,16 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid
     if (max_grid < 1) max_grid = 1;
     if (grid > max_grid) grid = (int)max_grid;
     if (grid < 1) grid = 1;
-#define CALL(L, V, F)                                                                         \
-    switch (scatter) {                                                                        \
-        case 1: sgd_update_hogwild_kernel<L, V, F, 1><<<grid, 256, 0, stream>>>(a); break;    \
-        case 2: sgd_update_hogwild_kernel<L, V, F, 2><<<grid, 256, 0, stream>>>(a); break;    \
-        case 3: sgd_update_hogwild_kernel<L, V, F, 3><<<grid, 256, 0, stream>>>(a); break;    \
-        case 4: sgd_update_hogwild_kernel<L, V, F, 4><<<grid, 256, 0, stream>>>(a); break;    \
-        case 5: sgd_update_hogwild_kernel<L, V, F, 5><<<grid, 256, 0, stream>>>(a); break;    \
-        case 6: sgd_update_hogwild_kernel<L, V, F, 6><<<grid, 256, 0, stream>>>(a); break;    \
-        default: sgd_update_hogwild_kernel<L, V, F, 0><<<grid, 256, 0, stream>>>(a); break;   \
+    if (scatter != 0) fast = false;           // the atomic scatter variants add exact-rule deltas
+    const bool deep = pipeline_depth() == 4 && g.vec == 1;
+#define CALL(L, V, F)                                                                                    \
+    if (fast && deep) sgd_update_hogwild_kernel<L, V, F, 0, true, 4><<<grid, 256, 0, stream>>>(a);       \
+    else if (fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2><<<grid, 256, 0, stream>>>(a);          \
+    else switch (scatter) {                                                                              \
+        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
+        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
+        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
+        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2><<<grid, 256, 0, stream>>>(a); break;    \
     }
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
@@ -322,27 +445,42 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, int grid
     return cudaGetLastError();
 }
 
-cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter,
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
                                   int grid, cudaStream_t stream, int* launches) {
     if (n_units <= 0) return cudaSuccess;
     const Geometry g = geometry_for(a.k);
     const int max_grid = (n_units + 7) / 8;   // 8 warps per CTA, one unit per warp at a time
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-#define CALL(L, V, F) sgd_update_hot_kernel<L, V, F><<<grid, 256, 0, stream>>>(a, units, n_units, counter)
+#define CALL(L, V, F)                                                                                         \
+    if (fast) sgd_update_hot_kernel<L, V, F, true><<<grid, 256, 0, stream>>>(a, units, n_units, counter);     \
+    else sgd_update_hot_kernel<L, V, F, false><<<grid, 256, 0, stream>>>(a, units, n_units, counter)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, int* ctas) {
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas) {
     const Geometry g = geometry_for(k);
     cudaError_t err = cudaSuccess;
-#define CALL(L, V, F)                                                                                          \
-    err = (scatter == 1)                                                                                       \
-              ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 1>, 256, 0) \
-              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0>, 256, 0)
+    if (scatter != 0) fast = false;
+    const bool deep = pipeline_depth() == 4 && g.vec == 1;
+#define CALL(L, V, F)                                                                                                          \
+    err = (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 4>, 256, 0) \
+          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2>, 256, 0)       \
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, false, 2>, 256, 0)
+    MFSGD_DISPATCH_GEOMETRY(g, CALL);
+#undef CALL
+    return err;
+}
+
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas) {
+    const Geometry g = geometry_for(k);
+    cudaError_t err = cudaSuccess;
+#define CALL(L, V, F)                                                                                              \
+    err = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, true>, 256, 0)     \
+               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, false>, 256, 0)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     return err;

@@ -24,7 +24,7 @@
 
 #define ORC_API extern "C" __attribute__((visibility("default")))
 
-enum { ORC_ORDER_SEQ = 0, ORC_ORDER_WARP_TREE = 1 };
+enum { ORC_ORDER_SEQ = 0, ORC_ORDER_WARP_TREE = 1, ORC_ORDER_WARP_TREE_FMA = 2 };
 
 static const uint64_t STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2, STREAM_USER = 3,
                       STREAM_ITEM = 4, STREAM_NOISE = 5, STREAM_HELDOUT = 6, STREAM_PSTAR = 7,
@@ -99,13 +99,55 @@ static inline float dot_warp_tree(const float* p, const float* q, int k) {
     return s[0];
 }
 
+/*
+ * ORC_ORDER_WARP_TREE_FMA: the arithmetic of the GPU's full-grid kernels (kernels_update.cu FAST):
+ * per lane a (lo, hi) pair accumulated with fused multiply-adds over (x, z) and (y, w) of its chunks, lo + hi,
+ * then the same butterfly; update p' = fma(b, q, a*p), q' = fma(b, p, a*q) with a = 1 - lr*lambda, b = lr*e.
+ * Algebraically the stand-in's rule (MatrixFactorizationSGD.java:95-101), a few ulp apart per update. Not in the
+ * stand-in: it exists so the Hogwild/DSGD kernels can be checked bit for bit on conflict-free data.
+ */
+static inline float dot_warp_tree_fma(const float* p, const float* q, int k) {
+    int chunks = k / 4, L = 1;
+    while (L < chunks && L < 32) L <<= 1;
+    float s[32];
+    for (int l = 0; l < L; l++) {
+        float lo = 0.0f, hi = 0.0f;
+        bool first = true;
+        for (int c = l; c < chunks; c += L) {
+            const float* pp = p + 4 * c;
+            const float* qq = q + 4 * c;
+            if (first) { lo = pp[0] * qq[0]; hi = pp[1] * qq[1]; first = false; }
+            else { lo = std::fmaf(pp[0], qq[0], lo); hi = std::fmaf(pp[1], qq[1], hi); }
+            lo = std::fmaf(pp[2], qq[2], lo);
+            hi = std::fmaf(pp[3], qq[3], hi);
+        }
+        s[l] = lo + hi;
+    }
+    for (int m = L >> 1; m >= 1; m >>= 1) {
+        float t[32];
+        for (int l = 0; l < L; l++) t[l] = s[l] + s[l ^ m];
+        for (int l = 0; l < L; l++) s[l] = t[l];
+    }
+    return s[0];
+}
+
 static inline float dot_ordered(const float* p, const float* q, int k, int order_mode) {
+    if (order_mode == ORC_ORDER_WARP_TREE_FMA) return dot_warp_tree_fma(p, q, k);
     return order_mode == ORC_ORDER_WARP_TREE ? dot_warp_tree(p, q, k) : dot_seq(p, q, k);
 }
 
 /* MatrixFactorizationSGD.java:89 sgdUpdate */
 ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float lambda, int order_mode) {
     float e = r - dot_ordered(p, q, k, order_mode);
+    if (order_mode == ORC_ORDER_WARP_TREE_FMA) {
+        const float a = 1.0f - lr * lambda, b = lr * e;
+        for (int f = 0; f < k; f++) {
+            float pf = p[f], qf = q[f];
+            p[f] = std::fmaf(b, qf, a * pf);
+            q[f] = std::fmaf(b, pf, a * qf);
+        }
+        return e;
+    }
     for (int f = 0; f < k; f++) {
         float pf = p[f], qf = q[f];
         p[f] = pf + lr * (e * qf - lambda * pf);

@@ -12,7 +12,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_DIR, "liboracle.so")
 
-ORDER_SEQ, ORDER_WARP_TREE = 0, 1
+ORDER_SEQ, ORDER_WARP_TREE, ORDER_WARP_TREE_FMA = 0, 1, 2
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")

@@ -37,7 +37,7 @@ def main():
     P, Q = ring.assemble_factors(dist, *eng.get_factors())
     eng.close()
     if rank == 0:
-        Po, Qo = orc.factorize(cu, ci, cr, m, m, 128, 0.02, 0.03, 3, seed, orc.ORDER_WARP_TREE)
+        Po, Qo = orc.factorize(cu, ci, cr, m, m, 128, 0.02, 0.03, 3, seed, orc.ORDER_WARP_TREE_FMA)
         out["conflict_free_bit_exact"] = bool(np.array_equal(P, Po) and np.array_equal(Q, Qo))
     # 2. convergence parity on the mid-size workload
     eng = ring.create_rank_engine(dist, rank, world, local, n_users=nu, n_items=ni, k=k, lr=lr, lambda_=lam, seed=seed)

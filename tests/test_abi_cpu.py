@@ -39,7 +39,7 @@ def test_struct_sizes_match_c_layout():
     # offsets the Java FFM layout (java/MatrixFactorizationSGDGpu.java) also hard-codes
     assert C.sizeof(capi.Config) == 232
     assert capi.Config.seed.offset == 24 and capi.Config.nccl_id.offset == 68 and capi.Config.ctas_per_sm.offset == 196
-    assert C.sizeof(capi.EpochStats) == 48
+    assert C.sizeof(capi.EpochStats) == 72
     assert C.sizeof(capi.SynthParams) == 40
     assert C.sizeof(capi.LayoutInfo) == 56
 

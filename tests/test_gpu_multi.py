@@ -30,7 +30,7 @@ def test_single_process_ring_real_devices(G):
     u, i = rng.permutation(n).astype(np.int32), rng.permutation(n).astype(np.int32)
     r = (1 + 4 * rng.random(n)).astype(np.float32)
     got = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, 128, 0.02, 0.03, 3, SEED, mode=capi.MODE_DSGD, n_gpus=G)
-    P, Q = orc.factorize(u, i, r, n, n, 128, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE)
+    P, Q = orc.factorize(u, i, r, n, n, 128, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE_FMA)
     assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
 
 

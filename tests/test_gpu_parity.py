@@ -179,7 +179,7 @@ def test_empty_and_single_record():
     one = mf.MatrixFactorizationSGD.factorize(np.array([4], np.int32), np.array([6], np.int32), np.array([2.5], np.float32),
                                               5, 7, 8, 0.1, 0.1, 3, SEED)   # hogwild, one record: order is forced
     P, Q = orc.factorize(np.array([4], np.int32), np.array([6], np.int32), np.array([2.5], np.float32), 5, 7, 8,
-                         0.1, 0.1, 3, SEED, orc.ORDER_WARP_TREE)
+                         0.1, 0.1, 3, SEED, orc.ORDER_WARP_TREE_FMA)
     assert np.array_equal(one.P, P) and np.array_equal(one.Q, Q)
 
 
@@ -235,7 +235,7 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         IB = G * mi
         H = info.n_hot_items
         icount = np.bincount(i, minlength=ni)
-        hot_ids = np.flatnonzero(icount >= max(np.float32(1e-4) * np.float64(n), 512))        # the default hot_share rule
+        hot_ids = np.flatnonzero(icount >= max(np.float32(3e-5) * np.float64(n), 512))        # the default hot_share rule
         assert H == len(hot_ids) and H > 0
         all_keys = []
         for g in range(G):
@@ -307,28 +307,42 @@ def midsize():
     return dict(nu=nu, ni=ni, k=k, lr=lr, lam=lam, epochs=epochs, train=tr, held=ho, oracle_rmse=orc.rmse(P, Q, *ho))
 
 
-@pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256])
-@pytest.mark.parametrize("scatter", [capi.SCATTER_STORE, capi.SCATTER_ATOMIC])
-def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, scatter):
+@pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256, 512])
+@pytest.mark.parametrize("arith", ["fast", "exact", "exact-atomic"])
+def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
     """Records with pairwise distinct users and items commute exactly, so the full-grid Hogwild kernel
-    (tiles, sub-warps, prefetch, tails, blocking) must reproduce the oracle bit for bit in any order."""
+    (tiles, sub-warps, prefetch, tails, blocking) must reproduce the oracle bit for bit in any order:
+    the FFMA2 arrangement against ORDER_WARP_TREE_FMA, MFSGD_FLAG_EXACT_ARITH against ORDER_WARP_TREE."""
     n = 5003                                           # not a multiple of 32
     rng = np.random.default_rng(k)
     u = rng.permutation(n).astype(np.int32)
     i = rng.permutation(n).astype(np.int32)
     r = (1 + 4 * rng.random(n)).astype(np.float32)
-    P, Q = orc.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE)
+    order = orc.ORDER_WARP_TREE_FMA if arith == "fast" else orc.ORDER_WARP_TREE
+    flags = 0 if arith == "fast" else capi.FLAG_EXACT_ARITH
+    scatter = capi.SCATTER_ATOMIC if arith == "exact-atomic" else capi.SCATTER_STORE
+    P, Q = orc.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, order)
     for mu, mi in ((1, 1), (3, 2)):
         got = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, mode=capi.MODE_HOGWILD,
-                                                  stripes_per_gpu=mu, shards_per_gpu=mi, scatter=scatter)
-        assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
-    ring = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, mode=capi.MODE_DSGD, n_gpus=4,
-                                               stripes_per_gpu=2, scatter=scatter, flags=capi.FLAG_VIRTUAL_RING)
-    assert np.array_equal(ring.P, P) and np.array_equal(ring.Q, Q)
+                                                  stripes_per_gpu=mu, shards_per_gpu=mi, scatter=scatter, flags=flags)
+        if arith == "exact-atomic":      # p + fl(delta) rounds once more than the store path: equal to 1 ulp
+            np.testing.assert_allclose(got.P, P, rtol=3e-7, atol=1e-9)
+            np.testing.assert_allclose(got.Q, Q, rtol=3e-7, atol=1e-9)
+        else:
+            assert np.array_equal(got.P, P) and np.array_equal(got.Q, Q)
+    if arith != "exact-atomic":
+        ring = mf.MatrixFactorizationSGD.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, mode=capi.MODE_DSGD, n_gpus=4,
+                                                   stripes_per_gpu=2, scatter=scatter, flags=flags | capi.FLAG_VIRTUAL_RING)
+        assert np.array_equal(ring.P, P) and np.array_equal(ring.Q, Q)
+    # the two arithmetics are the same rule: a few ulp apart per update
+    Pe, Qe = orc.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, orc.ORDER_SEQ)
+    np.testing.assert_allclose(P, Pe, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(Q, Qe, rtol=2e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("arith", ["fast", "exact"])
 @pytest.mark.parametrize("k", [128, 256])
-def test_hot_item_kernel_exact_sequential_runs(k):
+def test_hot_item_kernel_exact_sequential_runs(k, arith):
     """Hot-item path: with one run per item (hot_chunk >= run length, one sub-warp per warp) the kernel
     applies an item's ratings strictly in bucket order with q_i in registers -- must equal the oracle
     bit for bit when users are pairwise distinct. Cold records (distinct items) ride along."""
@@ -342,7 +356,7 @@ def test_hot_item_kernel_exact_sequential_runs(k):
     r = (1 + 4 * rng.random(n)).astype(np.float32)
     ni = n_hot + n_cold
     cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1,
-                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE)
+                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE | (capi.FLAG_EXACT_ARITH if arith == "exact" else 0))
     with mf.Engine(cfg) as eng:
         eng.load_ratings(u, i, r)
         assert eng.layout_info().n_hot_items == n_hot
@@ -351,7 +365,8 @@ def test_hot_item_kernel_exact_sequential_runs(k):
         eng.train(3)
         P, Q = eng.get_factors()
     Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
-    orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE, shuffled=False)
+    orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE if arith == "exact" else orc.ORDER_WARP_TREE_FMA,
+              shuffled=False)
     assert np.array_equal(P, Po) and np.array_equal(Q, Qo)
 
 

@@ -149,6 +149,23 @@ def test_tree_and_seq_orders_agree_per_update_1e5():
         np.testing.assert_allclose(q, post_q[j], rtol=1e-5, atol=1e-8)
 
 
+def test_fma_arrangement_is_the_same_rule_to_a_few_ulp():
+    """ORDER_WARP_TREE_FMA (the GPU full-grid arithmetic) vs the stand-in's rule, teacher-forced: << 1e-5."""
+    nu, ni, k = 943, 1682, 32
+    u, i, r, held = orc.generate(SEED, 0, 20_000, nu, ni)
+    P = orc.init_factors(nu, k, SEED, 0)
+    Q = orc.init_factors(ni, k, SEED, 1)
+    order, pre_p, pre_q, post_p, post_q, err = orc.train_tape(u, i, r, P, Q, 0.01, 0.05, 0, SEED)
+    worst = 0.0
+    for j in range(0, len(r), 5):
+        p, q = pre_p[j].copy(), pre_q[j].copy()
+        e = orc.lib.orc_sgd_update(p, q, k, r[order[j]], 0.01, 0.05, orc.ORDER_WARP_TREE_FMA)
+        worst = max(worst, np.max(np.abs(p - post_p[j]) / np.maximum(np.abs(post_p[j]), 1e-6)),
+                    np.max(np.abs(q - post_q[j]) / np.maximum(np.abs(post_q[j]), 1e-6)))
+        assert abs(e - err[j]) <= 1e-5 * max(1.0, abs(err[j]))
+    assert worst < 2e-6
+
+
 def test_trace_and_tape_consistent():
     nu, ni, k = 30, 40, 8
     u, i, r, _ = orc.generate(SEED, 0, 500, nu, ni)

@@ -83,3 +83,26 @@ if __name__ == "__main__":
     elif what == "sweep": sweep(sys.argv[2])
     elif what == "skew": skew(sys.argv[2])
     elif what == "curve": curve(sys.argv[2], *[float(x) if "." in x or "e" in x else int(x) for x in sys.argv[3:]])
+
+
+def smallblocks(wname):
+    """Proxy for the per-GPU work of an 8-member ring on one GPU: 64 user sub-stripes, rounds 1 -> every launch
+    holds 1/64 of the ratings, like one (member, sub-epoch) block at G = 8."""
+    w = mf.WORKLOADS[wname]
+    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    for mw in (128, 32, 8):
+        os.environ["MFSGD_MIN_WINDOWS"] = str(mw)
+        for chunk in (256, 128):
+            cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD,
+                                 stripes_per_gpu=64, rounds=1, hot_chunk=chunk, flags=capi.FLAG_TIME_KERNELS)
+            with mf.Engine(cfg) as eng:
+                eng.generate_synthetic(sp); eng.init_factors(); eng.train(1)
+                st = eng.train(3)
+                rm = eng.rmse_heldout()[0]
+            ms = np.median([s.epoch_ms for s in st])
+            print(json.dumps({"min_windows": mw, "hot_chunk": chunk, "epoch_ms": ms, "per_launch_pair_us": 1e3 * ms / 64,
+                              "gupdates_s": st[0].updates / ms / 1e6, "rmse4": rm}), flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "smallblocks":
+    smallblocks(sys.argv[2])
