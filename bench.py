@@ -47,6 +47,21 @@ def recorded_traffic(workload):
     return None
 
 
+class stdout_to_stderr:
+    """Route fd 1 to fd 2 while native libraries that print banners (NCCL's version line) initialise:
+    this script's stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -158,7 +173,8 @@ def run_ours(args):
                   stripes_per_gpu=args.stripes, shards_per_gpu=args.shards, scatter=args.scatter, flags=flags,
                   ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share)
     if world > 1:
-        eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
+        with stdout_to_stderr():
+            eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
     else:
         eng = mf.Engine(mf.make_config(mode=capi.MODE_HOGWILD, device=local_rank, **common))
     sp = mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
@@ -170,8 +186,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()           # nvidia-smi needs a moment to produce its first sample: start before the warm-up
-    if args.warmup > 0:
-        eng.train(args.warmup)
+    with stdout_to_stderr():
+        if args.warmup > 0:
+            eng.train(args.warmup)
     barrier()
     sampler.rows.clear()          # keep only samples taken during the timed region
     wall0 = time.time()

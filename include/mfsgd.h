@@ -53,6 +53,8 @@ extern "C" {
 #define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
 #define MFSGD_FLAG_VIRTUAL_RING   2u /* place all n_gpus ring members on one device (scheduler test mode) */
 #define MFSGD_FLAG_NO_SHUFFLE     4u /* skip the per-epoch reshuffle (measurement aid)                    */
+#define MFSGD_FLAG_SPLIT_SHARDS  16u /* one launch pair per item sub-shard (shards_per_gpu > 1) instead of one per
+                                        shard group: a single GPU then replays the launch sizes of a larger ring */
 #define MFSGD_FLAG_EXACT_ARITH    8u /* HOGWILD/DSGD kernels apply the reference rule operation by operation
                                         (no FMA) instead of the FFMA2 arrangement (a few ulp apart, 3x the issue slots);
                                         DETERMINISTIC mode is always exact                                   */
@@ -81,7 +83,7 @@ typedef struct mfsgd_config {
     int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
     int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
     float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
-                                  (q_i register-resident, model-averaged); 0 = default 3e-5, < 0 = off   */
+                                  (q_i register-resident, model-averaged); 0 = default 1e-5, < 0 = off   */
     int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 256              */
     int32_t  reserved[4];
 } mfsgd_config;

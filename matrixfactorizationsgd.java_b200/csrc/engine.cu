@@ -144,7 +144,7 @@ struct Member {              // one ring member ("GPU g")
     uint16_t* d_owner_i = nullptr;
     int32_t* d_hot_index = nullptr;  // item -> index into handle.hot_items, or -1
     HotUnit* d_units = nullptr;      // hot-item units of all visits, grouped by visit
-    std::vector<int> visit_units;    // [(a * G + grp) * rounds + rnd] -> first unit; one extra entry at the end
+    std::vector<int> visit_units;    // [(a * rounds + rnd) * IB + item block] -> first unit; one extra entry at the end
     unsigned int* d_counters = nullptr;   // one unit-claim counter per hot launch of an epoch
     int n_counters = 0, counter_next = 0;
     int hot_grid = 148;
@@ -177,7 +177,7 @@ struct mfsgd_handle {
     int G = 1, mu = 1, mi = 1, UB = 1, IB = 1;
     int rounds = 1;          // interleaved passes over the P sub-stripes per sub-epoch
     std::vector<int32_t> hot_items;     // global ids of the hot items, ascending (so grouped by item block)
-    std::vector<int32_t> hot_group_lo;  // [G + 1]: hot_items[hot_group_lo[g] .. hot_group_lo[g+1]) lie in Q shard group g
+    std::vector<int32_t> hot_block_lo;  // [IB + 1]: hot_items[hot_block_lo[b] .. hot_block_lo[b+1]) lie in item block b
     int H = 0;
     float scale = 0.f;
     std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
@@ -585,12 +585,15 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 #undef CKC
     // hot items: rated by at least hot_share of the training set (and often enough to fill a warp's run)
     h->hot_items.clear();
-    const float share = c.hot_share == 0.f ? 3e-5f : c.hot_share;
+    const float share = c.hot_share == 0.f ? 1e-5f : c.hot_share;
     if (bad_host == 0 && share > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0) {
         std::vector<uint32_t> icnt_host((size_t)c.n_items);
         cudaError_t e = cudaMemcpy(icnt_host.data(), icnt, (size_t)c.n_items * 4, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { cleanup(); return fail(MFSGD_E_CUDA, "copying item counts: %s", cudaGetErrorString(e)); }
-        const double thr = std::max((double)share * (double)total_train, 512.0);
+        // An item's ratings are spread over mu * G (* rounds) visits; a run should still hold ~32 of them, or the
+        // q_i load + merge (1 KB per run) is not amortised and the item is better served by the cold kernel.
+        const double min_count = 32.0 * h->mu * h->G * (h->mu > 1 ? 4 : 1);
+        const double thr = std::max((double)share * (double)total_train, min_count);
         std::vector<std::pair<uint32_t, int32_t>> cand;
         for (int32_t it = 0; it < c.n_items; it++)
             if ((double)icnt_host[(size_t)it] >= thr) cand.push_back({icnt_host[(size_t)it], it});
@@ -645,10 +648,10 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     cudaFree(d_b);
     CK(e);
     // hot-item lookup table and the per-group ranges of the (ascending) hot list
-    h->hot_group_lo.assign((size_t)h->G + 1, 0);
-    for (int grp = 0; grp <= h->G; grp++) {
-        const int32_t bound = grp == h->G ? c.n_items : group_lo(h, grp);
-        h->hot_group_lo[(size_t)grp] = (int32_t)(std::lower_bound(h->hot_items.begin(), h->hot_items.end(), bound) - h->hot_items.begin());
+    h->hot_block_lo.assign((size_t)h->IB + 1, 0);
+    for (int ib = 0; ib <= h->IB; ib++) {
+        const int32_t bound = h->item_bounds[(size_t)ib];
+        h->hot_block_lo[(size_t)ib] = (int32_t)(std::lower_bound(h->hot_items.begin(), h->hot_items.end(), bound) - h->hot_items.begin());
     }
     dev_free(m.d_hot_index);
     if (h->H > 0) {
@@ -738,7 +741,7 @@ static inline void slice_of(const Member& m, size_t blk_lo, size_t blk_hi, int r
 static int build_hot_units(mfsgd_handle* h, Member& m) {
     dev_free(m.d_units);
     dev_free(m.d_counters);
-    m.visit_units.assign((size_t)h->mu * h->G * h->rounds + 1, 0);
+    m.visit_units.assign((size_t)h->mu * h->rounds * h->IB + 1, 0);
     if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
     CK(cudaSetDevice(m.device));
     // Run length: a run is walked by one warp, one rating after another (only the p_u gathers are pipelined), so a
@@ -749,10 +752,10 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
     for (int sa = 0; sa < h->mu; sa++)
-        for (int grp = 0; grp < h->G; grp++)
-            for (int rnd = 0; rnd < h->rounds; rnd++) {
-                m.visit_units[((size_t)sa * h->G + grp) * h->rounds + rnd] = (int)units.size();
-                for (int hx = h->hot_group_lo[(size_t)grp]; hx < h->hot_group_lo[(size_t)grp + 1]; hx++) {
+        for (int rnd = 0; rnd < h->rounds; rnd++)
+            for (int ib = 0; ib < h->IB; ib++) {
+                m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib] = (int)units.size();
+                for (int hx = h->hot_block_lo[(size_t)ib]; hx < h->hot_block_lo[(size_t)ib + 1]; hx++) {
                     const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
                     int64_t lo, hi;
                     slice_of(m, blk, blk + 1, rnd, h->rounds, &lo, &hi);
@@ -770,7 +773,7 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                 }
             }
     m.visit_units.back() = (int)units.size();
-    m.n_counters = h->mu * h->G * h->rounds;
+    m.n_counters = h->mu * h->rounds * h->IB;
     CK(dev_alloc(&m.d_units, units.size()));
     CK(dev_alloc(&m.d_counters, (size_t)m.n_counters));
     if (!units.empty()) CK(cudaMemcpy(m.d_units, units.data(), units.size() * sizeof(HotUnit), cudaMemcpyHostToDevice));
@@ -1208,16 +1211,21 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     CK(cudaEventRecord(m.ev_fork, m.stream));
                     CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
                 }
+                // MFSGD_FLAG_SPLIT_SHARDS: one launch pair per item sub-shard instead of one per shard group
+                const int parts = (c.flags & MFSGD_FLAG_SPLIT_SHARDS) ? h->mi : 1;
+                const int blocks_per_part = h->mi / parts;
+                for (int part = 0; part < parts; part++)
                 for (int vis = 0; vis < h->mu * h->rounds; vis++) {
                     const int rnd = vis / h->mu;
                     // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
                     const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
                     const int pos = vis % h->mu;
                     const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
+                    const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
                     int64_t lo, hi;
-                    slice_of(m, (size_t)sa * h->IB + (size_t)grp * h->mi, (size_t)sa * h->IB + (size_t)(grp + 1) * h->mi, rnd, h->rounds, &lo, &hi);
-                    const size_t vkey = ((size_t)sa * h->G + grp) * h->rounds + rnd;
-                    const int unit_lo = m.visit_units[vkey], unit_hi = m.visit_units[vkey + 1];
+                    slice_of(m, (size_t)sa * h->IB + ib_lo, (size_t)sa * h->IB + ib_hi, rnd, h->rounds, &lo, &hi);
+                    const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
+                    const int unit_lo = m.visit_units[vkey + ib_lo], unit_hi = m.visit_units[vkey + ib_hi];
                     if (hi > lo) {      // cold records: full-grid Hogwild kernel
                         a.recs = m.recs[m.rcur] + lo;
                         a.n = hi - lo;
@@ -1315,8 +1323,8 @@ static int rmse_sets(mfsgd_handle* h, std::vector<EvalSet*>& sets, bool train_se
                                        m.d_sse, m.n_sms, m.stream, &m.launches));
                     if (h->H > 0) {   // the hot buckets of (sa, grp) are contiguous too
                         const size_t hb = (size_t)h->mu * h->IB + (size_t)sa * h->H;
-                        const int64_t hlo = m.block_off[hb + (size_t)h->hot_group_lo[(size_t)grp]];
-                        const int64_t hhi = m.block_off[hb + (size_t)h->hot_group_lo[(size_t)grp + 1]];
+                        const int64_t hlo = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)grp * h->mi]];
+                        const int64_t hhi = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)(grp + 1) * h->mi]];
                         CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                            m.d_sse, m.n_sms, m.stream, &m.launches));
                     }

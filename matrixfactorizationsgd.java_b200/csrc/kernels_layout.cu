@@ -156,6 +156,40 @@ __global__ void __launch_bounds__(BUCKET_THREADS) block_scatter_kernel(BucketArg
     }
 }
 
+// Many-bucket variants (hot-item sets of tens of thousands of (stripe, item) buckets): counters live in global
+// memory; with that many buckets the atomics spread out, and a warp first merges its lanes that hit the same bucket.
+__global__ void __launch_bounds__(256) block_histogram_global_kernel(BucketArgs b, unsigned long long* __restrict__ block_cnt) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (b.n + 31) & ~(int64_t)31;   // whole warps stay in the loop for the match below
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+        const int blk = (t < b.n) ? record_block(b, t) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, blk);
+        if (blk >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(block_cnt + blk, (unsigned long long)__popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(256) block_scatter_global_kernel(BucketArgs b, unsigned long long* __restrict__ cursors,
+                                                                   Rec* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (b.n + 31) & ~(int64_t)31;
+    const int lane = threadIdx.x & 31;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+        const int blk = (t < b.n) ? record_block(b, t) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, blk);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (blk >= 0 && lane == leader) base = atomicAdd(cursors + blk, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (blk >= 0) {
+            Rec rec;
+            rec.u = b.u[t];
+            rec.i = b.i[t];
+            rec.r = b.r[t];
+            out[base + (unsigned long long)__popc(peers & ((1u << lane) - 1u))] = rec;
+        }
+    }
+}
+
 // ---- in-block reshuffle: keyed Feistel bijection with cycle walking ------------------------------
 __device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
     uint32_t h = (x + key) * 0x9E3779B1u;
@@ -290,6 +324,11 @@ cudaError_t launch_block_histogram(const BucketArgs& b, unsigned long long* bloc
     if (b.n <= 0) return cudaSuccess;
     const int nblk = bucket_block_count(b);
     if (nblk > MAX_BUCKETS) return cudaErrorInvalidValue;
+    if (nblk > MAX_SMEM_BUCKETS) {
+        block_histogram_global_kernel<<<grid_for(b.n, 256 * 8, 148 * 8), 256, 0, stream>>>(b, block_cnt);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)nblk * sizeof(uint32_t);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(block_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -305,6 +344,11 @@ cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursor
     if (b.n <= 0) return cudaSuccess;
     const int nblk = bucket_block_count(b);
     if (nblk > MAX_BUCKETS) return cudaErrorInvalidValue;
+    if (nblk > MAX_SMEM_BUCKETS) {
+        block_scatter_global_kernel<<<grid_for(b.n, 256 * 8, 148 * 8), 256, 0, stream>>>(b, cursors, out);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)((nblk + 1) & ~1) * sizeof(uint32_t) + (size_t)nblk * sizeof(unsigned long long);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(block_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -235,7 +235,7 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         IB = G * mi
         H = info.n_hot_items
         icount = np.bincount(i, minlength=ni)
-        hot_ids = np.flatnonzero(icount >= max(np.float32(3e-5) * np.float64(n), 512))        # the default hot_share rule
+        hot_ids = np.flatnonzero(icount >= max(np.float32(1e-5) * np.float64(n), 32.0 * mu * G * (4 if mu > 1 else 1)))   # the default rule
         assert H == len(hot_ids) and H > 0
         all_keys = []
         for g in range(G):
@@ -379,7 +379,7 @@ def test_hot_item_path_can_be_disabled(midsize):
     cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED)
     with mf.Engine(cfg) as eng:
         eng.load_ratings(*m["train"])
-        assert eng.layout_info().n_hot_items > 50
+        assert eng.layout_info().n_hot_items > 500
 
 
 @pytest.mark.parametrize("mu", [1, 4])
