@@ -128,6 +128,8 @@ struct Member {              // one ring member ("GPU g")
     int n_sms = 148;
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, hot_stream = nullptr, shuffle_stream = nullptr;
+    std::vector<cudaEvent_t> ev_part_done, ev_part_recv;   // pipelined rotation: per item sub-shard of the held group
+    std::vector<char> part_recv_pending;
     int ahead_epoch = -1;    // epoch whose layout the background reshuffle has written (is writing) into recs[rcur ^ 1]
     int32_t u_lo = 0, u_hi = 0;      // owned P rows
     float* P = nullptr;
@@ -392,6 +394,8 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         free_member_data(m);
         dev_free(m.d_scratch);
         for (cudaEvent_t e : m.evpool) cudaEventDestroy(e);
+        for (cudaEvent_t e : m.ev_part_done) cudaEventDestroy(e);
+        for (cudaEvent_t e : m.ev_part_recv) cudaEventDestroy(e);
         cudaEvent_t evs[] = {m.ev_compute, m.ev_sent, m.ev_fork, m.ev_join, m.ev_shuffle_go, m.ev_shuffle_done};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
@@ -501,7 +505,8 @@ extern "C" int mfsgd_host_free(void* p) {
 // ------------------------------------------------------------------------------------------------
 static void choose_blocking(mfsgd_handle* h) {
     const mfsgd_config& c = h->cfg;
-    h->mi = c.shards_per_gpu > 0 ? c.shards_per_gpu : 1;
+    // a multi-process ring pipelines the rotation over item sub-shards: two by default (send one while the next trains)
+    h->mi = c.shards_per_gpu > 0 ? c.shards_per_gpu : (h->multi_process && h->G > 1 && c.mode == MFSGD_MODE_DSGD ? 2 : 1);
     if (c.mode == MFSGD_MODE_DETERMINISTIC) {
         h->mu = 1;
     } else if (c.stripes_per_gpu > 0) {
@@ -991,6 +996,41 @@ extern "C" int mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi
 // ------------------------------------------------------------------------------------------------
 // subsystem (4): ring rotation of the Q shard groups
 // ------------------------------------------------------------------------------------------------
+// Pipelined rotation (one process per GPU, shards_per_gpu > 1): as soon as the launches of item sub-shard `part` are
+// done, that slice of the held Q group travels on the copy stream (ncclSend to g-1 / ncclRecv from g+1) while the
+// compute stream trains the next sub-shard; the next sub-epoch waits per sub-shard, not for the whole group.
+static int ensure_part_events(mfsgd_handle* h, Member& m) {
+    while ((int)m.ev_part_done.size() < h->mi) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        m.ev_part_done.push_back(a);
+        m.ev_part_recv.push_back(b);
+        m.part_recv_pending.push_back(0);
+    }
+    return MFSGD_OK;
+}
+
+static int rotate_part(mfsgd_handle* h, Member& m, int part) {
+    const int G = h->G, k = h->cfg.k;
+    const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
+    const int send_grp = m.held_group, recv_grp = (m.held_group + 1) % G;
+    const int32_t s_lo = h->item_bounds[(size_t)send_grp * h->mi + part], s_hi = h->item_bounds[(size_t)send_grp * h->mi + part + 1];
+    const int32_t r_lo = h->item_bounds[(size_t)recv_grp * h->mi + part], r_hi = h->item_bounds[(size_t)recv_grp * h->mi + part + 1];
+    float* sptr = m.Q[m.cur] + (size_t)(s_lo - group_lo(h, send_grp)) * k;
+    float* rptr = m.Q[m.cur ^ 1] + (size_t)(r_lo - group_lo(h, recv_grp)) * k;
+    CK(cudaEventRecord(m.ev_part_done[(size_t)part], m.stream));
+    CK(cudaStreamWaitEvent(m.copy_stream, m.ev_part_done[(size_t)part], 0));
+    CKN(g_nccl.GroupStart());
+    CKN(g_nccl.Send(sptr, (size_t)(s_hi - s_lo) * k, ncclFloat, to, h->comm, m.copy_stream));
+    CKN(g_nccl.Recv(rptr, (size_t)(r_hi - r_lo) * k, ncclFloat, from, h->comm, m.copy_stream));
+    CKN(g_nccl.GroupEnd());
+    CK(cudaEventRecord(m.ev_part_recv[(size_t)part], m.copy_stream));
+    m.part_recv_pending[(size_t)part] = 1;
+    m.launches += 1;
+    return MFSGD_OK;
+}
+
 // After the kernels of a sub-epoch: member g hands the group it holds to member g-1 and takes the next
 // one from member g+1. Everything is stream/event ordered; the host never blocks inside an epoch.
 static int rotate_q(mfsgd_handle* h) {
@@ -998,6 +1038,11 @@ static int rotate_q(mfsgd_handle* h) {
     if (G == 1) return MFSGD_OK;
     if (h->multi_process) {
         Member& m = h->members[0];
+        for (size_t part = 0; part < m.part_recv_pending.size(); part++)
+            if (m.part_recv_pending[part]) {
+                CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[part], 0));
+                m.part_recv_pending[part] = 0;
+            }
         const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
         const int send_grp = m.held_group, recv_grp = (m.held_group + 1) % G;
         const size_t send_n = (size_t)(group_hi(h, send_grp) - group_lo(h, send_grp)) * k;
@@ -1207,47 +1252,60 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     CK(cudaEventRecord(e0, m.stream));
                 }
                 const bool has_hot = m.d_units != nullptr && m.visit_units.back() > 0;
-                if (has_hot) {
-                    CK(cudaEventRecord(m.ev_fork, m.stream));
-                    CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
-                }
-                // MFSGD_FLAG_SPLIT_SHARDS: one launch pair per item sub-shard instead of one per shard group
-                const int parts = (c.flags & MFSGD_FLAG_SPLIT_SHARDS) ? h->mi : 1;
+                // parts: item sub-shards launched separately -- always when the rotation is pipelined, else on request
+                // (MFSGD_FLAG_SPLIT_SHARDS: a single GPU then replays the launch sizes of a larger ring)
+                const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1;
+                const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
                 const int blocks_per_part = h->mi / parts;
-                for (int part = 0; part < parts; part++)
-                for (int vis = 0; vis < h->mu * h->rounds; vis++) {
-                    const int rnd = vis / h->mu;
-                    // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
-                    const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
-                    const int pos = vis % h->mu;
-                    const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
-                    const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
-                    int64_t lo, hi;
-                    slice_of(m, (size_t)sa * h->IB + ib_lo, (size_t)sa * h->IB + ib_hi, rnd, h->rounds, &lo, &hi);
-                    const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
-                    const int unit_lo = m.visit_units[vkey + ib_lo], unit_hi = m.visit_units[vkey + ib_hi];
-                    if (hi > lo) {      // cold records: full-grid Hogwild kernel
-                        a.recs = m.recs[m.rcur] + lo;
-                        a.n = hi - lo;
-                        CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, m.stream, &m.launches));
-                        m.update_launches++;
+                if (pipelined) CKRC(ensure_part_events(h, m));
+                for (int part = 0; part < parts; part++) {
+                    if (pipelined && m.part_recv_pending[(size_t)part]) {      // this slice of the group has to have arrived
+                        CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[(size_t)part], 0));
+                        m.part_recv_pending[(size_t)part] = 0;
                     }
-                    if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
-                        a.recs = m.recs[m.rcur];
-                        a.n = m.n_recs;
-                        if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
-                        CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith, m.hot_grid,
-                                                 m.hot_stream, &m.launches));
-                        m.update_launches++;
+                    if (has_hot) {
+                        CK(cudaEventRecord(m.ev_fork, m.stream));
+                        CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
                     }
+                    for (int vis = 0; vis < h->mu * h->rounds; vis++) {
+                        const int rnd = vis / h->mu;
+                        // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
+                        const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
+                        const int pos = vis % h->mu;
+                        const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
+                        const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
+                        int64_t lo, hi;
+                        slice_of(m, (size_t)sa * h->IB + ib_lo, (size_t)sa * h->IB + ib_hi, rnd, h->rounds, &lo, &hi);
+                        const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
+                        const int unit_lo = m.visit_units[vkey + ib_lo], unit_hi = m.visit_units[vkey + ib_hi];
+                        if (hi > lo) {      // cold records: full-grid Hogwild kernel
+                            a.recs = m.recs[m.rcur] + lo;
+                            a.n = hi - lo;
+                            CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, m.stream, &m.launches));
+                            m.update_launches++;
+                        }
+                        if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
+                            a.recs = m.recs[m.rcur];
+                            a.n = m.n_recs;
+                            if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
+                            CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith,
+                                                     m.hot_grid, m.hot_stream, &m.launches));
+                            m.update_launches++;
+                        }
+                    }
+                    if (time_kernels && part == parts - 1) {
+                        CK(cudaEventRecord(e_cold, m.stream));
+                        CK(cudaEventRecord(e_hot, has_hot ? m.hot_stream : m.stream));
+                    }
+                    if (has_hot) {
+                        CK(cudaEventRecord(m.ev_join, m.hot_stream));
+                        CK(cudaStreamWaitEvent(m.stream, m.ev_join, 0));
+                    }
+                    if (pipelined) CKRC(rotate_part(h, m, part));
                 }
-                if (time_kernels) {
-                    CK(cudaEventRecord(e_cold, m.stream));
-                    CK(cudaEventRecord(e_hot, has_hot ? m.hot_stream : m.stream));
-                }
-                if (has_hot) {
-                    CK(cudaEventRecord(m.ev_join, m.hot_stream));
-                    CK(cudaStreamWaitEvent(m.stream, m.ev_join, 0));
+                if (pipelined) {          // all slices are on their way: the other buffer holds the next group
+                    m.cur ^= 1;
+                    m.held_group = (m.held_group + 1) % h->G;
                 }
                 if (time_kernels) {
                     CK(cudaEventRecord(e1, m.stream));
@@ -1258,7 +1316,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     m.kev.push_back(e_xchg);
                 }
             }
-            CKRC(rotate_q(h));
+            if (!(h->multi_process && h->G > 1 && h->mi > 1 && c.mode != MFSGD_MODE_DETERMINISTIC)) CKRC(rotate_q(h));
             if (time_kernels && c.mode != MFSGD_MODE_DETERMINISTIC)
                 for (Member& m : h->members) {
                     CK(cudaSetDevice(m.device));
@@ -1268,6 +1326,14 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         for (Member& m : h->members) {
             Member::EpochRec& er = m.pending.back();
             CK(cudaSetDevice(m.device));
+            // Q is home again once the last slices have arrived. Between back-to-back epochs of one call that wait is left
+            // to the next epoch's first launches (per slice), so the pipeline keeps running across the epoch boundary.
+            const bool drain = (ep + 1 == epochs) || want_eval;
+            for (size_t part = 0; drain && part < m.part_recv_pending.size(); part++)
+                if (m.part_recv_pending[part]) {
+                    CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[part], 0));
+                    m.part_recv_pending[part] = 0;
+                }
             CK(cudaEventRecord(er.end, m.stream));
             er.kend = (int)m.kev.size();
             er.launches = m.launches;

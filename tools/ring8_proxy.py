@@ -13,7 +13,7 @@ hot_chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 epochs = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 w = mf.WORKLOADS["netflix"]
 nu, n = w.n_users // 8, w.n_ratings // 8
-cfg = mf.make_config(nu, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, shards_per_gpu=8,
+cfg = mf.make_config(nu, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, shards_per_gpu=int(os.environ.get("PROXY_SHARDS", "8")),
                      rounds=1, hot_share=hot_share, hot_chunk=hot_chunk,
                      flags=capi.FLAG_TIME_KERNELS | capi.FLAG_SPLIT_SHARDS)
 with mf.Engine(cfg) as eng:
@@ -23,6 +23,6 @@ with mf.Engine(cfg) as eng:
     st = eng.train(epochs)
     info = eng.layout_info()
 ms = float(np.median([s.epoch_ms for s in st]))
-print(json.dumps({"hot_share_equiv": hot_share or 3e-5, "hot_chunk": hot_chunk, "hot_items": info.n_hot_items, "epoch_ms": ms, "per_subepoch_us": 1e3 * ms / 8,
+print(json.dumps({"hot_share_equiv": hot_share or 3e-5, "hot_chunk": hot_chunk, "hot_items": info.n_hot_items, "epoch_ms": ms, "per_subepoch_us": 1e3 * ms / 8, "shards": int(os.environ.get("PROXY_SHARDS", "8")),
                   "cold_us": 1e3 * float(np.median([s.cold_ms for s in st])) / 8, "hot_us": 1e3 * float(np.median([s.hot_ms for s in st])) / 8,
                   "gupdates_s": st[0].updates / ms / 1e6, "launches": st[0].update_launches}))
