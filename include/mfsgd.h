@@ -55,6 +55,8 @@ extern "C" {
 #define MFSGD_FLAG_NO_SHUFFLE     4u /* skip the per-epoch reshuffle (measurement aid)                    */
 #define MFSGD_FLAG_SPLIT_SHARDS  16u /* one launch pair per item sub-shard (shards_per_gpu > 1) instead of one per
                                         shard group: a single GPU then replays the launch sizes of a larger ring */
+#define MFSGD_FLAG_MATERIALIZE_SHUFFLE 32u /* run the reshuffle kernel every epoch (two record buffers) instead of letting the
+                                        update kernels read each bucket through its per-epoch permutation (the default)  */
 #define MFSGD_FLAG_EXACT_ARITH    8u /* HOGWILD/DSGD kernels apply the reference rule operation by operation
                                         (no FMA) instead of the FFMA2 arrangement (a few ulp apart, 3x the issue slots);
                                         DETERMINISTIC mode is always exact                                   */

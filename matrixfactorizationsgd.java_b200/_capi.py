@@ -14,6 +14,7 @@ OK, E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
 MODE_DETERMINISTIC, MODE_HOGWILD, MODE_DSGD = 0, 1, 2
 SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
 FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE, FLAG_EXACT_ARITH, FLAG_SPLIT_SHARDS = 1, 2, 4, 8, 16
+FLAG_MATERIALIZE_SHUFFLE = 32
 ABI_VERSION = 1
 
 

@@ -70,6 +70,43 @@ __device__ __forceinline__ void st_stream_i32(int32_t* p, int32_t v, uint64_t po
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
+// ---- in-block reshuffle: keyed Feistel bijection with cycle walking (subsystem 1) -----------------
+// perm_b(j) for bucket b of n records in epoch e: the materialising kernel (kernels_layout.cu) writes
+// out[off+j] = in[off+perm(j)]; the update kernels can instead read record off+perm(j) directly.
+__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
+    uint32_t h = (x + key) * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    return h;
+}
+// bijection on [0, n): 4-round balanced Feistel over 2*hb bits (2^(2hb) >= n), re-applied until < n.
+__device__ __forceinline__ uint64_t block_perm(uint64_t x, uint64_t n, int hb, uint64_t key) {
+    const uint32_t mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    do {
+        uint32_t l = (uint32_t)(x >> hb) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; round++) {
+            const uint32_t f = feistel_round(r, (round & 1) ? (k1 + round) : (k0 + round)) & mask;
+            const uint32_t nl = r;
+            r = l ^ f;
+            l = nl;
+        }
+        x = ((uint64_t)l << hb) | (uint64_t)r;
+    } while (x >= n);
+    return x;
+}
+
+__device__ __forceinline__ int perm_half_bits(uint64_t n) {   // n > 1
+    int bits = 64 - __clzll((long long)(n - 1));
+    if (bits < 2) bits = 2;
+    return (bits + 1) >> 1;
+}
+__device__ __forceinline__ uint64_t bucket_perm_key(uint64_t seed, uint32_t epoch, uint32_t bucket_id) {
+    return hash64(seed, STREAM_BLOCK_SHUFFLE, ((uint64_t)epoch << 32) | (uint64_t)bucket_id);
+}
+
 // ---- the update rule -----------------------------------------------------------------------
 // Partial dot of one float4 chunk, continuing a running binary32 sum, element order x,y,z,w.
 __device__ __forceinline__ float dot4_acc(float acc, float4 a, float4 b) {

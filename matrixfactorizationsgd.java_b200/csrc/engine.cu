@@ -178,6 +178,7 @@ struct mfsgd_handle {
     mfsgd_config cfg;
     int G = 1, mu = 1, mi = 1, UB = 1, IB = 1;
     int rounds = 1;          // interleaved passes over the P sub-stripes per sub-epoch
+    bool virtual_shuffle = false;   // update kernels read records through the per-epoch permutation (no reshuffle pass)
     std::vector<int32_t> hot_items;     // global ids of the hot items, ascending (so grouped by item block)
     std::vector<int32_t> hot_block_lo;  // [IB + 1]: hot_items[hot_block_lo[b] .. hot_block_lo[b+1]) lie in item block b
     int H = 0;
@@ -769,6 +770,9 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                     const int64_t pieces = (n + chunk - 1) / chunk;
                     for (int64_t pc = 0; pc < pieces; pc++) {
                         HotUnit u{};
+                        u.bstart = m.block_off[blk];
+                        u.bn = (int32_t)(m.block_off[blk + 1] - m.block_off[blk]);
+                        u.bid = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + blk);
                         u.start = lo + n * pc / pieces;
                         u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
                         u.item = h->hot_items[(size_t)hx];
@@ -832,8 +836,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
             if (rc == MFSGD_OK) {
                 m.n_recs = m.block_off.back();
                 m.rcur = 0;
-                cudaError_t e = dev_alloc(&m.recs[1], (size_t)m.n_recs);
-                if (e == cudaSuccess) e = dev_alloc(&m.d_block_off, m.block_off.size());
+                cudaError_t e = dev_alloc(&m.d_block_off, m.block_off.size());   // recs[1] is allocated by the first materialising reshuffle
                 if (e == cudaSuccess) e = cudaMemcpy(m.d_block_off, m.block_off.data(), m.block_off.size() * 8, cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "record buffers: %s", cudaGetErrorString(e));
             }
@@ -860,6 +863,12 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
         const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
         const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
         h->rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+    }
+    {
+        const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1;
+        const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
+        h->virtual_shuffle = c.mode != MFSGD_MODE_DETERMINISTIC && !(c.flags & (MFSGD_FLAG_NO_SHUFFLE | MFSGD_FLAG_MATERIALIZE_SHUFFLE)) &&
+                             h->mi / parts == 1;   // every cold launch must lie inside one block
     }
     for (Member& m : h->members) {
         PhaseTimer pt("load: hot-unit lists");
@@ -1110,7 +1119,9 @@ static int shuffle_member(mfsgd_handle* h, Member& m, int epoch, bool prefetch_n
         m.rcur = 0;
         return MFSGD_OK;
     }
+    if (h->virtual_shuffle && prefetch_next) return MFSGD_OK;   // training: the kernels apply the permutation themselves
     const int nblk = (int)m.block_off.size() - 1;   // cold blocks + hot (stripe, item) buckets
+    if (!m.recs[1]) CK(dev_alloc(&m.recs[1], (size_t)m.n_recs));
     if (m.ahead_epoch == epoch) {
         CK(cudaStreamWaitEvent(m.stream, m.ev_shuffle_done, 0));      // prepared during the previous epoch
     } else {
@@ -1230,8 +1241,12 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 a.i_base = group_lo(h, grp);
                 a.lr = c.lr;
                 a.lambda = c.lambda;
+                a.seed = c.seed;
+                a.epoch = (uint32_t)h->epoch;
+                a.virt = h->virtual_shuffle ? 1 : 0;
                 if (c.mode == MFSGD_MODE_DETERMINISTIC) {
                     a.recs = m.recs[0];
+                    a.first = 0;
                     a.n = m.n_recs;
                     CK(launch_sgd_update_deterministic(a, d_trace, m.stream, &m.launches));
                     m.update_launches++;
@@ -1279,13 +1294,19 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
                         const int unit_lo = m.visit_units[vkey + ib_lo], unit_hi = m.visit_units[vkey + ib_hi];
                         if (hi > lo) {      // cold records: full-grid Hogwild kernel
-                            a.recs = m.recs[m.rcur] + lo;
+                            const size_t cblk = (size_t)sa * h->IB + ib_lo;
+                            a.recs = m.recs[m.rcur];
+                            a.first = lo;
                             a.n = hi - lo;
+                            a.blk_start = m.block_off[cblk];
+                            a.blk_n = m.block_off[cblk + 1] - m.block_off[cblk];
+                            a.blk_id = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + cblk);
                             CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, m.stream, &m.launches));
                             m.update_launches++;
                         }
                         if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
                             a.recs = m.recs[m.rcur];
+                            a.first = 0;
                             a.n = m.n_recs;
                             if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
                             CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith,

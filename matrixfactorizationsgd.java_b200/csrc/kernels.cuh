@@ -45,12 +45,19 @@ inline bool rank_supported(int k) { return k >= 4 && k <= 512 && (k % 4) == 0; }
     } while (0)
 
 struct UpdateArgs {
-    const Rec* recs;   // records of one block range
+    const Rec* recs;   // the member's record array (current layout)
+    int64_t first;     // cold / deterministic launches: positions [first, first + n) of that array
     int64_t n;
     float* P;          // row (u - u_base) of the local P stripe
     float* Q;          // row (i - i_base) of the held Q shard group
     int32_t k, u_base, i_base;
     float lr, lambda;
+    // virtual reshuffle (virt != 0): position j of a bucket reads record bucket_start + perm(j - bucket_start);
+    // for cold launches the range lies inside the single block described here, hot units carry their own bucket.
+    int32_t virt;
+    uint32_t epoch, blk_id;
+    uint64_t seed;
+    int64_t blk_start, blk_n;
 };
 
 // (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
@@ -71,10 +78,13 @@ cudaError_t launch_sgd_update_forced(int k, float lr, float lambda, int64_t n, c
 // the warp's registers for the whole run (no L2 round trips, no contention on the hot row); the run's net
 // change is merged into Q at the end, scaled by `weight` (model averaging across the units of one item).
 struct HotUnit {
-    int64_t start;     // first record (index into the launch's record array)
+    int64_t start;     // first position (index into the member's record array)
+    int64_t bstart;    // the (stripe, item) bucket the run lies in: [bstart, bstart + bn)
     int32_t count;
     int32_t item;      // global item id
     float   weight;    // 1 / (units of this item in the launch * sub-warps per warp)
+    int32_t bn;
+    uint32_t bid;      // bucket id keying the per-epoch permutation
     int32_t pad;
 };
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,

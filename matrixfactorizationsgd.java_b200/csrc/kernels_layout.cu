@@ -190,32 +190,7 @@ __global__ void __launch_bounds__(256) block_scatter_global_kernel(BucketArgs b,
     }
 }
 
-// ---- in-block reshuffle: keyed Feistel bijection with cycle walking ------------------------------
-__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
-    uint32_t h = (x + key) * 0x9E3779B1u;
-    h ^= h >> 15;
-    h *= 0x85EBCA77u;
-    h ^= h >> 13;
-    return h;
-}
-// bijection on [0, n): 4-round balanced Feistel over 2*hb bits (2^(2hb) >= n), re-applied until < n.
-__device__ __forceinline__ uint64_t block_perm(uint64_t x, uint64_t n, int hb, uint64_t key) {
-    const uint32_t mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
-    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-    do {
-        uint32_t l = (uint32_t)(x >> hb) & mask, r = (uint32_t)x & mask;
-#pragma unroll
-        for (int round = 0; round < 4; round++) {
-            const uint32_t f = feistel_round(r, (round & 1) ? (k1 + round) : (k0 + round)) & mask;
-            const uint32_t nl = r;
-            r = l ^ f;
-            l = nl;
-        }
-        x = ((uint64_t)l << hb) | (uint64_t)r;
-    } while (x >= n);
-    return x;
-}
-
+// ---- in-block reshuffle (the permutation itself lives in common.cuh: the update kernels apply it on the fly) ----
 __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restrict__ in, Rec* __restrict__ out,
                                                             const int64_t* __restrict__ block_off, int nblocks,
                                                             int64_t n, uint64_t seed, uint32_t epoch,
@@ -242,13 +217,7 @@ __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restric
         const int64_t off = soff[lo];
         const uint64_t nb = (uint64_t)(soff[lo + 1] - off);
         uint64_t src = (uint64_t)(j - off);
-        if (nb > 1) {
-            int bits = 64 - __clzll((long long)(nb - 1));
-            if (bits < 2) bits = 2;
-            const int hb = (bits + 1) >> 1;
-            const uint64_t key = hash64(seed, STREAM_BLOCK_SHUFFLE, ((uint64_t)epoch << 32) | (uint64_t)(block_id_base + (uint32_t)lo));
-            src = block_perm(src, nb, hb, key);
-        }
+        if (nb > 1) src = block_perm(src, nb, perm_half_bits(nb), bucket_perm_key(seed, epoch, block_id_base + (uint32_t)lo));
         const int64_t s3 = 3 * (off + (int64_t)src);
         const int32_t a = ld_stream_i32(win + s3, pol), bb = ld_stream_i32(win + s3 + 1, pol), c = ld_stream_i32(win + s3 + 2, pol);
         st_stream_i32(wout + 3 * j, a, pol);

@@ -211,12 +211,21 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
     const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
     const uint64_t pol = l2_policy_evict_first();
 
+    // position -> record index: identity, or the block's per-epoch permutation (virtual reshuffle)
+    const bool virt = a.virt != 0 && a.blk_n > 1;
+    const int vhb = virt ? perm_half_bits((uint64_t)a.blk_n) : 0;
+    const uint64_t vkey = virt ? bucket_perm_key(a.seed, a.epoch, a.blk_id) : 0;
+    auto record_index = [&](int64_t j) -> int64_t {   // j relative to a.first
+        const int64_t pos = a.first + j;
+        return virt ? a.blk_start + (int64_t)block_perm((uint64_t)(pos - a.blk_start), (uint64_t)a.blk_n, vhb, vkey) : pos;
+    };
     int64_t tile = warp;
     int buf = 0;
     if (tile < n_tiles) {
-        const int64_t idx = tile * 32 + lane;
+        const int64_t j = tile * 32 + lane;
         int4 rec = make_int4(0, 0, 0, 0);
-        if (idx < a.n) {
+        if (j < a.n) {
+            const int64_t idx = record_index(j);
             rec.x = ld_stream_i32(words + 3 * idx, pol);
             rec.y = ld_stream_i32(words + 3 * idx + 1, pol);
             rec.z = ld_stream_i32(words + 3 * idx + 2, pol);
@@ -229,8 +238,9 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
         const int cnt = (a.n - base) < 32 ? (int)(a.n - base) : 32;
         int4 nrec = make_int4(0, 0, 0, 0);            // the warp's next tile, fetched now, parked after this tile
         {
-            const int64_t idx = (tile + n_warps) * 32 + lane;
-            if (idx < a.n) {
+            const int64_t j = (tile + n_warps) * 32 + lane;
+            if (j < a.n) {
+                const int64_t idx = record_index(j);
                 nrec.x = ld_stream_i32(words + 3 * idx, pol);
                 nrec.y = ld_stream_i32(words + 3 * idx + 1, pol);
                 nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
@@ -273,6 +283,9 @@ __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= (unsigned int)n_units) break;
         const HotUnit hu = units[unit];
+        const bool virt = a.virt != 0 && hu.bn > 1;
+        const int vhb = virt ? perm_half_bits((uint64_t)hu.bn) : 0;
+        const uint64_t vkey = virt ? bucket_perm_key(a.seed, a.epoch, hu.bid) : 0;
         float* const qrow = a.Q + (int64_t)(hu.item - a.i_base) * k + 4 * gl;
         float4 q0[VEC], q[VEC];
 #pragma unroll
@@ -284,7 +297,8 @@ __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const
             const int cnt = (hu.count - base) < 32 ? (hu.count - base) : 32;
             __syncwarp();                                   // the previous tile's readers are done with the slot
             if (lane < cnt) {
-                const int64_t idx = hu.start + base + lane;
+                const int64_t pos = hu.start + base + lane;
+                const int64_t idx = virt ? hu.bstart + (int64_t)block_perm((uint64_t)(pos - hu.bstart), (uint64_t)hu.bn, vhb, vkey) : pos;
                 srec[wic][lane] = make_int2(ld_stream_i32(words + 3 * idx, pol), ld_stream_i32(words + 3 * idx + 2, pol));
             }
             __syncwarp();
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs
     const bool act = lane < LANES;
     const int chunks = a.k >> 2;
     for (int64_t j = 0; j < a.n; j++) {
-        const Rec rec = a.recs[j];
+        const Rec rec = a.recs[a.first + j];
         float* prow = a.P + (int64_t)(rec.u - a.u_base) * a.k;
         float* qrow = a.Q + (int64_t)(rec.i - a.i_base) * a.k;
         RowPair<LANES, VEC> rp;

@@ -277,6 +277,31 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         assert not np.array_equal(e0[0], e1[0])
 
 
+def test_virtual_reshuffle_visits_the_materialised_order():
+    """The permutation the update kernels apply on the fly is the one block_shuffle_kernel materialises: with one
+    run per hot item (sequential, hence order-sensitive) an epoch trained through the virtual reshuffle must equal
+    the oracle walking the order that mfsgd_shuffle_once materialises from the same layout."""
+    n_hot, per_hot, n_cold = 4, 2500, 3001
+    n = n_hot * per_hot + n_cold
+    rng = np.random.default_rng(11)
+    items = np.concatenate([np.repeat(np.arange(n_hot), per_hot), n_hot + np.arange(n_cold)]).astype(np.int32)
+    i = items[rng.permutation(n)]
+    u = rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    ni, k = n_hot + n_cold, 128
+    cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1, hot_chunk=4096)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)                 # bucketing order inside a bucket is arbitrary: stay on this one layout
+        eng.init_factors()
+        eng.train(1)                              # epoch 0, records read through the permutation, layout untouched
+        P, Q = eng.get_factors()
+        eng.shuffle_once(0)                       # now materialise epoch 0's permutation of that same layout
+        ou, oi, orr, _ = eng.records()
+    Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+    assert np.array_equal(Q, Qo) and np.array_equal(P, Po)
+
+
 def test_synthetic_on_device_matches_oracle_split():
     nu, ni, n = 20_000, 3_000, 1_000_000
     ou, oi, or_, oh = orc.generate(SEED, 0, n, nu, ni)
@@ -308,7 +333,7 @@ def midsize():
 
 
 @pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256, 512])
-@pytest.mark.parametrize("arith", ["fast", "exact", "exact-atomic"])
+@pytest.mark.parametrize("arith", ["fast", "exact", "exact-atomic", "fast-materialized"])
 def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
     """Records with pairwise distinct users and items commute exactly, so the full-grid Hogwild kernel
     (tiles, sub-warps, prefetch, tails, blocking) must reproduce the oracle bit for bit in any order:
@@ -318,8 +343,8 @@ def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
     u = rng.permutation(n).astype(np.int32)
     i = rng.permutation(n).astype(np.int32)
     r = (1 + 4 * rng.random(n)).astype(np.float32)
-    order = orc.ORDER_WARP_TREE_FMA if arith == "fast" else orc.ORDER_WARP_TREE
-    flags = 0 if arith == "fast" else capi.FLAG_EXACT_ARITH
+    order = orc.ORDER_WARP_TREE_FMA if arith.startswith("fast") else orc.ORDER_WARP_TREE
+    flags = {"fast": 0, "fast-materialized": capi.FLAG_MATERIALIZE_SHUFFLE}.get(arith, capi.FLAG_EXACT_ARITH)
     scatter = capi.SCATTER_ATOMIC if arith == "exact-atomic" else capi.SCATTER_STORE
     P, Q = orc.factorize(u, i, r, n, n, k, 0.02, 0.03, 3, SEED, order)
     for mu, mi in ((1, 1), (3, 2)):
@@ -382,11 +407,14 @@ def test_hot_item_path_can_be_disabled(midsize):
         assert eng.layout_info().n_hot_items > 500
 
 
+@pytest.mark.parametrize("flags", [0, capi.FLAG_MATERIALIZE_SHUFFLE])
 @pytest.mark.parametrize("mu", [1, 4])
-def test_hogwild_rmse_parity(midsize, mu):
+def test_hogwild_rmse_parity(midsize, mu, flags):
+    """Default: the update kernels read every bucket through its per-epoch permutation (virtual reshuffle);
+    MFSGD_FLAG_MATERIALIZE_SHUFFLE runs the reshuffle kernel instead. Both must reach the oracle's RMSE."""
     m = midsize
     cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_HOGWILD,
-                         stripes_per_gpu=mu)
+                         stripes_per_gpu=mu, flags=flags)
     with mf.Engine(cfg) as eng:
         eng.load_ratings(*m["train"])
         eng.load_heldout(*m["held"])
