@@ -106,3 +106,22 @@ def smallblocks(wname):
 
 if len(sys.argv) > 1 and sys.argv[1] == "smallblocks":
     smallblocks(sys.argv[2])
+
+
+def stripes_sweep(wname):
+    w = mf.WORKLOADS[wname]
+    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    for stripes in (2, 3, 4, 5, 7):
+        for rounds in (1, 2, 4):
+            cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD,
+                                 stripes_per_gpu=stripes, rounds=rounds)
+            with mf.Engine(cfg) as eng:
+                eng.generate_synthetic(sp); eng.init_factors(); eng.train(1, want_stats=False)
+                st = eng.train(5)
+                rm = eng.rmse_heldout()[0]
+            ms = float(np.median([s.epoch_ms for s in st]))
+            print(json.dumps({"workload": wname, "stripes": stripes, "rounds": rounds, "epoch_ms": ms, "gupdates_s": st[0].updates / ms / 1e6, "rmse6": rm}), flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "stripes":
+    stripes_sweep(sys.argv[2])
