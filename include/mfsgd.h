@@ -86,7 +86,8 @@ typedef struct mfsgd_config {
     int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
     float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
                                   (q_i register-resident, model-averaged); 0 = default 1e-5, < 0 = off   */
-    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = default 256              */
+    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = 256 (64..256 in rings that
+                                  merge an item >= 8 times per epoch and launch small blocks)              */
     int32_t  reserved[4];
 } mfsgd_config;
 

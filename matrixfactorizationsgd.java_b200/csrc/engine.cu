@@ -755,7 +755,17 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     // Run length: a run is walked by one warp, one rating after another (only the p_u gathers are pipelined), so a
     // launch lasts at least one run; shorter runs mean more parallelism but each makes less progress on q_i before
     // the item's runs are averaged (128 already costs ~1 % RMSE on small inputs; 256 does not -- profiles/r01_experiments.md).
-    const int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 256;
+    int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 256;
+    if (h->cfg.hot_chunk <= 0 && h->G * h->mu * h->rounds >= 8) {
+        // Large rings launch small blocks: 256-rating runs then leave half the warp slots empty. An item is merged
+        // G * mu * rounds times per epoch there, which keeps shorter runs converging (8-ring, Netflix-shaped: run 64
+        // ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags) -- offer ~2 runs per resident warp, >= 64.
+        const size_t hb = (size_t)h->mu * h->IB;
+        const double hot_recs = (double)(m.block_off.back() - m.block_off[hb]);
+        const double per_launch = hot_recs / ((double)h->mu * h->rounds * h->IB);
+        const double want = per_launch / (2.0 * m.hot_grid * 8.0);
+        chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
+    }
     const int gpw = 32 / geometry_for(h->cfg.k).lanes;
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;

@@ -261,11 +261,11 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
 // unit.weight (model averaging over the item's concurrent units); a unit that is alone on its item
 // (weight 1) stores q_i outright, which makes the path exactly sequential. Units are claimed from a
 // per-launch counter so uneven runs balance themselves.
-template <int LANES, int VEC, bool FULL, bool FAST>
+template <int LANES, int VEC, bool FULL, bool FAST, int HD>
 __global__ void __launch_bounds__(256) sgd_update_hot_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
                                                              unsigned int* __restrict__ counter) {
     constexpr int GPW = 32 / LANES;
-    constexpr int HDEPTH = VEC == 1 ? 4 : 2;
+    constexpr int HDEPTH = VEC == 1 ? HD : 2;
     __shared__ int2 srec[8][32];
     const int lane = threadIdx.x & 31;
     const int wic = threadIdx.x >> 5;
@@ -428,6 +428,15 @@ static int pipeline_depth() {   // MFSGD_DEPTH = 2 | 4 (tuning aid); gathers in 
     return depth;
 }
 
+static int hot_depth() {   // MFSGD_HDEPTH = 4 | 8: p_u gathers kept in flight per run (depth - 1)
+    static int depth = 0;
+    if (depth == 0) {
+        const char* e = getenv("MFSGD_HDEPTH");
+        depth = (e && atoi(e) == 8) ? 8 : 4;
+    }
+    return depth;
+}
+
 cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fast, int grid, int min_windows,
                                       cudaStream_t stream, int* launches) {
     if (min_windows < 1) min_windows = 1;
@@ -466,9 +475,11 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     const int max_grid = (n_units + 7) / 8;   // 8 warps per CTA, one unit per warp at a time
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-#define CALL(L, V, F)                                                                                         \
-    if (fast) sgd_update_hot_kernel<L, V, F, true><<<grid, 256, 0, stream>>>(a, units, n_units, counter);     \
-    else sgd_update_hot_kernel<L, V, F, false><<<grid, 256, 0, stream>>>(a, units, n_units, counter)
+    const bool deep = hot_depth() == 8;
+#define CALL(L, V, F)                                                                                                  \
+    if (fast && deep) sgd_update_hot_kernel<L, V, F, true, 8><<<grid, 256, 0, stream>>>(a, units, n_units, counter);   \
+    else if (fast) sgd_update_hot_kernel<L, V, F, true, 4><<<grid, 256, 0, stream>>>(a, units, n_units, counter);      \
+    else sgd_update_hot_kernel<L, V, F, false, 4><<<grid, 256, 0, stream>>>(a, units, n_units, counter)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;
@@ -492,9 +503,11 @@ cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas) {
 cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas) {
     const Geometry g = geometry_for(k);
     cudaError_t err = cudaSuccess;
-#define CALL(L, V, F)                                                                                              \
-    err = fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, true>, 256, 0)     \
-               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, false>, 256, 0)
+    const bool deep = hot_depth() == 8;
+#define CALL(L, V, F)                                                                                                        \
+    err = (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, true, 8>, 256, 0)  \
+          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, true, 4>, 256, 0)          \
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hot_kernel<L, V, F, false, 4>, 256, 0)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     return err;

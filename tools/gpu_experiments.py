@@ -125,3 +125,22 @@ def stripes_sweep(wname):
 
 if len(sys.argv) > 1 and sys.argv[1] == "stripes":
     stripes_sweep(sys.argv[2])
+
+
+def ringcurve(wname, G, chunk, shards=0):
+    """Held-out RMSE per epoch of the G-member DSGD schedule (virtual ring on one GPU) for a given run length."""
+    w = mf.WORKLOADS[wname]
+    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_DSGD, n_gpus=G, hot_chunk=chunk,
+                         shards_per_gpu=shards, flags=capi.FLAG_VIRTUAL_RING)
+    with mf.Engine(cfg) as eng:
+        eng.generate_synthetic(sp); eng.init_factors(); eng.set_eval_every_epoch(True)
+        st = eng.train(w.epochs)
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_rmse_%s.json" % wname)))["heldout_rmse_per_epoch"]
+    c = [s.heldout_rmse for s in st]
+    print(json.dumps({"workload": wname, "G": G, "hot_chunk": chunk, "shards": shards, "rel_pct_vs_oracle": [round(100 * (a - b) / b, 3) for a, b in zip(c, ref)],
+                      "final": c[-1]}), flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "ringcurve":
+    ringcurve(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 0)
