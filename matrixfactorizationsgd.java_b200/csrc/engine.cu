@@ -504,6 +504,9 @@ extern "C" int mfsgd_host_free(void* p) {
 // ------------------------------------------------------------------------------------------------
 // layout: bounds, owner tables, bucketing
 // ------------------------------------------------------------------------------------------------
+// Shortest run worth a warp of the hot-item kernel (one q_i load + merge per run).
+static const int MIN_RUN = 16;
+
 static void choose_blocking(mfsgd_handle* h) {
     const mfsgd_config& c = h->cfg;
     // a multi-process ring of >= 4 pipelines the rotation over item sub-shards: two by default (send one while the next
@@ -593,14 +596,15 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 #undef CKC
     // hot items: rated by at least hot_share of the training set (and often enough to fill a warp's run)
     h->hot_items.clear();
-    const float share = c.hot_share == 0.f ? 1e-5f : c.hot_share;
+    const float share = c.hot_share == 0.f ? 1e-6f : c.hot_share;
     if (bad_host == 0 && share > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0) {
         std::vector<uint32_t> icnt_host((size_t)c.n_items);
         cudaError_t e = cudaMemcpy(icnt_host.data(), icnt, (size_t)c.n_items * 4, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { cleanup(); return fail(MFSGD_E_CUDA, "copying item counts: %s", cudaGetErrorString(e)); }
-        // An item's ratings are spread over mu * G (* rounds) visits; a run should still hold ~32 of them, or the
-        // q_i load + merge (1 KB per run) is not amortised and the item is better served by the cold kernel.
-        const double min_count = 32.0 * h->mu * h->G * (c.rounds > 0 ? c.rounds : (h->mu > 1 ? 4 : 1));
+        // An item's ratings are spread over the mu * G (sub-stripe, ring member) buckets; a run should hold >= ~16 of
+        // them, or the q_i load + merge (1 KB per run) is not amortised and the item is better served by the cold
+        // kernel. (Rounds do not enter: build_hot_units spreads a bucket over as many rounds as it has full runs for.)
+        const double min_count = (double)MIN_RUN * h->mu * h->G;
         const double thr = std::max((double)share * (double)total_train, min_count);
         std::vector<std::pair<uint32_t, int32_t>> cand;
         for (int32_t it = 0; it < c.n_items; it++)
@@ -763,10 +767,11 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
         const size_t hb = (size_t)h->mu * h->IB;
         const double hot_recs = (double)(m.block_off.back() - m.block_off[hb]);
         const double per_launch = hot_recs / ((double)h->mu * h->rounds * h->IB);
-        const double want = per_launch / (2.0 * m.hot_grid * 8.0);
+        const int runs_per_warp = (32 / geometry_for(h->cfg.k).lanes) / hot_sub_warps_per_run(h->cfg.k);
+        const double want = per_launch / (2.0 * m.hot_grid * 8.0 * runs_per_warp);
         chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
     }
-    const int gpw = 32 / geometry_for(h->cfg.k).lanes;
+    const int gpw = hot_sub_warps_per_run(h->cfg.k);
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
     for (int sa = 0; sa < h->mu; sa++)
@@ -775,15 +780,25 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                 m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib] = (int)units.size();
                 for (int hx = h->hot_block_lo[(size_t)ib]; hx < h->hot_block_lo[(size_t)ib + 1]; hx++) {
                     const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
-                    int64_t lo, hi;
-                    slice_of(m, blk, blk + 1, rnd, h->rounds, &lo, &hi);
+                    // A bucket is spread over as many of the `rounds` interleaved passes as it has runs of >= 2 * MIN_RUN
+                    // records for (frequently rated items: all of them); a small bucket is walked whole in one pass,
+                    // which one depends on the item, so the passes stay balanced.
+                    const int64_t bn = m.block_off[blk + 1] - m.block_off[blk];
+                    if (bn <= 0) continue;
+                    const int spread = (int)std::min<int64_t>(h->rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
+                    const int first = (int)(hash64(h->cfg.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)h->hot_items[(size_t)hx]) % (uint64_t)h->rounds);
+                    int slice = -1;                 // the slice of this bucket that pass `rnd` walks, if any
+                    for (int sl = 0; sl < spread; sl++)
+                        if ((first + sl * h->rounds / spread) % h->rounds == rnd) slice = sl;
+                    if (slice < 0) continue;
+                    const int64_t lo = m.block_off[blk] + bn * slice / spread, hi = m.block_off[blk] + bn * (slice + 1) / spread;
                     const int64_t n = hi - lo;
                     if (n <= 0) continue;
                     const int64_t pieces = (n + chunk - 1) / chunk;
                     for (int64_t pc = 0; pc < pieces; pc++) {
                         HotUnit u{};
                         u.bstart = m.block_off[blk];
-                        u.bn = (int32_t)(m.block_off[blk + 1] - m.block_off[blk]);
+                        u.bn = (int32_t)bn;
                         u.bid = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + blk);
                         u.start = lo + n * pc / pieces;
                         u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
@@ -792,6 +807,10 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                         units.push_back(u);
                     }
                 }
+                // longest runs first: the launch's tail is then made of short runs, and the runs a warp walks side by side
+                // (ranks below 128) have about the same length
+                std::stable_sort(units.begin() + m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib], units.end(),
+                                 [](const HotUnit& x, const HotUnit& y) { return x.count > y.count; });
             }
     m.visit_units.back() = (int)units.size();
     m.n_counters = h->mu * h->rounds * h->IB;
@@ -871,12 +890,21 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
     // (With the hot-item path a single pass ends at the same RMSE and is ~10 % faster, but the first two epochs lag badly
     // -- held-out RMSE 1.62 / 0.49 vs 0.41 / 0.40 on the Netflix-shaped set -- so the interleaving stays on.)
     if (c.rounds > 0) h->rounds = c.rounds;
-    else if (h->mu <= 1 || c.mode == MFSGD_MODE_DETERMINISTIC) h->rounds = 1;
+    else if (c.mode == MFSGD_MODE_DETERMINISTIC) h->rounds = 1;
     else {
         const Member& m0 = h->members[0];
-        const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
-        const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
-        h->rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+        int rounds = 1;
+        if (h->mu > 1) {
+            const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
+            const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
+            rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+        }
+        // The hot-item path averages the runs of an item that share a launch, so an item's factor makes sequential
+        // progress only from launch to launch: keep >= 8 launches per epoch (G * mu * rounds) while a launch still holds
+        // >= 16 K records. (A 1.8 M-rating set trained with one launch per epoch ends 1 % above the oracle's RMSE after
+        // 8 epochs; with 8 it lands on it.)
+        while (h->G * h->mu * rounds < 8 && (double)m0.n_recs / ((double)h->mu * rounds * 2) >= 16384.0) rounds *= 2;
+        h->rounds = rounds;
     }
     {
         const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1;
@@ -1296,6 +1324,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         CK(cudaEventRecord(m.ev_fork, m.stream));
                         CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
                     }
+                    bool hot_chained = false;       // the previous operation on hot_stream is a hot launch of this part
                     for (int vis = 0; vis < h->mu * h->rounds; vis++) {
                         const int rnd = vis / h->mu;
                         // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
@@ -1324,7 +1353,8 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                             a.n = m.n_recs;
                             if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
                             CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith,
-                                                     m.hot_grid, m.hot_stream, &m.launches));
+                                                     m.hot_grid, hot_chained, m.hot_stream, &m.launches));
+                            hot_chained = true;
                             m.update_launches++;
                         }
                     }

@@ -68,6 +68,9 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fas
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
 cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas);
 cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas);
+// Sub-warps that share (and average) one hot-item run at rank k: 1 where the cp.async kernel serves the rank
+// (every sub-warp walks a run of its own), else 32 / lanes.
+int hot_sub_warps_per_run(int k);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
 cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches);
 // Teacher-forced check: n independent row pairs.
@@ -87,8 +90,10 @@ struct HotUnit {
     uint32_t bid;      // bucket id keying the per-epoch permutation
     int32_t pad;
 };
+// follows_hot_launch: the previous operation on `stream` is a hot launch of the same sub-epoch (it may then be overlapped
+// by programmatic dependent launch, see kernels_update.cu).
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
-                                  int grid, cudaStream_t stream, int* launches);
+                                  int grid, bool follows_hot_launch, cudaStream_t stream, int* launches);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.

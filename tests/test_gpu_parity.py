@@ -235,7 +235,7 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         IB = G * mi
         H = info.n_hot_items
         icount = np.bincount(i, minlength=ni)
-        hot_ids = np.flatnonzero(icount >= max(np.float32(1e-5) * np.float64(n), 32.0 * mu * G * (4 if mu > 1 else 1)))   # the default rule
+        hot_ids = np.flatnonzero(icount >= max(np.float32(1e-6) * np.float64(n), 16.0 * mu * G))   # the default rule
         assert H == len(hot_ids) and H > 0
         all_keys = []
         for g in range(G):
@@ -366,11 +366,12 @@ def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
 
 
 @pytest.mark.parametrize("arith", ["fast", "exact"])
-@pytest.mark.parametrize("k", [128, 256])
+@pytest.mark.parametrize("k", [32, 64, 100, 128, 256])
 def test_hot_item_kernel_exact_sequential_runs(k, arith):
-    """Hot-item path: with one run per item (hot_chunk >= run length, one sub-warp per warp) the kernel
-    applies an item's ratings strictly in bucket order with q_i in registers -- must equal the oracle
-    bit for bit when users are pairwise distinct. Cold records (distinct items) ride along."""
+    """Hot-item path: with one run per item (hot_chunk >= run length) the kernel applies an item's ratings strictly
+    in bucket order with q_i in registers -- must equal the oracle bit for bit when users are pairwise distinct.
+    k <= 128: the cp.async kernel, every sub-warp of a warp on a run of its own (32 / 64: 4 / 2 runs side by side,
+    100: partial last chunk); 256: the register-ring kernel. Cold records (distinct items) ride along."""
     n_hot, per_hot, n_cold = 5, 3000, 5003
     n = n_hot * per_hot + n_cold
     rng = np.random.default_rng(7)
@@ -393,6 +394,50 @@ def test_hot_item_kernel_exact_sequential_runs(k, arith):
     orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE if arith == "exact" else orc.ORDER_WARP_TREE_FMA,
               shuffled=False)
     assert np.array_equal(P, Po) and np.array_equal(Q, Qo)
+
+
+@pytest.mark.parametrize("k", [16])
+def test_hot_item_kernel_sub_warp_runs_average(k):
+    """Ranks below 32 (register-ring kernel) put 32/LANES sub-warps on one run: sub-warp g walks records g, g+GPW, ... of
+    the run from the same q_i and the run merges q_i + sum_g (q_g - q_i) / GPW. P rows (pairwise distinct users) must
+    match the oracle bit for bit; Q matches up to the order of the GPW atomic adds."""
+    gpw = 32 // (k // 4)
+    n_hot, per_hot, n_cold = 5, 3001, 4099
+    n = n_hot * per_hot + n_cold
+    rng = np.random.default_rng(13)
+    items = np.concatenate([np.repeat(np.arange(n_hot), per_hot), n_hot + np.arange(n_cold)]).astype(np.int32)
+    i = items[rng.permutation(n)]
+    u = rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    ni = n_hot + n_cold
+    cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1,
+                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)
+        assert eng.layout_info().n_hot_items == n_hot
+        ou, oi, orr, off = eng.records()
+        eng.init_factors()
+        eng.train(1)
+        P, Q = eng.get_factors()
+    Po, Q0 = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    rank_in_item = np.zeros(n, dtype=np.int64)
+    for h in range(n_hot):
+        pos = np.flatnonzero(oi == h)
+        rank_in_item[pos] = np.arange(len(pos))
+    cold = oi >= n_hot
+    Qc = Q0.copy()
+    orc.train(ou[cold].copy(), oi[cold].copy(), orr[cold].copy(), Po, Qc, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+    delta = np.zeros((n_hot, k), dtype=np.float64)
+    w = np.float32(1.0 / gpw)
+    for g in range(gpw):
+        sel = ~cold & (rank_in_item % gpw == g)
+        Qg = Q0.copy()
+        orc.train(ou[sel].copy(), oi[sel].copy(), orr[sel].copy(), Po, Qg, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+        delta += ((Qg[:n_hot] - Q0[:n_hot]).astype(np.float32) * w).astype(np.float64)
+    assert np.array_equal(P, Po)
+    assert np.array_equal(Q[n_hot:], Qc[n_hot:])
+    want = Q0[:n_hot].astype(np.float64) + delta
+    assert np.max(np.abs(Q[:n_hot] - want)) < 1e-7 * gpw      # gpw binary32 roundings of values < 1
 
 
 def test_hot_item_path_can_be_disabled(midsize):

@@ -18,10 +18,23 @@ def main():
     w = wl["WORKLOADS"][name]; seed = wl["SEED"]
     epochs = int(sys.argv[2]) if len(sys.argv) > 2 else w.epochs
     t0 = time.time()
-    u, i, r, held = orc.generate(seed, 0, w.n_ratings, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
-    tu, ti, tr = u[~held].copy(), i[~held].copy(), r[~held].copy()
-    hu, hi, hr = u[held].copy(), i[held].copy(), r[held].copy()
-    del u, i, r
+    # generated in chunks straight into the train / held-out arrays: the 2 B-record shape must stay inside host RAM
+    step = 50_000_000
+    tu = np.empty(w.n_ratings, np.int32); ti = np.empty(w.n_ratings, np.int32); tr = np.empty(w.n_ratings, np.float32)
+    hus, his, hrs = [], [], []
+    nt = 0
+    for start in range(0, w.n_ratings, step):
+        u, i, r, held = orc.generate(seed, start, min(step, w.n_ratings - start), w.n_users, w.n_items,
+                                     w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+        keep = ~held
+        m = int(keep.sum())
+        tu[nt:nt + m] = u[keep]; ti[nt:nt + m] = i[keep]; tr[nt:nt + m] = r[keep]
+        nt += m
+        hus.append(u[held]); his.append(i[held]); hrs.append(r[held])
+    tu, ti, tr = tu[:nt], ti[:nt], tr[:nt]
+    hu, hi, hr = np.concatenate(hus), np.concatenate(his), np.concatenate(hrs)
+    del u, i, r, held, hus, his, hrs
+    print(name, "generated", nt, "train", len(hr), "held-out", "%.0fs" % (time.time() - t0), flush=True)
     P = orc.init_factors(w.n_users, w.k, seed, 0); Q = orc.init_factors(w.n_items, w.k, seed, 1)
     curve = []
     for ep in range(epochs):
