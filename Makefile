@@ -6,11 +6,11 @@ PKG       := matrixfactorizationsgd.java_b200
 CSRC      := $(PKG)/csrc
 OBJDIR    := build/obj
 LIB       := $(PKG)/lib/libmfsgd.so
-OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
+OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
 
 all: $(LIB) oracle harness host
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh include/mfsgd.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh $(CSRC)/update_math.cuh include/mfsgd.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

@@ -767,11 +767,10 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
         const size_t hb = (size_t)h->mu * h->IB;
         const double hot_recs = (double)(m.block_off.back() - m.block_off[hb]);
         const double per_launch = hot_recs / ((double)h->mu * h->rounds * h->IB);
-        const int runs_per_warp = (32 / geometry_for(h->cfg.k).lanes) / hot_sub_warps_per_run(h->cfg.k);
+        const int runs_per_warp = 32 / run_kernel_lanes(h->cfg.k);
         const double want = per_launch / (2.0 * m.hot_grid * 8.0 * runs_per_warp);
         chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
     }
-    const int gpw = hot_sub_warps_per_run(h->cfg.k);
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
     for (int sa = 0; sa < h->mu; sa++)
@@ -803,7 +802,7 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                         u.start = lo + n * pc / pieces;
                         u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
                         u.item = h->hot_items[(size_t)hx];
-                        u.weight = 1.0f / (float)(pieces * gpw);
+                        u.weight = 1.0f / (float)pieces;
                         units.push_back(u);
                     }
                 }

@@ -68,24 +68,23 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fas
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
 cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas);
 cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas);
-// Sub-warps that share (and average) one hot-item run at rank k: 1 where the cp.async kernel serves the rank
-// (every sub-warp walks a run of its own), else 32 / lanes.
-int hot_sub_warps_per_run(int k);
+// Lanes per rating of the run kernel at rank k (kernels_hot.cu): a warp walks 32 / lanes runs side by side.
+int run_kernel_lanes(int k);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
 cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches);
 // Teacher-forced check: n independent row pairs.
 cudaError_t launch_sgd_update_forced(int k, float lr, float lambda, int64_t n, const float* pre_p, const float* pre_q,
                                      const float* r, float* post_p, float* post_q, float* err, cudaStream_t stream);
 
-// (2b) hot-item path: one warp per unit = a run of records that all rate the same (hot) item. q_i lives in
-// the warp's registers for the whole run (no L2 round trips, no contention on the hot row); the run's net
+// (2b) run path (kernels_hot.cu): one sub-warp per unit = a run of records that all rate the same item. q_i lives in
+// the sub-warp's registers for the whole run (no L2 round trips, no contention on the row); the run's net
 // change is merged into Q at the end, scaled by `weight` (model averaging across the units of one item).
 struct HotUnit {
     int64_t start;     // first position (index into the member's record array)
     int64_t bstart;    // the (stripe, item) bucket the run lies in: [bstart, bstart + bn)
     int32_t count;
     int32_t item;      // global item id
-    float   weight;    // 1 / (units of this item in the launch * sub-warps per warp)
+    float   weight;    // 1 / (units of this item in the launch)
     int32_t bn;
     uint32_t bid;      // bucket id keying the per-epoch permutation
     int32_t pad;

@@ -1,0 +1,291 @@
+// kernels_hot.cu -- subsystem (2b): the run kernel of the SGD update path (sm_100a), the dominant kernel.
+//
+// Update rule = baseline/java/MatrixFactorizationSGD.java:89-105 (sgdUpdate). A unit is a run of records that all
+// rate one item. A LANES-wide sub-warp walks the run strictly in order with q_i in its registers: gather p_u,
+// dot, scatter p_u, update q_i -- the item row costs no L2 traffic and sees no concurrent writer inside the run.
+// At the end the run's net change is merged into Q scaled by unit.weight (model averaging over the item's
+// concurrent runs); a run that is alone on its item in the launch (weight 1) stores q_i outright, which makes
+// the path exactly sequential.
+//
+// Geometry: LANES lanes per rating, each holding VEC <= 4 float4 chunks of the row (chunk c belongs to lane c % LANES,
+// so every load/store instruction moves >= 128 contiguous bytes per sub-warp = full sectors); the warp's 32/LANES
+// sub-warps walk as many runs side by side, each strictly sequentially. Default: one chunk per lane up to k = 128
+// (one warp per rating at k = 128), never fewer than 8 lanes. Narrower sub-warps (8 lanes x 4 chunks at k = 128:
+// 3 shuffles per dot product serving 4 ratings, 28 instead of 43 warp instructions per update) were measured and
+// run no faster: the launch is bound by L2 sector throughput (profiles/r01_experiments.md section 8).
+//
+// Pipeline: the run's (u, r) pairs are staged in shared memory by cp.async two LANES-record tiles ahead (ring of
+// 4 tiles per sub-warp; under the virtual reshuffle position j of a bucket reads record bucket_start + perm(j));
+// the p_u gathers go to a D-slot register ring, D-1 steps ahead, and the pipeline runs through the whole run.
+// Steps are unrolled by D, so ring slots are compile-time; a tile (LANES steps, a multiple of D) always opens at
+// the top of an unrolled block. Units are claimed from a per-launch counter (32/LANES at a time), longest first.
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "update_math.cuh"
+
+namespace mfsgd {
+
+namespace {
+
+__device__ __forceinline__ void cp_async_4_stream(void* smem_dst, const void* gsrc, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Programmatic dependent launch: lets the next launch on the stream (if it asked for programmatic stream
+// serialisation) become resident as this grid's CTAs retire, instead of after the grid has drained. The update
+// launches of consecutive visits only ever meet Hogwild-style, so nothing waits on the other side ...
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... but a grid must not COMPLETE before the grid it was allowed to overtake: the stream's later operations (events,
+// the next sub-epoch, the Q rotation) take this grid's completion for the completion of everything before it.
+// Every thread therefore waits for the prerequisite grid as its last action (a no-op without the launch attribute).
+__device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <int LANES, int VEC, bool FULL, bool FAST, int D>
+__global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
+                                                                                 unsigned int* __restrict__ counter) {
+    constexpr int GPW = 32 / LANES;                   // runs walked side by side by one warp
+    constexpr int S = LANES;                          // steps per record tile (a sub-warp stages LANES records at a time)
+    constexpr int RING = 4 * LANES;                   // records of a run resident in shared memory (4 tiles)
+    static_assert((D & (D - 1)) == 0 && S >= D && S % D == 0, "pipeline depth");
+    __shared__ int2 srec[8][GPW][RING];               // per sub-warp: (u, r bits), record j of the run at j % RING
+    __shared__ __align__(16) float4 sq0[VEC][8][32];  // q_i as the run found it (only the merge needs it again)
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int wic = threadIdx.x >> 5;
+    const int gl = lane & (LANES - 1);
+    const int grp = lane / LANES;
+    const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;
+    const int chunks = (int)(k >> 2);
+    float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;
+    const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
+    const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
+    const uint64_t pol = l2_policy_evict_first();
+    int2* const recs = srec[wic][grp];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (;;) {
+        unsigned int first = 0;
+        if (lane == 0) first = atomicAdd(counter, (unsigned int)GPW);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= (unsigned int)n_units) break;
+        const bool has = first + (unsigned int)grp < (unsigned int)n_units;     // the sub-warp has a run of its own
+        const HotUnit hu = units[has ? first + grp : first];
+        const int count = has ? hu.count : 0;
+        const int steps = GPW == 1 ? count : __reduce_max_sync(0xffffffffu, count);   // warp-uniform trip count
+        const bool virt = a.virt != 0 && hu.bn > 1;
+        const int vhb = virt ? perm_half_bits((uint64_t)hu.bn) : 0;
+        const uint64_t vkey = virt ? bucket_perm_key(a.seed, a.epoch, hu.bid) : 0;
+        float* const qrow = a.Q + (int64_t)(hu.item - a.i_base) * k + 4 * gl;
+        float4 q[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            q[v] = (has && (FULL || gl + v * LANES < chunks)) ? ld_row4(qrow + 4 * v * LANES) : zero4;
+            sq0[v][wic][lane] = q[v];
+        }
+        auto stage_tile = [&](int tile) {               // lane gl copies (u, r) of record LANES*tile + gl of its run
+            const int j = tile * LANES + gl;
+            if (j < count) {
+                const int64_t pos = hu.start + j;
+                const int64_t idx = virt ? hu.bstart + (int64_t)block_perm((uint64_t)(pos - hu.bstart), (uint64_t)hu.bn, vhb, vkey) : pos;
+                cp_async_4_stream(&recs[j & (RING - 1)].x, words + 3 * idx, pol);
+                cp_async_4_stream(&recs[j & (RING - 1)].y, words + 3 * idx + 2, pol);
+            }
+            cp_async_commit();
+        };
+        auto gather = [&](float4 (&slot)[VEC], int t) {   // p_u of step t -> a ring slot (nothing past the run's end)
+            if (t < count) {
+                const float* xp = Pl + (int64_t)recs[t & (RING - 1)].x * k;
+#pragma unroll
+                for (int v = 0; v < VEC; v++)
+                    if (FULL || gl + v * LANES < chunks) slot[v] = ld_row4(xp + 4 * v * LANES);
+            }
+        };
+        // prologue: tiles 0 and 1 staged and visible, D-1 gathers in flight
+        stage_tile(0);
+        stage_tile(1);
+        cp_async_wait<0>();
+        __syncwarp();
+        float4 ring[D][VEC];
+#pragma unroll
+        for (int d = 0; d < D; d++)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) ring[d][v] = zero4;
+#pragma unroll
+        for (int d = 0; d < D - 1; d++) gather(ring[d], d);
+        for (int t0 = 0; t0 < steps; t0 += D) {
+            if ((t0 & (S - 1)) == 0) {                  // warp-uniform: a tile opens
+                stage_tile(t0 / S + 2);
+                cp_async_wait<1>();                     // the tile staged one tile ago has landed ...
+                __syncwarp();                           // ... and is visible to every lane of the sub-warp
+            }
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const int t = t0 + d;
+                if (t >= steps) break;                  // warp-uniform
+                gather(ring[(d + D - 1) & (D - 1)], t + D - 1);   // into the slot step t - 1 has just released
+                const int2 rec = recs[t & (RING - 1)];
+                const float e = __fsub_rn(__int_as_float(rec.y), rows_dot<LANES, VEC, FAST>(ring[d], q));
+                const float b = __fmul_rn(cf.lr, e);
+                if (t < count) {
+                    float* const cp = Pl + (int64_t)rec.x * k;
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        if (FULL || gl + v * LANES < chunks) {
+                            st_row4(cp + 4 * v * LANES, new_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                            q[v] = new_chunk<FAST>(q[v], ring[d][v], e, cf.lr, cf.lambda, cf.acoef, b);
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();                                   // every lane is done with the runs' record tiles
+        if (has) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                if (FULL || gl + v * LANES < chunks) {
+                    if (hu.weight == 1.0f) {
+                        st_row4(qrow + 4 * v * LANES, q[v]);
+                    } else {
+                        const float w = hu.weight;
+                        const float4 q0 = sq0[v][wic][lane];
+                        red_add_row4(qrow + 4 * v * LANES,
+                                     make_float4(__fmul_rn(__fsub_rn(q[v].x, q0.x), w), __fmul_rn(__fsub_rn(q[v].y, q0.y), w),
+                                                 __fmul_rn(__fsub_rn(q[v].z, q0.z), w), __fmul_rn(__fsub_rn(q[v].w, q0.w), w)));
+                    }
+                }
+            }
+        }
+    }
+    pdl_wait_prerequisites();
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// Lanes per rating of the run kernel at rank k: one float4 chunk per lane up to k = 128 (32 lanes = one warp per
+// rating there, 16 at k = 64, never fewer than 8), up to 4 chunks per lane beyond. MFSGD_HOT_LANES = 8 | 16 | 32
+// overrides it where that needs at most 4 chunks per lane (tuning aid: on the Netflix-shaped workload 8, 16 and 32
+// lanes at k = 128 run within 4 % of each other -- the launch is bound by L2 sector throughput, not by issue slots).
+Geometry run_geometry_for(int k) {
+    const int chunks = k / 4;
+    int lanes = chunks <= 8 ? 8 : (chunks <= 16 ? 16 : 32);
+    static int forced = -1;
+    if (forced < 0) forced = env_int("MFSGD_HOT_LANES", 0);
+    if ((forced == 8 || forced == 16 || forced == 32) && (chunks + forced - 1) / forced <= 4) lanes = forced;
+    Geometry g;
+    g.lanes = lanes;
+    g.vec = (chunks + lanes - 1) / lanes;
+    g.full = (lanes * g.vec == chunks);
+    return g;
+}
+
+int run_kernel_lanes(int k) { return run_geometry_for(k).lanes; }
+
+// MFSGD_HDEPTH = 2 | 4: slots of the register ring of gathered rows (depth - 1 gathers in flight per run).
+static int run_depth() {
+    static int dep = 0;
+    if (dep == 0) dep = env_int("MFSGD_HDEPTH", 4) == 2 ? 2 : 4;
+    return dep;
+}
+// MFSGD_PDL = 0: plain stream order between the run launches of consecutive visits. Default: programmatic
+// dependent launch, so a visit's first runs fill the SMs the previous visit's last runs no longer occupy.
+static int run_pdl() {
+    static int on = -1;
+    if (on < 0) on = env_int("MFSGD_PDL", 1);
+    return on;
+}
+
+// CALL(LANES, VEC, FULL) for the run geometry g
+#define MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL)                                                              \
+    do {                                                                                                  \
+        if ((g).lanes == 8) {                                                                             \
+            switch ((g).vec) {                                                                            \
+                case 1:  if ((g).full) { CALL(8, 1, true); } else { CALL(8, 1, false); } break;           \
+                case 2:  if ((g).full) { CALL(8, 2, true); } else { CALL(8, 2, false); } break;           \
+                case 3:  if ((g).full) { CALL(8, 3, true); } else { CALL(8, 3, false); } break;           \
+                default: if ((g).full) { CALL(8, 4, true); } else { CALL(8, 4, false); } break;           \
+            }                                                                                             \
+        } else if ((g).lanes == 16) {                                                                     \
+            switch ((g).vec) {                                                                            \
+                case 1:  if ((g).full) { CALL(16, 1, true); } else { CALL(16, 1, false); } break;         \
+                case 2:  if ((g).full) { CALL(16, 2, true); } else { CALL(16, 2, false); } break;         \
+                case 3:  if ((g).full) { CALL(16, 3, true); } else { CALL(16, 3, false); } break;         \
+                default: if ((g).full) { CALL(16, 4, true); } else { CALL(16, 4, false); } break;         \
+            }                                                                                             \
+        } else {                                                                                          \
+            switch ((g).vec) {                                                                            \
+                case 1:  if ((g).full) { CALL(32, 1, true); } else { CALL(32, 1, false); } break;         \
+                case 2:  if ((g).full) { CALL(32, 2, true); } else { CALL(32, 2, false); } break;         \
+                case 3:  if ((g).full) { CALL(32, 3, true); } else { CALL(32, 3, false); } break;         \
+                default: if ((g).full) { CALL(32, 4, true); } else { CALL(32, 4, false); } break;         \
+            }                                                                                             \
+        }                                                                                                 \
+    } while (0)
+
+template <typename Kernel>
+static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, bool pdl, const UpdateArgs& a, const HotUnit* units,
+                               int n_units, unsigned int* counter) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, a, units, n_units, counter);
+}
+
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
+                                  int grid, bool follows_hot_launch, cudaStream_t stream, int* launches) {
+    if (n_units <= 0) return cudaSuccess;
+    const Geometry g = run_geometry_for(a.k);
+    const int per_warp = 32 / g.lanes;            // runs a warp walks side by side
+    const int full_grid = grid;
+    // 8 warps per CTA -- and at least two waves of runs per launch: the runs of an item that are in flight together
+    // start from the same q_i and are averaged, the next wave builds on their result.
+    const int max_grid = (n_units + 16 * per_warp - 1) / (16 * per_warp);
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    // Overlap with the previous visit's launch only where it is a tail effect: both launches fill the machine (this
+    // one offers >= 2 runs per resident sub-warp), so this grid's CTAs become resident as the other's retire. Letting
+    // the small launches of a small data set all run at once makes SGD diverge (ML-100K-shaped: NaN after 4 epochs).
+    // MFSGD_PDL = 2 overlaps every chained launch (tuning aid).
+    const bool pdl = follows_hot_launch && run_pdl() != 0 && (run_pdl() == 2 || (int64_t)n_units >= 2LL * full_grid * 8 * per_warp);
+    const bool d2 = run_depth() == 2;
+    cudaError_t err = cudaSuccess;
+#define CALL(L, V, F)                                                                                                        \
+    err = (fast && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2>, grid, stream, pdl, a, units, n_units, counter)  \
+          : fast       ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4>, grid, stream, pdl, a, units, n_units, counter)  \
+                       : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4>, grid, stream, pdl, a, units, n_units, counter)
+    MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
+#undef CALL
+    if (launches) *launches += 1;
+    return err != cudaSuccess ? err : cudaGetLastError();
+}
+
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas) {
+    const Geometry g = run_geometry_for(k);
+    const bool d2 = run_depth() == 2;
+    cudaError_t err = cudaSuccess;
+#define CALL(L, V, F)                                                                                                              \
+    err = (fast && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2>, 256, 0)     \
+          : fast       ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4>, 256, 0)     \
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4>, 256, 0)
+    MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
+#undef CALL
+    const int cap = env_int("MFSGD_HOT_CTAS", 0);    // tuning aid: resident run-kernel CTAs per SM
+    if (err == cudaSuccess && cap > 0 && *ctas > cap) *ctas = cap;
+    return err;
+}
+
+}  // namespace mfsgd

@@ -81,9 +81,19 @@ static inline float dot_seq(const float* p, const float* q, int k) {
  * c = l, l+L, l+2L, ... (< k/4), ascending; then an xor butterfly over masks L/2 .. 1.
  * Not in the stand-in: it exists so the GPU's deterministic mode can be checked bit for bit.
  */
-static inline float dot_warp_tree(const float* p, const float* q, int k) {
-    int chunks = k / 4, L = 1;
+/* Lanes per rating: min(32, pow2ceil(k/4)) as in the GPU's cold / deterministic / RMSE kernels, or the value set by
+ * orc_set_tree_lanes (the GPU's run kernel, kernels_hot.cu, puts 8 lanes on a rating up to k = 128). */
+static int g_tree_lanes = 0;
+ORC_API void orc_set_tree_lanes(int lanes) { g_tree_lanes = (lanes == 8 || lanes == 16 || lanes == 32) ? lanes : 0; }
+static inline int tree_lanes(int chunks) {
+    if (g_tree_lanes > 0) return g_tree_lanes;
+    int L = 1;
     while (L < chunks && L < 32) L <<= 1;
+    return L;
+}
+
+static inline float dot_warp_tree(const float* p, const float* q, int k) {
+    const int chunks = k / 4, L = tree_lanes(chunks);
     float s[32];
     for (int l = 0; l < L; l++) {
         float acc = 0.0f;
@@ -107,8 +117,7 @@ static inline float dot_warp_tree(const float* p, const float* q, int k) {
  * stand-in: it exists so the Hogwild/DSGD kernels can be checked bit for bit on conflict-free data.
  */
 static inline float dot_warp_tree_fma(const float* p, const float* q, int k) {
-    int chunks = k / 4, L = 1;
-    while (L < chunks && L < 32) L <<= 1;
+    const int chunks = k / 4, L = tree_lanes(chunks);
     float s[32];
     for (int l = 0; l < L; l++) {
         float lo = 0.0f, hi = 0.0f;

@@ -63,10 +63,31 @@ def _load():
     lib.orc_generate.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_int, C.c_double, _i32p, _i32p, _f32p, _u8p, C.c_int]
     lib.orc_hardware_threads.restype = C.c_int
+    lib.orc_set_tree_lanes.restype = None
+    lib.orc_set_tree_lanes.argtypes = [C.c_int]
     return lib
 
 
 lib = _load()
+
+
+class tree_lanes:
+    """with tree_lanes(8): ... -- ORDER_WARP_TREE* sums with that many lanes per rating (the GPU's run kernel:
+    run_lanes(k)); outside, the default min(32, pow2ceil(k/4)) of the cold / deterministic / RMSE kernels."""
+
+    def __init__(self, lanes):
+        self.lanes = lanes
+
+    def __enter__(self):
+        lib.orc_set_tree_lanes(self.lanes)
+
+    def __exit__(self, *exc):
+        lib.orc_set_tree_lanes(0)
+
+
+def run_lanes(k):
+    """Lanes per rating of the GPU's run kernel at rank k (kernels_hot.cu run_geometry_for)."""
+    return 8 if k <= 32 else (16 if k <= 64 else 32)
 
 
 def hardware_threads():

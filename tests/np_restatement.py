@@ -60,13 +60,15 @@ def dot_seq(p, q):
     return dot
 
 
-def dot_warp_tree(p, q):
-    """DESIGN.md 4.2 summation order (not in the stand-in)."""
+def dot_warp_tree(p, q, lanes=0):
+    """DESIGN.md 4.2 summation order (not in the stand-in). lanes = 0: the cold / deterministic / RMSE kernels'
+    min(32, pow2ceil(k/4)) lanes per rating; 8 / 16 / 32: the run kernel's geometry."""
     k = len(p)
     chunks = k // 4
-    lanes = 1
-    while lanes < chunks and lanes < 32:
-        lanes *= 2
+    if lanes == 0:
+        lanes = 1
+        while lanes < chunks and lanes < 32:
+            lanes *= 2
     s = np.zeros(lanes, dtype=np.float32)
     for l in range(lanes):
         acc = np.float32(0.0)

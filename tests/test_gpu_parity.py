@@ -29,6 +29,15 @@ def assert_rmse_parity(got, want):
     assert got >= want * (1 - 0.02), (got, want)
 
 
+def train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, lr, lam, e0, e1, order):
+    """Oracle twin of a layout whose items < n_hot go through the run kernel (orc.run_lanes(k) lanes per rating) and
+    the others through the cold kernel (default lanes). Valid when the two sets share no P or Q row."""
+    hot = oi < n_hot
+    with orc.tree_lanes(orc.run_lanes(k)):
+        orc.train(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, order, shuffled=False)
+    orc.train(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, order, shuffled=False)
+
+
 def split(u, i, r, held):
     return (u[~held].copy(), i[~held].copy(), r[~held].copy()), (u[held].copy(), i[held].copy(), r[held].copy())
 
@@ -298,7 +307,7 @@ def test_virtual_reshuffle_visits_the_materialised_order():
         eng.shuffle_once(0)                       # now materialise epoch 0's permutation of that same layout
         ou, oi, orr, _ = eng.records()
     Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
-    orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+    train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, 0.01, 0.03, 0, 1, orc.ORDER_WARP_TREE_FMA)
     assert np.array_equal(Q, Qo) and np.array_equal(P, Po)
 
 
@@ -366,12 +375,12 @@ def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
 
 
 @pytest.mark.parametrize("arith", ["fast", "exact"])
-@pytest.mark.parametrize("k", [32, 64, 100, 128, 256])
+@pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 200, 256, 512])
 def test_hot_item_kernel_exact_sequential_runs(k, arith):
-    """Hot-item path: with one run per item (hot_chunk >= run length) the kernel applies an item's ratings strictly
-    in bucket order with q_i in registers -- must equal the oracle bit for bit when users are pairwise distinct.
-    k <= 128: the cp.async kernel, every sub-warp of a warp on a run of its own (32 / 64: 4 / 2 runs side by side,
-    100: partial last chunk); 256: the register-ring kernel. Cold records (distinct items) ride along."""
+    """Run path: with one run per item (hot_chunk >= run length) the kernel applies an item's ratings strictly in
+    bucket order with q_i in registers -- must equal the oracle bit for bit when users are pairwise distinct.
+    Geometries of the run kernel: 8 lanes (k = 8 with idle lanes, 32: 4 runs side by side per warp), 16 lanes (64),
+    32 lanes x 1..4 chunks (100 with a partial chunk, 128, 200, 256, 512). Cold records (distinct items) ride along."""
     n_hot, per_hot, n_cold = 5, 3000, 5003
     n = n_hot * per_hot + n_cold
     rng = np.random.default_rng(7)
@@ -391,53 +400,9 @@ def test_hot_item_kernel_exact_sequential_runs(k, arith):
         eng.train(3)
         P, Q = eng.get_factors()
     Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
-    orc.train(ou, oi, orr, Po, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE if arith == "exact" else orc.ORDER_WARP_TREE_FMA,
-              shuffled=False)
+    train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, 0.01, 0.03, 0, 3,
+                         orc.ORDER_WARP_TREE if arith == "exact" else orc.ORDER_WARP_TREE_FMA)
     assert np.array_equal(P, Po) and np.array_equal(Q, Qo)
-
-
-@pytest.mark.parametrize("k", [16])
-def test_hot_item_kernel_sub_warp_runs_average(k):
-    """Ranks below 32 (register-ring kernel) put 32/LANES sub-warps on one run: sub-warp g walks records g, g+GPW, ... of
-    the run from the same q_i and the run merges q_i + sum_g (q_g - q_i) / GPW. P rows (pairwise distinct users) must
-    match the oracle bit for bit; Q matches up to the order of the GPW atomic adds."""
-    gpw = 32 // (k // 4)
-    n_hot, per_hot, n_cold = 5, 3001, 4099
-    n = n_hot * per_hot + n_cold
-    rng = np.random.default_rng(13)
-    items = np.concatenate([np.repeat(np.arange(n_hot), per_hot), n_hot + np.arange(n_cold)]).astype(np.int32)
-    i = items[rng.permutation(n)]
-    u = rng.permutation(n).astype(np.int32)
-    r = (1 + 4 * rng.random(n)).astype(np.float32)
-    ni = n_hot + n_cold
-    cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1,
-                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE)
-    with mf.Engine(cfg) as eng:
-        eng.load_ratings(u, i, r)
-        assert eng.layout_info().n_hot_items == n_hot
-        ou, oi, orr, off = eng.records()
-        eng.init_factors()
-        eng.train(1)
-        P, Q = eng.get_factors()
-    Po, Q0 = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
-    rank_in_item = np.zeros(n, dtype=np.int64)
-    for h in range(n_hot):
-        pos = np.flatnonzero(oi == h)
-        rank_in_item[pos] = np.arange(len(pos))
-    cold = oi >= n_hot
-    Qc = Q0.copy()
-    orc.train(ou[cold].copy(), oi[cold].copy(), orr[cold].copy(), Po, Qc, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
-    delta = np.zeros((n_hot, k), dtype=np.float64)
-    w = np.float32(1.0 / gpw)
-    for g in range(gpw):
-        sel = ~cold & (rank_in_item % gpw == g)
-        Qg = Q0.copy()
-        orc.train(ou[sel].copy(), oi[sel].copy(), orr[sel].copy(), Po, Qg, 0.01, 0.03, 0, 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
-        delta += ((Qg[:n_hot] - Q0[:n_hot]).astype(np.float32) * w).astype(np.float64)
-    assert np.array_equal(P, Po)
-    assert np.array_equal(Q[n_hot:], Qc[n_hot:])
-    want = Q0[:n_hot].astype(np.float64) + delta
-    assert np.max(np.abs(Q[:n_hot] - want)) < 1e-7 * gpw      # gpw binary32 roundings of values < 1
 
 
 def test_hot_item_path_can_be_disabled(midsize):

@@ -209,3 +209,19 @@ def test_ml100k_shaped_converges_and_hogwild_matches():
     assert abs(hog - seq) / seq < 0.015            # thread interleaving varies with host load; the GPU bar (0.5 %) is tested on the GPU
     Pt, Qt = orc.factorize(tu, ti, tr, nu, ni, k, lr, lam, epochs, SEED, orc.ORDER_WARP_TREE)
     assert abs(orc.rmse(Pt, Qt, hu, hi, hr) - seq) / seq < 1e-4
+
+
+@pytest.mark.parametrize("k,lanes", [(8, 8), (32, 8), (64, 16), (100, 32), (128, 32), (512, 32)])
+def test_tree_lanes_override_matches_numpy(k, lanes):
+    """orc.tree_lanes(L): the run kernel's summation geometry (never fewer than 8 lanes per rating) -- the oracle against
+    the independent NumPy restatement, bit for bit, and back to the default geometry outside the with-block."""
+    assert orc.run_lanes(k) == lanes
+    rng = np.random.default_rng(k)
+    p = rng.standard_normal(k).astype(np.float32)
+    q = rng.standard_normal(k).astype(np.float32)
+    want = np.float32(1.5) - npr.dot_warp_tree(p, q, lanes)
+    with orc.tree_lanes(lanes):
+        e = orc.lib.orc_sgd_update(p.copy(), q.copy(), k, 1.5, 0.01, 0.05, orc.ORDER_WARP_TREE)
+    assert np.float32(e) == np.float32(want)
+    e_default = orc.lib.orc_sgd_update(p.copy(), q.copy(), k, 1.5, 0.01, 0.05, orc.ORDER_WARP_TREE)
+    assert np.float32(e_default) == np.float32(np.float32(1.5) - npr.dot_warp_tree(p, q))
