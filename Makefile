@@ -8,7 +8,7 @@ OBJDIR    := build/obj
 LIB       := $(PKG)/lib/libmfsgd.so
 OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
 
-all: $(LIB) oracle harness host
+all: $(LIB) oracle harness host tools/l2_peak
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh $(CSRC)/update_math.cuh include/mfsgd.h
 	@mkdir -p $(OBJDIR)
@@ -29,8 +29,12 @@ host: host/factorize_demo
 host/factorize_demo: host/factorize_demo.cpp host/MatrixFactorizationSGD.hpp include/mfsgd.h
 	g++ -O1 -std=c++17 -Wall -Wextra -o $@ $< -ldl
 
+# measured ceilings of the update path's access pattern (bench/profile aid, not product code)
+tools/l2_peak: tools/l2_peak.cu
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
 clean:
-	rm -rf build $(LIB) tests/c/abi_harness host/factorize_demo
+	rm -rf build $(LIB) tests/c/abi_harness host/factorize_demo tools/l2_peak
 	$(MAKE) -s -C oracle clean
 
 .PHONY: all oracle harness host clean

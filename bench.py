@@ -47,6 +47,16 @@ def recorded_traffic(workload):
     return None
 
 
+def l2_ceiling():
+    """Measured ceiling of the update path's access pattern on this pool's B200 (tools/l2_peak.cu: random 512-B row
+    gather + scatter inside an L2-resident buffer), committed as profiles/l2_peak.json; None if absent."""
+    path = os.path.join(ROOT, "profiles", "l2_peak.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
+
+
 class stdout_to_stderr:
     """Route fd 1 to fd 2 while native libraries that print banners (NCCL's version line) initialise:
     this script's stdout carries exactly one JSON line."""
@@ -221,13 +231,23 @@ def run_ours(args):
     traffic = recorded_traffic(args.workload) if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "sgd_update_hogwild_kernel + sgd_update_hot_kernel (concurrent streams, timed as one span per sub-epoch)",
+                "kernel": "sgd_update_runs_kernel (+ sgd_update_hogwild_kernel for rarely rated items; concurrent streams, timed as one span per sub-epoch)",
                 "bytes_per_update": bpu, "updates_per_step": rank_updates / args.steps,
                 "algorithmic_bytes_per_step": rank_updates * bpu / args.steps,
                 "update_phase_ms_per_step": kernel_ms / args.steps, "update_launches_per_step": n_launch / args.steps,
                 "kernel_share_of_step": kernel_ms / max(dev_ms, 1e-9), "frac_of_nominal_8TBs": achieved / 8000.0,
-                "note": "frac > 1 is expected: the P sub-stripe and Q stay L2-resident (stratified blocks) and hot q_i rows "
-                        "live in registers, so DRAM traffic (see traffic) is a small fraction of the algorithmic bytes"}
+                "note": "frac > 1 is expected: the P sub-stripe and Q stay L2-resident (stratified blocks) and q_i rows "
+                        "live in registers for a whole run, so DRAM traffic (see traffic) is a small fraction of the algorithmic "
+                        "bytes; the binding resource is L2 sector throughput (see l2_bound)"}
+    l2 = l2_ceiling()
+    if l2 is not None and w.k == 128:
+        # what an update of the run kernel moves through L2: p_u read + written (2 x 4k B) and its record (two 32-B sectors)
+        l2_bytes = 8 * w.k + 64
+        l2_achieved = rank_updates * l2_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        roofline["l2_bound"] = {"achieved": l2_achieved, "peak": l2["row_gather_scatter_gbs"], "unit": "GB/s",
+                                "frac": l2_achieved / l2["row_gather_scatter_gbs"], "l2_bytes_per_update": l2_bytes,
+                                "peak_source": "measured: tools/l2_peak.cu on this pool's B200 (profiles/l2_peak.json), random 512-B "
+                                               "row gather + scatter in an L2-resident buffer, no arithmetic"}
 
     # e2e: the reference-facing call with HOST buffers: H2D + bucketing + init + K epochs + D2H of P, Q
     e2e = None

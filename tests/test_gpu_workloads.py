@@ -42,6 +42,25 @@ def test_hogwild_reaches_oracle_rmse_at_equal_epochs(name):
         assert curve[e] <= want[e] * 1.01, (e, curve[e], want[e])
 
 
+def test_ml100k_shaped_hogwild_close_to_oracle():
+    """configs[0] (the reference's own CPU-sized case) through the full-grid Hogwild path. 90 K ratings are far fewer than
+    the ratings a B200 keeps in flight, so parallel SGD trails the sequential oracle in the first epochs; after the
+    workload's 20 epochs it is within 1 % (measured +0.4 %). The 0.5 % bar of the north star is held on the ML-20M- and
+    Netflix-shaped workloads above; bit-level parity on this config is the deterministic mode's job (test_gpu_parity.py)."""
+    w = mf.WORKLOADS["ml100k"]
+    ref = oracle_curve("ml100k")
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
+    with mf.Engine(cfg) as eng:
+        nt, nh = eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user,
+                                                        w.log2_alpha_item, w.c_item))
+        assert (nt, nh) == (ref["n_train"], ref["n_heldout"])
+        eng.init_factors()
+        eng.train(w.epochs, want_stats=False)
+        got = eng.rmse_heldout()[0]
+    want = ref["heldout_rmse_per_epoch"][-1]
+    assert np.isfinite(got) and got <= want * 1.01 and got >= want * 0.98, (got, want)
+
+
 def test_dsgd_virtual_ring_netflix_shaped_reaches_oracle_rmse():
     """The 8-member DSGD schedule (virtual ring on one GPU) on the full Netflix-shaped workload."""
     w = mf.WORKLOADS["netflix"]
