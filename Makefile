@@ -6,13 +6,17 @@ PKG       := matrixfactorizationsgd.java_b200
 CSRC      := $(PKG)/csrc
 OBJDIR    := build/obj
 LIB       := $(PKG)/lib/libmfsgd.so
-OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o
+OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o $(OBJDIR)/ratings_io.o
 
 all: $(LIB) oracle harness host tools/l2_peak
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh $(CSRC)/update_math.cuh include/mfsgd.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/ratings_io.o: $(CSRC)/ratings_io.cpp include/mfsgd.h
+	@mkdir -p $(OBJDIR)
+	g++ -O2 -std=c++17 -Wall -Wextra -fPIC -fvisibility=hidden -c $< -o $@
 
 $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib

@@ -34,6 +34,8 @@ public:
         bind(load_ratings_, "mfsgd_load_ratings");
         bind(set_factors_, "mfsgd_set_factors");
         bind(rmse_, "mfsgd_rmse");
+        bind(read_ratings_, "mfsgd_read_ratings");
+        bind(free_ratings_, "mfsgd_free_ratings");
     }
     ~MatrixFactorizationSGD() {
         if (lib_) dlclose(lib_);
@@ -51,6 +53,29 @@ public:
         mfsgd_config cfg = config(nUsers, nItems, k, lr, lambda, seed, mode, n_gpus);
         Factors f{std::vector<float>((size_t)nUsers * k), std::vector<float>((size_t)nItems * k), nUsers, nItems, k};
         check(factorize_(users.data(), items.data(), ratings.data(), (int64_t)ratings.size(), &cfg, epochs, f.P.data(), f.Q.data()));
+        return f;
+    }
+
+    // A ratings file (MovieLens u.data / ratings.csv / ratings.dat, Netflix-Prize text) as the triplets factorize takes;
+    // userIds[u] / itemIds[i] give the file's id of dense row u / i. Host-only (mfsgd_read_ratings).
+    struct RatingsFile {
+        std::vector<int32_t> users, items;
+        std::vector<float> ratings;
+        std::vector<int64_t> userIds, itemIds;
+        int nUsers = 0, nItems = 0;
+    };
+    RatingsFile readRatings(const std::string& path, int format = MFSGD_FORMAT_AUTO) const {
+        mfsgd_ratings r;
+        check(read_ratings_(path.c_str(), format, &r));
+        RatingsFile f;
+        f.users.assign(r.users, r.users + r.n);
+        f.items.assign(r.items, r.items + r.n);
+        f.ratings.assign(r.ratings, r.ratings + r.n);
+        f.userIds.assign(r.user_ids, r.user_ids + r.n_users);
+        f.itemIds.assign(r.item_ids, r.item_ids + r.n_items);
+        f.nUsers = r.n_users;
+        f.nItems = r.n_items;
+        free_ratings_(&r);
         return f;
     }
 
@@ -95,4 +120,6 @@ private:
     int (*load_ratings_)(mfsgd_handle*, const int32_t*, const int32_t*, const float*, int64_t) = nullptr;
     int (*set_factors_)(mfsgd_handle*, const float*, const float*) = nullptr;
     int (*rmse_)(mfsgd_handle*, const int32_t*, const int32_t*, const float*, int64_t, double*) = nullptr;
+    int (*read_ratings_)(const char*, int32_t, mfsgd_ratings*) = nullptr;
+    void (*free_ratings_)(mfsgd_ratings*) = nullptr;
 };

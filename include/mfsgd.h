@@ -83,10 +83,12 @@ typedef struct mfsgd_config {
     int32_t  rank;             /* ring member driven by this process when world_size == n_gpus       */
     uint8_t  nccl_id[128];     /* world_size > 1: ncclUniqueId from mfsgd_nccl_unique_id() of rank 0 */
     int32_t  ctas_per_sm;      /* 0 = auto; update-kernel CTAs per SM (tuning aid)                   */
-    int32_t  rounds;           /* 0 = auto; each sub-epoch visits its P sub-stripes in `rounds` interleaved passes */
-    float    hot_share;        /* items rated by >= this share of the training set take the hot-item path
-                                  (q_i register-resident, model-averaged); 0 = default 1e-5, < 0 = off   */
-    int32_t  hot_chunk;        /* max records per hot-item unit (one warp); 0 = 256 (64..256 in rings that
+    int32_t  rounds;           /* 0 = auto (>= 8 launches per epoch where the data allows); each sub-epoch visits its
+                                  P sub-stripes in `rounds` interleaved passes */
+    float    hot_share;        /* items rated by >= this share of the training set -- and by >= 16 ratings per
+                                  (sub-stripe, ring member) bucket -- take the run path (q_i register-resident for a
+                                  run of its ratings, model-averaged over concurrent runs); 0 = default 1e-6, < 0 = off */
+    int32_t  hot_chunk;        /* max records per run (one sub-warp); 0 = 256 (64..256 in rings that
                                   merge an item >= 8 times per epoch and launch small blocks)              */
     int32_t  reserved[4];
 } mfsgd_config;
@@ -104,7 +106,7 @@ typedef struct mfsgd_epoch_stats {
     double  heldout_rmse;       /* NaN unless a held-out set is loaded and eval_every_epoch is on     */
     /* MFSGD_FLAG_TIME_KERNELS breakdown, summed over the epoch's sub-epochs (the two kernels overlap): */
     double  cold_ms;            /* fork -> last cold (full-grid) launch done                          */
-    double  hot_ms;             /* fork -> last hot-item launch done                                  */
+    double  hot_ms;             /* fork -> last run-kernel launch done                                */
     double  exchange_ms;        /* join -> Q rotation enqueued on the compute stream done (NCCL path) */
 } mfsgd_epoch_stats;
 
@@ -128,7 +130,7 @@ typedef struct mfsgd_layout_info {
     int64_t n_heldout_local;
     int64_t n_train_total;      /* records in the whole data set (all processes)                     */
     int32_t rounds;             /* interleaved passes per sub-epoch (see mfsgd_config.rounds)        */
-    int32_t n_hot_items;        /* items on the hot-item path (whole data set)                       */
+    int32_t n_hot_items;        /* items on the run path (whole data set)                            */
 } mfsgd_layout_info;
 
 MFSGD_API int  mfsgd_abi_version(void);
@@ -196,6 +198,27 @@ MFSGD_API int  mfsgd_generate_to_host(int32_t device, const mfsgd_synth_params* 
 /* Multi-process ring bootstrap: rank 0 calls this, ships the 128 bytes to every rank (any channel),
  * every rank puts them in mfsgd_config.nccl_id. */
 MFSGD_API int  mfsgd_nccl_unique_id(uint8_t out[128]);
+
+/* Ratings-file ingest: text file -> the triplet arrays of mfsgd_load_ratings / mfsgd_factorize, sparse file
+ * ids compacted to dense rows (ascending file id). Host-only: works without a GPU. */
+#define MFSGD_FORMAT_AUTO          0 /* NETFLIX_PRIZE if the first data line is "<digits>:", else TRIPLETS           */
+#define MFSGD_FORMAT_TRIPLETS      1 /* "user item rating [...]" per line; separators tab blank , ; : | (MovieLens u.data,
+                                        ratings.csv with its header line, ratings.dat with "::"); non-numeric lines skipped */
+#define MFSGD_FORMAT_NETFLIX_PRIZE 2 /* "movie:" lines, each followed by its "customer,rating[,date]" lines              */
+typedef struct mfsgd_ratings {
+    int32_t* users;      /* n dense user rows                                   (library-owned: mfsgd_free_ratings)   */
+    int32_t* items;      /* n dense item rows                                                                         */
+    float*   ratings;    /* n ratings                                                                                 */
+    int64_t  n;
+    int32_t  n_users;    /* distinct users = rows of P                                                                */
+    int32_t  n_items;    /* distinct items = rows of Q                                                                */
+    int64_t* user_ids;   /* n_users: dense row -> id in the file (ascending)                                          */
+    int64_t* item_ids;   /* n_items                                                                                   */
+    int32_t  format;     /* the format that was parsed (AUTO resolved)                                                */
+    int32_t  reserved;
+} mfsgd_ratings;
+MFSGD_API int  mfsgd_read_ratings(const char* path, int32_t format, mfsgd_ratings* out);
+MFSGD_API void mfsgd_free_ratings(mfsgd_ratings* r);
 
 /* Pinned host staging helpers (optional; plain host memory works too, at lower H2D bandwidth). */
 MFSGD_API int  mfsgd_host_alloc(void** out, int64_t bytes);

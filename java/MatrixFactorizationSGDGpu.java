@@ -73,6 +73,47 @@ public final class MatrixFactorizationSGDGpu {
     private static final MethodHandle GET_FACTORS = down("mfsgd_get_factors", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle RMSE = down("mfsgd_rmse", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
 
+    private static final MethodHandle READ_RATINGS = down("mfsgd_read_ratings", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle FREE_RATINGS = down("mfsgd_free_ratings", FunctionDescriptor.ofVoid(ADDRESS));
+
+    /** A parsed ratings file: dense triplets for factorize plus the file's id of every dense row. */
+    public static final class RatingsFile {
+        public int[] users, items;
+        public float[] ratings;
+        public long[] userIds, itemIds;
+        public int nUsers, nItems;
+    }
+
+    /**
+     * mfsgd_read_ratings: MovieLens u.data / ratings.csv / ratings.dat or Netflix-Prize text (format 0 = detect)
+     * into the triplet arrays factorize takes. struct mfsgd_ratings (include/mfsgd.h, 64 bytes): users@0 items@8
+     * ratings@16 (pointers), n@24 (int64), n_users@32, n_items@36 (int32), user_ids@40, item_ids@48 (pointers).
+     */
+    public static RatingsFile readRatings(String path, int format) {
+        try (Arena arena = Arena.ofConfined()) {
+            MemorySegment out = arena.allocate(64, 8);
+            check((int) READ_RATINGS.invokeExact(arena.allocateFrom(path), format, out));
+            try {
+                RatingsFile f = new RatingsFile();
+                final long n = out.get(JAVA_LONG, 24);
+                f.nUsers = out.get(JAVA_INT, 32);
+                f.nItems = out.get(JAVA_INT, 36);
+                f.users = out.get(ADDRESS, 0).reinterpret(4 * n).toArray(JAVA_INT);
+                f.items = out.get(ADDRESS, 8).reinterpret(4 * n).toArray(JAVA_INT);
+                f.ratings = out.get(ADDRESS, 16).reinterpret(4 * n).toArray(JAVA_FLOAT);
+                f.userIds = out.get(ADDRESS, 40).reinterpret(8L * f.nUsers).toArray(JAVA_LONG);
+                f.itemIds = out.get(ADDRESS, 48).reinterpret(8L * f.nItems).toArray(JAVA_LONG);
+                return f;
+            } finally {
+                FREE_RATINGS.invokeExact(out);
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
     private static void check(int rc) throws Throwable {
         if (rc != 0) {
             MemorySegment msg = ((MemorySegment) LAST_ERROR.invokeExact()).reinterpret(512);

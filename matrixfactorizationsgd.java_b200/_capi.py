@@ -46,6 +46,14 @@ class LayoutInfo(C.Structure):
                 ("n_hot_items", C.c_int32)]
 
 
+class Ratings(C.Structure):
+    _fields_ = [("users", C.POINTER(C.c_int32)), ("items", C.POINTER(C.c_int32)), ("ratings", C.POINTER(C.c_float)),
+                ("n", C.c_int64), ("n_users", C.c_int32), ("n_items", C.c_int32), ("user_ids", C.POINTER(C.c_int64)),
+                ("item_ids", C.POINTER(C.c_int64)), ("format", C.c_int32), ("reserved", C.c_int32)]
+
+
+FORMAT_AUTO, FORMAT_TRIPLETS, FORMAT_NETFLIX_PRIZE = 0, 1, 2
+
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes): every symbol include/mfsgd.h declares
@@ -56,6 +64,8 @@ SIGNATURES = {
     "mfsgd_config_default": (C.c_int, [C.POINTER(Config)]),
     "mfsgd_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
     "mfsgd_destroy": (None, [_vp]),
+    "mfsgd_read_ratings": (C.c_int, [C.c_char_p, _i32, C.POINTER(Ratings)]),
+    "mfsgd_free_ratings": (None, [C.POINTER(Ratings)]),
     "mfsgd_load_ratings": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
     "mfsgd_load_heldout": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
     "mfsgd_generate_synthetic": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -35,6 +35,17 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+namespace mfsgd {
+// the same message slot for the library's other translation units (ratings_io.cpp)
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace mfsgd
+
 #define CK(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
@@ -773,27 +784,27 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     }
     const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
-    for (int sa = 0; sa < h->mu; sa++)
-        for (int rnd = 0; rnd < h->rounds; rnd++)
-            for (int ib = 0; ib < h->IB; ib++) {
-                m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib] = (int)units.size();
-                for (int hx = h->hot_block_lo[(size_t)ib]; hx < h->hot_block_lo[(size_t)ib + 1]; hx++) {
-                    const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
-                    // A bucket is spread over as many of the `rounds` interleaved passes as it has runs of >= 2 * MIN_RUN
-                    // records for (frequently rated items: all of them); a small bucket is walked whole in one pass,
-                    // which one depends on the item, so the passes stay balanced.
-                    const int64_t bn = m.block_off[blk + 1] - m.block_off[blk];
-                    if (bn <= 0) continue;
-                    const int spread = (int)std::min<int64_t>(h->rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
-                    const int first = (int)(hash64(h->cfg.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)h->hot_items[(size_t)hx]) % (uint64_t)h->rounds);
-                    int slice = -1;                 // the slice of this bucket that pass `rnd` walks, if any
-                    for (int sl = 0; sl < spread; sl++)
-                        if ((first + sl * h->rounds / spread) % h->rounds == rnd) slice = sl;
-                    if (slice < 0) continue;
-                    const int64_t lo = m.block_off[blk] + bn * slice / spread, hi = m.block_off[blk] + bn * (slice + 1) / spread;
+    units.reserve((size_t)((m.block_off.back() - m.block_off[hot_base]) / chunk) + (size_t)h->mu * h->H + 16);
+    std::vector<std::vector<HotUnit>> seg((size_t)h->rounds * h->IB);       // the (round, item block) segments of one sub-stripe
+    for (int sa = 0; sa < h->mu; sa++) {
+        for (auto& v : seg) v.clear();
+        for (int ib = 0; ib < h->IB; ib++)
+            for (int hx = h->hot_block_lo[(size_t)ib]; hx < h->hot_block_lo[(size_t)ib + 1]; hx++) {
+                const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
+                // A bucket is spread over as many of the `rounds` interleaved passes as it has runs of >= 2 * MIN_RUN
+                // records for (frequently rated items: all of them); a small bucket is walked whole in one pass,
+                // which one depends on the item, so the passes stay balanced.
+                const int64_t bn = m.block_off[blk + 1] - m.block_off[blk];
+                if (bn <= 0) continue;
+                const int spread = (int)std::min<int64_t>(h->rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
+                const int first = (int)(hash64(h->cfg.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)h->hot_items[(size_t)hx]) % (uint64_t)h->rounds);
+                for (int sl = 0; sl < spread; sl++) {
+                    const int rnd = (first + sl * h->rounds / spread) % h->rounds;     // distinct for distinct sl (spread <= rounds)
+                    const int64_t lo = m.block_off[blk] + bn * sl / spread, hi = m.block_off[blk] + bn * (sl + 1) / spread;
                     const int64_t n = hi - lo;
                     if (n <= 0) continue;
                     const int64_t pieces = (n + chunk - 1) / chunk;
+                    std::vector<HotUnit>& out = seg[(size_t)rnd * h->IB + ib];
                     for (int64_t pc = 0; pc < pieces; pc++) {
                         HotUnit u{};
                         u.bstart = m.block_off[blk];
@@ -803,14 +814,20 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
                         u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
                         u.item = h->hot_items[(size_t)hx];
                         u.weight = 1.0f / (float)pieces;
-                        units.push_back(u);
+                        out.push_back(u);
                     }
                 }
+            }
+        for (int rnd = 0; rnd < h->rounds; rnd++)
+            for (int ib = 0; ib < h->IB; ib++) {
+                std::vector<HotUnit>& v = seg[(size_t)rnd * h->IB + ib];
                 // longest runs first: the launch's tail is then made of short runs, and the runs a warp walks side by side
                 // (ranks below 128) have about the same length
-                std::stable_sort(units.begin() + m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib], units.end(),
-                                 [](const HotUnit& x, const HotUnit& y) { return x.count > y.count; });
+                std::stable_sort(v.begin(), v.end(), [](const HotUnit& x, const HotUnit& y) { return x.count > y.count; });
+                m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib] = (int)units.size();
+                units.insert(units.end(), v.begin(), v.end());
             }
+    }
     m.visit_units.back() = (int)units.size();
     m.n_counters = h->mu * h->rounds * h->IB;
     CK(dev_alloc(&m.d_units, units.size()));

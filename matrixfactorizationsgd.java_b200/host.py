@@ -17,6 +17,22 @@ from . import _capi as capi
 from .engine import Engine, make_config
 
 Factors = namedtuple("Factors", ["P", "Q", "nUsers", "nItems", "k"])
+#: a parsed ratings file: dense triplets + the file ids of every row (RatingsFile.userIds[u] is the file's id of row u)
+RatingsFile = namedtuple("RatingsFile", ["users", "items", "ratings", "nUsers", "nItems", "userIds", "itemIds", "format"])
+
+
+def read_ratings(path, format=capi.FORMAT_AUTO):
+    """mfsgd_read_ratings: MovieLens u.data / ratings.csv / ratings.dat or Netflix-Prize text -> RatingsFile
+    (copies of the library's buffers; ids compacted in ascending file-id order). Host-only, needs no GPU."""
+    out = capi.Ratings()
+    capi.check(capi.lib.mfsgd_read_ratings(str(path).encode(), int(format), C.byref(out)))
+    try:
+        n, nu, ni = out.n, out.n_users, out.n_items
+        grab = lambda p, m, dt: (np.ctypeslib.as_array(p, shape=(m,)).astype(dt, copy=True) if m > 0 else np.empty(0, dt))
+        return RatingsFile(grab(out.users, n, np.int32), grab(out.items, n, np.int32), grab(out.ratings, n, np.float32), nu, ni,
+                           grab(out.user_ids, nu, np.int64), grab(out.item_ids, ni, np.int64), out.format)
+    finally:
+        capi.lib.mfsgd_free_ratings(C.byref(out))
 
 
 class MatrixFactorizationSGD:

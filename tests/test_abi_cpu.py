@@ -42,6 +42,7 @@ def test_struct_sizes_match_c_layout():
     assert C.sizeof(capi.EpochStats) == 72
     assert C.sizeof(capi.SynthParams) == 40
     assert C.sizeof(capi.LayoutInfo) == 56
+    assert C.sizeof(capi.Ratings) == 64 and capi.Ratings.n.offset == 24 and capi.Ratings.user_ids.offset == 40
 
 
 def test_c_harness_dlopen_dlsym():
