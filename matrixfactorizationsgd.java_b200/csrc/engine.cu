@@ -774,12 +774,13 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     if (h->cfg.hot_chunk <= 0 && h->G * h->mu * h->rounds >= 8) {
         // Large rings launch small blocks: 256-rating runs then leave half the warp slots empty. An item is merged
         // G * mu * rounds times per epoch there, which keeps shorter runs converging (8-ring, Netflix-shaped: run 64
-        // ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags) -- offer ~2 runs per resident warp, >= 64.
+        // ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags) -- offer ~3 runs per resident sub-warp, >= 64
+        // (8-ring proxy, 0.7 M-rating launches: run 64 -> 1.34 ms per epoch, 96 -> 1.42, 128 -> 1.40, 192 -> 1.65, 256 -> 1.98).
         const size_t hb = (size_t)h->mu * h->IB;
         const double hot_recs = (double)(m.block_off.back() - m.block_off[hb]);
         const double per_launch = hot_recs / ((double)h->mu * h->rounds * h->IB);
         const int runs_per_warp = 32 / run_kernel_lanes(h->cfg.k);
-        const double want = per_launch / (2.0 * m.hot_grid * 8.0 * runs_per_warp);
+        const double want = per_launch / (3.0 * m.hot_grid * 8.0 * runs_per_warp);
         chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
     }
     const size_t hot_base = (size_t)h->mu * h->IB;

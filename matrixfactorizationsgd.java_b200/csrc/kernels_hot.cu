@@ -258,7 +258,9 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     if (grid < 1) grid = 1;
     // Overlap with the previous visit's launch only where it is a tail effect: both launches fill the machine (this
     // one offers >= 2 runs per resident sub-warp), so this grid's CTAs become resident as the other's retire. Letting
-    // the small launches of a small data set all run at once makes SGD diverge (ML-100K-shaped: NaN after 4 epochs).
+    // the small launches of a small data set all run at once makes SGD diverge (ML-100K-shaped: NaN after 4 epochs):
+    // with a whole epoch in flight p_u and q_i are both corrected from the same stale state and the product overshoots
+    // (profiles/r01_experiments.md section 8).
     // MFSGD_PDL = 2 overlaps every chained launch (tuning aid).
     const bool pdl = follows_hot_launch && run_pdl() != 0 && (run_pdl() == 2 || (int64_t)n_units >= 2LL * full_grid * 8 * per_warp);
     const bool d2 = run_depth() == 2;
