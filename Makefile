@@ -10,7 +10,7 @@ OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot
 
 all: $(LIB) oracle harness host tools/l2_peak
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh $(CSRC)/update_math.cuh include/mfsgd.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.cuh $(CSRC)/update_math.cuh $(CSRC)/run_plan.hpp include/mfsgd.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

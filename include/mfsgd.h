@@ -186,6 +186,14 @@ MFSGD_API int  mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs,
 /* Runs the reshuffle kernel once for `epoch` (HOGWILD/DSGD) or the stand-in order sort (DETERMINISTIC). */
 MFSGD_API int  mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch);
 
+/* Test hook, host-only: plans the run kernel's work for caller-provided bucket offsets (csrc/run_plan.hpp).
+ * block_off[stripes * (item_blocks + n_hot) + 1] as mfsgd_get_records reports them; *n_units: in = slots in the
+ * unit_* arrays (each nullable), out = runs planned; visit_units[stripes * rounds * item_blocks + 1]. */
+MFSGD_API int  mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks,
+                     const int32_t* hot_block_lo, const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed,
+                     int32_t member, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
+                     int64_t* n_units, int32_t* visit_units);
+
 /* Teacher-forced per-update check: applies the update rule to n independent
  * (pre_p[j], pre_q[j], r[j]) row pairs on the device, returns post rows and errors. Host pointers. */
 MFSGD_API int  mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,

@@ -19,6 +19,7 @@
 
 #include "../../include/mfsgd.h"
 #include "kernels.cuh"
+#include "run_plan.hpp"
 
 using namespace mfsgd;
 
@@ -515,9 +516,6 @@ extern "C" int mfsgd_host_free(void* p) {
 // ------------------------------------------------------------------------------------------------
 // layout: bounds, owner tables, bucketing
 // ------------------------------------------------------------------------------------------------
-// Shortest run worth a warp of the hot-item kernel (one q_i load + merge per run).
-static const int MIN_RUN = 16;
-
 static void choose_blocking(mfsgd_handle* h) {
     const mfsgd_config& c = h->cfg;
     // a multi-process ring of >= 4 pipelines the rotation over item sub-shards: two by default (send one while the next
@@ -783,53 +781,16 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
         const double want = per_launch / (3.0 * m.hot_grid * 8.0 * runs_per_warp);
         chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
     }
-    const size_t hot_base = (size_t)h->mu * h->IB;
     std::vector<HotUnit> units;
-    units.reserve((size_t)((m.block_off.back() - m.block_off[hot_base]) / chunk) + (size_t)h->mu * h->H + 16);
-    std::vector<std::vector<HotUnit>> seg((size_t)h->rounds * h->IB);       // the (round, item block) segments of one sub-stripe
-    for (int sa = 0; sa < h->mu; sa++) {
-        for (auto& v : seg) v.clear();
-        for (int ib = 0; ib < h->IB; ib++)
-            for (int hx = h->hot_block_lo[(size_t)ib]; hx < h->hot_block_lo[(size_t)ib + 1]; hx++) {
-                const size_t blk = hot_base + (size_t)sa * h->H + (size_t)hx;
-                // A bucket is spread over as many of the `rounds` interleaved passes as it has runs of >= 2 * MIN_RUN
-                // records for (frequently rated items: all of them); a small bucket is walked whole in one pass,
-                // which one depends on the item, so the passes stay balanced.
-                const int64_t bn = m.block_off[blk + 1] - m.block_off[blk];
-                if (bn <= 0) continue;
-                const int spread = (int)std::min<int64_t>(h->rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
-                const int first = (int)(hash64(h->cfg.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)h->hot_items[(size_t)hx]) % (uint64_t)h->rounds);
-                for (int sl = 0; sl < spread; sl++) {
-                    const int rnd = (first + sl * h->rounds / spread) % h->rounds;     // distinct for distinct sl (spread <= rounds)
-                    const int64_t lo = m.block_off[blk] + bn * sl / spread, hi = m.block_off[blk] + bn * (sl + 1) / spread;
-                    const int64_t n = hi - lo;
-                    if (n <= 0) continue;
-                    const int64_t pieces = (n + chunk - 1) / chunk;
-                    std::vector<HotUnit>& out = seg[(size_t)rnd * h->IB + ib];
-                    for (int64_t pc = 0; pc < pieces; pc++) {
-                        HotUnit u{};
-                        u.bstart = m.block_off[blk];
-                        u.bn = (int32_t)bn;
-                        u.bid = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + blk);
-                        u.start = lo + n * pc / pieces;
-                        u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
-                        u.item = h->hot_items[(size_t)hx];
-                        u.weight = 1.0f / (float)pieces;
-                        out.push_back(u);
-                    }
-                }
-            }
-        for (int rnd = 0; rnd < h->rounds; rnd++)
-            for (int ib = 0; ib < h->IB; ib++) {
-                std::vector<HotUnit>& v = seg[(size_t)rnd * h->IB + ib];
-                // longest runs first: the launch's tail is then made of short runs, and the runs a warp walks side by side
-                // (ranks below 128) have about the same length
-                std::stable_sort(v.begin(), v.end(), [](const HotUnit& x, const HotUnit& y) { return x.count > y.count; });
-                m.visit_units[((size_t)sa * h->rounds + rnd) * h->IB + ib] = (int)units.size();
-                units.insert(units.end(), v.begin(), v.end());
-            }
-    }
-    m.visit_units.back() = (int)units.size();
+    RunPlanArgs pa{};
+    pa.block_off = m.block_off.data();
+    pa.n_blocks = m.block_off.size() - 1;
+    pa.mu = h->mu; pa.H = h->H; pa.IB = h->IB; pa.rounds = h->rounds; pa.chunk = chunk;
+    pa.member = m.g;
+    pa.seed = h->cfg.seed;
+    pa.hot_block_lo = h->hot_block_lo.data();
+    pa.hot_items = h->hot_items.data();
+    plan_runs(pa, units, m.visit_units);
     m.n_counters = h->mu * h->rounds * h->IB;
     CK(dev_alloc(&m.d_units, units.size()));
     CK(dev_alloc(&m.d_counters, (size_t)m.n_counters));
@@ -1599,6 +1560,37 @@ extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const
 // ------------------------------------------------------------------------------------------------
 // introspection + test hooks
 // ------------------------------------------------------------------------------------------------
+// Test hook: the run planner (run_plan.hpp) on caller-provided bucket offsets. Host-only.
+extern "C" int mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
+                               const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,
+                               int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight, int64_t* n_units,
+                               int32_t* visit_units) {
+    if (!block_off || !hot_block_lo || (n_hot > 0 && !hot_items) || !n_units || !visit_units) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (stripes < 1 || n_hot < 0 || item_blocks < 1 || rounds < 1 || chunk < 1 || member < 0) return fail(MFSGD_E_INVALID_ARG, "bad shape");
+    RunPlanArgs pa{};
+    pa.block_off = block_off;
+    pa.n_blocks = (size_t)stripes * ((size_t)item_blocks + (size_t)n_hot);
+    pa.mu = stripes; pa.H = n_hot; pa.IB = item_blocks; pa.rounds = rounds; pa.chunk = chunk;
+    pa.member = member;
+    pa.seed = seed;
+    pa.hot_block_lo = hot_block_lo;
+    pa.hot_items = hot_items;
+    std::vector<HotUnit> units;
+    std::vector<int> visits;
+    plan_runs(pa, units, visits);
+    const int64_t cap = *n_units;
+    *n_units = (int64_t)units.size();
+    for (size_t v = 0; v < visits.size(); v++) visit_units[v] = visits[v];
+    if ((int64_t)units.size() > cap) return fail(MFSGD_E_INVALID_ARG, "%zu runs do not fit the %lld provided slots", units.size(), (long long)cap);
+    for (size_t j = 0; j < units.size(); j++) {
+        if (unit_start) unit_start[j] = units[j].start;
+        if (unit_count) unit_count[j] = units[j].count;
+        if (unit_item) unit_item[j] = units[j].item;
+        if (unit_weight) unit_weight[j] = units[j].weight;
+    }
+    return MFSGD_OK;
+}
+
 extern "C" int mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out) {
     if (!h || !out) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");

@@ -1,0 +1,85 @@
+"""The run planner (csrc/run_plan.hpp through the host-only hook mfsgd_plan_runs): which records of which run bucket every
+launch of the run kernel walks. Pure host logic -- runs without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from matrixfactorizationsgd.java_b200 import _capi as capi
+
+MIN_RUN = 16
+
+
+def plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed=7, member=0):
+    sizes = np.concatenate([np.asarray(sizes_cold, np.int64).ravel(), np.asarray(sizes_hot, np.int64).ravel()])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cap = int(np.sum((np.asarray(sizes_hot) + chunk - 1) // chunk + rounds)) + 16
+    start = np.zeros(cap, np.int64); count = np.zeros(cap, np.int32); item = np.zeros(cap, np.int32)
+    weight = np.zeros(cap, np.float32)
+    n = C.c_int64(cap)
+    visits = np.zeros(mu * rounds * IB + 1, np.int32)
+    hbl = np.asarray(hot_block_lo, np.int32); hit = np.asarray(hot_items, np.int32)
+    capi.check(capi.lib.mfsgd_plan_runs(capi.ptr(off), mu, H, IB, capi.ptr(hbl), capi.ptr(hit), rounds, chunk, seed, member,
+                                        capi.ptr(start), capi.ptr(count), capi.ptr(item), capi.ptr(weight), C.byref(n), capi.ptr(visits)))
+    m = n.value
+    return off, start[:m], count[:m], item[:m], weight[:m], visits
+
+
+@pytest.mark.parametrize("mu,IB,rounds,chunk", [(1, 1, 1, 256), (4, 1, 4, 256), (2, 3, 4, 64), (3, 2, 8, 96), (1, 2, 2, 4096)])
+def test_every_record_of_every_run_bucket_is_walked_once_per_epoch(mu, IB, rounds, chunk):
+    rng = np.random.default_rng(mu * 100 + IB * 10 + rounds)
+    H = 37
+    hot_items = np.sort(rng.choice(5000, H, replace=False)).astype(np.int32)
+    cut = np.sort(rng.choice(np.arange(1, H), IB - 1, replace=False)) if IB > 1 else np.array([], int)
+    hot_block_lo = np.concatenate([[0], cut, [H]]).astype(np.int32)
+    sizes_cold = rng.integers(0, 500, (mu, IB))
+    sizes_hot = rng.choice([0, 1, 15, 16, 31, 32, 63, 64, 65, 100, 255, 256, 257, 1000, 5000], (mu, H))
+    off, start, count, item, weight, visits = plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chunk)
+    assert visits[0] == 0 and visits[-1] == len(start) and np.all(np.diff(visits) >= 0)
+    assert np.all(count >= 1) and np.all(count <= chunk)
+    hot_base = mu * IB
+    covered = np.zeros(off[-1], np.int32)
+    for s, c in zip(start, count):
+        covered[s:s + c] += 1
+    assert np.all(covered[:off[hot_base]] == 0)                      # cold blocks are not the run kernel's
+    assert np.all(covered[off[hot_base]:] == 1)                      # every run-bucket record exactly once per epoch
+    item_block = np.searchsorted(hot_block_lo, np.arange(H), side="right") - 1
+    for sa in range(mu):
+        rounds_of_bucket = {}
+        for rnd in range(rounds):
+            for ib in range(IB):
+                v = (sa * rounds + rnd) * IB + ib
+                lo, hi = visits[v], visits[v + 1]
+                assert np.all(np.diff(count[lo:hi]) <= 0)                # longest first
+                for j in range(lo, hi):
+                    hx = int(np.searchsorted(hot_items, item[j]))
+                    assert hot_items[hx] == item[j] and item_block[hx] == ib
+                    blk = hot_base + sa * H + hx
+                    assert off[blk] <= start[j] and start[j] + count[j] <= off[blk + 1]     # inside its own bucket
+                    rounds_of_bucket.setdefault(hx, {}).setdefault(rnd, []).append(j)
+        for hx, per_round in rounds_of_bucket.items():
+            bn = int(sizes_hot[sa, hx])
+            assert len(per_round) == min(rounds, max(1, bn // (2 * MIN_RUN)))      # small buckets: one pass
+            for rnd, js in per_round.items():
+                n = int(count[js].sum())
+                assert len(js) == -(-n // chunk)                                      # ceil(n / chunk) equal runs
+                assert np.allclose(weight[js], 1.0 / len(js)) and count[js].max() - count[js].min() <= 1
+
+
+def test_small_buckets_spread_evenly_over_the_rounds():
+    mu, IB, rounds, H = 1, 1, 4, 4000
+    hot_items = np.arange(H, dtype=np.int32)
+    off, start, count, item, weight, visits = plan(np.zeros((1, 1)), np.full((1, H), 40), mu, H, IB, [0, H], hot_items, rounds, 256)
+    per_round = np.diff(visits)
+    assert per_round.sum() == H and per_round.min() > 0.8 * H / rounds and per_round.max() < 1.2 * H / rounds
+
+
+def test_plan_arguments_are_checked():
+    n = C.c_int64(0)
+    v = np.zeros(2, np.int32)
+    off = np.zeros(2, np.int64)
+    hbl = np.zeros(2, np.int32)
+    assert capi.lib.mfsgd_plan_runs(None, 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
+    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 0, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
+    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.OK
+    assert n.value == 0
