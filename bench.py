@@ -220,8 +220,8 @@ def run_ours(args):
     if world == 1:
         eng.close()
 
-    # Roofline of the update phase on rank 0: the cold (sgd_update_hogwild_kernel) and hot-item
-    # (sgd_update_hot_kernel) launches of an epoch run concurrently on two streams, so they are timed together:
+    # Roofline of the update phase on rank 0: the run-kernel (sgd_update_runs_kernel) and cold (sgd_update_hogwild_kernel)
+    # launches of an epoch run concurrently on two streams, so they are timed together:
     # one CUDA-event span per sub-epoch on the launching stream, fork to join. Algorithmic bytes = 12 + 16k per
     # update x the updates in the span.
     peak, peak_src = peaks()
