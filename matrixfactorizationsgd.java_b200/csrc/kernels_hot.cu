@@ -12,7 +12,7 @@
 // sub-warps walk as many runs side by side, each strictly sequentially. Default: one chunk per lane up to k = 128
 // (one warp per rating at k = 128), never fewer than 8 lanes. Narrower sub-warps (8 lanes x 4 chunks at k = 128:
 // 3 shuffles per dot product serving 4 ratings, 28 instead of 43 warp instructions per update) were measured and
-// run no faster: the launch is bound by L2 sector throughput (profiles/r01_experiments.md section 8).
+// run no faster: the launch is bound by L2 sector throughput (profiles/r01_experiments.md section 7).
 //
 // Pipeline: the run's (u, r) pairs are staged in shared memory by cp.async two LANES-record tiles ahead (ring of
 // 4 tiles per sub-warp; under the virtual reshuffle position j of a bucket reads record bucket_start + perm(j));
