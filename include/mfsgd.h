@@ -194,6 +194,12 @@ MFSGD_API int  mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_
                      int32_t member, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
                      int64_t* n_units, int32_t* visit_units);
 
+/* Test hook, host-only: the automatic layout (csrc/run_plan.hpp) for a configuration, an L2 size and one ring member's
+ * share of the data: P sub-stripes and Q sub-shards per member, interleaved passes, longest run. */
+MFSGD_API int  mfsgd_plan_layout(const mfsgd_config* cfg, int64_t l2_bytes, int64_t member_records, int32_t member_users,
+                       int64_t run_records, int32_t resident_ctas, int32_t* stripes, int32_t* shards, int32_t* rounds,
+                       int32_t* run_length);
+
 /* Teacher-forced per-update check: applies the update rule to n independent
  * (pre_p[j], pre_q[j], r[j]) row pairs on the device, returns post rows and errors. Host pointers. */
 MFSGD_API int  mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,

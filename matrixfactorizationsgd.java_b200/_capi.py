@@ -64,6 +64,8 @@ SIGNATURES = {
     "mfsgd_config_default": (C.c_int, [C.POINTER(Config)]),
     "mfsgd_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
     "mfsgd_destroy": (None, [_vp]),
+    "mfsgd_plan_layout": (C.c_int, [C.POINTER(Config), _i64, _i64, _i32, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32),
+                                    C.POINTER(_i32), C.POINTER(_i32)]),
     "mfsgd_plan_runs": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, C.c_uint64, _i32, _vp, _vp, _vp, _vp,
                                   C.POINTER(_i64), _vp]),
     "mfsgd_read_ratings": (C.c_int, [C.c_char_p, _i32, C.POINTER(Ratings)]),

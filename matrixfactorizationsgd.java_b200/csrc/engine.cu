@@ -518,26 +518,10 @@ extern "C" int mfsgd_host_free(void* p) {
 // ------------------------------------------------------------------------------------------------
 static void choose_blocking(mfsgd_handle* h) {
     const mfsgd_config& c = h->cfg;
-    // a multi-process ring of >= 4 pipelines the rotation over item sub-shards: two by default (send one while the next
-    // trains); with 2 members the rotation is 2 of ~20 launches per epoch and not worth the smaller launches.
-    // (Running the sub-shards' launches concurrently on prioritised streams was measured too: no gain, 1.69 vs 1.64 ms.)
-    h->mi = c.shards_per_gpu > 0 ? c.shards_per_gpu : (h->multi_process && h->G >= 4 && c.mode == MFSGD_MODE_DSGD ? 2 : 1);
-    if (c.mode == MFSGD_MODE_DETERMINISTIC) {
-        h->mu = 1;
-    } else if (c.stripes_per_gpu > 0) {
-        h->mu = c.stripes_per_gpu;
-    } else {
-        // auto: keep one P sub-stripe plus the held Q shard group resident in L2
-        const double l2 = (double)h->members[0].l2_bytes;
-        const double p_bytes = (double)c.n_users * c.k * 4.0 / h->G;
-        const double q_bytes = (double)c.n_items * c.k * 4.0 / h->G;
-        int mu = 1;
-        if (l2 > 0 && p_bytes + q_bytes > 0.6 * l2) {
-            const double budget = std::max(0.6 * l2 - q_bytes, 0.1 * l2);   // measured: 61 MB sub-stripes beat 35 MB and 82 MB ones
-            mu = (int)std::ceil(p_bytes / budget);
-        }
-        h->mu = std::min(std::max(mu, 1), 256);
-    }
+    const Blocking b = plan_blocking(c.n_users, c.n_items, c.k, h->G, c.mode, c.stripes_per_gpu, c.shards_per_gpu, h->multi_process,
+                                     (double)h->members[0].l2_bytes);     // run_plan.hpp
+    h->mu = b.mu;
+    h->mi = b.mi;
     h->UB = h->G * h->mu;
     h->IB = h->G * h->mi;
 }
@@ -765,22 +749,9 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     m.visit_units.assign((size_t)h->mu * h->rounds * h->IB + 1, 0);
     if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
     CK(cudaSetDevice(m.device));
-    // Run length: a run is walked by one warp, one rating after another (only the p_u gathers are pipelined), so a
-    // launch lasts at least one run; shorter runs mean more parallelism but each makes less progress on q_i before
-    // the item's runs are averaged (128 already costs ~1 % RMSE on small inputs; 256 does not -- profiles/r01_experiments.md).
-    int chunk = h->cfg.hot_chunk > 0 ? h->cfg.hot_chunk : 256;
-    if (h->cfg.hot_chunk <= 0 && h->G * h->mu * h->rounds >= 8) {
-        // Large rings launch small blocks: 256-rating runs then leave half the warp slots empty. An item is merged
-        // G * mu * rounds times per epoch there, which keeps shorter runs converging (8-ring, Netflix-shaped: run 64
-        // ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags) -- offer ~3 runs per resident sub-warp, >= 64
-        // (8-ring proxy, 0.7 M-rating launches: run 64 -> 1.34 ms per epoch, 96 -> 1.42, 128 -> 1.40, 192 -> 1.65, 256 -> 1.98).
-        const size_t hb = (size_t)h->mu * h->IB;
-        const double hot_recs = (double)(m.block_off.back() - m.block_off[hb]);
-        const double per_launch = hot_recs / ((double)h->mu * h->rounds * h->IB);
-        const int runs_per_warp = 32 / run_kernel_lanes(h->cfg.k);
-        const double want = per_launch / (3.0 * m.hot_grid * 8.0 * runs_per_warp);
-        chunk = (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
-    }
+    const size_t hb = (size_t)h->mu * h->IB;
+    const int chunk = plan_run_length(h->cfg.hot_chunk, h->G, h->mu, h->rounds, h->IB, m.block_off.back() - m.block_off[hb],
+                                      m.hot_grid, 32 / run_kernel_lanes(h->cfg.k));      // run_plan.hpp
     std::vector<HotUnit> units;
     RunPlanArgs pa{};
     pa.block_off = m.block_off.data();
@@ -861,29 +832,8 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
         for (Member& m : h->members) free_member_data(m);
         return rc;
     }
-    // Interleaving: a sub-epoch sweeps its mu sub-stripes `rounds` times, a 1/rounds slice of each block per
-    // visit, so Q sees every user stripe many times per epoch (a plain stripe-after-stripe order biases the
-    // item factors toward the last stripe and costs ~1 % RMSE at equal epochs) while each visit is still long
-    // enough (>= ~16 touches per P row) to keep the sub-stripe L2-resident.
-    // (With the hot-item path a single pass ends at the same RMSE and is ~10 % faster, but the first two epochs lag badly
-    // -- held-out RMSE 1.62 / 0.49 vs 0.41 / 0.40 on the Netflix-shaped set -- so the interleaving stays on.)
-    if (c.rounds > 0) h->rounds = c.rounds;
-    else if (c.mode == MFSGD_MODE_DETERMINISTIC) h->rounds = 1;
-    else {
-        const Member& m0 = h->members[0];
-        int rounds = 1;
-        if (h->mu > 1) {
-            const double block_recs = (double)m0.n_recs / ((double)h->mu * h->G);
-            const double stripe_rows = std::max(1.0, (double)(m0.u_hi - m0.u_lo) / h->mu);
-            rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
-        }
-        // The hot-item path averages the runs of an item that share a launch, so an item's factor makes sequential
-        // progress only from launch to launch: keep >= 8 launches per epoch (G * mu * rounds) while a launch still holds
-        // >= 16 K records. (A 1.8 M-rating set trained with one launch per epoch ends 1 % above the oracle's RMSE after
-        // 8 epochs; with 8 it lands on it.)
-        while (h->G * h->mu * rounds < 8 && (double)m0.n_recs / ((double)h->mu * rounds * 2) >= 16384.0) rounds *= 2;
-        h->rounds = rounds;
-    }
+    // interleaved passes per sub-epoch (run_plan.hpp: plan_rounds)
+    h->rounds = plan_rounds(c.rounds, c.mode, h->G, h->mu, h->members[0].n_recs, h->members[0].u_hi - h->members[0].u_lo);
     {
         const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1;
         const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
@@ -1560,6 +1510,23 @@ extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const
 // ------------------------------------------------------------------------------------------------
 // introspection + test hooks
 // ------------------------------------------------------------------------------------------------
+// Test hook: the layout planner (run_plan.hpp) for a configuration and a data size. Host-only.
+extern "C" int mfsgd_plan_layout(const mfsgd_config* cfg, int64_t l2_bytes, int64_t member_records, int32_t member_users,
+                                 int64_t run_records, int32_t resident_ctas, int32_t* stripes, int32_t* shards, int32_t* rounds,
+                                 int32_t* run_length) {
+    if (!cfg || !stripes || !shards || !rounds || !run_length) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    int rc = validate_config(cfg);
+    if (rc != MFSGD_OK) return rc;
+    const int G = cfg->mode == MFSGD_MODE_DSGD ? cfg->n_gpus : 1;
+    const Blocking b = plan_blocking(cfg->n_users, cfg->n_items, cfg->k, G, cfg->mode, cfg->stripes_per_gpu, cfg->shards_per_gpu,
+                                     cfg->world_size > 1, (double)l2_bytes);
+    *stripes = b.mu;
+    *shards = b.mi;
+    *rounds = plan_rounds(cfg->rounds, cfg->mode, G, b.mu, member_records, member_users);
+    *run_length = plan_run_length(cfg->hot_chunk, G, b.mu, *rounds, G * b.mi, run_records, resident_ctas, 32 / run_kernel_lanes(cfg->k));
+    return MFSGD_OK;
+}
+
 // Test hook: the run planner (run_plan.hpp) on caller-provided bucket offsets. Host-only.
 extern "C" int mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
                                const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,

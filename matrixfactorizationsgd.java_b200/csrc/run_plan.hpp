@@ -10,14 +10,81 @@
 // Exposed for CPU tests through mfsgd_plan_runs (include/mfsgd.h).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
+#include "../../include/mfsgd.h"
 #include "kernels.cuh"
 
 namespace mfsgd {
 
 static const int MIN_RUN = 16;   // shortest run worth a sub-warp of the run kernel (one q_i load + merge per run)
+
+// ---- blocking of a ring member's work (pure functions of the configuration) -----------------------------------------
+// Sub-stripes of P per ring member (mu) and item sub-shards per member (mi). Auto mu keeps one P sub-stripe plus the
+// held Q shard group resident in L2 (measured on the Netflix-shaped workload: 61 MB sub-stripes beat 35 MB and 82 MB
+// ones); auto mi = 2 where the rotation is pipelined (a multi-process ring of >= 4 sends one slice of Q while the next
+// trains; with 2 members the rotation is 2 of ~20 launches per epoch and not worth the smaller launches).
+struct Blocking {
+    int mu, mi;
+};
+inline Blocking plan_blocking(int n_users, int n_items, int k, int G, int mode, int stripes_per_gpu, int shards_per_gpu,
+                              bool multi_process, double l2_bytes) {
+    Blocking b;
+    b.mi = shards_per_gpu > 0 ? shards_per_gpu : (multi_process && G >= 4 && mode == MFSGD_MODE_DSGD ? 2 : 1);
+    if (mode == MFSGD_MODE_DETERMINISTIC) {
+        b.mu = 1;
+    } else if (stripes_per_gpu > 0) {
+        b.mu = stripes_per_gpu;
+    } else {
+        const double p_bytes = (double)n_users * k * 4.0 / G;
+        const double q_bytes = (double)n_items * k * 4.0 / G;
+        int mu = 1;
+        if (l2_bytes > 0 && p_bytes + q_bytes > 0.6 * l2_bytes) {
+            const double budget = std::max(0.6 * l2_bytes - q_bytes, 0.1 * l2_bytes);
+            mu = (int)std::ceil(p_bytes / budget);
+        }
+        b.mu = std::min(std::max(mu, 1), 256);
+    }
+    return b;
+}
+
+// Interleaved passes per sub-epoch. A sub-epoch sweeps its mu sub-stripes `rounds` times, a slice of each bucket per
+// visit, so Q sees every user stripe many times per epoch (a plain stripe-after-stripe order biases the item factors
+// toward the last stripe and costs ~1 % RMSE at equal epochs) while each visit is still long enough (>= ~16 touches
+// per P row) to keep the sub-stripe L2-resident. The run path averages the runs of an item that share a launch, so an
+// item's factor makes sequential progress only from launch to launch: keep >= 8 launches per epoch (G * mu * rounds)
+// while a launch still holds >= 16 K records (a 1.8 M-rating set trained with one launch per epoch ends 1 % above the
+// oracle's RMSE after 8 epochs; with 8 it lands on it).
+inline int plan_rounds(int rounds_cfg, int mode, int G, int mu, int64_t member_records, int64_t member_users) {
+    if (rounds_cfg > 0) return rounds_cfg;
+    if (mode == MFSGD_MODE_DETERMINISTIC) return 1;
+    int rounds = 1;
+    if (mu > 1) {
+        const double block_recs = (double)member_records / ((double)mu * G);
+        const double stripe_rows = std::max(1.0, (double)member_users / mu);
+        rounds = (int)std::min(4.0, std::max(1.0, std::floor(block_recs / (16.0 * stripe_rows))));
+    }
+    while (G * mu * rounds < 8 && (double)member_records / ((double)mu * rounds * 2) >= 16384.0) rounds *= 2;
+    return rounds;
+}
+
+// Longest run. 256 by default: a run is walked by one sub-warp, one rating after another, so a launch lasts at least
+// one run; shorter runs mean more parallelism but each makes less progress on q_i before the item's runs are averaged
+// (128 already costs ~1 % RMSE on small inputs; 256 does not). Rings that merge an item >= 8 times per epoch launch
+// small blocks, where 256-rating runs leave warp slots empty while the more frequent merges keep shorter runs
+// converging (8-ring, Netflix-shaped: run 64 ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags): offer ~3
+// runs per resident sub-warp, 64..256 (8-ring proxy, 0.7 M-rating launches: run 64 -> 1.34 ms per epoch, 96 -> 1.42,
+// 128 -> 1.40, 192 -> 1.65, 256 -> 1.98).
+inline int plan_run_length(int hot_chunk_cfg, int G, int mu, int rounds, int IB, int64_t run_records, int resident_ctas,
+                           int runs_per_warp) {
+    if (hot_chunk_cfg > 0) return hot_chunk_cfg;
+    if (G * mu * rounds < 8) return 256;
+    const double per_launch = (double)run_records / ((double)mu * rounds * IB);
+    const double want = per_launch / (3.0 * resident_ctas * 8.0 * runs_per_warp);
+    return (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
+}
 
 struct RunPlanArgs {
     const int64_t* block_off;      // offsets of the member's buckets: mu * IB cold blocks, then mu * H run buckets (+1)

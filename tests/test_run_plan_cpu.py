@@ -83,3 +83,51 @@ def test_plan_arguments_are_checked():
     assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 0, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
     assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.OK
     assert n.value == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# automatic layout (plan_blocking / plan_rounds / plan_run_length) for the BASELINE.json shapes
+# ------------------------------------------------------------------------------------------------
+import matrixfactorizationsgd.java_b200 as mf
+
+L2 = 132_644_864          # cudaDeviceProp::l2CacheSize of the pool's B200s (profiles/l2_peak.json: 132.6 MB)
+
+
+def layout(name, G=1, world=1, resident_ctas=592, **kw):
+    w = mf.WORKLOADS[name]
+    mode = capi.MODE_DSGD if G > 1 else capi.MODE_HOGWILD
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, mode=mode, n_gpus=G, world_size=world, rank=0,
+                         nccl_id=bytes(128) if world > 1 else None, **kw)
+    n_train = int(w.n_ratings * 0.9)
+    out = [C.c_int32(0) for _ in range(4)]
+    capi.check(capi.lib.mfsgd_plan_layout(C.byref(cfg), L2, n_train // G, w.n_users // G, n_train // G, resident_ctas,
+                                          *[C.byref(x) for x in out]))
+    return tuple(x.value for x in out)      # (stripes, shards, rounds, run length)
+
+
+def test_layout_of_the_baseline_shapes():
+    # Netflix-shaped on 1 GPU: 246 MB of P in 4 L2-resident sub-stripes, 4 interleaved rounds, full-length runs
+    assert layout("netflix") == (4, 1, 4, 256)
+    # one process per GPU: the rotation is pipelined over 2 item sub-shards from 4 members on, runs shorten with the launches
+    assert layout("netflix", G=2, world=2) == (2, 1, 4, 224)
+    assert layout("netflix", G=4, world=4) == (1, 2, 2, 128)
+    assert layout("netflix", G=8, world=8) == (1, 2, 1, 64)
+    # a single process driving 8 devices (peer copies, no pipelining): one shard group per member
+    assert layout("netflix", G=8, world=1)[:3] == (1, 1, 1)
+    assert layout("ml20m") == (2, 1, 4, 160)
+    # 90 K ratings: one sub-stripe, but still 4 launches per epoch of >= 16 K records each
+    assert layout("ml100k")[:3] == (1, 1, 4)
+    # the large shapes on their own configuration (8 GPUs) and squeezed onto one
+    assert layout("yahoo", G=8, world=8) == (2, 2, 2, 96) and layout("powerlaw", G=8, world=8) == (7, 2, 1, 96)
+    assert layout("yahoo") == (70, 1, 4, 160) and layout("powerlaw") == (193, 1, 4, 96)
+
+
+def test_layout_overrides_and_modes():
+    assert layout("netflix", stripes_per_gpu=7, shards_per_gpu=3, rounds=11, hot_chunk=100) == (7, 3, 11, 100)
+    w = mf.WORKLOADS["ml100k"]
+    cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, mode=capi.MODE_DETERMINISTIC)
+    out = [C.c_int32(0) for _ in range(4)]
+    capi.check(capi.lib.mfsgd_plan_layout(C.byref(cfg), L2, 90_000, w.n_users, 0, 592, *[C.byref(x) for x in out]))
+    assert (out[0].value, out[1].value, out[2].value) == (1, 1, 1)          # parity mode: one block, one pass
+    bad = mf.make_config(10, 10, 6, 0.1, 0.1)
+    assert capi.lib.mfsgd_plan_layout(C.byref(bad), L2, 1, 1, 1, 1, *[C.byref(x) for x in out]) == capi.E_INVALID_ARG
