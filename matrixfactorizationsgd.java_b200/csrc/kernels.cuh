@@ -150,7 +150,8 @@ inline int bucket_rows(const BucketArgs& b) { return (b.ub_hi - b.ub_lo + b.row_
 inline int bucket_block_count(const BucketArgs& b) {
     return bucket_rows(b) * b.n_cols + (b.hot_index ? bucket_rows(b) * b.n_hot : 0);
 }
-constexpr int MAX_BUCKETS = 1 << 23;      // per ring member: cold blocks + run (stripe, item) buckets (8 B of offsets each)
+constexpr int MAX_BUCKETS = 1 << 20;      // per ring member: cold blocks + run (stripe, item) buckets. (2^23 was tried on the two largest
+                                          // shapes squeezed onto ONE GPU: 7x more items on the run path, no faster -- their buckets are tiny.)
 constexpr int MAX_SMEM_BUCKETS = 16384;   // up to here histogram/scatter keep per-CTA counters in shared memory
 cudaError_t launch_block_histogram(const BucketArgs& b, unsigned long long* block_cnt, cudaStream_t stream, int* launches);
 // cursors start as the exclusive offsets; each record claims a slot with atomicAdd.

@@ -1,5 +1,5 @@
 """Phase timings (MFSGD_TRACE=1) of the resident-caller sequence bench.py times as e2e for N > 1: a live handle is
-re-loaded from host triplets, re-initialised, trained and read back. usage: python tools/reload_trace.py [epochs]"""
+re-loaded from host triplets, re-initialised, trained and read back. usage: python tools/reload_trace.py [epochs] [workload]"""
 import ctypes as C, os, sys, time
 import numpy as np
 os.environ["MFSGD_TRACE"] = "1"
@@ -9,8 +9,8 @@ import matrixfactorizationsgd.java_b200 as mf
 capi = mf.capi
 sys.path.insert(0, ROOT)
 import bench
-w = mf.WORKLOADS["netflix"]
 epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+w = mf.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "netflix"]
 eng = mf.Engine(mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD, flags=capi.FLAG_TIME_KERNELS))
 eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
 eng.init_factors()
@@ -46,3 +46,10 @@ for rep in range(2):
     x = torch.from_numpy(hu).cuda(); y = torch.from_numpy(hi).cuda(); z = torch.from_numpy(hr).cuda()
     torch.cuda.synchronize()
     print("torch H2D of the three arrays: %.3f s (%.1f GB/s)" % (time.time() - t0, 12e-9 * len(hr) / (time.time() - t0)), flush=True)
+
+# (d) the one-shot entry point bench.py times at N = 1
+cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
+for rep in range(2):
+    t0 = time.time()
+    capi.check(capi.lib.mfsgd_factorize(capi.ptr(hu), capi.ptr(hi), capi.ptr(hr), len(hr), C.byref(cfg), epochs, capi.ptr(P), capi.ptr(Q)))
+    print("mfsgd_factorize %d epochs: %.3f s" % (epochs, time.time() - t0), flush=True)
