@@ -20,7 +20,7 @@ $(OBJDIR)/ratings_io.o: $(CSRC)/ratings_io.cpp include/mfsgd.h
 
 $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl -lpthread
 
 oracle:
 	$(MAKE) -s -C oracle
