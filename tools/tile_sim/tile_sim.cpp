@@ -11,6 +11,7 @@
 //
 // build: g++ -O2 -ffp-contract=off -shared -fPIC -o libtilesim.so tile_sim.cpp      (driver: tools/tile_sim/run.py)
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <queue>
@@ -32,7 +33,11 @@ struct Event {
     bool operator<(const Event& o) const { return t > o.t; }   // min-heap
 };
 
+int g_gpu_arith = 0;
+
 }  // namespace
+
+extern "C" void tilesim_set_gpu_arithmetic(int on) { g_gpu_arith = on; }
 
 // records sorted by (tile, item order); tile_off[n_tiles+1]; tile_order[n_tiles] = this epoch's visiting order
 extern "C" int tilesim_epoch(const int32_t* u, const int32_t* it, const float* r, const int64_t* tile_off, int32_t n_tiles,
@@ -87,13 +92,45 @@ extern "C" int tilesim_epoch(const int32_t* u, const int32_t* it, const float* r
         while (w.pos < w.end && it[w.pos] == item) {
             float* p = P + (int64_t)u[w.pos] * k;
             float* q = w.q.data();
-            float dot = 0.0f;
-            for (int f = 0; f < k; f++) dot = dot + p[f] * q[f];
-            const float e = r[w.pos] - dot;
-            for (int f = 0; f < k; f++) {
-                const float pf = p[f], qf = q[f];
-                p[f] = pf + lr * (e * qf - lambda * pf);
-                q[f] = qf + lr * (e * pf - lambda * qf);
+            if (g_gpu_arith) {
+                // the GPU kernels' FAST arrangement at k = 128, one float4 chunk per lane, 32 lanes (update_math.cuh;
+                // oracle.cpp ORC_ORDER_WARP_TREE_FMA): makes the simulation with one CTA of one warp the bit-exact twin
+                // of tools/tile_kernel_draft/tile_kernel.cu run in its checking mode
+                float s[32];
+                for (int l = 0; l < 32; l++) {
+                    float lo = 0.f, hi = 0.f;
+                    bool first = true;
+                    for (int c = l; c < k / 4; c += 32) {
+                        const float* pp = p + 4 * c;
+                        const float* qq = q + 4 * c;
+                        if (first) { lo = pp[0] * qq[0]; hi = pp[1] * qq[1]; first = false; }
+                        else { lo = std::fmaf(pp[0], qq[0], lo); hi = std::fmaf(pp[1], qq[1], hi); }
+                        lo = std::fmaf(pp[2], qq[2], lo);
+                        hi = std::fmaf(pp[3], qq[3], hi);
+                    }
+                    s[l] = lo + hi;
+                }
+                for (int m = 16; m >= 1; m >>= 1) {
+                    float t2[32];
+                    for (int l = 0; l < 32; l++) t2[l] = s[l] + s[l ^ m];
+                    for (int l = 0; l < 32; l++) s[l] = t2[l];
+                }
+                const float e = r[w.pos] - s[0];
+                const float a_ = 1.0f - lr * lambda, b_ = lr * e;
+                for (int f = 0; f < k; f++) {
+                    const float pf = p[f], qf = q[f];
+                    p[f] = std::fmaf(b_, qf, a_ * pf);
+                    q[f] = std::fmaf(b_, pf, a_ * qf);
+                }
+            } else {
+                float dot = 0.0f;
+                for (int f = 0; f < k; f++) dot = dot + p[f] * q[f];
+                const float e = r[w.pos] - dot;
+                for (int f = 0; f < k; f++) {
+                    const float pf = p[f], qf = q[f];
+                    p[f] = pf + lr * (e * qf - lambda * pf);
+                    q[f] = qf + lr * (e * pf - lambda * qf);
+                }
             }
             w.pos++;
             len++;
