@@ -41,4 +41,11 @@ clean:
 	rm -rf build $(LIB) tests/c/abi_harness host/factorize_demo tools/l2_peak
 	$(MAKE) -s -C oracle clean
 
-.PHONY: all oracle harness host clean
+# The Java host and the reference stand-in (JDK 22+; this image has none, so the target only reports that)
+java:
+	@if command -v javac >/dev/null 2>&1; then \
+	    mkdir -p build/java && javac --release 22 -d build/java java/MatrixFactorizationSGDGpu.java baseline/java/MatrixFactorizationSGD.java && \
+	    echo "built build/java; run: java --enable-native-access=ALL-UNNAMED -cp build/java -Dmfsgd.lib=$(abspath $(LIB)) MatrixFactorizationSGDGpu"; \
+	else echo "no JDK on PATH: java/ and baseline/java/ stay source-only (see java/README.md)"; fi
+
+.PHONY: all oracle harness host java clean
