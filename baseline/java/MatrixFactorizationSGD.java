@@ -184,7 +184,10 @@ public final class MatrixFactorizationSGD {
      * ------------------------------------------------------------------------------------------ */
 
     public static final int PLANTED_RANK = 16;
-    public static final float PLANTED_AMPLITUDE = 0.8660254f;   /* sqrt(0.75): planted dot has unit variance */
+    public static final float PLANTED_AMPLITUDE = 0.8660254f;   /* default: sqrt(0.75), planted dot of std 0.25 (noise-dominant sets) */
+    public static final float NOISE_SCALE = 0.5f;               /* default noise scale (noise std 0.289)                              */
+    public static final float SIGNAL_AMPLITUDE = 1.7320508f;    /* signal-dominant variant (SURVEY.md 8d): planted dot of std 1.0 ... */
+    public static final float SIGNAL_NOISE_SCALE = 0.125f;      /* ... and noise std 0.072                                            */
     public static final long ID_MULT = 2654435761L;              /* prime > 2^31, so coprime to every id count */
 
     /** 53-bit uniform double in [0,1). */
@@ -212,25 +215,33 @@ public final class MatrixFactorizationSGD {
         return (int) ((((long) rank * ID_MULT) + (long) (count / 2)) % (long) count);
     }
 
-    public static float plantedEntry(long seed, long stream, int row, int f) {
-        return (uniform(seed, stream, (long) row * PLANTED_RANK + f) - 0.5f) * PLANTED_AMPLITUDE;
+    public static float plantedEntry(long seed, long stream, int row, int f, float amplitude) {
+        return (uniform(seed, stream, (long) row * PLANTED_RANK + f) - 0.5f) * amplitude;
+    }
+
+    /** Record n of the default (noise-dominant) synthetic data set. */
+    public static boolean syntheticRecord(long seed, long n, int nUsers, int nItems,
+                                          int log2AlphaU, double cU, int log2AlphaI, double cI,
+                                          int[] u, int[] i, float[] r) {
+        return syntheticRecord(seed, n, nUsers, nItems, log2AlphaU, cU, log2AlphaI, cI, PLANTED_AMPLITUDE, NOISE_SCALE, u, i, r);
     }
 
     /** Record n of the synthetic data set: fills u[0], i[0], r[0]; returns true when n is held out. */
     public static boolean syntheticRecord(long seed, long n, int nUsers, int nItems,
                                           int log2AlphaU, double cU, int log2AlphaI, double cI,
+                                          float amplitude, float noiseScale,
                                           int[] u, int[] i, float[] r) {
         int uu = scatterId(skewedRank(uniform53(seed, STREAM_USER, n), nUsers, log2AlphaU, cU), nUsers);
         int ii = scatterId(skewedRank(uniform53(seed, STREAM_ITEM, n), nItems, log2AlphaI, cI), nItems);
         float dot = 0.0f;
         for (int f = 0; f < PLANTED_RANK; f++) {
-            dot = dot + plantedEntry(seed, STREAM_PSTAR, uu, f) * plantedEntry(seed, STREAM_QSTAR, ii, f);
+            dot = dot + plantedEntry(seed, STREAM_PSTAR, uu, f, amplitude) * plantedEntry(seed, STREAM_QSTAR, ii, f, amplitude);
         }
         float noise = 0.0f;
         for (int j = 0; j < 4; j++) noise = noise + uniform(seed, STREAM_NOISE, 4L * n + j);
         noise = noise - 2.0f;
         float rating = 3.5f + dot;
-        rating = rating + 0.5f * noise;
+        rating = rating + noiseScale * noise;
         if (rating < 1.0f) rating = 1.0f;
         if (rating > 5.0f) rating = 5.0f;
         u[0] = uu; i[0] = ii; r[0] = rating;

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MFSGD_ABI_VERSION 1
+#define MFSGD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MFSGD_API __attribute__((visibility("default")))
@@ -88,9 +88,11 @@ typedef struct mfsgd_config {
     float    hot_share;        /* items rated by >= this share of the training set -- and by >= 16 ratings per
                                   (sub-stripe, ring member) bucket -- take the run path (q_i register-resident for a
                                   run of its ratings, model-averaged over concurrent runs); 0 = default 1e-6, < 0 = off */
-    int32_t  hot_chunk;        /* max records per run (one sub-warp); 0 = 256 (64..256 in rings that
-                                  merge an item >= 8 times per epoch and launch small blocks)              */
-    int32_t  reserved[4];
+    int32_t  hot_chunk;        /* max records per run (one sub-warp); 0 = auto: the per-sub-warp share of a launch,
+                                  64..1024                                                                  */
+    float    merge_boost;      /* runs of one item that share a launch are merged with weight min(1, merge_boost / runs);
+                                  0 = default 1.25, 1 = plain model averaging; must be < 2                      */
+    int32_t  reserved[3];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
@@ -119,6 +121,9 @@ typedef struct mfsgd_synth_params {
     int32_t  log2_alpha_item;   /* 3  (alpha 8; top 1 % of items ~30 %), 4 = heavy (alpha 16; ~60 %)  */
     double   c_user;            /* 0.25                                                              */
     double   c_item;            /* 0.375                                                             */
+    float    planted_amplitude; /* 0 = 0.8660254 (planted dot of unit variance x 0.25: noise-dominant sets);
+                                   1.7320508 = the signal-dominant variant                */
+    float    noise_scale;       /* 0 = 0.5; 0.125 = the signal-dominant variant                         */
 } mfsgd_synth_params;
 
 /* Layout report for tests and tools (all counts are for this process's ring members). */
@@ -191,8 +196,8 @@ MFSGD_API int  mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch);
  * unit_* arrays (each nullable), out = runs planned; visit_units[stripes * rounds * item_blocks + 1]. */
 MFSGD_API int  mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks,
                      const int32_t* hot_block_lo, const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed,
-                     int32_t member, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
-                     int64_t* n_units, int32_t* visit_units);
+                     int32_t member, float merge_boost, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item,
+                     float* unit_weight, int64_t* n_units, int32_t* visit_units);
 
 /* Test hook, host-only: the automatic layout (csrc/run_plan.hpp) for a configuration, an L2 size and one ring member's
  * share of the data: P sub-stripes and Q sub-shards per member, interleaved passes, longest run. */

@@ -15,7 +15,7 @@ MODE_DETERMINISTIC, MODE_HOGWILD, MODE_DSGD = 0, 1, 2
 SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
 FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE, FLAG_EXACT_ARITH, FLAG_SPLIT_SHARDS = 1, 2, 4, 8, 16
 FLAG_MATERIALIZE_SHUFFLE = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Config(C.Structure):
@@ -24,7 +24,8 @@ class Config(C.Structure):
                 ("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
                 ("scatter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32), ("world_size", C.c_int32),
                 ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
-                ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("merge_boost", C.c_float),
+                ("reserved", C.c_int32 * 3)]
 
 
 class EpochStats(C.Structure):
@@ -36,7 +37,8 @@ class EpochStats(C.Structure):
 
 class SynthParams(C.Structure):
     _fields_ = [("n_total", C.c_int64), ("seed", C.c_uint64), ("log2_alpha_user", C.c_int32),
-                ("log2_alpha_item", C.c_int32), ("c_user", C.c_double), ("c_item", C.c_double)]
+                ("log2_alpha_item", C.c_int32), ("c_user", C.c_double), ("c_item", C.c_double),
+                ("planted_amplitude", C.c_float), ("noise_scale", C.c_float)]
 
 
 class LayoutInfo(C.Structure):
@@ -66,7 +68,7 @@ SIGNATURES = {
     "mfsgd_destroy": (None, [_vp]),
     "mfsgd_plan_layout": (C.c_int, [C.POINTER(Config), _i64, _i64, _i32, _i64, _i32, C.POINTER(_i32), C.POINTER(_i32),
                                     C.POINTER(_i32), C.POINTER(_i32)]),
-    "mfsgd_plan_runs": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, C.c_uint64, _i32, _vp, _vp, _vp, _vp,
+    "mfsgd_plan_runs": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, C.c_uint64, _i32, _f32, _vp, _vp, _vp, _vp,
                                   C.POINTER(_i64), _vp]),
     "mfsgd_read_ratings": (C.c_int, [C.c_char_p, _i32, C.POINTER(Ratings)]),
     "mfsgd_free_ratings": (None, [C.POINTER(Ratings)]),

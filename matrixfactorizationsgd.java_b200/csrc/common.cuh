@@ -70,40 +70,65 @@ __device__ __forceinline__ void st_stream_i32(int32_t* p, int32_t v, uint64_t po
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
-// ---- in-block reshuffle: keyed Feistel bijection with cycle walking (subsystem 1) -----------------
+// ---- in-block reshuffle: tile-coherent keyed bijection (subsystem 1) -----------------------------
 // perm_b(j) for bucket b of n records in epoch e: the materialising kernel (kernels_layout.cu) writes
 // out[off+j] = in[off+perm(j)]; the update kernels can instead read record off+perm(j) directly.
-__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
+//
+// Round 2: the permutation keeps every aligned group of 32 consecutive positions inside ONE aligned group of 32
+// records (384 contiguous bytes = 12 sectors), so a warp staging 32 positions of a bucket reads whole sectors instead
+// of 32 scattered 12-byte records (round 1: one or two 32-B sectors from DRAM per 12-B record, 10.7 GB of DRAM
+// traffic per Netflix-shaped epoch against 1.08 GB of records). Per epoch the ORDER OF THE TILES is a keyed 4-round
+// balanced Feistel bijection with cycle walking over the n/32 full tiles, the order INSIDE a tile a keyed affine
+// bijection of the 5 lane bits, and the < 32 records behind the last full tile are rotated by a keyed offset.
+// The CPU checker restates this function (tests/test_gpu_parity.py compares the two bit for bit).
+__host__ __device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
     uint32_t h = (x + key) * 0x9E3779B1u;
     h ^= h >> 15;
     h *= 0x85EBCA77u;
     h ^= h >> 13;
     return h;
 }
-// bijection on [0, n): 4-round balanced Feistel over 2*hb bits (2^(2hb) >= n), re-applied until < n.
-__device__ __forceinline__ uint64_t block_perm(uint64_t x, uint64_t n, int hb, uint64_t key) {
-    const uint32_t mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
+// bijection on [0, n), n > 1; hb = perm_half_bits(n)
+__host__ __device__ __forceinline__ uint64_t block_perm(uint64_t x, uint64_t n, int hb, uint64_t key) {
+    const uint64_t tiles = n >> 5, full = tiles << 5;
     const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-    do {
-        uint32_t l = (uint32_t)(x >> hb) & mask, r = (uint32_t)x & mask;
+    if (x >= full) {                                   // the partial tile at the end: rotate
+        const uint32_t rem = (uint32_t)(n - full);
+        return full + (uint64_t)(((uint32_t)(x - full) + (k1 >> 8) % rem) % rem);
+    }
+    uint64_t t = x >> 5;
+    if (tiles > 1) {                                   // tile order: Feistel over 2*hb bits (2^(2hb) >= tiles), cycle walking
+        const uint32_t mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
+        do {
+            uint32_t l = (uint32_t)(t >> hb) & mask, r = (uint32_t)t & mask;
 #pragma unroll
-        for (int round = 0; round < 4; round++) {
-            const uint32_t f = feistel_round(r, (round & 1) ? (k1 + round) : (k0 + round)) & mask;
-            const uint32_t nl = r;
-            r = l ^ f;
-            l = nl;
-        }
-        x = ((uint64_t)l << hb) | (uint64_t)r;
-    } while (x >= n);
-    return x;
+            for (int round = 0; round < 4; round++) {
+                const uint32_t f = feistel_round(r, (round & 1) ? (k1 + round) : (k0 + round)) & mask;
+                const uint32_t nl = r;
+                r = l ^ f;
+                l = nl;
+            }
+            t = ((uint64_t)l << hb) | (uint64_t)r;
+        } while (t >= tiles);
+    }
+    const uint32_t h = feistel_round((uint32_t)t ^ k1, k0);   // lane order inside the tile: ((l ^ c) * a + b) mod 32, a odd
+    const uint32_t lane = ((((uint32_t)x & 31u) ^ ((h >> 16) & 31u)) * ((h & 31u) | 1u) + ((h >> 8) & 31u)) & 31u;
+    return (t << 5) | (uint64_t)lane;
 }
 
-__device__ __forceinline__ int perm_half_bits(uint64_t n) {   // n > 1
-    int bits = 64 - __clzll((long long)(n - 1));
+__host__ __device__ __forceinline__ int perm_half_bits(uint64_t n) {   // half the bits of the Feistel domain over the n/32 tiles
+    const uint64_t tiles = n >> 5;
+    if (tiles <= 1) return 1;
+#ifdef __CUDA_ARCH__
+    int bits = 64 - __clzll((long long)(tiles - 1));
+#else
+    int bits = 0;
+    while (bits < 63 && (1ULL << bits) < tiles) bits++;
+#endif
     if (bits < 2) bits = 2;
     return (bits + 1) >> 1;
 }
-__device__ __forceinline__ uint64_t bucket_perm_key(uint64_t seed, uint32_t epoch, uint32_t bucket_id) {
+__host__ __device__ __forceinline__ uint64_t bucket_perm_key(uint64_t seed, uint32_t epoch, uint32_t bucket_id) {
     return hash64(seed, STREAM_BLOCK_SHUFFLE, ((uint64_t)epoch << 32) | (uint64_t)bucket_id);
 }
 

@@ -134,8 +134,15 @@ struct EvalSet {            // held-out records of one ring member, bucketed per
     std::vector<int64_t> group_off;  // [G + 1]
 };
 
+struct Lane {                // a pair of streams that carries the update launches of an item sub-shard (lane mode, see train_impl)
+    cudaStream_t cold = nullptr, hot = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, done = nullptr;
+    bool used = false;       // work enqueued since the last join into the member's main stream
+};
+
 struct Member {              // one ring member ("GPU g")
     int g = 0;               // ring index
+    std::vector<Lane> lanes; // created on first use
     int device = 0;          // CUDA ordinal
     int n_sms = 148;
     size_t l2_bytes = 0;
@@ -159,8 +166,9 @@ struct Member {              // one ring member ("GPU g")
     int32_t* d_hot_index = nullptr;  // item -> index into handle.hot_items, or -1
     HotUnit* d_units = nullptr;      // hot-item units of all visits, grouped by visit
     std::vector<int> visit_units;    // [(a * rounds + rnd) * IB + item block] -> first unit; one extra entry at the end
-    unsigned int* d_counters = nullptr;   // one unit-claim counter per hot launch of an epoch
+    unsigned int* d_counters = nullptr;   // one unit-claim counter per hot launch; COUNTER_EPOCHS epochs' worth, zeroed per batch
     int n_counters = 0, counter_next = 0;
+    cudaEvent_t ev_epoch_go = nullptr;
     int hot_grid = 148;
     EvalSet heldout;
     double* d_scratch = nullptr;     // rmse partials + 1 accumulator at the end
@@ -273,6 +281,7 @@ struct Chunk {                     // per-device staging buffers
     int64_t start = -1, count = 0; // what is currently staged
 };
 
+static const int COUNTER_EPOCHS = 64;          // epochs whose run-claim counters are zeroed by one memset (lanes run across epoch boundaries)
 static const int64_t CHUNK_MAX = 256LL << 20;  // records per staging chunk (3.3 GB of device buffers)
 
 static int chunk_alloc(Chunk& c, int64_t cap, bool with_held) {
@@ -353,7 +362,9 @@ static int validate_config(const mfsgd_config* c) {
     if (c->mode == MFSGD_MODE_DETERMINISTIC && (c->stripes_per_gpu > 1 || c->shards_per_gpu > 1))
         return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode keeps the caller's record order: no blocking");
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
-    if (c->hot_chunk < 0) return fail(MFSGD_E_INVALID_ARG, "hot_chunk < 0");
+    if (c->hot_chunk < 0 || c->hot_chunk > 65536) return fail(MFSGD_E_INVALID_ARG, "hot_chunk=%d out of range (0..65536)", c->hot_chunk);
+    if (!(c->merge_boost >= 0.f) || c->merge_boost >= 2.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
+    if (c->merge_boost > 0.f && c->merge_boost < 1.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
     if (c->rounds < 0 || c->rounds > 256) return fail(MFSGD_E_INVALID_ARG, "rounds=%d out of range", c->rounds);
     return MFSGD_OK;
 }
@@ -379,6 +390,7 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     CK(cudaEventCreateWithFlags(&m.ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m.ev_shuffle_go, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m.ev_shuffle_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m.ev_epoch_go, cudaEventDisableTiming));
     CK(dev_alloc(&m.d_scratch, (size_t)rmse_scratch_doubles() + 1));
     m.d_sse = m.d_scratch + rmse_scratch_doubles();
     int ctas = 0;
@@ -401,6 +413,10 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         if (m.copy_stream) cudaStreamSynchronize(m.copy_stream);
         if (m.hot_stream) cudaStreamSynchronize(m.hot_stream);
         if (m.shuffle_stream) cudaStreamSynchronize(m.shuffle_stream);
+        for (Lane& l : m.lanes) {
+            if (l.cold) cudaStreamSynchronize(l.cold);
+            if (l.hot) cudaStreamSynchronize(l.hot);
+        }
     }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (Member& m : h->members) {
@@ -409,7 +425,14 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         for (cudaEvent_t e : m.evpool) cudaEventDestroy(e);
         for (cudaEvent_t e : m.ev_part_done) cudaEventDestroy(e);
         for (cudaEvent_t e : m.ev_part_recv) cudaEventDestroy(e);
-        cudaEvent_t evs[] = {m.ev_compute, m.ev_sent, m.ev_fork, m.ev_join, m.ev_shuffle_go, m.ev_shuffle_done};
+        for (Lane& l : m.lanes) {
+            cudaEvent_t levs[] = {l.fork, l.join, l.done};
+            for (cudaEvent_t e : levs)
+                if (e) cudaEventDestroy(e);
+            if (l.cold) cudaStreamDestroy(l.cold);
+            if (l.hot) cudaStreamDestroy(l.hot);
+        }
+        cudaEvent_t evs[] = {m.ev_compute, m.ev_sent, m.ev_fork, m.ev_join, m.ev_shuffle_go, m.ev_shuffle_done, m.ev_epoch_go};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
         if (m.stream) cudaStreamDestroy(m.stream);
@@ -759,12 +782,13 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     pa.mu = h->mu; pa.H = h->H; pa.IB = h->IB; pa.rounds = h->rounds; pa.chunk = chunk;
     pa.member = m.g;
     pa.seed = h->cfg.seed;
+    pa.boost = h->cfg.merge_boost > 0.f ? h->cfg.merge_boost : DEFAULT_MERGE_BOOST;
     pa.hot_block_lo = h->hot_block_lo.data();
     pa.hot_items = h->hot_items.data();
     plan_runs(pa, units, m.visit_units);
     m.n_counters = h->mu * h->rounds * h->IB;
     CK(dev_alloc(&m.d_units, units.size()));
-    CK(dev_alloc(&m.d_counters, (size_t)m.n_counters));
+    CK(dev_alloc(&m.d_counters, (size_t)m.n_counters * COUNTER_EPOCHS));
     if (!units.empty()) CK(cudaMemcpy(m.d_units, units.data(), units.size() * sizeof(HotUnit), cudaMemcpyHostToDevice));
     return MFSGD_OK;
 }
@@ -863,7 +887,8 @@ extern "C" int mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const i
 extern "C" int mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout) {
     if (!h || !sp) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (sp->n_total < 0 || sp->log2_alpha_user < 0 || sp->log2_alpha_user > 6 || sp->log2_alpha_item < 0 || sp->log2_alpha_item > 6 ||
-        !(sp->c_user >= 0.0 && sp->c_user < 1.0) || !(sp->c_item >= 0.0 && sp->c_item < 1.0))
+        !(sp->c_user >= 0.0 && sp->c_user < 1.0) || !(sp->c_item >= 0.0 && sp->c_item < 1.0) || !(sp->planted_amplitude >= 0.f) ||
+        !(sp->noise_scale >= 0.f))
         return fail(MFSGD_E_INVALID_ARG, "bad synthetic parameters");
     Source s;
     s.synthetic = true;
@@ -875,6 +900,8 @@ extern "C" int mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_param
     s.synth.l2ai = sp->log2_alpha_item;
     s.synth.cu = sp->c_user;
     s.synth.ci = sp->c_item;
+    s.synth.amplitude = sp->planted_amplitude > 0.f ? sp->planted_amplitude : 0.8660254f;
+    s.synth.noise_scale = sp->noise_scale > 0.f ? sp->noise_scale : 0.5f;
     CKRC(load_training(h, s, true));
     int64_t nt = 0, nh = 0;
     for (Member& m : h->members) { nt += m.n_recs; nh += m.heldout.n; }
@@ -990,7 +1017,7 @@ static int ensure_part_events(mfsgd_handle* h, Member& m) {
     return MFSGD_OK;
 }
 
-static int rotate_part(mfsgd_handle* h, Member& m, int part) {
+static int rotate_part(mfsgd_handle* h, Member& m, int part, cudaStream_t after) {
     const int G = h->G, k = h->cfg.k;
     const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
     const int send_grp = m.held_group, recv_grp = (m.held_group + 1) % G;
@@ -998,7 +1025,7 @@ static int rotate_part(mfsgd_handle* h, Member& m, int part) {
     const int32_t r_lo = h->item_bounds[(size_t)recv_grp * h->mi + part], r_hi = h->item_bounds[(size_t)recv_grp * h->mi + part + 1];
     float* sptr = m.Q[m.cur] + (size_t)(s_lo - group_lo(h, send_grp)) * k;
     float* rptr = m.Q[m.cur ^ 1] + (size_t)(r_lo - group_lo(h, recv_grp)) * k;
-    CK(cudaEventRecord(m.ev_part_done[(size_t)part], m.stream));
+    CK(cudaEventRecord(m.ev_part_done[(size_t)part], after));
     CK(cudaStreamWaitEvent(m.copy_stream, m.ev_part_done[(size_t)part], 0));
     CKN(g_nccl.GroupStart());
     CKN(g_nccl.Send(sptr, (size_t)(s_hi - s_lo) * k, ncclFloat, to, h->comm, m.copy_stream));
@@ -1115,6 +1142,109 @@ static int shuffle_member(mfsgd_handle* h, Member& m, int epoch, bool prefetch_n
 
 static int rmse_pass(mfsgd_handle* h, bool heldout, double* sse_out, int64_t* n_out);
 
+// Lane mode: the item sub-shards ("parts") of a sub-epoch are launched separately (pipelined rotation of a multi-process
+// ring, or MFSGD_FLAG_SPLIT_SHARDS). Part p's launches go to lane p % N_LANES, a stream pair of its own: consecutive parts
+// work on disjoint item rows (and Hogwild-style on the same P stripe), so they may run side by side -- the next part's
+// runs fill the SMs the previous part's last runs leave idle, its Q slice travels while the other lane computes, and the
+// chain of a lane runs ahead across sub-epoch and epoch boundaries as far as its own slices allow. The member's main
+// stream only coordinates (timing events, joins). Round 1 launched all parts on one stream with an event in between,
+// which cost ~25 % of an 8-GPU epoch in launch tails (profiles/r01_bench.md).
+static const int N_LANES = 2;
+
+static int ensure_lanes(Member& m) {
+    while ((int)m.lanes.size() < N_LANES) {
+        Lane l;
+        CK(cudaStreamCreateWithFlags(&l.cold, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&l.hot, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        m.lanes.push_back(l);
+    }
+    return MFSGD_OK;
+}
+
+// main stream waits for everything the lanes have been given so far
+static int join_lanes(Member& m) {
+    for (Lane& l : m.lanes)
+        if (l.used) {
+            CK(cudaEventRecord(l.done, l.cold));
+            CK(cudaStreamWaitEvent(m.stream, l.done, 0));
+            l.used = false;
+        }
+    return MFSGD_OK;
+}
+
+// The update launches of item blocks [ib_lo, ib_hi) of sub-epoch s: every (sub-stripe, round) visit's cold records on
+// `cold_s` (full-grid Hogwild kernel) and its runs on `hot_s` (run kernel); hot_s forks from cold_s before and joins after.
+static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_t ib_lo, size_t ib_hi, bool fast_arith,
+                          cudaStream_t cold_s, cudaStream_t hot_s, cudaEvent_t ev_fork, cudaEvent_t ev_join, cudaEvent_t mark_cold,
+                          cudaEvent_t mark_hot, bool* any_cold, bool* any_hot) {
+    const mfsgd_config& c = h->cfg;
+    struct Visit { int64_t lo, hi; size_t cblk; int unit_lo, unit_hi; };
+    std::vector<Visit> visits;
+    visits.reserve((size_t)h->mu * h->rounds);
+    bool has_hot = false;
+    for (int vis = 0; vis < h->mu * h->rounds; vis++) {
+        const int rnd = vis / h->mu;
+        // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
+        const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
+        const int pos = vis % h->mu;
+        const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
+        Visit v;
+        slice_of(m, (size_t)sa * h->IB + ib_lo, (size_t)sa * h->IB + ib_hi, rnd, h->rounds, &v.lo, &v.hi);
+        v.cblk = (size_t)sa * h->IB + ib_lo;
+        const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
+        v.unit_lo = m.d_units ? m.visit_units[vkey + ib_lo] : 0;
+        v.unit_hi = m.d_units ? m.visit_units[vkey + ib_hi] : 0;
+        has_hot = has_hot || v.unit_hi > v.unit_lo;
+        visits.push_back(v);
+    }
+    if (has_hot) {
+        CK(cudaEventRecord(ev_fork, cold_s));
+        CK(cudaStreamWaitEvent(hot_s, ev_fork, 0));
+    }
+    bool hot_chained = false;       // the previous operation on hot_s is a run launch of this part
+    for (size_t vi = 0; vi < visits.size(); vi++) {
+        const Visit& v = visits[vi];
+        if (v.hi > v.lo) {          // cold records: full-grid Hogwild kernel
+            a.recs = m.recs[m.rcur];
+            a.first = v.lo;
+            a.n = v.hi - v.lo;
+            a.blk_start = m.block_off[v.cblk];
+            a.blk_n = m.block_off[v.cblk + 1] - m.block_off[v.cblk];
+            a.blk_id = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + v.cblk);
+            CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, cold_s, &m.launches));
+            m.update_launches++;
+            *any_cold = true;
+        }
+        if (v.unit_hi > v.unit_lo) {   // runs: one sub-warp per run, q_i in registers
+            a.recs = m.recs[m.rcur];
+            a.first = 0;
+            a.n = m.n_recs;
+            if (m.counter_next >= m.n_counters * COUNTER_EPOCHS) return fail(MFSGD_E_STATE, "run launch counters exhausted");
+            bool next_overlaps = false;    // will the next run launch of this chain overlap this one's tail?
+            for (size_t vj = vi + 1; vj < visits.size(); vj++)
+                if (visits[vj].unit_hi > visits[vj].unit_lo) {
+                    next_overlaps = hot_launch_overlaps(c.k, visits[vj].unit_hi - visits[vj].unit_lo, m.hot_grid);
+                    break;
+                }
+            CK(launch_sgd_update_hot(a, m.d_units + v.unit_lo, v.unit_hi - v.unit_lo, m.d_counters + m.counter_next++, fast_arith,
+                                     m.hot_grid, hot_chained, next_overlaps, hot_s, &m.launches));
+            hot_chained = true;
+            m.update_launches++;
+            *any_hot = true;
+        }
+    }
+    if (mark_cold) CK(cudaEventRecord(mark_cold, cold_s));
+    if (mark_hot) CK(cudaEventRecord(mark_hot, has_hot ? hot_s : cold_s));
+    if (has_hot) {
+        CK(cudaEventRecord(ev_join, hot_s));
+        CK(cudaStreamWaitEvent(cold_s, ev_join, 0));
+    }
+    return MFSGD_OK;
+}
+
 static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (epochs < 0) return fail(MFSGD_E_INVALID_ARG, "epochs < 0");
@@ -1124,17 +1254,34 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
     if (err_trace && c.mode != MFSGD_MODE_DETERMINISTIC) return fail(MFSGD_E_STATE, "error traces exist in DETERMINISTIC mode only");
     const bool time_kernels = (c.flags & MFSGD_FLAG_TIME_KERNELS) != 0;
     const bool fast_arith = !(c.flags & MFSGD_FLAG_EXACT_ARITH);
-    float* d_trace = nullptr;
+    struct TraceBuf {            // freed on every exit path
+        float* p = nullptr;
+        int device = 0;
+        ~TraceBuf() {
+            if (p) {
+                cudaSetDevice(device);
+                cudaFree(p);
+            }
+        }
+    } trace;
     if (err_trace && h->members[0].n_recs > 0) {
-        CK(cudaSetDevice(h->members[0].device));
-        CK(dev_alloc(&d_trace, (size_t)h->members[0].n_recs));
+        trace.device = h->members[0].device;
+        CK(cudaSetDevice(trace.device));
+        CK(dev_alloc(&trace.p, (size_t)h->members[0].n_recs));
     }
+    float* const d_trace = trace.p;
     int rc = MFSGD_OK;
     for (Member& m : h->members) {
         m.ev_used = 0;
         m.pending.clear();
         m.kev.clear();
     }
+    // parts: item sub-shards launched separately -- always when the rotation is pipelined, else on request
+    // (MFSGD_FLAG_SPLIT_SHARDS: a single GPU then replays the launch sizes of a larger ring)
+    const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1 && c.mode != MFSGD_MODE_DETERMINISTIC;
+    const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
+    const int blocks_per_part = h->mi / parts;
+    const bool lane_mode = parts > 1 && c.mode != MFSGD_MODE_DETERMINISTIC;
     int resolved = 0;   // epochs of this call whose stats are final
     // Epochs are enqueued back to back (no host sync in between) unless per-epoch evaluation is on;
     // their event records are resolved after the next synchronisation point.
@@ -1157,12 +1304,14 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     float t = 0.f;
                     CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 1]));
                     kms += t;
-                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 2]));
-                    cms += t;
-                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 3]));
-                    hms += t;
-                    CK(cudaEventElapsedTime(&t, m.kev[(size_t)j + 1], m.kev[(size_t)j + 4]));
-                    xms += t;
+                    if (!lane_mode) {     // lanes overlap parts and sub-epochs: only the span is meaningful there
+                        CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 2]));
+                        cms += t;
+                        CK(cudaEventElapsedTime(&t, m.kev[(size_t)j], m.kev[(size_t)j + 3]));
+                        hms += t;
+                        CK(cudaEventElapsedTime(&t, m.kev[(size_t)j + 1], m.kev[(size_t)j + 4]));
+                        xms += t;
+                    }
                 }
                 st.cold_ms = std::max(st.cold_ms, cms);
                 st.hot_ms = std::max(st.hot_ms, hms);
@@ -1186,18 +1335,31 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             m.update_launches = 0;
             Member::EpochRec er{};
             CK(cudaSetDevice(m.device));
+            if (lane_mode) CKRC(ensure_lanes(m));
             CKRC(timing_event(m, &er.start));
             CKRC(timing_event(m, &er.shuffled));
             CKRC(timing_event(m, &er.end));
             er.kbeg = er.kend = (int)m.kev.size();
             m.pending.push_back(er);
             CK(cudaEventRecord(er.start, m.stream));
-            if (m.d_counters) {
-                CK(cudaMemsetAsync(m.d_counters, 0, (size_t)m.n_counters * sizeof(unsigned int), m.stream));
+            bool gate = false;   // lanes must wait for something the main stream does at this epoch's start
+            if (m.d_counters && ep % COUNTER_EPOCHS == 0) {
+                if (lane_mode) CKRC(join_lanes(m));     // no launch of an earlier batch may still be claiming runs
+                CK(cudaMemsetAsync(m.d_counters, 0, (size_t)m.n_counters * COUNTER_EPOCHS * sizeof(unsigned int), m.stream));
                 m.counter_next = 0;
+                gate = true;
+            }
+            const bool reshuffles = c.mode == MFSGD_MODE_DETERMINISTIC || (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) && !h->virtual_shuffle);
+            if (lane_mode && reshuffles) {
+                CKRC(join_lanes(m));                    // the reshuffle rewrites the record buffer the lanes read
+                gate = true;
             }
             if (!(c.flags & MFSGD_FLAG_NO_SHUFFLE) || c.mode == MFSGD_MODE_DETERMINISTIC) CKRC(shuffle_member(h, m, h->epoch, true));
             CK(cudaEventRecord(er.shuffled, m.stream));
+            if (lane_mode && gate) {
+                CK(cudaEventRecord(m.ev_epoch_go, m.stream));
+                for (Lane& l : m.lanes) CK(cudaStreamWaitEvent(l.cold, m.ev_epoch_go, 0));
+            }
         }
         for (int s = 0; s < h->G; s++) {
             for (Member& m : h->members) {
@@ -1224,9 +1386,6 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                         CK(cudaMemcpyAsync(err_trace + (size_t)ep * m.n_recs, d_trace, (size_t)m.n_recs * 4, cudaMemcpyDeviceToHost, m.stream));
                     continue;
                 }
-                // The cold (full-grid Hogwild) launches go to m.stream, the hot-item launches to m.hot_stream:
-                // they touch the same P sub-stripes Hogwild-style and fill each other's tails. Fork here, join
-                // before the Q rotation.
                 cudaEvent_t e0 = nullptr, e1 = nullptr, e_cold = nullptr, e_hot = nullptr, e_xchg = nullptr;
                 if (time_kernels) {
                     CKRC(timing_event(m, &e0));
@@ -1236,69 +1395,41 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     CKRC(timing_event(m, &e_xchg));
                     CK(cudaEventRecord(e0, m.stream));
                 }
-                const bool has_hot = m.d_units != nullptr && m.visit_units.back() > 0;
-                // parts: item sub-shards launched separately -- always when the rotation is pipelined, else on request
-                // (MFSGD_FLAG_SPLIT_SHARDS: a single GPU then replays the launch sizes of a larger ring)
-                const bool pipelined = h->multi_process && h->G > 1 && h->mi > 1;
-                const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
-                const int blocks_per_part = h->mi / parts;
-                if (pipelined) CKRC(ensure_part_events(h, m));
-                for (int part = 0; part < parts; part++) {
-                    if (pipelined && m.part_recv_pending[(size_t)part]) {      // this slice of the group has to have arrived
-                        CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[(size_t)part], 0));
-                        m.part_recv_pending[(size_t)part] = 0;
-                    }
-                    if (has_hot) {
-                        CK(cudaEventRecord(m.ev_fork, m.stream));
-                        CK(cudaStreamWaitEvent(m.hot_stream, m.ev_fork, 0));
-                    }
-                    bool hot_chained = false;       // the previous operation on hot_stream is a hot launch of this part
-                    for (int vis = 0; vis < h->mu * h->rounds; vis++) {
-                        const int rnd = vis / h->mu;
-                        // sub-stripe order of this round: a fresh rotation + direction per (epoch, sub-epoch, round)
-                        const uint64_t hv = hash64(c.seed, 10, ((uint64_t)h->epoch << 24) ^ ((uint64_t)s << 12) ^ (uint64_t)rnd);
-                        const int pos = vis % h->mu;
-                        const int sa = (int)(((hv >> 1) + (uint64_t)((hv & 1) ? pos : h->mu - 1 - pos)) % (uint64_t)h->mu);
+                bool any_cold = false, any_hot = false;
+                if (!lane_mode) {
+                    // The cold (full-grid Hogwild) launches go to m.stream, the run launches to m.hot_stream: they touch the
+                    // same P sub-stripes Hogwild-style and fill each other's tails. Fork here, join before the Q rotation.
+                    const size_t ib_lo = (size_t)grp * h->mi, ib_hi = ib_lo + (size_t)h->mi;
+                    // (the time marks are recorded on the two streams before they join: cold = last Hogwild launch done,
+                    // hot = last run launch done, both measured from the sub-epoch's start)
+                    CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, m.stream, m.hot_stream, m.ev_fork, m.ev_join, e_cold, e_hot,
+                                        &any_cold, &any_hot));
+                } else {
+                    if (pipelined) CKRC(ensure_part_events(h, m));
+                    for (int part = 0; part < parts; part++) {
+                        Lane& l = m.lanes[(size_t)(part % N_LANES)];
+                        if (pipelined && m.part_recv_pending[(size_t)part]) {      // this slice of the group has to have arrived
+                            CK(cudaStreamWaitEvent(l.cold, m.ev_part_recv[(size_t)part], 0));
+                            m.part_recv_pending[(size_t)part] = 0;
+                        }
                         const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
-                        int64_t lo, hi;
-                        slice_of(m, (size_t)sa * h->IB + ib_lo, (size_t)sa * h->IB + ib_hi, rnd, h->rounds, &lo, &hi);
-                        const size_t vkey = ((size_t)sa * h->rounds + rnd) * h->IB;
-                        const int unit_lo = m.visit_units[vkey + ib_lo], unit_hi = m.visit_units[vkey + ib_hi];
-                        if (hi > lo) {      // cold records: full-grid Hogwild kernel
-                            const size_t cblk = (size_t)sa * h->IB + ib_lo;
-                            a.recs = m.recs[m.rcur];
-                            a.first = lo;
-                            a.n = hi - lo;
-                            a.blk_start = m.block_off[cblk];
-                            a.blk_n = m.block_off[cblk + 1] - m.block_off[cblk];
-                            a.blk_id = (uint32_t)((size_t)m.g * (m.block_off.size() - 1) + cblk);
-                            CK(launch_sgd_update_hogwild(a, c.scatter, fast_arith, m.grid, h->min_windows, m.stream, &m.launches));
-                            m.update_launches++;
-                        }
-                        if (unit_hi > unit_lo) {   // hot items: one warp per run, q_i in registers
-                            a.recs = m.recs[m.rcur];
-                            a.first = 0;
-                            a.n = m.n_recs;
-                            if (m.counter_next >= m.n_counters) return fail(MFSGD_E_STATE, "hot launch counters exhausted");
-                            CK(launch_sgd_update_hot(a, m.d_units + unit_lo, unit_hi - unit_lo, m.d_counters + m.counter_next++, fast_arith,
-                                                     m.hot_grid, hot_chained, m.hot_stream, &m.launches));
-                            hot_chained = true;
-                            m.update_launches++;
-                        }
+                        CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, l.cold, l.hot, l.fork, l.join, nullptr, nullptr, &any_cold,
+                                            &any_hot));
+                        l.used = true;
+                        if (pipelined) CKRC(rotate_part(h, m, part, l.cold));
                     }
-                    if (time_kernels && part == parts - 1) {
+                    if (pipelined) {          // all slices are on their way: the other buffer holds the next group
+                        m.cur ^= 1;
+                        m.held_group = (m.held_group + 1) % h->G;
+                    }
+                    if (time_kernels) {       // span of this sub-epoch's launches on the coordinating stream (does not hold the lanes back)
+                        for (Lane& l : m.lanes) {
+                            CK(cudaEventRecord(l.done, l.cold));
+                            CK(cudaStreamWaitEvent(m.stream, l.done, 0));
+                        }
                         CK(cudaEventRecord(e_cold, m.stream));
-                        CK(cudaEventRecord(e_hot, has_hot ? m.hot_stream : m.stream));
+                        CK(cudaEventRecord(e_hot, m.stream));
                     }
-                    if (has_hot) {
-                        CK(cudaEventRecord(m.ev_join, m.hot_stream));
-                        CK(cudaStreamWaitEvent(m.stream, m.ev_join, 0));
-                    }
-                    if (pipelined) CKRC(rotate_part(h, m, part));
-                }
-                if (pipelined) {          // all slices are on their way: the other buffer holds the next group
-                    m.cur ^= 1;
-                    m.held_group = (m.held_group + 1) % h->G;
                 }
                 if (time_kernels) {
                     CK(cudaEventRecord(e1, m.stream));
@@ -1309,7 +1440,21 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     m.kev.push_back(e_xchg);
                 }
             }
-            if (!(h->multi_process && h->G > 1 && h->mi > 1 && c.mode != MFSGD_MODE_DETERMINISTIC)) CKRC(rotate_q(h));
+            if (!pipelined) {
+                const bool around = lane_mode && h->G > 1;     // whole-group rotation between laned sub-epochs: lanes -> main -> lanes
+                if (around)
+                    for (Member& m : h->members) {
+                        CK(cudaSetDevice(m.device));
+                        CKRC(join_lanes(m));
+                    }
+                CKRC(rotate_q(h));
+                if (around)
+                    for (Member& m : h->members) {
+                        CK(cudaSetDevice(m.device));
+                        CK(cudaEventRecord(m.ev_epoch_go, m.stream));
+                        for (Lane& l : m.lanes) CK(cudaStreamWaitEvent(l.cold, m.ev_epoch_go, 0));
+                    }
+            }
             if (time_kernels && c.mode != MFSGD_MODE_DETERMINISTIC)
                 for (Member& m : h->members) {
                     CK(cudaSetDevice(m.device));
@@ -1319,6 +1464,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         for (Member& m : h->members) {
             Member::EpochRec& er = m.pending.back();
             CK(cudaSetDevice(m.device));
+            if (lane_mode) CKRC(join_lanes(m));        // the main stream only observes: the lanes are not held back by this
             // Q is home again once the last slices have arrived. Between back-to-back epochs of one call that wait is left
             // to the next epoch's first launches (per slice), so the pipeline keeps running across the epoch boundary.
             const bool drain = (ep + 1 == epochs) || want_eval;
@@ -1342,10 +1488,6 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         }
     }
     if (rc == MFSGD_OK) rc = resolve(epochs);
-    if (d_trace) {
-        cudaSetDevice(h->members[0].device);
-        cudaFree(d_trace);
-    }
     return rc;
 }
 
@@ -1530,16 +1672,19 @@ extern "C" int mfsgd_plan_layout(const mfsgd_config* cfg, int64_t l2_bytes, int6
 // Test hook: the run planner (run_plan.hpp) on caller-provided bucket offsets. Host-only.
 extern "C" int mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
                                const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,
-                               int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight, int64_t* n_units,
-                               int32_t* visit_units) {
+                               float merge_boost, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
+                               int64_t* n_units, int32_t* visit_units) {
     if (!block_off || !hot_block_lo || (n_hot > 0 && !hot_items) || !n_units || !visit_units) return fail(MFSGD_E_INVALID_ARG, "null argument");
-    if (stripes < 1 || n_hot < 0 || item_blocks < 1 || rounds < 1 || chunk < 1 || member < 0) return fail(MFSGD_E_INVALID_ARG, "bad shape");
+    if (stripes < 1 || n_hot < 0 || item_blocks < 1 || rounds < 1 || chunk < 1 || chunk > 65536 || member < 0 || !(merge_boost >= 0.f) ||
+        merge_boost >= 2.f)
+        return fail(MFSGD_E_INVALID_ARG, "bad shape");
     RunPlanArgs pa{};
     pa.block_off = block_off;
     pa.n_blocks = (size_t)stripes * ((size_t)item_blocks + (size_t)n_hot);
     pa.mu = stripes; pa.H = n_hot; pa.IB = item_blocks; pa.rounds = rounds; pa.chunk = chunk;
     pa.member = member;
     pa.seed = seed;
+    pa.boost = merge_boost > 0.f ? merge_boost : DEFAULT_MERGE_BOOST;
     pa.hot_block_lo = hot_block_lo;
     pa.hot_items = hot_items;
     std::vector<HotUnit> units;
@@ -1646,6 +1791,8 @@ extern "C" int mfsgd_generate_to_host(int32_t device, const mfsgd_synth_params* 
     SynthArgs s{};
     s.seed = sp->seed; s.n_users = n_users; s.n_items = n_items;
     s.l2au = sp->log2_alpha_user; s.l2ai = sp->log2_alpha_item; s.cu = sp->c_user; s.ci = sp->c_item;
+    s.amplitude = sp->planted_amplitude > 0.f ? sp->planted_amplitude : 0.8660254f;
+    s.noise_scale = sp->noise_scale > 0.f ? sp->noise_scale : 0.5f;
     int32_t *du = nullptr, *di = nullptr;
     float* dr = nullptr;
     uint8_t* dh = nullptr;

@@ -91,8 +91,10 @@ struct HotUnit {
 };
 // follows_hot_launch: the previous operation on `stream` is a hot launch of the same sub-epoch (it may then be overlapped
 // by programmatic dependent launch, see kernels_update.cu).
+// overlapped_by_next: the NEXT launch on the chain will overlap this one's tail (hot_launch_overlaps of its size).
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
-                                  int grid, bool follows_hot_launch, cudaStream_t stream, int* launches);
+                                  int grid, bool follows_hot_launch, bool overlapped_by_next, cudaStream_t stream, int* launches);
+bool hot_launch_overlaps(int k, int n_units, int full_grid);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
@@ -110,6 +112,7 @@ struct SynthArgs {
     uint64_t seed;
     int32_t n_users, n_items, l2au, l2ai;
     double cu, ci;
+    float amplitude, noise_scale;   // planted amplitude and noise scale (stand-in defaults: PLANTED_AMPLITUDE, 0.5)
 };
 cudaError_t launch_generate(const SynthArgs& s, int64_t start, int64_t count, int32_t* u, int32_t* i, float* r,
                             uint8_t* held, cudaStream_t stream, int* launches);

@@ -122,9 +122,8 @@ __device__ __forceinline__ int32_t skewed_rank(double x, int32_t count, int log2
 __device__ __forceinline__ int32_t scatter_id(int32_t rank, int32_t count) {
     return (int32_t)((((uint64_t)rank * ID_MULT) + (uint64_t)(count / 2)) % (uint64_t)count);
 }
-__device__ __forceinline__ float planted_entry(uint64_t seed, uint64_t stream, int32_t row, int f) {
-    return __fmul_rn(__fsub_rn(uniform24(seed, stream, (uint64_t)row * PLANTED_RANK + (uint64_t)f), 0.5f),
-                     PLANTED_AMPLITUDE);
+__device__ __forceinline__ float planted_entry(uint64_t seed, uint64_t stream, int32_t row, int f, float amplitude) {
+    return __fmul_rn(__fsub_rn(uniform24(seed, stream, (uint64_t)row * PLANTED_RANK + (uint64_t)f), 0.5f), amplitude);
 }
 
 __global__ void __launch_bounds__(256) generate_kernel(SynthArgs s, int64_t start, int64_t count,
@@ -138,14 +137,14 @@ __global__ void __launch_bounds__(256) generate_kernel(SynthArgs s, int64_t star
         float dot = 0.0f;
 #pragma unroll
         for (int f = 0; f < PLANTED_RANK; f++)
-            dot = __fadd_rn(dot, __fmul_rn(planted_entry(s.seed, STREAM_PSTAR, uu, f),
-                                           planted_entry(s.seed, STREAM_QSTAR, ii, f)));
+            dot = __fadd_rn(dot, __fmul_rn(planted_entry(s.seed, STREAM_PSTAR, uu, f, s.amplitude),
+                                           planted_entry(s.seed, STREAM_QSTAR, ii, f, s.amplitude)));
         float noise = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; j++) noise = __fadd_rn(noise, uniform24(s.seed, STREAM_NOISE, 4ULL * n + (uint64_t)j));
         noise = __fsub_rn(noise, 2.0f);
         float rating = __fadd_rn(3.5f, dot);
-        rating = __fadd_rn(rating, __fmul_rn(0.5f, noise));
+        rating = __fadd_rn(rating, __fmul_rn(s.noise_scale, noise));
         if (rating < 1.0f) rating = 1.0f;
         if (rating > 5.0f) rating = 5.0f;
         u[t] = uu;

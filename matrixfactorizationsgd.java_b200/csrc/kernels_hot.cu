@@ -5,7 +5,9 @@
 // dot, scatter p_u, update q_i -- the item row costs no L2 traffic and sees no concurrent writer inside the run.
 // At the end the run's net change is merged into Q scaled by unit.weight (model averaging over the item's
 // concurrent runs); a run that is alone on its item in the launch (weight 1) stores q_i outright, which makes
-// the path exactly sequential.
+// the path exactly sequential -- unless the launch overlaps its predecessor (programmatic dependent launch): then a
+// run of the same item from the previous visit's tail may still be merging, and the weight-1 run adds its net
+// change with red.global.add as well instead of overwriting the row (always_add).
 //
 // Geometry: LANES lanes per rating, each holding VEC <= 4 float4 chunks of the row (chunk c belongs to lane c % LANES,
 // so every load/store instruction moves >= 128 contiguous bytes per sub-warp = full sectors); the warp's 32/LANES
@@ -45,7 +47,7 @@ __device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddep
 
 template <int LANES, int VEC, bool FULL, bool FAST, int D>
 __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
-                                                                                 unsigned int* __restrict__ counter) {
+                                                                                 unsigned int* __restrict__ counter, int always_add) {
     constexpr int GPW = 32 / LANES;                   // runs walked side by side by one warp
     constexpr int S = LANES;                          // steps per record tile (a sub-warp stages LANES records at a time)
     constexpr int RING = 4 * LANES;                   // records of a run resident in shared memory (4 tiles)
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 if (FULL || gl + v * LANES < chunks) {
-                    if (hu.weight == 1.0f) {
+                    if (hu.weight == 1.0f && !always_add) {
                         st_row4(qrow + 4 * v * LANES, q[v]);
                     } else {
                         const float w = hu.weight;
@@ -230,8 +232,8 @@ static int run_pdl() {
     } while (0)
 
 template <typename Kernel>
-static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, bool pdl, const UpdateArgs& a, const HotUnit* units,
-                               int n_units, unsigned int* counter) {
+static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, bool pdl, int always_add, const UpdateArgs& a,
+                               const HotUnit* units, int n_units, unsigned int* counter) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(256);
@@ -242,11 +244,17 @@ static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, boo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, a, units, n_units, counter);
+    return cudaLaunchKernelEx(&cfg, kernel, a, units, n_units, counter, always_add);
+}
+
+// Does a run launch of n_units on a chain of run launches overlap its predecessor's tail (programmatic dependent launch)?
+bool hot_launch_overlaps(int k, int n_units, int full_grid) {
+    const int per_warp = 32 / run_geometry_for(k).lanes;
+    return run_pdl() != 0 && (run_pdl() == 2 || (int64_t)n_units >= 2LL * full_grid * 8 * per_warp);
 }
 
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
-                                  int grid, bool follows_hot_launch, cudaStream_t stream, int* launches) {
+                                  int grid, bool follows_hot_launch, bool overlapped_by_next, cudaStream_t stream, int* launches) {
     if (n_units <= 0) return cudaSuccess;
     const Geometry g = run_geometry_for(a.k);
     const int per_warp = 32 / g.lanes;            // runs a warp walks side by side
@@ -262,13 +270,15 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     // with a whole epoch in flight p_u and q_i are both corrected from the same stale state and the product overshoots
     // (profiles/r01_experiments.md section 8).
     // MFSGD_PDL = 2 overlaps every chained launch (tuning aid).
-    const bool pdl = follows_hot_launch && run_pdl() != 0 && (run_pdl() == 2 || (int64_t)n_units >= 2LL * full_grid * 8 * per_warp);
+    const bool pdl = follows_hot_launch && hot_launch_overlaps(a.k, n_units, full_grid);
+    // a launch that overlaps a neighbour (either side) never overwrites an item row: its weight-1 runs add their net change too
+    const int always_add = (pdl || overlapped_by_next) ? 1 : 0;
     const bool d2 = run_depth() == 2;
     cudaError_t err = cudaSuccess;
 #define CALL(L, V, F)                                                                                                        \
-    err = (fast && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2>, grid, stream, pdl, a, units, n_units, counter)  \
-          : fast       ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4>, grid, stream, pdl, a, units, n_units, counter)  \
-                       : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4>, grid, stream, pdl, a, units, n_units, counter)
+    err = (fast && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+          : fast       ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+                       : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4>, grid, stream, pdl, always_add, a, units, n_units, counter)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;

@@ -3,8 +3,8 @@
 //   * a bucket is spread over as many of the `rounds` interleaved passes as it has runs of >= 2 * MIN_RUN records for
 //     (frequently rated items: all of them); a small bucket is walked whole in one pass -- which one is hashed from
 //     (sub-stripe, item), so the passes stay balanced;
-//   * a pass's slice is cut into ceil(n / chunk) equal runs; a run's merge weight is 1 / (runs of its slice), i.e.
-//     the runs of one item in one launch are averaged (kernels_hot.cu);
+//   * a pass's slice is cut into ceil(n / chunk) equal runs; a run's merge weight is min(1, boost / runs of its slice), i.e.
+//     the runs of one item in one launch are averaged, slightly over-relaxed (kernels_hot.cu; merge_weight below);
 //   * inside a visit the runs are ordered longest first (stable), so the launch's tail is made of short runs and the
 //     runs a warp walks side by side have about the same length.
 // Exposed for CPU tests through mfsgd_plan_runs (include/mfsgd.h).
@@ -24,15 +24,15 @@ static const int MIN_RUN = 16;   // shortest run worth a sub-warp of the run ker
 // ---- blocking of a ring member's work (pure functions of the configuration) -----------------------------------------
 // Sub-stripes of P per ring member (mu) and item sub-shards per member (mi). Auto mu keeps one P sub-stripe plus the
 // held Q shard group resident in L2 (measured on the Netflix-shaped workload: 61 MB sub-stripes beat 35 MB and 82 MB
-// ones); auto mi = 2 where the rotation is pipelined (a multi-process ring of >= 4 sends one slice of Q while the next
-// trains; with 2 members the rotation is 2 of ~20 launches per epoch and not worth the smaller launches).
+// ones); auto mi = 2 where the rotation is pipelined (a multi-process ring sends one slice of Q while the other trains;
+// the two slices' launches run on two stream lanes and fill each other's tails, engine.cu lane mode).
 struct Blocking {
     int mu, mi;
 };
 inline Blocking plan_blocking(int n_users, int n_items, int k, int G, int mode, int stripes_per_gpu, int shards_per_gpu,
                               bool multi_process, double l2_bytes) {
     Blocking b;
-    b.mi = shards_per_gpu > 0 ? shards_per_gpu : (multi_process && G >= 4 && mode == MFSGD_MODE_DSGD ? 2 : 1);
+    b.mi = shards_per_gpu > 0 ? shards_per_gpu : (multi_process && G >= 2 && mode == MFSGD_MODE_DSGD ? 2 : 1);
     if (mode == MFSGD_MODE_DETERMINISTIC) {
         b.mu = 1;
     } else if (stripes_per_gpu > 0) {
@@ -70,20 +70,32 @@ inline int plan_rounds(int rounds_cfg, int mode, int G, int mu, int64_t member_r
     return rounds;
 }
 
-// Longest run. 256 by default: a run is walked by one sub-warp, one rating after another, so a launch lasts at least
-// one run; shorter runs mean more parallelism but each makes less progress on q_i before the item's runs are averaged
-// (128 already costs ~1 % RMSE on small inputs; 256 does not). Rings that merge an item >= 8 times per epoch launch
-// small blocks, where 256-rating runs leave warp slots empty while the more frequent merges keep shorter runs
-// converging (8-ring, Netflix-shaped: run 64 ends 0.35 % BELOW the oracle's RMSE, only the first epoch lags): offer ~3
-// runs per resident sub-warp, 64..256 (8-ring proxy, 0.7 M-rating launches: run 64 -> 1.34 ms per epoch, 96 -> 1.42,
-// 128 -> 1.40, 192 -> 1.65, 256 -> 1.98).
+// Longest run. A run is walked by one sub-warp, one rating after another, and the runs of an item that share a launch
+// all start from the same q_i and are merged by a weighted average (plan_runs): every split of an item's slice costs
+// sequential progress on that item. Round 2 (tools/run_sim.py, signal-dominant sets -- on round 1's noise-dominant sets the
+// effect was invisible): runs of <= 256 trail the sequential oracle by 24 % / 9 % / 3.7 % in held-out RMSE after epochs
+// 1 / 2 / 3 of a Netflix-shaped set, runs of <= 1024 by 1.4 % / 0.1 % / 0.2 %. So runs are as long as the launch can
+// balance: the launch hands its runs out longest first, so its duration is about max(records / resident sub-warps,
+// longest run) -- the longest run may be about the per-sub-warp share of the launch. 64 <= run <= 1024, multiple of 32.
 inline int plan_run_length(int hot_chunk_cfg, int G, int mu, int rounds, int IB, int64_t run_records, int resident_ctas,
                            int runs_per_warp) {
+    (void)G;
     if (hot_chunk_cfg > 0) return hot_chunk_cfg;
-    if (G * mu * rounds < 8) return 256;
     const double per_launch = (double)run_records / ((double)mu * rounds * IB);
-    const double want = per_launch / (3.0 * resident_ctas * 8.0 * runs_per_warp);
-    return (int)std::min(256.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
+    const double want = per_launch / (1.25 * resident_ctas * 8.0 * runs_per_warp);
+    return (int)std::min(1024.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
+}
+
+// Merge weight of a run whose slice of its item's bucket was cut into `pieces` runs for one launch: min(1, boost / pieces).
+// boost = 1 is plain model averaging; the default 1.25 over-relaxes the average a little (the runs of a slice each saw only
+// 1 / pieces of its ratings, so their mean under-shoots what a sequential walk of the whole slice reaches; summing
+// them -- boost = pieces -- diverges). Chosen on tools/run_sim.py: held-out RMSE within +-0.6 % of the sequential oracle
+// at every epoch of the signal-dominant Netflix-shaped set (plain averaging ends 0.5 % below it, boost 1.9 3 % above).
+static const float DEFAULT_MERGE_BOOST = 1.25f;
+inline float merge_weight(int64_t pieces, float boost) {
+    if (pieces <= 1) return 1.0f;
+    const float w = (boost > 1.0f ? boost : 1.0f) / (float)pieces;
+    return w > 1.0f ? 1.0f : w;
 }
 
 struct RunPlanArgs {
@@ -92,6 +104,7 @@ struct RunPlanArgs {
     int mu, H, IB, rounds, chunk;  // sub-stripes, run items, item blocks, passes per sub-epoch, longest run
     int member;                    // ring member g (keys the buckets' per-epoch permutations)
     uint64_t seed;
+    float boost;                   // merge over-relaxation (merge_weight)
     const int32_t* hot_block_lo;   // IB + 1: run items [hot_block_lo[b], hot_block_lo[b+1]) lie in item block b
     const int32_t* hot_items;      // H global item ids, ascending
 };
@@ -129,7 +142,7 @@ inline void plan_runs(const RunPlanArgs& a, std::vector<HotUnit>& units, std::ve
                         u.start = lo + n * pc / pieces;
                         u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
                         u.item = a.hot_items[hx];
-                        u.weight = 1.0f / (float)pieces;
+                        u.weight = merge_weight(pieces, a.boost);
                         out.push_back(u);
                     }
                 }

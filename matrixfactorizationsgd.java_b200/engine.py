@@ -11,7 +11,8 @@ from ._capi import Config, EpochStats, LayoutInfo, SynthParams, check, lib, ptr,
 
 def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_HOGWILD, n_gpus=1,
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
-                world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0):
+                world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0,
+                merge_boost=0.0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -20,15 +21,17 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.stripes_per_gpu, cfg.shards_per_gpu = int(stripes_per_gpu), int(shards_per_gpu)
     cfg.scatter, cfg.flags, cfg.device = int(scatter), int(flags), int(device)
     cfg.world_size, cfg.rank, cfg.ctas_per_sm, cfg.rounds = int(world_size), int(rank), int(ctas_per_sm), int(rounds)
-    cfg.hot_share, cfg.hot_chunk = float(hot_share), int(hot_chunk)
+    cfg.hot_share, cfg.hot_chunk, cfg.merge_boost = float(hot_share), int(hot_chunk), float(merge_boost)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg
 
 
-def synth_params(n_total, seed=20261018, log2_alpha_user=2, c_user=0.25, log2_alpha_item=3, c_item=0.375):
+def synth_params(n_total, seed=20261018, log2_alpha_user=2, c_user=0.25, log2_alpha_item=3, c_item=0.375, amplitude=0.0,
+                 noise_scale=0.0):
+    """amplitude / noise_scale 0 = the stand-in's defaults (noise-dominant); see workloads.SIGNAL for the signal-dominant variant."""
     return SynthParams(int(n_total), int(seed), int(log2_alpha_user), int(log2_alpha_item), float(c_user),
-                       float(c_item))
+                       float(c_item), float(amplitude), float(noise_scale))
 
 
 def device_count():

@@ -275,7 +275,8 @@ ORC_API double orc_rmse(const float* P, const float* Q, int k, const int32_t* u,
 /* ---- synthetic power-law ratings: MatrixFactorizationSGD.java:186-239 ---- */
 
 static const int PLANTED_RANK = 16;
-static const float PLANTED_AMPLITUDE = 0.8660254f;
+static const float PLANTED_AMPLITUDE = 0.8660254f;   /* default planted amplitude (noise-dominant sets) */
+static const float NOISE_SCALE = 0.5f;               /* default noise scale */
 static const uint64_t ID_MULT = 2654435761ULL;
 
 /* MatrixFactorizationSGD.java:191 uniform53 */
@@ -301,23 +302,23 @@ ORC_API int32_t orc_scatter_id(int32_t rank, int32_t count) {
 }
 
 /* MatrixFactorizationSGD.java:215 plantedEntry */
-static inline float planted_entry(uint64_t seed, uint64_t stream, int32_t row, int f) {
-    return (orc_uniform(seed, stream, (uint64_t)row * PLANTED_RANK + (uint64_t)f) - 0.5f) * PLANTED_AMPLITUDE;
+static inline float planted_entry(uint64_t seed, uint64_t stream, int32_t row, int f, float amplitude) {
+    return (orc_uniform(seed, stream, (uint64_t)row * PLANTED_RANK + (uint64_t)f) - 0.5f) * amplitude;
 }
 
 /* MatrixFactorizationSGD.java:220 syntheticRecord */
 static inline bool synthetic_record(uint64_t seed, uint64_t n, int nU, int nI, int l2au, double cu, int l2ai,
-                                    double ci, int32_t* u, int32_t* i, float* r) {
+                                    double ci, float amplitude, float noise_scale, int32_t* u, int32_t* i, float* r) {
     int32_t uu = orc_scatter_id(orc_skewed_rank(uniform53(seed, STREAM_USER, n), nU, l2au, cu), nU);
     int32_t ii = orc_scatter_id(orc_skewed_rank(uniform53(seed, STREAM_ITEM, n), nI, l2ai, ci), nI);
     float dot = 0.0f;
     for (int f = 0; f < PLANTED_RANK; f++)
-        dot = dot + planted_entry(seed, STREAM_PSTAR, uu, f) * planted_entry(seed, STREAM_QSTAR, ii, f);
+        dot = dot + planted_entry(seed, STREAM_PSTAR, uu, f, amplitude) * planted_entry(seed, STREAM_QSTAR, ii, f, amplitude);
     float noise = 0.0f;
     for (int j = 0; j < 4; j++) noise = noise + orc_uniform(seed, STREAM_NOISE, 4ULL * n + (uint64_t)j);
     noise = noise - 2.0f;
     float rating = 3.5f + dot;
-    rating = rating + 0.5f * noise;
+    rating = rating + noise_scale * noise;
     if (rating < 1.0f) rating = 1.0f;
     if (rating > 5.0f) rating = 5.0f;
     *u = uu; *i = ii; *r = rating;
@@ -328,18 +329,159 @@ static inline bool synthetic_record(uint64_t seed, uint64_t n, int nU, int nI, i
  * Records [start, start+count) of the synthetic set, in record order; held[t] = 1 when record
  * start+t belongs to the held-out tenth. Split across `threads` host threads (pure function of n).
  */
-ORC_API void orc_generate(uint64_t seed, int64_t start, int64_t count, int nU, int nI, int l2au, double cu,
-                          int l2ai, double ci, int32_t* u, int32_t* i, float* r, uint8_t* held, int threads) {
+ORC_API void orc_generate2(uint64_t seed, int64_t start, int64_t count, int nU, int nI, int l2au, double cu,
+                           int l2ai, double ci, float amplitude, float noise_scale, int32_t* u, int32_t* i, float* r,
+                           uint8_t* held, int threads) {
     if (threads < 1) threads = 1;
+    if (!(amplitude > 0.0f)) amplitude = PLANTED_AMPLITUDE;      /* 0 = the default (noise-dominant) set */
+    if (!(noise_scale > 0.0f)) noise_scale = NOISE_SCALE;
     std::vector<std::thread> pool;
     for (int w = 0; w < threads; w++)
         pool.emplace_back([=]() {
             int64_t lo = count * w / threads, hi = count * (w + 1) / threads;
             for (int64_t t = lo; t < hi; t++)
-                held[t] = synthetic_record(seed, (uint64_t)(start + t), nU, nI, l2au, cu, l2ai, ci,
+                held[t] = synthetic_record(seed, (uint64_t)(start + t), nU, nI, l2au, cu, l2ai, ci, amplitude, noise_scale,
                                            u + t, i + t, r + t) ? 1 : 0;
         });
     for (auto& th : pool) th.join();
 }
 
+ORC_API void orc_generate(uint64_t seed, int64_t start, int64_t count, int nU, int nI, int l2au, double cu,
+                          int l2ai, double ci, int32_t* u, int32_t* i, float* r, uint8_t* held, int threads) {
+    orc_generate2(seed, start, count, nU, nI, l2au, cu, l2ai, ci, PLANTED_AMPLITUDE, NOISE_SCALE, u, i, r, held, threads);
+}
+
 ORC_API int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+/* ---- twins of the GPU engine's run path (no counterpart in the stand-in) ------------------------------------------
+ * The stand-in applies every rating sequentially (MatrixFactorizationSGD.java:127-133). The GPU's run kernel
+ * (csrc/kernels_hot.cu) applies RUNS of one item's ratings sequentially with q_i in registers and merges the runs of an
+ * item that share a launch by a weighted sum of their net changes. The functions below restate exactly that, on the
+ * CPU, from the same plan (mfsgd_plan_runs) -- so that the averaged-merge branch has an exact check, and so that the
+ * convergence of the merge rule can be studied without a GPU (tools/run_sim.py).
+ */
+
+/* csrc/common.cuh feistel_round / block_perm / perm_half_bits / bucket_perm_key, restated. */
+static inline uint32_t feistel_round(uint32_t x, uint32_t key) {
+    uint32_t h = (x + key) * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    return h;
+}
+
+ORC_API uint64_t orc_bucket_perm_key(uint64_t seed, uint32_t epoch, uint32_t bucket_id) {
+    return orc_hash64(seed, 9 /* STREAM_BLOCK_SHUFFLE */, ((uint64_t)epoch << 32) | (uint64_t)bucket_id);
+}
+
+/* position x of a bucket of n records reads record orc_block_perm(x, n, key) of that bucket (n > 1) */
+ORC_API uint64_t orc_block_perm(uint64_t x, uint64_t n, uint64_t key) {
+    const uint64_t tiles = n >> 5, full = tiles << 5;
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    if (x >= full) {
+        const uint32_t rem = (uint32_t)(n - full);
+        return full + (uint64_t)(((uint32_t)(x - full) + (k1 >> 8) % rem) % rem);
+    }
+    uint64_t t = x >> 5;
+    if (tiles > 1) {
+        int bits = 0;
+        while (bits < 63 && (1ULL << bits) < tiles) bits++;
+        if (bits < 2) bits = 2;
+        const int hb = (bits + 1) >> 1;
+        const uint32_t mask = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
+        do {
+            uint32_t l = (uint32_t)(t >> hb) & mask, r = (uint32_t)t & mask;
+            for (int round = 0; round < 4; round++) {
+                const uint32_t f = feistel_round(r, (round & 1) ? (k1 + round) : (k0 + round)) & mask;
+                const uint32_t nl = r;
+                r = l ^ f;
+                l = nl;
+            }
+            t = ((uint64_t)l << hb) | (uint64_t)r;
+        } while (t >= tiles);
+    }
+    const uint32_t h = feistel_round((uint32_t)t ^ k1, k0);
+    const uint32_t lane = ((((uint32_t)x & 31u) ^ ((h >> 16) & 31u)) * ((h & 31u) | 1u) + ((h >> 8) & 31u)) & 31u;
+    return (t << 5) | (uint64_t)lane;
+}
+
+/* out[j] = record index (relative to the bucket) read at position j, j in [0, n) */
+ORC_API void orc_block_perm_fill(uint64_t n, uint64_t seed, uint32_t epoch, uint32_t bucket_id, int64_t* out) {
+    const uint64_t key = orc_bucket_perm_key(seed, epoch, bucket_id);
+    for (uint64_t j = 0; j < n; j++) out[j] = n > 1 ? (int64_t)orc_block_perm(j, n, key) : (int64_t)j;
+}
+
+/*
+ * One launch of the run kernel. Units [0, n_units) in claim order (mfsgd_plan_runs: longest first). `resident`
+ * sub-warps walk runs side by side, one rating per tick each; sub-warps come in groups of `gpw` (the runs one warp
+ * walks side by side): a group claims gpw units at a time when all its runs are done. A run loads q_i when it starts,
+ * applies its ratings strictly in order (p_u read and written in place, q_i private), then merges:
+ * weight == 1 (and !always_add): Q[i] = q; else Q[i] += (q - q_at_start) * weight  (weight from the planner:
+ * min(1, merge_boost / runs of the slice), csrc/run_plan.hpp merge_weight).
+ * rec_u / rec_r: the member's record array in layout order (SoA); run position p reads record
+ * bstart + perm(p - bstart) when virt != 0, else record p.  P row = u - u_base, Q row = item - i_base.
+ */
+ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int64_t n_recs,
+                                  const int64_t* unit_start, const int32_t* unit_count, const int32_t* unit_item,
+                                  const float* unit_weight, const int64_t* unit_bstart, const int32_t* unit_bn,
+                                  const uint32_t* unit_bid, int64_t n_units, int virt, uint64_t seed, uint32_t epoch,
+                                  float* P, int32_t u_base, float* Q, int32_t i_base, int k, float lr, float lambda,
+                                  int order_mode, int resident, int gpw, int always_add) {
+    if (resident < 1 || gpw < 1 || resident % gpw) return -1;
+    struct Slot { int64_t unit; int step; std::vector<float> q, q0; uint64_t key; };
+    std::vector<Slot> slots((size_t)resident);
+    for (auto& s : slots) { s.unit = -1; s.step = 0; s.q.resize((size_t)k); s.q0.resize((size_t)k); s.key = 0; }
+    int64_t next = 0, done = 0;
+    const int groups = resident / gpw;
+    auto claim = [&](int g) {
+        for (int j = 0; j < gpw; j++) {
+            Slot& s = slots[(size_t)g * gpw + j];
+            if (next < n_units) {
+                s.unit = next++;
+                s.step = 0;
+                const float* qr = Q + (int64_t)(unit_item[s.unit] - i_base) * k;
+                std::memcpy(s.q.data(), qr, sizeof(float) * k);
+                std::memcpy(s.q0.data(), qr, sizeof(float) * k);
+                s.key = (virt && unit_bn[s.unit] > 1) ? orc_bucket_perm_key(seed, epoch, unit_bid[s.unit]) : 0;
+            } else s.unit = -1;
+        }
+    };
+    for (int g = 0; g < groups; g++) claim(g);
+    while (done < n_units) {
+        for (auto& s : slots) {                            /* one rating per active run */
+            if (s.unit < 0 || s.step >= unit_count[s.unit]) continue;
+            const int64_t pos = unit_start[s.unit] + s.step;
+            int64_t idx = pos;
+            if (virt && unit_bn[s.unit] > 1)
+                idx = unit_bstart[s.unit] + (int64_t)orc_block_perm((uint64_t)(pos - unit_bstart[s.unit]), (uint64_t)unit_bn[s.unit], s.key);
+            if (idx < 0 || idx >= n_recs) return -2;
+            orc_sgd_update(P + (int64_t)(rec_u[idx] - u_base) * k, s.q.data(), k, rec_r[idx], lr, lambda, order_mode);
+            s.step++;
+        }
+        for (int g = 0; g < groups; g++) {                 /* a warp merges its runs when the longest is done, then claims again */
+            bool all_done = true, any = false;
+            for (int j = 0; j < gpw; j++) {
+                const Slot& s = slots[(size_t)g * gpw + j];
+                if (s.unit < 0) continue;
+                any = true;
+                if (s.step < unit_count[s.unit]) all_done = false;
+            }
+            if (!any || !all_done) continue;
+            for (int j = 0; j < gpw; j++) {
+                Slot& s = slots[(size_t)g * gpw + j];
+                if (s.unit < 0) continue;
+                float* qr = Q + (int64_t)(unit_item[s.unit] - i_base) * k;
+                const float planned = unit_weight[s.unit];
+                if (planned == 1.0f && !always_add) {
+                    std::memcpy(qr, s.q.data(), sizeof(float) * k);
+                } else {
+                    const float w = planned;               /* the planner's weight: min(1, merge_boost / runs of the slice) */
+                    for (int f = 0; f < k; f++) qr[f] = qr[f] + (s.q[f] - s.q0[f]) * w;
+                }
+                done++;
+            }
+            claim(g);
+        }
+    }
+    return 0;
+}

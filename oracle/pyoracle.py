@@ -62,7 +62,22 @@ def _load():
     lib.orc_generate.restype = None
     lib.orc_generate.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
                                  C.c_int, C.c_double, _i32p, _i32p, _f32p, _u8p, C.c_int]
+    lib.orc_generate2.restype = None
+    lib.orc_generate2.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                  C.c_int, C.c_double, C.c_float, C.c_float, _i32p, _i32p, _f32p, _u8p, C.c_int]
     lib.orc_hardware_threads.restype = C.c_int
+    _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+    _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+    lib.orc_bucket_perm_key.restype = C.c_uint64
+    lib.orc_bucket_perm_key.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+    lib.orc_block_perm.restype = C.c_uint64
+    lib.orc_block_perm.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.orc_block_perm_fill.restype = None
+    lib.orc_block_perm_fill.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _i64p]
+    lib.orc_train_runs_launch.restype = C.c_int
+    lib.orc_train_runs_launch.argtypes = [_i32p, _f32p, C.c_int64, _i64p, _i32p, _i32p, _f32p, _i64p, _i32p, _u32p, C.c_int64,
+                                          C.c_int, C.c_uint64, C.c_uint32, _f32p, C.c_int32, _f32p, C.c_int32, C.c_int,
+                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.orc_set_tree_lanes.restype = None
     lib.orc_set_tree_lanes.argtypes = [C.c_int]
     return lib
@@ -108,13 +123,15 @@ def shuffle(seed, epoch, n):
     return out
 
 
-def generate(seed, start, count, n_users, n_items, l2au=2, cu=0.25, l2ai=3, ci=0.375, threads=None):
+def generate(seed, start, count, n_users, n_items, l2au=2, cu=0.25, l2ai=3, ci=0.375, threads=None, amplitude=0.0,
+             noise_scale=0.0):
+    """amplitude / noise_scale 0 = the defaults of the stand-in (PLANTED_AMPLITUDE, 0.5)."""
     u = np.empty(count, dtype=np.int32)
     i = np.empty(count, dtype=np.int32)
     r = np.empty(count, dtype=np.float32)
     held = np.empty(count, dtype=np.uint8)
-    lib.orc_generate(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci, u, i, r, held,
-                     threads or hardware_threads())
+    lib.orc_generate2(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci, amplitude, noise_scale, u, i, r, held,
+                      threads or hardware_threads())
     return u, i, r, held.astype(bool)
 
 
@@ -163,3 +180,38 @@ def train_hogwild(u, i, r, P, Q, lr, lam, epoch_begin, epoch_end, seed, threads,
 
 def rmse(P, Q, u, i, r, order_mode=ORDER_SEQ):
     return float(lib.orc_rmse(P, Q, P.shape[1], u, i, r, len(r), order_mode))
+
+
+def block_perm(n, seed, epoch, bucket_id):
+    """The engine's per-epoch permutation of a bucket of n records (csrc/common.cuh block_perm, restated in oracle.cpp):
+    out[j] = index inside the bucket of the record read at position j."""
+    out = np.empty(n, dtype=np.int64)
+    lib.orc_block_perm_fill(n, seed, epoch, bucket_id, out)
+    return out
+
+
+class RunPlan:
+    """The run kernel's work for one ring member: units (mfsgd_plan_runs) plus the bucket every unit lies in."""
+
+    def __init__(self, start, count, item, weight, block_off, member=0):
+        self.start = np.ascontiguousarray(start, np.int64)
+        self.count = np.ascontiguousarray(count, np.int32)
+        self.item = np.ascontiguousarray(item, np.int32)
+        self.weight = np.ascontiguousarray(weight, np.float32)
+        off = np.asarray(block_off, np.int64)
+        blk = np.searchsorted(off, self.start, side="right") - 1
+        self.bstart = np.ascontiguousarray(off[blk], np.int64)
+        self.bn = np.ascontiguousarray(off[blk + 1] - off[blk], np.int32)
+        self.bid = np.ascontiguousarray(member * (len(off) - 1) + blk, np.uint32)
+
+
+def train_runs_launch(rec_u, rec_r, plan, lo, hi, P, Q, lr, lam, order_mode, resident, gpw=1, virt=False, seed=0, epoch=0,
+                      u_base=0, i_base=0, always_add=False):
+    """Twin of one sgd_update_runs_kernel launch over units [lo, hi) of `plan` (oracle.cpp orc_train_runs_launch)."""
+    sl = slice(lo, hi)
+    rc = lib.orc_train_runs_launch(rec_u, rec_r, len(rec_r), plan.start[sl].copy(), plan.count[sl].copy(), plan.item[sl].copy(),
+                                   plan.weight[sl].copy(), plan.bstart[sl].copy(), plan.bn[sl].copy(), plan.bid[sl].copy(),
+                                   hi - lo, int(virt), seed, epoch, P, u_base, Q, i_base, P.shape[1], lr, lam, order_mode,
+                                   resident, gpw, int(always_add))
+    if rc:
+        raise ValueError("oracle: bad run plan (%d)" % rc)

@@ -10,7 +10,7 @@ from matrixfactorizationsgd.java_b200 import _capi as capi
 MIN_RUN = 16
 
 
-def plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed=7, member=0):
+def plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed=7, member=0, boost=1.0):
     sizes = np.concatenate([np.asarray(sizes_cold, np.int64).ravel(), np.asarray(sizes_hot, np.int64).ravel()])
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     cap = int(np.sum((np.asarray(sizes_hot) + chunk - 1) // chunk + rounds)) + 16
@@ -19,7 +19,7 @@ def plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chun
     n = C.c_int64(cap)
     visits = np.zeros(mu * rounds * IB + 1, np.int32)
     hbl = np.asarray(hot_block_lo, np.int32); hit = np.asarray(hot_items, np.int32)
-    capi.check(capi.lib.mfsgd_plan_runs(capi.ptr(off), mu, H, IB, capi.ptr(hbl), capi.ptr(hit), rounds, chunk, seed, member,
+    capi.check(capi.lib.mfsgd_plan_runs(capi.ptr(off), mu, H, IB, capi.ptr(hbl), capi.ptr(hit), rounds, chunk, seed, member, boost,
                                         capi.ptr(start), capi.ptr(count), capi.ptr(item), capi.ptr(weight), C.byref(n), capi.ptr(visits)))
     m = n.value
     return off, start[:m], count[:m], item[:m], weight[:m], visits
@@ -79,9 +79,9 @@ def test_plan_arguments_are_checked():
     v = np.zeros(2, np.int32)
     off = np.zeros(2, np.int64)
     hbl = np.zeros(2, np.int32)
-    assert capi.lib.mfsgd_plan_runs(None, 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
-    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 0, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
-    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.OK
+    assert capi.lib.mfsgd_plan_runs(None, 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, 1.0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
+    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 0, 256, 0, 0, 1.0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.E_INVALID_ARG
+    assert capi.lib.mfsgd_plan_runs(capi.ptr(off), 1, 0, 1, capi.ptr(hbl), None, 1, 256, 0, 0, 1.0, None, None, None, None, C.byref(n), capi.ptr(v)) == capi.OK
     assert n.value == 0
 
 
@@ -106,20 +106,21 @@ def layout(name, G=1, world=1, resident_ctas=592, **kw):
 
 
 def test_layout_of_the_baseline_shapes():
-    # Netflix-shaped on 1 GPU: 246 MB of P in 4 L2-resident sub-stripes, 4 interleaved rounds, full-length runs
-    assert layout("netflix") == (4, 1, 4, 256)
-    # one process per GPU: the rotation is pipelined over 2 item sub-shards from 4 members on, runs shorten with the launches
-    assert layout("netflix", G=2, world=2) == (2, 1, 4, 224)
-    assert layout("netflix", G=4, world=4) == (1, 2, 2, 128)
-    assert layout("netflix", G=8, world=8) == (1, 2, 1, 64)
+    # Netflix-shaped on 1 GPU: 246 MB of P in 4 L2-resident sub-stripes, 4 interleaved rounds, runs as long as a
+    # sub-warp's share of the launch (round 2: long runs, few merges per item)
+    assert layout("netflix") == (4, 1, 4, 960) and layout("netflix", resident_ctas=444) == (4, 1, 4, 1024)
+    # one process per GPU: the rotation is pipelined over 2 item sub-shards, runs shorten with the launches
+    assert layout("netflix", G=2, world=2) == (2, 2, 4, 256)
+    assert layout("netflix", G=4, world=4) == (1, 2, 2, 256)
+    assert layout("netflix", G=8, world=8) == (1, 2, 1, 128)
     # a single process driving 8 devices (peer copies, no pipelining): one shard group per member
-    assert layout("netflix", G=8, world=1)[:3] == (1, 1, 1)
-    assert layout("ml20m") == (2, 1, 4, 160)
-    # 90 K ratings: one sub-stripe, but still 4 launches per epoch of >= 16 K records each
-    assert layout("ml100k")[:3] == (1, 1, 4)
+    assert layout("netflix", G=8, world=1) == (1, 1, 1, 256)
+    assert layout("ml20m") == (2, 1, 4, 384)
+    # 90 K ratings: one sub-stripe, but still 4 launches per epoch of >= 16 K records each; shortest runs
+    assert layout("ml100k") == (1, 1, 4, 64)
     # the large shapes on their own configuration (8 GPUs) and squeezed onto one
-    assert layout("yahoo", G=8, world=8) == (2, 2, 2, 96) and layout("powerlaw", G=8, world=8) == (7, 2, 1, 96)
-    assert layout("yahoo") == (70, 1, 4, 160) and layout("powerlaw") == (193, 1, 4, 96)
+    assert layout("yahoo", G=8, world=8) == (2, 2, 2, 224) and layout("powerlaw", G=8, world=8) == (7, 2, 1, 192)
+    assert layout("yahoo") == (70, 1, 4, 384) and layout("powerlaw") == (193, 1, 4, 224)
 
 
 def test_layout_overrides_and_modes():
