@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -60,6 +62,21 @@ int set_error(int code, const char* fmt, ...) {
         int rc__ = (call);       \
         if (rc__ != MFSGD_OK) return rc__; \
     } while (0)
+
+// No C++ exception crosses the C boundary (include/mfsgd.h: "no exceptions, no abort"): host allocations that fail
+// (std::vector, new) surface as MFSGD_E_OOM.
+template <typename F>
+static int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(MFSGD_E_OOM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(MFSGD_E_STATE, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(MFSGD_E_STATE, "internal error");
+    }
+}
 
 // MFSGD_TRACE=1: phase timings on stderr (diagnostic aid)
 static inline bool trace_on() {
@@ -284,20 +301,22 @@ struct Chunk {                     // per-device staging buffers
 static const int COUNTER_EPOCHS = 64;          // epochs whose run-claim counters are zeroed by one memset (lanes run across epoch boundaries)
 static const int64_t CHUNK_MAX = 256LL << 20;  // records per staging chunk (3.3 GB of device buffers)
 
-static int chunk_alloc(Chunk& c, int64_t cap, bool with_held) {
-    c.cap = cap;
-    CK(dev_alloc(&c.u, (size_t)cap));
-    CK(dev_alloc(&c.i, (size_t)cap));
-    CK(dev_alloc(&c.r, (size_t)cap));
-    if (with_held) CK(dev_alloc(&c.held, (size_t)cap));
-    return MFSGD_OK;
-}
 static void chunk_free(Chunk& c) {
     dev_free(c.u);
     dev_free(c.i);
     dev_free(c.r);
     dev_free(c.held);
     c.start = -1;
+}
+static int chunk_alloc(Chunk& c, int64_t cap, bool with_held) {
+    c.cap = cap;
+    cudaError_t e = dev_alloc(&c.u, (size_t)cap);
+    if (e == cudaSuccess) e = dev_alloc(&c.i, (size_t)cap);
+    if (e == cudaSuccess) e = dev_alloc(&c.r, (size_t)cap);
+    if (e == cudaSuccess && with_held) e = dev_alloc(&c.held, (size_t)cap);
+    if (e != cudaSuccess) chunk_free(c);        // nothing half-allocated is left behind
+    CK(e);
+    return MFSGD_OK;
 }
 // Stage records [start, start+count) on the current device (no-op when already staged).
 static int chunk_stage(Chunk& c, const Source& s, int64_t start, int64_t count, cudaStream_t stream, int* launches) {
@@ -443,7 +462,11 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
     delete h;
 }
 
+static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out);
 extern "C" int mfsgd_create(const mfsgd_config* cfg, mfsgd_handle** out) {
+    return guarded([&]() { return mfsgd_create_body(cfg, out); });
+}
+static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     if (!out) return fail(MFSGD_E_INVALID_ARG, "out is null");
     *out = nullptr;
     CKRC(validate_config(cfg));
@@ -517,7 +540,11 @@ extern "C" int mfsgd_create(const mfsgd_config* cfg, mfsgd_handle** out) {
     return MFSGD_OK;
 }
 
+static int mfsgd_nccl_unique_id_body(uint8_t out[128]);
 extern "C" int mfsgd_nccl_unique_id(uint8_t out[128]) {
+    return guarded([&]() { return mfsgd_nccl_unique_id_body(out); });
+}
+static int mfsgd_nccl_unique_id_body(uint8_t out[128]) {
     if (!out) return fail(MFSGD_E_INVALID_ARG, "out is null");
     CKRC(nccl_load());
     ncclUniqueId id;
@@ -801,8 +828,8 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
     h->epoch = 0;
     choose_blocking(h);
     if (h->UB > 65535 || h->IB > 65535) return fail(MFSGD_E_INVALID_ARG, "too many blocks");
-    if (c.mode == MFSGD_MODE_DETERMINISTIC && src.total > 0x7fffffffLL)
-        return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode takes at most 2^31-1 records");
+    if (c.mode == MFSGD_MODE_DETERMINISTIC && src.total > CHUNK_MAX)     // staged and sorted as one chunk (one warp walks it anyway)
+        return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode takes at most 2^28 records");
     const int64_t cap = std::max<int64_t>(1, std::min(src.total, CHUNK_MAX));
     int rc = MFSGD_OK;
     for (size_t mi_ = 0; mi_ < h->members.size() && rc == MFSGD_OK; mi_++) {
@@ -876,7 +903,11 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
     return MFSGD_OK;
 }
 
+static int mfsgd_load_ratings_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n);
 extern "C" int mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    return guarded([&]() { return mfsgd_load_ratings_body(h, users, items, ratings, n); });
+}
+static int mfsgd_load_ratings_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
     Source s;
@@ -884,7 +915,11 @@ extern "C" int mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const i
     return load_training(h, s, false);
 }
 
+static int mfsgd_generate_synthetic_body(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout);
 extern "C" int mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout) {
+    return guarded([&]() { return mfsgd_generate_synthetic_body(h, sp, n_train, n_heldout); });
+}
+static int mfsgd_generate_synthetic_body(mfsgd_handle* h, const mfsgd_synth_params* sp, int64_t* n_train, int64_t* n_heldout) {
     if (!h || !sp) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (sp->n_total < 0 || sp->log2_alpha_user < 0 || sp->log2_alpha_user > 6 || sp->log2_alpha_item < 0 || sp->log2_alpha_item > 6 ||
         !(sp->c_user >= 0.0 && sp->c_user < 1.0) || !(sp->c_item >= 0.0 && sp->c_item < 1.0) || !(sp->planted_amplitude >= 0.f) ||
@@ -930,7 +965,11 @@ static int build_eval_set(mfsgd_handle* h, Member& m, const int32_t* users, cons
     return rc;
 }
 
+static int mfsgd_load_heldout_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n);
 extern "C" int mfsgd_load_heldout(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    return guarded([&]() { return mfsgd_load_heldout_body(h, users, items, ratings, n); });
+}
+static int mfsgd_load_heldout_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->loaded) return fail(MFSGD_E_STATE, "call mfsgd_load_ratings first (it fixes the stripe bounds)");
     if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
@@ -941,7 +980,11 @@ extern "C" int mfsgd_load_heldout(mfsgd_handle* h, const int32_t* users, const i
 // ------------------------------------------------------------------------------------------------
 // factors
 // ------------------------------------------------------------------------------------------------
+static int mfsgd_init_factors_body(mfsgd_handle* h);
 extern "C" int mfsgd_init_factors(mfsgd_handle* h) {
+    return guarded([&]() { return mfsgd_init_factors_body(h); });
+}
+static int mfsgd_init_factors_body(mfsgd_handle* h) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before initialising factors");
     for (Member& m : h->members) {
@@ -955,7 +998,11 @@ extern "C" int mfsgd_init_factors(mfsgd_handle* h) {
     return MFSGD_OK;
 }
 
+static int mfsgd_set_factors_body(mfsgd_handle* h, const float* P, const float* Q);
 extern "C" int mfsgd_set_factors(mfsgd_handle* h, const float* P, const float* Q) {
+    return guarded([&]() { return mfsgd_set_factors_body(h, P, Q); });
+}
+static int mfsgd_set_factors_body(mfsgd_handle* h, const float* P, const float* Q) {
     if (!h || !P || !Q) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before setting factors");
     const int k = h->cfg.k;
@@ -970,7 +1017,11 @@ extern "C" int mfsgd_set_factors(mfsgd_handle* h, const float* P, const float* Q
     return MFSGD_OK;
 }
 
+static int mfsgd_get_factors_body(mfsgd_handle* h, float* P, float* Q);
 extern "C" int mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q) {
+    return guarded([&]() { return mfsgd_get_factors_body(h, P, Q); });
+}
+static int mfsgd_get_factors_body(mfsgd_handle* h, float* P, float* Q) {
     if (!h || !P || !Q) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
     const int k = h->cfg.k;
@@ -984,7 +1035,11 @@ extern "C" int mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q) {
     return MFSGD_OK;
 }
 
+static int mfsgd_get_partition_body(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi);
 extern "C" int mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi) {
+    return guarded([&]() { return mfsgd_get_partition_body(h, u_lo, u_hi, i_lo, i_hi); });
+}
+static int mfsgd_get_partition_body(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     int32_t ul = h->cfg.n_users, uh = 0, il = h->cfg.n_items, ih = 0;
@@ -1491,10 +1546,12 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
     return rc;
 }
 
-extern "C" int mfsgd_train(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats) { return train_impl(h, epochs, stats, nullptr); }
+extern "C" int mfsgd_train(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats) {
+    return guarded([&]() { return train_impl(h, epochs, stats, nullptr); });
+}
 extern "C" int mfsgd_train_traced(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace) {
     if (!err_trace) return fail(MFSGD_E_INVALID_ARG, "err_trace is null");
-    return train_impl(h, epochs, stats, err_trace);
+    return guarded([&]() { return train_impl(h, epochs, stats, err_trace); });
 }
 extern "C" int mfsgd_set_eval_every_epoch(mfsgd_handle* h, int32_t on) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
@@ -1570,7 +1627,11 @@ static int finish_rmse(double sse, int64_t n, double* rmse_out, double* sse_out,
     return MFSGD_OK;
 }
 
+static int mfsgd_rmse_heldout_body(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out);
 extern "C" int mfsgd_rmse_heldout(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
+    return guarded([&]() { return mfsgd_rmse_heldout_body(h, rmse_out, sse_out, n_out); });
+}
+static int mfsgd_rmse_heldout_body(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
     for (Member& m : h->members)
@@ -1581,7 +1642,11 @@ extern "C" int mfsgd_rmse_heldout(mfsgd_handle* h, double* rmse_out, double* sse
     return finish_rmse(sse, n, rmse_out, sse_out, n_out);
 }
 
+static int mfsgd_rmse_train_body(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out);
 extern "C" int mfsgd_rmse_train(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
+    return guarded([&]() { return mfsgd_rmse_train_body(h, rmse_out, sse_out, n_out); });
+}
+static int mfsgd_rmse_train_body(mfsgd_handle* h, double* rmse_out, double* sse_out, int64_t* n_out) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->factors_ready || !h->loaded) return fail(MFSGD_E_STATE, "need loaded ratings and factors");
     if (h->cfg.mode == MFSGD_MODE_DETERMINISTIC) {
@@ -1601,7 +1666,11 @@ extern "C" int mfsgd_rmse_train(mfsgd_handle* h, double* rmse_out, double* sse_o
     return finish_rmse(sse, n, rmse_out, sse_out, n_out);
 }
 
+static int mfsgd_rmse_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n, double* rmse_out);
 extern "C" int mfsgd_rmse(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n, double* rmse_out) {
+    return guarded([&]() { return mfsgd_rmse_body(h, users, items, ratings, n, rmse_out); });
+}
+static int mfsgd_rmse_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n, double* rmse_out) {
     if (!h || !rmse_out) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
     if (!h->loaded || !h->factors_ready) return fail(MFSGD_E_STATE, "need loaded ratings and factors");
@@ -1627,7 +1696,13 @@ extern "C" int mfsgd_rmse(mfsgd_handle* h, const int32_t* users, const int32_t* 
 // ------------------------------------------------------------------------------------------------
 // one-shot entry point (MatrixFactorizationSGD.java:109 factorize)
 // ------------------------------------------------------------------------------------------------
+static int mfsgd_factorize_body(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                               const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out);
 extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                               const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out) {
+    return guarded([&]() { return mfsgd_factorize_body(users, items, ratings, n, cfg, epochs, P_out, Q_out); });
+}
+static int mfsgd_factorize_body(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
                                const mfsgd_config* cfg, int32_t epochs, float* P_out, float* Q_out) {
     if (!P_out || !Q_out) return fail(MFSGD_E_INVALID_ARG, "output arrays are null");
     if (epochs < 0) return fail(MFSGD_E_INVALID_ARG, "epochs < 0");
@@ -1653,7 +1728,15 @@ extern "C" int mfsgd_factorize(const int32_t* users, const int32_t* items, const
 // introspection + test hooks
 // ------------------------------------------------------------------------------------------------
 // Test hook: the layout planner (run_plan.hpp) for a configuration and a data size. Host-only.
+static int mfsgd_plan_layout_body(const mfsgd_config* cfg, int64_t l2_bytes, int64_t member_records, int32_t member_users,
+                                 int64_t run_records, int32_t resident_ctas, int32_t* stripes, int32_t* shards, int32_t* rounds,
+                                 int32_t* run_length);
 extern "C" int mfsgd_plan_layout(const mfsgd_config* cfg, int64_t l2_bytes, int64_t member_records, int32_t member_users,
+                                 int64_t run_records, int32_t resident_ctas, int32_t* stripes, int32_t* shards, int32_t* rounds,
+                                 int32_t* run_length) {
+    return guarded([&]() { return mfsgd_plan_layout_body(cfg, l2_bytes, member_records, member_users, run_records, resident_ctas, stripes, shards, rounds, run_length); });
+}
+static int mfsgd_plan_layout_body(const mfsgd_config* cfg, int64_t l2_bytes, int64_t member_records, int32_t member_users,
                                  int64_t run_records, int32_t resident_ctas, int32_t* stripes, int32_t* shards, int32_t* rounds,
                                  int32_t* run_length) {
     if (!cfg || !stripes || !shards || !rounds || !run_length) return fail(MFSGD_E_INVALID_ARG, "null argument");
@@ -1670,7 +1753,17 @@ extern "C" int mfsgd_plan_layout(const mfsgd_config* cfg, int64_t l2_bytes, int6
 }
 
 // Test hook: the run planner (run_plan.hpp) on caller-provided bucket offsets. Host-only.
+static int mfsgd_plan_runs_body(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
+                               const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,
+                               float merge_boost, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
+                               int64_t* n_units, int32_t* visit_units);
 extern "C" int mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
+                               const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,
+                               float merge_boost, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
+                               int64_t* n_units, int32_t* visit_units) {
+    return guarded([&]() { return mfsgd_plan_runs_body(block_off, stripes, n_hot, item_blocks, hot_block_lo, hot_items, rounds, chunk, seed, member, merge_boost, unit_start, unit_count, unit_item, unit_weight, n_units, visit_units); });
+}
+static int mfsgd_plan_runs_body(const int64_t* block_off, int32_t stripes, int32_t n_hot, int32_t item_blocks, const int32_t* hot_block_lo,
                                const int32_t* hot_items, int32_t rounds, int32_t chunk, uint64_t seed, int32_t member,
                                float merge_boost, int64_t* unit_start, int32_t* unit_count, int32_t* unit_item, float* unit_weight,
                                int64_t* n_units, int32_t* visit_units) {
@@ -1703,7 +1796,11 @@ extern "C" int mfsgd_plan_runs(const int64_t* block_off, int32_t stripes, int32_
     return MFSGD_OK;
 }
 
+static int mfsgd_get_layout_info_body(mfsgd_handle* h, mfsgd_layout_info* out);
 extern "C" int mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out) {
+    return guarded([&]() { return mfsgd_get_layout_info_body(h, out); });
+}
+static int mfsgd_get_layout_info_body(mfsgd_handle* h, mfsgd_layout_info* out) {
     if (!h || !out) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     memset(out, 0, sizeof(*out));
@@ -1722,7 +1819,11 @@ extern "C" int mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out) {
     return MFSGD_OK;
 }
 
+static int mfsgd_get_bounds_body(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds);
 extern "C" int mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds) {
+    return guarded([&]() { return mfsgd_get_bounds_body(h, user_bounds, item_bounds); });
+}
+static int mfsgd_get_bounds_body(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds) {
     if (!h || !user_bounds || !item_bounds) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     memcpy(user_bounds, h->user_bounds.data(), h->user_bounds.size() * 4);
@@ -1730,7 +1831,11 @@ extern "C" int mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* 
     return MFSGD_OK;
 }
 
+static int mfsgd_get_records_body(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n);
 extern "C" int mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n) {
+    return guarded([&]() { return mfsgd_get_records_body(h, member, recs, block_offsets, n); });
+}
+static int mfsgd_get_records_body(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n) {
     if (!h || !n) return fail(MFSGD_E_INVALID_ARG, "null argument");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     if (member < 0 || member >= (int)h->members.size()) return fail(MFSGD_E_INVALID_ARG, "bad member index");
@@ -1745,7 +1850,11 @@ extern "C" int mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs,
     return MFSGD_OK;
 }
 
+static int mfsgd_shuffle_once_body(mfsgd_handle* h, int32_t epoch);
 extern "C" int mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch) {
+    return guarded([&]() { return mfsgd_shuffle_once_body(h, epoch); });
+}
+static int mfsgd_shuffle_once_body(mfsgd_handle* h, int32_t epoch) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
     if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded");
     for (Member& m : h->members) {
@@ -1755,7 +1864,13 @@ extern "C" int mfsgd_shuffle_once(mfsgd_handle* h, int32_t epoch) {
     return MFSGD_OK;
 }
 
+static int mfsgd_apply_updates_forced_body(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,
+                                          const float* pre_q, const float* r, float* post_p, float* post_q, float* err);
 extern "C" int mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,
+                                          const float* pre_q, const float* r, float* post_p, float* post_q, float* err) {
+    return guarded([&]() { return mfsgd_apply_updates_forced_body(device, k, lr, lambda, n, pre_p, pre_q, r, post_p, post_q, err); });
+}
+static int mfsgd_apply_updates_forced_body(int32_t device, int32_t k, float lr, float lambda, int64_t n, const float* pre_p,
                                           const float* pre_q, const float* r, float* post_p, float* post_q, float* err) {
     if (!rank_supported(k)) return fail(MFSGD_E_INVALID_ARG, "k=%d unsupported", k);
     if (n < 0 || (n > 0 && (!pre_p || !pre_q || !r || !post_p || !post_q || !err))) return fail(MFSGD_E_INVALID_ARG, "null argument");
@@ -1782,7 +1897,13 @@ extern "C" int mfsgd_apply_updates_forced(int32_t device, int32_t k, float lr, f
     return MFSGD_OK;
 }
 
+static int mfsgd_generate_to_host_body(int32_t device, const mfsgd_synth_params* sp, int32_t n_users, int32_t n_items,
+                                      int64_t start, int64_t count, int32_t* users, int32_t* items, float* ratings, uint8_t* held);
 extern "C" int mfsgd_generate_to_host(int32_t device, const mfsgd_synth_params* sp, int32_t n_users, int32_t n_items,
+                                      int64_t start, int64_t count, int32_t* users, int32_t* items, float* ratings, uint8_t* held) {
+    return guarded([&]() { return mfsgd_generate_to_host_body(device, sp, n_users, n_items, start, count, users, items, ratings, held); });
+}
+static int mfsgd_generate_to_host_body(int32_t device, const mfsgd_synth_params* sp, int32_t n_users, int32_t n_items,
                                       int64_t start, int64_t count, int32_t* users, int32_t* items, float* ratings, uint8_t* held) {
     if (!sp || count < 0 || start < 0 || n_users <= 0 || n_items <= 0) return fail(MFSGD_E_INVALID_ARG, "bad arguments");
     if (count > 0 && (!users || !items || !ratings || !held)) return fail(MFSGD_E_INVALID_ARG, "null output arrays");

@@ -70,14 +70,20 @@ __device__ __forceinline__ int upper_block(const int32_t* bounds, int nblocks, i
     return lo;
 }
 
+constexpr size_t FILL_OWNER_SMEM_MAX = 48 * 1024;
+
 __global__ void __launch_bounds__(256) fill_owner_kernel(const int32_t* __restrict__ bounds, int32_t nblocks,
                                                          int32_t n_rows, uint16_t* __restrict__ owner) {
     extern __shared__ int32_t sb[];
-    for (int j = threadIdx.x; j <= nblocks; j += blockDim.x) sb[j] = bounds[j];
-    __syncthreads();
+    const int32_t* __restrict__ tab = bounds;            // more bounds than fit the default 48 KB: search them in global memory
+    if ((size_t)(nblocks + 1) * sizeof(int32_t) <= FILL_OWNER_SMEM_MAX) {
+        for (int j = threadIdx.x; j <= nblocks; j += blockDim.x) sb[j] = bounds[j];
+        __syncthreads();
+        tab = sb;
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += stride)
-        owner[row] = (uint16_t)upper_block(sb, nblocks, (int32_t)row);
+        owner[row] = (uint16_t)upper_block(tab, nblocks, (int32_t)row);
 }
 
 __device__ __forceinline__ int record_block(const BucketArgs& b, int64_t t) {
@@ -283,8 +289,9 @@ cudaError_t launch_balanced_bounds(const uint64_t* cum, int32_t n_rows, int32_t 
 
 cudaError_t launch_fill_owner(const int32_t* bounds, int32_t nblocks, int32_t n_rows, uint16_t* owner,
                               cudaStream_t stream, int* launches) {
-    fill_owner_kernel<<<grid_for(n_rows, 256, 148 * 8), 256, (nblocks + 1) * sizeof(int32_t), stream>>>(bounds, nblocks,
-                                                                                                       n_rows, owner);
+    size_t smem = (size_t)(nblocks + 1) * sizeof(int32_t);
+    if (smem > FILL_OWNER_SMEM_MAX) smem = 0;            // the kernel then reads the bounds from global memory
+    fill_owner_kernel<<<grid_for(n_rows, 256, 148 * 8), 256, smem, stream>>>(bounds, nblocks, n_rows, owner);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

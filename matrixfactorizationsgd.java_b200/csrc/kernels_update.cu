@@ -98,10 +98,12 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
         for (int d = 0; d < DEPTH; d++) {
             const int t = t0 + d;
             if ((!FULLTILE || FULL_STEPS % DEPTH != 0) && t >= steps) break;   // warp-uniform; compiled out for full tiles
-            // keep DEPTH-1 gathers ahead: step t + DEPTH - 1 goes into the slot that step t - 1 just freed
-            // (past the end of a partial tile slot_load sees j >= cnt and loads nothing)
-            slot_load<LANES, VEC, FULL, FULLTILE>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp,
-                                                  (FULLTILE && t + DEPTH - 1 >= FULL_STEPS) ? 0 : cnt, Pl, Ql, k, lane_chunk, chunks);
+            // keep DEPTH-1 gathers ahead: step t + DEPTH - 1 goes into the slot that step t - 1 just freed. Past the end of
+            // a partial tile slot_load sees j >= cnt and loads nothing; a full tile has no such predicate, so the look-ahead
+            // itself is skipped there (warp-uniform) -- it would gather rows of wrapped records that are never used.
+            if (!FULLTILE || t + DEPTH - 1 < FULL_STEPS)
+                slot_load<LANES, VEC, FULL, FULLTILE>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp, cnt, Pl, Ql, k,
+                                                      lane_chunk, chunks);
             const int j = t * GPW + grp;
             const int4 rec = tile[j & 31];
             const bool act = FULLTILE ? true : j < cnt;

@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -162,15 +164,31 @@ void parse_slice(const char* base, const char* begin, const char* end, int forma
     }
 }
 
+// Runs f(t) for every slice, side by side when asked to. An exception inside a worker thread (std::bad_alloc from a
+// growing vector) would end in std::terminate: it is caught there and re-thrown as std::bad_alloc on the calling thread,
+// where mfsgd_read_ratings turns it into MFSGD_E_OOM (include/mfsgd.h: no exceptions, no abort).
 template <typename F>
 void for_each_slice(size_t n_slices, bool parallel, F f) {
     if (!parallel || n_slices == 1) {
         for (size_t t = 0; t < n_slices; t++) f(t);
         return;
     }
+    std::atomic<bool> failed(false);
     std::vector<std::thread> pool;
-    for (size_t t = 0; t < n_slices; t++) pool.emplace_back(f, t);
+    try {
+        for (size_t t = 0; t < n_slices; t++)
+            pool.emplace_back([&failed, &f, t]() {
+                try {
+                    f(t);
+                } catch (...) {
+                    failed.store(true);
+                }
+            });
+    } catch (...) {          // thread creation failed: finish what runs, then report
+        failed.store(true);
+    }
     for (auto& th : pool) th.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 // Dense rank (ascending original id) of every id of every slice, written to dense[offset[t] + j]; ids_out = the sorted
@@ -231,7 +249,21 @@ extern "C" void mfsgd_free_ratings(mfsgd_ratings* r) {
     memset(r, 0, sizeof(*r));
 }
 
+static int read_ratings_body(const char* path, int32_t format, mfsgd_ratings* out);
+
 extern "C" int mfsgd_read_ratings(const char* path, int32_t format, mfsgd_ratings* out) {
+    try {
+        return read_ratings_body(path, format, out);
+    } catch (const std::bad_alloc&) {
+        if (out) mfsgd_free_ratings(out);
+        return mfsgd::set_error(MFSGD_E_OOM, "out of host memory while reading %s", path ? path : "(null)");
+    } catch (...) {
+        if (out) mfsgd_free_ratings(out);
+        return mfsgd::set_error(MFSGD_E_STATE, "internal error while reading %s", path ? path : "(null)");
+    }
+}
+
+static int read_ratings_body(const char* path, int32_t format, mfsgd_ratings* out) {
     using mfsgd::set_error;
     if (!path || !out) return set_error(MFSGD_E_INVALID_ARG, "path or out is null");
     if (format < MFSGD_FORMAT_AUTO || format > MFSGD_FORMAT_NETFLIX_PRIZE) return set_error(MFSGD_E_INVALID_ARG, "unknown format %d", format);
@@ -282,13 +314,7 @@ extern "C" int mfsgd_read_ratings(const char* path, int32_t format, mfsgd_rating
     }
     std::vector<Slice> slices((size_t)threads);
     auto work = [&](int t) { parse_slice(m.p, cut[(size_t)t], cut[(size_t)t + 1], format, slices[(size_t)t]); };
-    if (threads == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < threads; t++) pool.emplace_back(work, t);
-        for (auto& th : pool) th.join();
-    }
+    for_each_slice((size_t)threads, threads > 1, [&](size_t t) { work((int)t); });
     std::vector<size_t> offset(slices.size() + 1, 0);
     for (size_t t = 0; t < slices.size(); t++) {
         const Slice& sl = slices[t];
