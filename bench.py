@@ -23,9 +23,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "sgd_rating_updates_per_sec"
-E2E_REPEATS = 2     # the end-to-end call is made twice and the faster one reported: single calls showed host-side stalls of up to 1 s
-                    # on some boxes of the pool (pinned H2D at 1.4 GB/s instead of 50; profiles/r01_bench.md)
+E2E_REPEATS = 2     # the end-to-end call is made twice; e2e.value is the FIRST call (what a caller's first call costs in a process
+                    # whose CUDA context exists), the second is reported beside it
 UNIT = "updates/s"
+
+
+def load_workloads():
+    """workloads.py by path: pure data, loads no native library (the reference arm must not map libmfsgd.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mfsgd_workloads", os.path.join(ROOT, "matrixfactorizationsgd.java_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def peaks():
@@ -38,25 +47,35 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload):
-    """dram bytes per update-kernel launch from the committed ncu --set full capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        try:
-            return json.load(open(path)).get(workload)
-        except Exception:
-            return None
-    return None
-
-
-def l2_ceiling():
-    """Measured ceiling of the update path's access pattern on this pool's B200 (tools/l2_peak.cu: random 512-B row
-    gather + scatter inside an L2-resident buffer), committed as profiles/l2_peak.json; None if absent."""
-    path = os.path.join(ROOT, "profiles", "l2_peak.json")
+def measured_traffic(workload, timeout_s=240):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (sgd_update_runs_kernel), measured now,
+    on this box, by a side run of the same workload under ncu (tools/profile_target.py, the 21st run-kernel launch: a
+    steady-state visit of the second epoch). None when ncu is unavailable or fails -- never a stale constant."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none", "-k",
+           "regex:sgd_update_runs_kernel", "-s", "20", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "profile_target.py"),
+           workload, "0", "0", "2"]
     try:
-        return json.load(open(path))
-    except Exception:
-        return None
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+    except Exception as e:      # noqa: BLE001
+        return None, "ncu side run failed: %r" % (e,)
+    vals = {}
+    for line in out.stdout.splitlines():
+        cells = [c.strip().strip('"') for c in line.split('","')]
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            if name in cells:
+                try:
+                    unit, val = cells[cells.index(name) + 1], float(cells[cells.index(name) + 2].replace(",", ""))
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6}.get(unit, 1.0)
+                    vals[name] = val * scale
+                except Exception:      # noqa: BLE001
+                    pass
+    if "dram__bytes_read.sum" not in vals or "dram__bytes_write.sum" not in vals:
+        return None, "ncu produced no dram counters (rc %d): %s" % (out.returncode, (out.stderr or out.stdout)[-200:].replace("\n", " "))
+    return vals, "ncu side run in this bench process's box: launch 21 of sgd_update_runs_kernel (tools/profile_target.py)"
 
 
 class stdout_to_stderr:
@@ -116,7 +135,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 def host_training_set(mf, w, device, pinned):
     """Host triplets of the workload's training records (generated on the GPU, held-out tenth removed)."""
-    sp = mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     us, is_, rs = [], [], []
     step = 25_000_000
     for start in range(0, w.n_ratings, step):
@@ -189,7 +208,7 @@ def run_ours(args):
             eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
     else:
         eng = mf.Engine(mf.make_config(mode=capi.MODE_HOGWILD, device=local_rank, **common))
-    sp = mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     t0 = time.time()
     n_train_local, n_held_local = eng.generate_synthetic(sp)
     setup_s = time.time() - t0
@@ -230,30 +249,46 @@ def run_ours(args):
     bpu = mf.bytes_per_update(w.k)
     rank_updates = float(sum(s.updates for s in stats))
     achieved = rank_updates * bpu / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-    traffic = recorded_traffic(args.workload) if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": None, "peak_source": peak_src,
                 "kernel": "sgd_update_runs_kernel (+ sgd_update_hogwild_kernel for rarely rated items; concurrent streams, timed as one span per sub-epoch)",
                 "bytes_per_update": bpu, "updates_per_step": rank_updates / args.steps,
+                "updates_per_launch": rank_updates / max(n_launch, 1),
+                "algorithmic_bytes_per_launch": rank_updates * bpu / max(n_launch, 1),
+                "avg_launch_ms": kernel_ms / max(n_launch, 1),
                 "algorithmic_bytes_per_step": rank_updates * bpu / args.steps,
                 "update_phase_ms_per_step": kernel_ms / args.steps, "update_launches_per_step": n_launch / args.steps,
                 "kernel_share_of_step": kernel_ms / max(dev_ms, 1e-9), "frac_of_nominal_8TBs": achieved / 8000.0,
                 "note": "frac > 1 is expected: the P sub-stripe and Q stay L2-resident (stratified blocks) and q_i rows "
                         "live in registers for a whole run, so DRAM traffic (see traffic) is a small fraction of the algorithmic "
                         "bytes; the binding resource is L2 sector throughput (see l2_bound)"}
-    l2 = l2_ceiling()
-    if l2 is not None and w.k == 128:
-        # what an update of the run kernel moves through L2: p_u read + written (2 x 4k B) and its record (two 32-B sectors)
-        l2_bytes = 8 * w.k + 64
+    if world == 1 and rank == 0 and not args.no_traffic:
+        vals, src = measured_traffic(args.workload)
+        roofline["traffic_source"] = src
+        if vals is not None:
+            roofline["traffic"] = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+            roofline["traffic_detail"] = {"unit": "bytes per launch", "dram_read": vals["dram__bytes_read.sum"],
+                                          "dram_write": vals["dram__bytes_write.sum"],
+                                          "launch_us_under_ncu": vals.get("gpu__time_duration.sum", 0.0) / 1e3,
+                                          "per_step_estimate": (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) * n_launch / args.steps}
+    if rank == 0 and w.k == 128 and not args.no_ceilings:
+        # The ceiling of the run kernel's access pattern, measured NOW in this process on this box (mfsgd_measure_ceilings):
+        # random 512-B row gather + scatter inside an L2-resident buffer the size of one P sub-stripe, no arithmetic.
+        ceil = mf.measure_ceilings(local_rank, 61.0)
+        # what an update of the run kernel moves through L2: p_u read + written (2 x 4k B) and its record (12 B, whole sectors shared by a tile)
+        l2_bytes = 8 * w.k + 12
         l2_achieved = rank_updates * l2_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-        roofline["l2_bound"] = {"achieved": l2_achieved, "peak": l2["row_gather_scatter_gbs"], "unit": "GB/s",
-                                "frac": l2_achieved / l2["row_gather_scatter_gbs"], "l2_bytes_per_update": l2_bytes,
-                                "peak_source": "measured: tools/l2_peak.cu on this pool's B200 (profiles/l2_peak.json), random 512-B "
-                                               "row gather + scatter in an L2-resident buffer, no arithmetic"}
+        roofline["l2_bound"] = {"achieved": l2_achieved, "peak": ceil["row_gather_scatter_gbs"], "unit": "GB/s",
+                                "frac": l2_achieved / ceil["row_gather_scatter_gbs"], "l2_bytes_per_update": l2_bytes,
+                                "ceilings_measured_in_process": ceil,
+                                "peak_source": "measured in this process after the timed region: mfsgd_measure_ceilings (csrc/kernels_diag.cu), "
+                                               "random 512-B row gather + scatter in a 61 MB L2-resident buffer, no arithmetic"}
 
     # e2e: the reference-facing call with HOST buffers: H2D + bucketing + init + K epochs + D2H of P, Q
     e2e = None
     if not args.no_e2e:
+        if args.trace_e2e:
+            os.environ["MFSGD_TRACE"] = "1"
         hu, hi, hr, pins = host_training_set(mf, w, local_rank, pinned=True)
         n_host = len(hr)
         # pinned output buffers too (a Java caller would hand in off-heap segments from mfsgd_host_alloc)
@@ -275,15 +310,18 @@ def run_ours(args):
             for _rep in range(E2E_REPEATS):
                 barrier()
                 t0 = time.time()
-                capi.check(capi.lib.mfsgd_load_ratings(eng2._h, capi.ptr(hu), capi.ptr(hi), capi.ptr(hr), n_host))
+                lo_, hi_ = n_host * rank // world, n_host * (rank + 1) // world      # every rank uploads only its 1/N slice
+                capi.check(capi.lib.mfsgd_load_ratings_sharded(eng2._h, capi.ptr(hu[lo_:hi_]), capi.ptr(hi[lo_:hi_]), capi.ptr(hr[lo_:hi_]),
+                                                               hi_ - lo_))
                 eng2.init_factors()
                 eng2.train(args.steps, want_stats=False)
                 capi.check(capi.lib.mfsgd_get_factors(eng2._h, capi.ptr(P), capi.ptr(Q)))
                 barrier()
                 e2e_all.append(allmax(time.time() - t0))
-            e2e_s = min(e2e_all)
+            e2e_s = e2e_all[0]
             eng2.close()
-            e2e_call = "mfsgd_load_ratings + init_factors + train + get_factors on a live ring handle (pinned host buffers)"
+            e2e_call = ("mfsgd_load_ratings_sharded (each rank uploads 1/N of the triplets, records exchanged by stripe owner over NCCL) "
+                        "+ init_factors + train + get_factors on a live ring handle (pinned host buffers)")
         else:
             cfg = mf.make_config(mode=capi.MODE_HOGWILD, device=local_rank, **e2e_cfg)
             e2e_all = []
@@ -294,21 +332,24 @@ def run_ours(args):
                                                     capi.ptr(P), capi.ptr(Q)))
                 barrier()
                 e2e_all.append(allmax(time.time() - t0))
-            e2e_s = min(e2e_all)
+            e2e_s = e2e_all[0]
             e2e_call = "mfsgd_factorize(host triplets -> host P,Q), pinned host buffers"
         e2e_check = float(np.abs(P[:1000]).sum() + np.abs(Q[:1000]).sum())   # the result was really read back
         for p in pins + out_ptrs:
             capi.lib.mfsgd_host_free(p)
         e2e = {"value": float(n_host) * args.steps / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": 12.0 * n_host * world / args.steps,
+               "h2d_bytes_per_step": 12.0 * n_host / args.steps,
                "d2h_bytes_per_step": 4.0 * w.k * (w.n_users + w.n_items) / args.steps,
-               "seconds": e2e_s, "seconds_each_call": e2e_all, "call": e2e_call + " -- the faster of %d complete calls" % E2E_REPEATS,
+               "seconds": e2e_s, "seconds_each_call": e2e_all,
+               "value_second_call": float(n_host) * args.steps / e2e_all[-1],
+               "call": e2e_call + " -- the FIRST of %d complete calls (the second is in seconds_each_call / value_second_call)" % E2E_REPEATS,
                "result_checksum": e2e_check,
                "epochs": args.steps}
 
-    cpu = None
+    cpu = cpu_ml100k = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(w, sample=args.cpu_sample, threads=1)
+        cpu_ml100k = cpu_baseline_ml100k()
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -320,6 +361,9 @@ def run_ours(args):
                           "stripes_per_gpu": int(info.stripes_per_gpu), "shards_per_gpu": int(info.shards_per_gpu),
                           "rounds": int(info.rounds), "hot_items": int(info.n_hot_items),
                           "scatter": "store" if args.scatter == 0 else "atomic",
+                          "arith": "fma (FFMA2 arrangement of the update rule, a few ulp per update from the stand-in's unfused rule; "
+                                   "MFSGD_FLAG_EXACT_ARITH selects the unfused one)",
+                          "merge": "runs of one item in one launch: weight min(1, 1.25 / runs)",
                           "l2": "inputs larger than L2: %.2f GB of records + %.0f MB of factors streamed per step" % (
                               12e-9 * info.n_train_total, 4e-6 * w.k * (w.n_users + w.n_items)),
                           "setup_seconds_excluded": setup_s},
@@ -332,6 +376,8 @@ def run_ours(args):
                                                "note": "cold and hot overlap (two streams); spans start at the sub-epoch fork"}}
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if cpu_ml100k is not None:
+            out["cpu_baseline_ml100k"] = cpu_ml100k
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -343,54 +389,91 @@ def cpu_baseline(w, sample, threads):
     bounded sample: the first `sample` records of the same synthetic set, full-size P and Q."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as orc
-    import matrixfactorizationsgd.java_b200 as mf
+    seed = load_workloads().SEED
     n = min(sample, w.n_ratings)
-    u, i, r, held = orc.generate(mf.SEED, 0, n, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    u, i, r, held = orc.generate(seed, 0, n, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item,
+                                 amplitude=w.amplitude, noise_scale=w.noise_scale)
     u, i, r = u[~held].copy(), i[~held].copy(), r[~held].copy()
-    P = orc.init_factors(w.n_users, w.k, mf.SEED, 0)
-    Q = orc.init_factors(w.n_items, w.k, mf.SEED, 1)
+    P = orc.init_factors(w.n_users, w.k, seed, 0)
+    Q = orc.init_factors(w.n_items, w.k, seed, 1)
     if threads == 1:
         t0 = time.time()
-        orc.train(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, mf.SEED, shuffled=False)
+        orc.train(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, seed, shuffled=False)
         secs = time.time() - t0
     else:
-        secs = orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, mf.SEED, threads, shuffled=False)
+        secs = orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, 0, 1, seed, threads, shuffled=False)
     return {"value": len(r) / secs, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "1 epoch over the first %d records (%d train) of %s, full-size P/Q, k=%d" % (n, len(r), w.name, w.k),
             "host_cores_available": orc.hardware_threads(), "seconds": secs}
 
 
+def cpu_baseline_ml100k():
+    """configs[0] (ML-100K-shaped, k=32, 20 epochs) through the reference's CPU path on THIS box's host cores, sequential and
+    thread-parallel, in this run (north_star): oracle/oracle_cli is the C++ port of the stand-in's main()."""
+    exe = os.path.join(ROOT, "oracle", "oracle_cli")
+    if not os.path.exists(exe):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    cores = orc.hardware_threads()
+    rows = []
+    for mode in ["seq"] + ["threads=%d" % t for t in sorted({2, 4, 8, cores}) if t <= cores]:
+        try:
+            line = subprocess.run([exe, "--mode", mode], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+            d = json.loads(line)
+            rows.append({"mode": d["mode"], "threads": d["threads"], "updates_per_sec": d["updates_per_sec"],
+                         "heldout_rmse": d["heldout_rmse"], "seconds": d["seconds"]})
+        except Exception as e:      # noqa: BLE001
+            rows.append({"mode": mode, "error": repr(e)})
+    return {"workload": "ml100k-shaped: 943 users x 1682 items, 100000 ratings, k=32, 20 epochs (BASELINE.json configs[0])",
+            "kind": "port", "host_cores": cores, "runs": rows,
+            "note": "whole runs incl. the per-epoch shuffle sort; the set is so small that sort and thread start-up dominate the threaded runs"}
+
+
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path, all host threads, same workload/metric."""
+    """--impl reference: the CPU implementation of the path (the stand-in's factorizeThreaded, C++ oracle port), all host
+    threads, the SAME workload as the product arm: every training record, the per-epoch shuffle included in the step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as orc
-    import matrixfactorizationsgd.java_b200 as mf
-    w = mf.WORKLOADS[args.workload]
+    wl = load_workloads()          # pure data: this process never maps libmfsgd.so
+    w, seed = wl.WORKLOADS[args.workload], wl.SEED
     threads = orc.hardware_threads()
-    n = min(args.ref_sample, w.n_ratings)
-    u, i, r, held = orc.generate(mf.SEED, 0, n, w.n_users, w.n_items, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
-    u, i, r = u[~held].copy(), i[~held].copy(), r[~held].copy()
-    P = orc.init_factors(w.n_users, w.k, mf.SEED, 0)
-    Q = orc.init_factors(w.n_items, w.k, mf.SEED, 1)
+    n = w.n_ratings if args.ref_sample <= 0 else min(args.ref_sample, w.n_ratings)
+    us, is_, rs = [], [], []
+    step = 25_000_000
+    for start in range(0, n, step):
+        u, i, r, held = orc.generate(seed, start, min(step, n - start), w.n_users, w.n_items, w.log2_alpha_user, w.c_user,
+                                     w.log2_alpha_item, w.c_item, amplitude=w.amplitude, noise_scale=w.noise_scale)
+        us.append(u[~held]); is_.append(i[~held]); rs.append(r[~held])
+    u, i, r = np.concatenate(us), np.concatenate(is_), np.concatenate(rs)
+    del us, is_, rs
+    P = orc.init_factors(w.n_users, w.k, seed, 0)
+    Q = orc.init_factors(w.n_items, w.k, seed, 1)
     for s in range(args.warmup):
-        orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, mf.SEED, threads, shuffled=False)
-    secs = 0.0
-    for s in range(args.steps):
-        secs += orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, mf.SEED, threads, shuffled=False)
-    value = len(r) * args.steps / secs
-    sample = "each step = 1 Hogwild epoch, %d host threads, over the first %d records (%d train) of %s, full-size P/Q" % (
-        threads, n, len(r), w.name)
+        orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, seed, threads, shuffled=True)
+    wall = loops = 0.0
+    for s in range(args.warmup, args.warmup + args.steps):
+        t0 = time.time()
+        loops += orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, seed, threads, shuffled=True)
+        wall += time.time() - t0
+    value = len(r) * args.steps / wall
+    full = n == w.n_ratings
+    sample = "each step = 1 Hogwild epoch (per-epoch shuffle + update loops), %d host threads, over %s records (%d train) of %s, full-size P/Q" % (
+        threads, "ALL %d" % n if full else "the first %d" % n, len(r), w.name)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "%s: %d users x %d items, k=%d, lr=%g, lambda=%g (bounded sample)" % (
-               w.name, w.n_users, w.n_items, w.k, w.lr, w.lambda_), "parallelism": "cpu-hogwild-%dthreads" % threads},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "config": {"workload": "%s: %d users x %d items, %d ratings (%d train), k=%d, lr=%g, lambda=%g" % (
+               w.name, w.n_users, w.n_items, n, len(r), w.k, w.lr, w.lambda_), "parallelism": "cpu-hogwild-%dthreads" % threads,
+               "same_workload_as_product_arm": full, "shuffled_every_epoch": True},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                            "update_loops_only": len(r) * args.steps / loops},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "reference = C++ oracle port of the Java stand-in (no JDK in the image; /root/reference has no source)"}
+           "note": "reference = C++ oracle port of the Java stand-in's factorizeThreaded (no JDK in the image; /root/reference has no "
+                   "source); the per-epoch order is the stand-in's (same permutation), produced with all host threads"}
     print(json.dumps(out), flush=True)
 
 
@@ -410,7 +493,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=12_000_000)
-    ap.add_argument("--ref-sample", type=int, default=20_000_000)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: records per step, 0 = the whole workload")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side run that measures roofline.traffic")
+    ap.add_argument("--no-ceilings", action="store_true")
+    ap.add_argument("--trace-e2e", action="store_true", help="MFSGD_TRACE=1 during the end-to-end calls (phase timings on stderr)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

@@ -92,7 +92,11 @@ typedef struct mfsgd_config {
                                   64..1024                                                                  */
     float    merge_boost;      /* runs of one item that share a launch are merged with weight min(1, merge_boost / runs);
                                   0 = default 1.25, 1 = plain model averaging; must be < 2                      */
-    int32_t  reserved[3];
+    float    p_atomic_threshold; /* run kernel: a user expected to have >= this many ratings in flight at once (its share of a
+                                  launch's records x the ratings the resident sub-warps hold in flight) is a HEAVY user: its row is
+                                  updated in memory with red.global.add instead of a store, so concurrent updates are not lost.
+                                  0 = default 0.25, < 0 = never (round-1 behaviour); MFSGD_SCATTER_ATOMIC_P = every user       */
+    int32_t  reserved[2];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
@@ -136,6 +140,8 @@ typedef struct mfsgd_layout_info {
     int64_t n_train_total;      /* records in the whole data set (all processes)                     */
     int32_t rounds;             /* interleaved passes per sub-epoch (see mfsgd_config.rounds)        */
     int32_t n_hot_items;        /* items on the run path (whole data set)                            */
+    int32_t n_heavy_users;      /* users whose rows the run kernel updates with red.global.add (whole data set) */
+    int32_t run_length;         /* longest run of the plan (mfsgd_config.hot_chunk resolved)         */
 } mfsgd_layout_info;
 
 MFSGD_API int  mfsgd_abi_version(void);
@@ -150,6 +156,12 @@ MFSGD_API void mfsgd_destroy(mfsgd_handle* h);
  * multi-process ring every rank passes the same full arrays; each keeps its own user stripe. */
 MFSGD_API int  mfsgd_load_ratings(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings,
                         int64_t n);
+/* Multi-process ring: every rank passes ITS OWN disjoint slice of the training triplets (any split; slices may be empty).
+ * The ranks sum their per-row counts (ncclAllReduce), derive the same stripe bounds, and exchange the records by stripe owner
+ * on the device (grouped ncclSend/ncclRecv): host-to-device traffic is 12 B per rating in total instead of per rank.
+ * Collective: every rank of the ring must call it. With world_size == 1 it is mfsgd_load_ratings. */
+MFSGD_API int  mfsgd_load_ratings_sharded(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings,
+                                int64_t n_local);
 /* Optional held-out triplets kept on the device for mfsgd_rmse_heldout / per-epoch evaluation. */
 MFSGD_API int  mfsgd_load_heldout(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings,
                         int64_t n);
@@ -184,7 +196,8 @@ MFSGD_API int  mfsgd_factorize(const int32_t* users, const int32_t* items, const
 MFSGD_API int  mfsgd_get_layout_info(mfsgd_handle* h, mfsgd_layout_info* out);
 /* user_bounds[user_blocks+1], item_bounds[item_blocks+1] (global row ids). */
 MFSGD_API int  mfsgd_get_bounds(mfsgd_handle* h, int32_t* user_bounds, int32_t* item_bounds);
-/* Ring member `member`'s current record layout: recs = 3*n int32 words (u,i,r-bits per record);
+/* Ring member `member`'s current record layout: recs = 3*n int32 words (u,i,r-bits per record; bit 31 of u marks a heavy
+ * user, see p_atomic_threshold -- mask with 0x7fffffff for the id);
  * block_offsets[stripes_per_gpu*(item_blocks+n_hot_items)+1]: the cold blocks (stripe-major), then one
  * bucket per (stripe, hot item). Pass recs=NULL to query *n only. */
 MFSGD_API int  mfsgd_get_records(mfsgd_handle* h, int32_t member, int32_t* recs, int64_t* block_offsets, int64_t* n);
@@ -238,6 +251,20 @@ typedef struct mfsgd_ratings {
 } mfsgd_ratings;
 MFSGD_API int  mfsgd_read_ratings(const char* path, int32_t format, mfsgd_ratings* out);
 MFSGD_API void mfsgd_free_ratings(mfsgd_ratings* r);
+
+/* Diagnostic (bench.py): measured ceilings of the update path's access pattern on `device`, taken in the caller's process:
+ * random 512-B row gather + scatter inside a buffer_mb-sized (L2-resident: 61 MB is one Netflix-shaped P sub-stripe) buffer
+ * counting 1024 B per row, the same rows read only (512 B per row), and a 1 GB streaming copy (read + write bytes). ~50 ms. */
+typedef struct mfsgd_ceilings {
+    double  row_gather_scatter_gbs;
+    double  row_gather_only_gbs;
+    double  hbm_stream_copy_gbs;
+    double  buffer_mb;
+    double  l2_mb;             /* cudaDeviceProp::l2CacheSize */
+    int32_t sm_count;
+    int32_t reserved;
+} mfsgd_ceilings;
+MFSGD_API int  mfsgd_measure_ceilings(int32_t device, double buffer_mb, mfsgd_ceilings* out);
 
 /* Pinned host staging helpers (optional; plain host memory works too, at lower H2D bandwidth). */
 MFSGD_API int  mfsgd_host_alloc(void** out, int64_t bytes);

@@ -25,7 +25,7 @@ class Config(C.Structure):
                 ("scatter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32), ("world_size", C.c_int32),
                 ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
                 ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("merge_boost", C.c_float),
-                ("reserved", C.c_int32 * 3)]
+                ("p_atomic_threshold", C.c_float), ("reserved", C.c_int32 * 2)]
 
 
 class EpochStats(C.Structure):
@@ -45,13 +45,18 @@ class LayoutInfo(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("stripes_per_gpu", C.c_int32), ("shards_per_gpu", C.c_int32),
                 ("user_blocks", C.c_int32), ("item_blocks", C.c_int32), ("n_train_local", C.c_int64),
                 ("n_heldout_local", C.c_int64), ("n_train_total", C.c_int64), ("rounds", C.c_int32),
-                ("n_hot_items", C.c_int32)]
+                ("n_hot_items", C.c_int32), ("n_heavy_users", C.c_int32), ("run_length", C.c_int32)]
 
 
 class Ratings(C.Structure):
     _fields_ = [("users", C.POINTER(C.c_int32)), ("items", C.POINTER(C.c_int32)), ("ratings", C.POINTER(C.c_float)),
                 ("n", C.c_int64), ("n_users", C.c_int32), ("n_items", C.c_int32), ("user_ids", C.POINTER(C.c_int64)),
                 ("item_ids", C.POINTER(C.c_int64)), ("format", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Ceilings(C.Structure):
+    _fields_ = [("row_gather_scatter_gbs", C.c_double), ("row_gather_only_gbs", C.c_double), ("hbm_stream_copy_gbs", C.c_double),
+                ("buffer_mb", C.c_double), ("l2_mb", C.c_double), ("sm_count", C.c_int32), ("reserved", C.c_int32)]
 
 
 FORMAT_AUTO, FORMAT_TRIPLETS, FORMAT_NETFLIX_PRIZE = 0, 1, 2
@@ -73,6 +78,7 @@ SIGNATURES = {
     "mfsgd_read_ratings": (C.c_int, [C.c_char_p, _i32, C.POINTER(Ratings)]),
     "mfsgd_free_ratings": (None, [C.POINTER(Ratings)]),
     "mfsgd_load_ratings": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "mfsgd_load_ratings_sharded": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
     "mfsgd_load_heldout": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
     "mfsgd_generate_synthetic": (C.c_int, [_vp, C.POINTER(SynthParams), C.POINTER(_i64), C.POINTER(_i64)]),
     "mfsgd_init_factors": (C.c_int, [_vp]),
@@ -93,6 +99,7 @@ SIGNATURES = {
     "mfsgd_apply_updates_forced": (C.c_int, [_i32, _i32, _f32, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mfsgd_generate_to_host": (C.c_int, [_i32, C.POINTER(SynthParams), _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mfsgd_nccl_unique_id": (C.c_int, [_vp]),
+    "mfsgd_measure_ceilings": (C.c_int, [_i32, C.c_double, C.POINTER(Ceilings)]),
     "mfsgd_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "mfsgd_host_free": (C.c_int, [_vp]),
 }

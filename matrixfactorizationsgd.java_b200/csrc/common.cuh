@@ -16,6 +16,10 @@ struct Rec {
     float   r;
 };
 static_assert(sizeof(Rec) == 12, "Rec must be 12 bytes");
+// Bit 31 of Rec::u in the bucketed (Hogwild / DSGD) layouts marks a HEAVY user: one whose ratings are so many that several of
+// them are in flight at once, so that its row is updated in memory with red.global.add (no lost updates) instead of a store
+// (engine.cu heavy_user_threshold). Ids are < 2^31, every reader masks the bit.
+constexpr int32_t REC_USER_MASK = 0x7fffffff;
 
 enum : uint64_t {
     STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2, STREAM_USER = 3, STREAM_ITEM = 4,

@@ -79,11 +79,7 @@ static int guarded(F&& body) {
 }
 
 // MFSGD_TRACE=1: phase timings on stderr (diagnostic aid)
-static inline bool trace_on() {
-    static int on = -1;
-    if (on < 0) on = getenv("MFSGD_TRACE") != nullptr ? 1 : 0;
-    return on == 1;
-}
+static inline bool trace_on() { return getenv("MFSGD_TRACE") != nullptr; }     // read every time: callers switch it on mid-process
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct PhaseTimer {
     const char* what;
@@ -104,6 +100,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -127,6 +125,8 @@ static int nccl_load() {
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -181,8 +181,11 @@ struct Member {              // one ring member ("GPU g")
     uint16_t* d_owner_u = nullptr;
     uint16_t* d_owner_i = nullptr;
     int32_t* d_hot_index = nullptr;  // item -> index into handle.hot_items, or -1
+    uint32_t* d_heavy_bits = nullptr; // bit u: heavy user (rows updated with red.global.add by the run kernel)
     HotUnit* d_units = nullptr;      // hot-item units of all visits, grouped by visit
     std::vector<int> visit_units;    // [(a * rounds + rnd) * IB + item block] -> first unit; one extra entry at the end
+    std::vector<int64_t> unit_recs_cum;   // records of units [0, j): prefix sums over the unit list
+    int run_chunk = 0;               // longest run of the plan
     unsigned int* d_counters = nullptr;   // one unit-claim counter per hot launch; COUNTER_EPOCHS epochs' worth, zeroed per batch
     int n_counters = 0, counter_next = 0;
     cudaEvent_t ev_epoch_go = nullptr;
@@ -219,6 +222,8 @@ struct mfsgd_handle {
     std::vector<int32_t> hot_items;     // global ids of the hot items, ascending (so grouped by item block)
     std::vector<int32_t> hot_block_lo;  // [IB + 1]: hot_items[hot_block_lo[b] .. hot_block_lo[b+1]) lie in item block b
     int H = 0;
+    std::vector<uint32_t> heavy_bits;   // bit u set: heavy user (empty: none)
+    int n_heavy = 0;
     float scale = 0.f;
     std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
     std::vector<Member> members;                    // the ring members this process drives
@@ -265,6 +270,7 @@ static void free_member_data(Member& m) {
     dev_free(m.d_owner_u);
     dev_free(m.d_owner_i);
     dev_free(m.d_hot_index);
+    dev_free(m.d_heavy_bits);
     dev_free(m.d_units);
     dev_free(m.d_counters);
     m.visit_units.clear();
@@ -287,6 +293,8 @@ struct Source {
     SynthArgs synth{};
     int64_t total = 0;
     bool all_held = false;         // host arrays are a held-out set
+    bool sharded = false;          // multi-process ring: the host arrays are THIS rank's slice of the training set
+    const Rec* drecs = nullptr;    // device records (what the other members sent this one), instead of host arrays
 };
 
 struct Chunk {                     // per-device staging buffers
@@ -323,6 +331,8 @@ static int chunk_stage(Chunk& c, const Source& s, int64_t start, int64_t count, 
     if (c.start == start && c.count == count) return MFSGD_OK;
     if (s.synthetic) {
         CK(launch_generate(s.synth, start, count, c.u, c.i, c.r, c.held, stream, launches));
+    } else if (s.drecs) {
+        CK(launch_unpack_records(s.drecs + start, count, c.u, c.i, c.r, stream, launches));
     } else {
         CK(cudaMemcpyAsync(c.u, s.hu + start, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(c.i, s.hi + start, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
@@ -382,11 +392,15 @@ static int validate_config(const mfsgd_config* c) {
         return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode keeps the caller's record order: no blocking");
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
     if (c->hot_chunk < 0 || c->hot_chunk > 65536) return fail(MFSGD_E_INVALID_ARG, "hot_chunk=%d out of range (0..65536)", c->hot_chunk);
+    if (c->p_atomic_threshold != c->p_atomic_threshold) return fail(MFSGD_E_INVALID_ARG, "p_atomic_threshold is NaN");
     if (!(c->merge_boost >= 0.f) || c->merge_boost >= 2.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
     if (c->merge_boost > 0.f && c->merge_boost < 1.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
     if (c->rounds < 0 || c->rounds > 256) return fail(MFSGD_E_INVALID_ARG, "rounds=%d out of range", c->rounds);
     return MFSGD_OK;
 }
+
+// Run kernel: p_u updated in memory by red.global.add (MFSGD_SCATTER_ATOMIC_P / MFSGD_SCATTER_ATOMIC) or stored (last writer wins)
+static inline bool run_p_red(const mfsgd_config& c) { return c.scatter == MFSGD_SCATTER_ATOMIC_P || c.scatter == MFSGD_SCATTER_ATOMIC; }
 
 static int member_setup(mfsgd_handle* h, Member& m) {
     CK(cudaSetDevice(m.device));
@@ -419,7 +433,7 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     if (h->cfg.ctas_per_sm > 0 && h->cfg.ctas_per_sm < ctas) ctas = h->cfg.ctas_per_sm;
     m.grid = m.n_sms * ctas;
     int hot_ctas = 0;
-    CK(hot_max_ctas_per_sm(h->cfg.k, fast, &hot_ctas));
+    CK(hot_max_ctas_per_sm(h->cfg.k, fast, run_p_red(h->cfg), &hot_ctas));
     m.hot_grid = m.n_sms * std::max(1, hot_ctas);
     return MFSGD_OK;
 }
@@ -618,6 +632,16 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
         CKC(launch_count_rows(ch.u, ch.i, src.synthetic ? ch.held : nullptr, count, ucnt, icnt, c.n_users, c.n_items, bad,
                               m.stream, &m.launches));
     }
+    if (src.sharded) {     // every rank counted its own slice: sum the per-row counts (and the bad-id flag) over the ring
+        ncclResult_t r1 = g_nccl.AllReduce(ucnt, ucnt, (size_t)c.n_users, ncclUint32, ncclSum, h->comm, m.stream);
+        ncclResult_t r2 = r1 == ncclSuccess ? g_nccl.AllReduce(icnt, icnt, (size_t)c.n_items, ncclUint32, ncclSum, h->comm, m.stream) : r1;
+        ncclResult_t r3 = r2 == ncclSuccess ? g_nccl.AllReduce(bad, bad, 1, ncclInt32, ncclMax, h->comm, m.stream) : r2;
+        if (r3 != ncclSuccess) {
+            cleanup();
+            return fail(MFSGD_E_NCCL, "all-reduce of the row counts: %s", g_nccl.GetErrorString(r3));
+        }
+        m.launches += 3;
+    }
     size_t tb_u = 0, tb_i = 0;
     CKC(exclusive_cumsum_u32(ucnt, ucum, c.n_users, nullptr, &tb_u, m.stream, nullptr));
     CKC(exclusive_cumsum_u32(icnt, icum, c.n_items, nullptr, &tb_i, m.stream, nullptr));
@@ -661,6 +685,26 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
         std::sort(h->hot_items.begin(), h->hot_items.end());
     }
     h->H = (int)h->hot_items.size();
+    // heavy users: expected ratings in flight at once >= p_atomic_threshold. A launch of the run kernel walks one P sub-stripe
+    // (1 / (G * mu) of the ratings, evenly over the rounds) with every resident sub-warp holding ~2 ratings between the
+    // gather of p_u and its scatter, so user u has about cnt_u * G * mu / total * (2 * resident sub-warps) ratings in flight.
+    h->heavy_bits.clear();
+    h->n_heavy = 0;
+    const float tau = c.p_atomic_threshold == 0.f ? 0.25f : c.p_atomic_threshold;
+    if (bad_host == 0 && tau > 0.f && c.mode != MFSGD_MODE_DETERMINISTIC && total_train > 0 && h->H > 0) {
+        std::vector<uint32_t> ucnt_host((size_t)c.n_users);
+        cudaError_t e = cudaMemcpy(ucnt_host.data(), ucnt, (size_t)c.n_users * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { cleanup(); return fail(MFSGD_E_CUDA, "copying user counts: %s", cudaGetErrorString(e)); }
+        const double in_flight = 2.0 * (double)m.hot_grid * 8.0 * (32 / run_kernel_lanes(c.k));
+        const double thr = (double)tau * (double)total_train / (in_flight * (double)h->G * (double)h->mu);
+        h->heavy_bits.assign(((size_t)c.n_users + 31) / 32, 0u);
+        for (int32_t u = 0; u < c.n_users; u++)
+            if ((double)ucnt_host[(size_t)u] >= thr) {
+                h->heavy_bits[(size_t)u >> 5] |= 1u << (u & 31);
+                h->n_heavy++;
+            }
+        if (h->n_heavy == 0) h->heavy_bits.clear();
+    }
     cleanup();
     if (bad_host) return fail(MFSGD_E_INVALID_ARG, "a rating has a user or item id outside [0,n_users) x [0,n_items)");
     h->n_train_total = (int64_t)total_train;
@@ -670,6 +714,8 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
 static void uniform_bounds(mfsgd_handle* h) {
     h->hot_items.clear();
     h->H = 0;
+    h->heavy_bits.clear();
+    h->n_heavy = 0;
     h->user_bounds.resize((size_t)h->UB + 1);
     h->item_bounds.resize((size_t)h->IB + 1);
     for (int b = 0; b <= h->UB; b++) h->user_bounds[(size_t)b] = (int32_t)((int64_t)h->cfg.n_users * b / h->UB);
@@ -708,6 +754,11 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
         const int32_t bound = h->item_bounds[(size_t)ib];
         h->hot_block_lo[(size_t)ib] = (int32_t)(std::lower_bound(h->hot_items.begin(), h->hot_items.end(), bound) - h->hot_items.begin());
     }
+    dev_free(m.d_heavy_bits);
+    if (!h->heavy_bits.empty()) {
+        CK(dev_alloc(&m.d_heavy_bits, h->heavy_bits.size()));
+        CK(cudaMemcpy(m.d_heavy_bits, h->heavy_bits.data(), h->heavy_bits.size() * 4, cudaMemcpyHostToDevice));
+    }
     dev_free(m.d_hot_index);
     if (h->H > 0) {
         std::vector<int32_t> idx((size_t)c.n_items, -1);
@@ -720,9 +771,10 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
 
 // Bucket the member's share of the source into `nblk` blocks. On success *out_recs (device, owned by the
 // caller) holds the records sorted by block and off[nblk+1] the offsets.
+static int bucket_with(Member& m, const Source& src, Chunk& ch, BucketArgs b, Rec** out_recs, std::vector<int64_t>& off);
+
 static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& ch, int want_held, int row_div, int col_div,
                          int n_cols, bool split_hot, Rec** out_recs, std::vector<int64_t>& off) {
-    CK(cudaSetDevice(m.device));
     BucketArgs b{};
     b.owner_u = m.d_owner_u;
     b.owner_i = m.d_owner_i;
@@ -736,7 +788,14 @@ static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& c
         b.hot_index = m.d_hot_index;
         b.n_hot = h->H;
         b.hot_base = bucket_rows(b) * n_cols;
+        b.heavy_bits = m.d_heavy_bits;      // training layout: mark the heavy users' records for the run kernel
     }
+    return bucket_with(m, src, ch, b, out_recs, off);
+}
+
+// The source's records that fall into the blocks `b` describes, sorted by block: histogram pass, scatter pass.
+static int bucket_with(Member& m, const Source& src, Chunk& ch, BucketArgs b, Rec** out_recs, std::vector<int64_t>& off) {
+    CK(cudaSetDevice(m.device));
     const int nblk = bucket_block_count(b);
     if (nblk > MAX_BUCKETS) return fail(MFSGD_E_INVALID_ARG, "%d blocks per ring member exceed the %d limit", nblk, MAX_BUCKETS);
     unsigned long long* d_cnt = nullptr;
@@ -784,6 +843,69 @@ static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& c
     return MFSGD_OK;
 }
 
+// Multi-process ring, sharded input: this rank's slice is sorted by the ring member that owns each record's user stripe and
+// the slices travel member to member in one grouped ncclSend / ncclRecv round (an all-to-all of 12-byte records over NVLink).
+// On return *recv holds every training record of this member's stripe (device, caller frees), *n_recv their number.
+static int exchange_slices(mfsgd_handle* h, Member& m, const Source& src, Chunk& ch, Rec** recv, int64_t* n_recv) {
+    const int G = h->G;
+    *recv = nullptr;
+    *n_recv = 0;
+    BucketArgs b{};                       // one block per destination member: row = owner_u / mu, a single column
+    b.owner_u = m.d_owner_u;
+    b.owner_i = m.d_owner_i;
+    b.ub_lo = 0;
+    b.ub_hi = h->UB;
+    b.row_div = h->mu;
+    b.col_div = h->IB;
+    b.n_cols = 1;
+    b.want_held = 0;
+    Rec* send = nullptr;
+    std::vector<int64_t> soff;
+    CKRC(bucket_with(m, src, ch, b, &send, soff));
+    std::vector<unsigned long long> cnt((size_t)G), all((size_t)G * G);
+    for (int p = 0; p < G; p++) cnt[(size_t)p] = (unsigned long long)(soff[(size_t)p + 1] - soff[(size_t)p]);
+    unsigned long long *d_cnt = nullptr, *d_all = nullptr;
+    int rc = MFSGD_OK;
+    cudaError_t e = dev_alloc(&d_cnt, (size_t)G);
+    if (e == cudaSuccess) e = dev_alloc(&d_all, (size_t)G * G);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)G * 8, cudaMemcpyHostToDevice, m.stream);
+    if (e == cudaSuccess) {
+        ncclResult_t r = g_nccl.AllGather(d_cnt, d_all, (size_t)G, ncclUint64, h->comm, m.stream);
+        if (r != ncclSuccess) rc = fail(MFSGD_E_NCCL, "all-gather of the slice sizes: %s", g_nccl.GetErrorString(r));
+    }
+    if (rc == MFSGD_OK && e == cudaSuccess) e = cudaMemcpyAsync(all.data(), d_all, (size_t)G * G * 8, cudaMemcpyDeviceToHost, m.stream);
+    if (rc == MFSGD_OK && e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+    std::vector<int64_t> roff((size_t)G + 1, 0);
+    if (rc == MFSGD_OK && e == cudaSuccess) {
+        for (int p = 0; p < G; p++) roff[(size_t)p + 1] = roff[(size_t)p] + (int64_t)all[(size_t)p * G + (size_t)m.g];   // what p sends to me
+        e = dev_alloc(recv, (size_t)roff[(size_t)G]);
+    }
+    if (rc == MFSGD_OK && e == cudaSuccess) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int p = 0; p < G && r == ncclSuccess; p++) {
+            const int64_t ns = soff[(size_t)p + 1] - soff[(size_t)p], nr = roff[(size_t)p + 1] - roff[(size_t)p];
+            if (ns > 0) r = g_nccl.Send(send + soff[(size_t)p], (size_t)ns * sizeof(Rec), ncclChar, p, h->comm, m.stream);
+            if (r == ncclSuccess && nr > 0) r = g_nccl.Recv(*recv + roff[(size_t)p], (size_t)nr * sizeof(Rec), ncclChar, p, h->comm, m.stream);
+        }
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) rc = fail(MFSGD_E_NCCL, "record exchange: %s", g_nccl.GetErrorString(r));
+        else e = cudaStreamSynchronize(m.stream);
+        m.launches += 1;
+    }
+    cudaFree(d_cnt);
+    cudaFree(d_all);
+    cudaFree(send);
+    if (rc == MFSGD_OK && e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "record exchange: %s", cudaGetErrorString(e));
+    if (rc != MFSGD_OK) {
+        if (*recv) cudaFree(*recv);
+        *recv = nullptr;
+        return rc;
+    }
+    *n_recv = roff[(size_t)G];
+    return MFSGD_OK;
+}
+
 // Record range of visit (sub-stripe sa, round rnd) inside bucket `blk` (cold block or hot bucket).
 static inline void slice_of(const Member& m, size_t blk_lo, size_t blk_hi, int rnd, int rounds, int64_t* lo, int64_t* hi) {
     const int64_t blo = m.block_off[blk_lo], bhi = m.block_off[blk_hi];
@@ -800,7 +922,8 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     if (h->H == 0 || h->cfg.mode == MFSGD_MODE_DETERMINISTIC) return MFSGD_OK;
     CK(cudaSetDevice(m.device));
     const size_t hb = (size_t)h->mu * h->IB;
-    const int chunk = plan_run_length(h->cfg.hot_chunk, h->G, h->mu, h->rounds, h->IB, m.block_off.back() - m.block_off[hb],
+    const bool laned = (h->multi_process && h->G > 1 && h->mi > 1) || ((h->cfg.flags & MFSGD_FLAG_SPLIT_SHARDS) && h->mi > 1);
+    const int chunk = plan_run_length(h->cfg.hot_chunk, laned ? 2 : 1, h->mu, h->rounds, h->IB, m.block_off.back() - m.block_off[hb],
                                       m.hot_grid, 32 / run_kernel_lanes(h->cfg.k));      // run_plan.hpp
     std::vector<HotUnit> units;
     RunPlanArgs pa{};
@@ -813,6 +936,9 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     pa.hot_block_lo = h->hot_block_lo.data();
     pa.hot_items = h->hot_items.data();
     plan_runs(pa, units, m.visit_units);
+    m.run_chunk = chunk;
+    m.unit_recs_cum.assign(units.size() + 1, 0);
+    for (size_t j = 0; j < units.size(); j++) m.unit_recs_cum[j + 1] = m.unit_recs_cum[j] + units[j].count;
     m.n_counters = h->mu * h->rounds * h->IB;
     CK(dev_alloc(&m.d_units, units.size()));
     CK(dev_alloc(&m.d_counters, (size_t)m.n_counters * COUNTER_EPOCHS));
@@ -863,6 +989,21 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
             m.block_off.assign(2, 0);
             m.block_off[1] = src.total;
         } else if (rc == MFSGD_OK) {
+            Rec* mine = nullptr;          // sharded input: the records the ring sent this member
+            if (src.sharded) {
+                int64_t n_mine = 0;
+                { PhaseTimer pt("load: record exchange (route by stripe owner + all-to-all)"); rc = exchange_slices(h, m, src, ch, &mine, &n_mine); }
+                if (rc == MFSGD_OK) {
+                    Source own;
+                    own.drecs = mine;
+                    own.total = n_mine;
+                    Chunk ch2;
+                    rc = chunk_alloc(ch2, std::max<int64_t>(1, std::min(n_mine, CHUNK_MAX)), false);
+                    if (rc == MFSGD_OK) { PhaseTimer pt("load: bucketing (histogram + scatter)"); rc = bucket_member(h, m, own, ch2, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off); }
+                    chunk_free(ch2);
+                }
+                if (mine) cudaFree(mine);
+            } else
             { PhaseTimer pt("load: bucketing (histogram + scatter)"); rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off); }
             if (rc == MFSGD_OK) {
                 m.n_recs = m.block_off.back();
@@ -912,6 +1053,20 @@ static int mfsgd_load_ratings_body(mfsgd_handle* h, const int32_t* users, const 
     if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
     Source s;
     s.hu = users; s.hi = items; s.hr = ratings; s.total = n;
+    return load_training(h, s, false);
+}
+
+static int mfsgd_load_ratings_sharded_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n);
+extern "C" int mfsgd_load_ratings_sharded(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    return guarded([&]() { return mfsgd_load_ratings_sharded_body(h, users, items, ratings, n); });
+}
+static int mfsgd_load_ratings_sharded_body(mfsgd_handle* h, const int32_t* users, const int32_t* items, const float* ratings, int64_t n) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (n < 0 || (n > 0 && (!users || !items || !ratings))) return fail(MFSGD_E_INVALID_ARG, "null triplet arrays or negative n");
+    if (!h->multi_process) return mfsgd_load_ratings(h, users, items, ratings, n);     // one process holds everything anyway
+    Source s;
+    s.hu = users; s.hi = items; s.hr = ratings; s.total = n;
+    s.sharded = true;
     return load_training(h, s, false);
 }
 
@@ -1278,14 +1433,18 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
             a.first = 0;
             a.n = m.n_recs;
             if (m.counter_next >= m.n_counters * COUNTER_EPOCHS) return fail(MFSGD_E_STATE, "run launch counters exhausted");
+            auto overlaps = [&](const Visit& w) {
+                return hot_launch_overlaps(c.k, w.unit_hi - w.unit_lo, m.unit_recs_cum[(size_t)w.unit_hi] - m.unit_recs_cum[(size_t)w.unit_lo],
+                                           m.run_chunk, m.hot_grid);
+            };
             bool next_overlaps = false;    // will the next run launch of this chain overlap this one's tail?
             for (size_t vj = vi + 1; vj < visits.size(); vj++)
                 if (visits[vj].unit_hi > visits[vj].unit_lo) {
-                    next_overlaps = hot_launch_overlaps(c.k, visits[vj].unit_hi - visits[vj].unit_lo, m.hot_grid);
+                    next_overlaps = overlaps(visits[vj]);
                     break;
                 }
             CK(launch_sgd_update_hot(a, m.d_units + v.unit_lo, v.unit_hi - v.unit_lo, m.d_counters + m.counter_next++, fast_arith,
-                                     m.hot_grid, hot_chained, next_overlaps, hot_s, &m.launches));
+                                     run_p_red(c), m.hot_grid, hot_chained && overlaps(v), next_overlaps, hot_s, &m.launches));
             hot_chained = true;
             m.update_launches++;
             *any_hot = true;
@@ -1721,6 +1880,7 @@ static int mfsgd_factorize_body(const int32_t* users, const int32_t* items, cons
     if (rc == MFSGD_OK) rc = mfsgd_get_factors(h, P_out, Q_out);
     if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] get_factors %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     mfsgd_destroy(h);
+    if (trace) { t1 = now(); fprintf(stderr, "[mfsgd] destroy %.1f ms\n", (t1 - t0) * 1e3); t0 = t1; }
     return rc;
 }
 
@@ -1748,7 +1908,8 @@ static int mfsgd_plan_layout_body(const mfsgd_config* cfg, int64_t l2_bytes, int
     *stripes = b.mu;
     *shards = b.mi;
     *rounds = plan_rounds(cfg->rounds, cfg->mode, G, b.mu, member_records, member_users);
-    *run_length = plan_run_length(cfg->hot_chunk, G, b.mu, *rounds, G * b.mi, run_records, resident_ctas, 32 / run_kernel_lanes(cfg->k));
+    const bool laned = (cfg->world_size > 1 && G > 1 && b.mi > 1) || ((cfg->flags & MFSGD_FLAG_SPLIT_SHARDS) && b.mi > 1);
+    *run_length = plan_run_length(cfg->hot_chunk, laned ? 2 : 1, b.mu, *rounds, G * b.mi, run_records, resident_ctas, 32 / run_kernel_lanes(cfg->k));
     return MFSGD_OK;
 }
 
@@ -1816,6 +1977,8 @@ static int mfsgd_get_layout_info_body(mfsgd_handle* h, mfsgd_layout_info* out) {
     out->n_train_total = h->n_train_total;
     out->rounds = h->rounds;
     out->n_hot_items = h->H;
+    out->n_heavy_users = h->n_heavy;
+    out->run_length = h->members[0].run_chunk;
     return MFSGD_OK;
 }
 

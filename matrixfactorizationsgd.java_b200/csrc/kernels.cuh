@@ -67,7 +67,7 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fas
                                       cudaStream_t stream, int* launches);
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
 cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas);
-cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas);
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, int* ctas);
 // Lanes per rating of the run kernel at rank k (kernels_hot.cu): a warp walks 32 / lanes runs side by side.
 int run_kernel_lanes(int k);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
@@ -91,10 +91,12 @@ struct HotUnit {
 };
 // follows_hot_launch: the previous operation on `stream` is a hot launch of the same sub-epoch (it may then be overlapped
 // by programmatic dependent launch, see kernels_update.cu).
-// overlapped_by_next: the NEXT launch on the chain will overlap this one's tail (hot_launch_overlaps of its size).
-cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
-                                  int grid, bool follows_hot_launch, bool overlapped_by_next, cudaStream_t stream, int* launches);
-bool hot_launch_overlaps(int k, int n_units, int full_grid);
+// overlaps_previous: launch with programmatic stream serialisation (it follows a run launch on `stream` and
+// hot_launch_overlaps says so); overlapped_by_next: the NEXT launch on the chain will overlap this one's tail.
+// p_red: p_u is updated in memory by red.global.add of its increment (no lost updates between concurrent writers of a row).
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast, bool p_red,
+                                  int grid, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream, int* launches);
+bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
@@ -148,6 +150,7 @@ struct BucketArgs {
     // hot_index[i] >= 0 goes to bucket hot_base + row * n_hot + hot_index[i] instead of its cold block.
     const int32_t* hot_index;
     int32_t hot_base, n_hot;
+    const uint32_t* heavy_bits;   // nullable: bit u set -> the scattered record carries the heavy-user mark (common.cuh REC_USER_MASK)
 };
 inline int bucket_rows(const BucketArgs& b) { return (b.ub_hi - b.ub_lo + b.row_div - 1) / b.row_div; }
 inline int bucket_block_count(const BucketArgs& b) {
@@ -166,6 +169,8 @@ cudaError_t launch_block_shuffle(const Rec* in, Rec* out, const int64_t* block_o
 // SoA -> AoS in input order (deterministic mode keeps the caller's record order).
 cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, Rec* out,
                                 cudaStream_t stream, int* launches);
+// AoS -> SoA
+cudaError_t launch_unpack_records(const Rec* in, int64_t n, int32_t* u, int32_t* i, float* r, cudaStream_t stream, int* launches);
 // Stand-in visiting order (MatrixFactorizationSGD.java:72): out[j] = in[order_j]; device radix sort of the
 // packed (key31<<32 | idx) words. temp/temp_bytes: caller-owned scratch, query with temp == nullptr.
 cudaError_t deterministic_order_gather(const Rec* in, Rec* out, int32_t n, uint64_t seed, uint32_t epoch,

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __res
         const int cnt = (n - base) < 32 ? (int)(n - base) : 32;
         int32_t ru = 0, ri = 0, rr = 0;
         if (lane < cnt) {
-            ru = ld_stream_i32(words + 3 * (base + lane), pol);
+            ru = ld_stream_i32(words + 3 * (base + lane), pol) & REC_USER_MASK;
             ri = ld_stream_i32(words + 3 * (base + lane) + 1, pol);
             rr = ld_stream_i32(words + 3 * (base + lane) + 2, pol);
         }

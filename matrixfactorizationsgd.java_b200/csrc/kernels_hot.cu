@@ -45,7 +45,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Every thread therefore waits for the prerequisite grid as its last action (a no-op without the launch attribute).
 __device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int LANES, int VEC, bool FULL, bool FAST, int D>
+template <int LANES, int VEC, bool FULL, bool FAST, int D, bool PRED>
 __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
                                                                                  unsigned int* __restrict__ counter, int always_add) {
     constexpr int GPW = 32 / LANES;                   // runs walked side by side by one warp
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
     const int chunks = (int)(k >> 2);
     float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;
     const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
+    const float ccoef = -__fmul_rn(a.lr, a.lambda);   // PRED: p_u += b * q_i + ccoef * p_u, added in memory
     const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
     const uint64_t pol = l2_policy_evict_first();
     int2* const recs = srec[wic][grp];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
         };
         auto gather = [&](float4 (&slot)[VEC], int t) {   // p_u of step t -> a ring slot (nothing past the run's end)
             if (t < count) {
-                const float* xp = Pl + (int64_t)recs[t & (RING - 1)].x * k;
+                const float* xp = Pl + (int64_t)(recs[t & (RING - 1)].x & REC_USER_MASK) * k;
 #pragma unroll
                 for (int v = 0; v < VEC; v++)
                     if (FULL || gl + v * LANES < chunks) slot[v] = ld_row4(xp + 4 * v * LANES);
@@ -131,11 +132,13 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
                 const float e = __fsub_rn(__int_as_float(rec.y), rows_dot<LANES, VEC, FAST>(ring[d], q));
                 const float b = __fmul_rn(cf.lr, e);
                 if (t < count) {
-                    float* const cp = Pl + (int64_t)rec.x * k;
+                    float* const cp = Pl + (int64_t)(rec.x & REC_USER_MASK) * k;
+                    const bool p_red = PRED || rec.x < 0;       // heavy user (or every user): add the increment in memory
 #pragma unroll
                     for (int v = 0; v < VEC; v++) {
                         if (FULL || gl + v * LANES < chunks) {
-                            st_row4(cp + 4 * v * LANES, new_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                            if (p_red) red_add_row4(cp + 4 * v * LANES, delta_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, ccoef, b));
+                            else st_row4(cp + 4 * v * LANES, new_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
                             q[v] = new_chunk<FAST>(q[v], ring[d][v], e, cf.lr, cf.lambda, cf.acoef, b);
                         }
                     }
@@ -247,14 +250,22 @@ static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, boo
     return cudaLaunchKernelEx(&cfg, kernel, a, units, n_units, counter, always_add);
 }
 
-// Does a run launch of n_units on a chain of run launches overlap its predecessor's tail (programmatic dependent launch)?
-bool hot_launch_overlaps(int k, int n_units, int full_grid) {
+// Does a run launch on a chain of run launches overlap its predecessor's tail (programmatic dependent launch)? Only where
+// that is a tail effect: the launch fills the machine (>= 2 runs per resident sub-warp; the resident grid is the occupancy
+// limit, so the dependent's CTAs only get SM slots as the predecessor's retire -- MFSGD_HOT_CTAS below that limit would make
+// whole launches co-resident, which diverges: round-2 experiment, NaN in the first epoch) and its longest run is no longer
+// than twice a sub-warp's share of the launch (runs are handed out longest first, so long runs end well before the launch
+// does; a launch whose hot-item runs outlast everything else would still be merging when the next launch reads q_i).
+bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid) {
     const int per_warp = 32 / run_geometry_for(k).lanes;
-    return run_pdl() != 0 && (run_pdl() == 2 || (int64_t)n_units >= 2LL * full_grid * 8 * per_warp);
+    if (run_pdl() == 2) return true;                       // tuning aid: force it
+    if (run_pdl() == 0 || env_int("MFSGD_HOT_CTAS", 0) > 0) return false;
+    const int64_t sub_warps = (int64_t)full_grid * 8 * per_warp;
+    return (int64_t)n_units >= 2 * sub_warps && (int64_t)longest_run * sub_warps <= 2 * n_records;
 }
 
-cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast,
-                                  int grid, bool follows_hot_launch, bool overlapped_by_next, cudaStream_t stream, int* launches) {
+cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast, bool p_red,
+                                  int grid, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream, int* launches) {
     if (n_units <= 0) return cudaSuccess;
     const Geometry g = run_geometry_for(a.k);
     const int per_warp = 32 / g.lanes;            // runs a warp walks side by side
@@ -270,29 +281,36 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     // with a whole epoch in flight p_u and q_i are both corrected from the same stale state and the product overshoots
     // (profiles/r01_experiments.md section 8).
     // MFSGD_PDL = 2 overlaps every chained launch (tuning aid).
-    const bool pdl = follows_hot_launch && hot_launch_overlaps(a.k, n_units, full_grid);
+    (void)full_grid;
+    const bool pdl = overlaps_previous;      // decided by the caller (hot_launch_overlaps of this launch, and it follows a run launch)
     // a launch that overlaps a neighbour (either side) never overwrites an item row: its weight-1 runs add their net change too
     const int always_add = (pdl || overlapped_by_next) ? 1 : 0;
     const bool d2 = run_depth() == 2;
     cudaError_t err = cudaSuccess;
 #define CALL(L, V, F)                                                                                                        \
-    err = (fast && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-          : fast       ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-                       : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4>, grid, stream, pdl, always_add, a, units, n_units, counter)
+    err = (fast && p_red && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+          : (fast && p_red)     ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+          : (fast && d2)        ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+          : fast                ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+          : p_red               ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 4, true>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+                                : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4, false>, grid, stream, pdl, always_add, a, units, n_units, counter)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;
     return err != cudaSuccess ? err : cudaGetLastError();
 }
 
-cudaError_t hot_max_ctas_per_sm(int k, bool fast, int* ctas) {
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, int* ctas) {
     const Geometry g = run_geometry_for(k);
     const bool d2 = run_depth() == 2;
     cudaError_t err = cudaSuccess;
 #define CALL(L, V, F)                                                                                                              \
-    err = (fast && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2>, 256, 0)     \
-          : fast       ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4>, 256, 0)     \
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4>, 256, 0)
+    err = (fast && p_red && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, true>, 256, 0)   \
+          : (fast && p_red)     ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, true>, 256, 0)   \
+          : (fast && d2)        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, false>, 256, 0)  \
+          : fast                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, false>, 256, 0)  \
+          : p_red               ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4, true>, 256, 0)  \
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4, false>, 256, 0)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
     const int cap = env_int("MFSGD_HOT_CTAS", 0);    // tuning aid: resident run-kernel CTAs per SM

@@ -103,6 +103,11 @@ __device__ __forceinline__ int record_block(const BucketArgs& b, int64_t t) {
     return row * b.n_cols + (int)b.owner_i[item] / b.col_div;
 }
 
+__device__ __forceinline__ int32_t marked_user(const BucketArgs& b, int32_t u) {
+    if (b.heavy_bits != nullptr && ((b.heavy_bits[u >> 5] >> (u & 31)) & 1u)) return u | (int32_t)0x80000000;
+    return u;
+}
+
 constexpr int BUCKET_THREADS = 256;
 constexpr int BUCKET_ITEMS = 8;
 constexpr int BUCKET_CHUNK = BUCKET_THREADS * BUCKET_ITEMS;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) block_scatter_kernel(BucketArg
             if (blk[it] >= 0) {
                 const int64_t t = chunk * BUCKET_CHUNK + it * BUCKET_THREADS + threadIdx.x;
                 Rec rec;
-                rec.u = b.u[t];
+                rec.u = marked_user(b, b.u[t]);
                 rec.i = b.i[t];
                 rec.r = b.r[t];
                 out[base[blk[it]] + slot[it]] = rec;
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(256) block_scatter_global_kernel(BucketArgs b,
         base = __shfl_sync(0xffffffffu, base, leader);
         if (blk >= 0) {
             Rec rec;
-            rec.u = b.u[t];
+            rec.u = marked_user(b, b.u[t]);
             rec.i = b.i[t];
             rec.r = b.r[t];
             out[base + (unsigned long long)__popc(peers & ((1u << lane) - 1u))] = rec;
@@ -241,6 +246,18 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const int32_t* __rest
         rec.i = i[t];
         rec.r = r[t];
         out[t] = rec;
+    }
+}
+
+// AoS -> SoA (records received from other ring members are re-bucketed through the same SoA staging as host input)
+__global__ void __launch_bounds__(256) unpack_records_kernel(const Rec* __restrict__ in, int64_t n, int32_t* __restrict__ u,
+                                                             int32_t* __restrict__ i, float* __restrict__ r) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const Rec rec = in[t];
+        u[t] = rec.u & REC_USER_MASK;
+        i[t] = rec.i;
+        r[t] = rec.r;
     }
 }
 
@@ -349,6 +366,13 @@ cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float*
                                 cudaStream_t stream, int* launches) {
     if (n <= 0) return cudaSuccess;
     pack_records_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, stream>>>(u, i, r, n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_records(const Rec* in, int64_t n, int32_t* u, int32_t* i, float* r, cudaStream_t stream, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    unpack_records_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, stream>>>(in, n, u, i, r);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

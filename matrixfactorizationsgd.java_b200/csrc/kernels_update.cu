@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
         int4 rec = make_int4(0, 0, 0, 0);
         if (j < a.n) {
             const int64_t idx = record_index(j);
-            rec.x = ld_stream_i32(words + 3 * idx, pol);
+            rec.x = ld_stream_i32(words + 3 * idx, pol) & REC_USER_MASK;
             rec.y = ld_stream_i32(words + 3 * idx + 1, pol);
             rec.z = ld_stream_i32(words + 3 * idx + 2, pol);
         }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
             const int64_t j = (tile + n_warps) * 32 + lane;
             if (j < a.n) {
                 const int64_t idx = record_index(j);
-                nrec.x = ld_stream_i32(words + 3 * idx, pol);
+                nrec.x = ld_stream_i32(words + 3 * idx, pol) & REC_USER_MASK;
                 nrec.y = ld_stream_i32(words + 3 * idx + 1, pol);
                 nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
             }

@@ -74,16 +74,19 @@ inline int plan_rounds(int rounds_cfg, int mode, int G, int mu, int64_t member_r
 // all start from the same q_i and are merged by a weighted average (plan_runs): every split of an item's slice costs
 // sequential progress on that item. Round 2 (tools/run_sim.py, signal-dominant sets -- on round 1's noise-dominant sets the
 // effect was invisible): runs of <= 256 trail the sequential oracle by 24 % / 9 % / 3.7 % in held-out RMSE after epochs
-// 1 / 2 / 3 of a Netflix-shaped set, runs of <= 1024 by 1.4 % / 0.1 % / 0.2 %. So runs are as long as the launch can
-// balance: the launch hands its runs out longest first, so its duration is about max(records / resident sub-warps,
-// longest run) -- the longest run may be about the per-sub-warp share of the launch. 64 <= run <= 1024, multiple of 32.
-inline int plan_run_length(int hot_chunk_cfg, int G, int mu, int rounds, int IB, int64_t run_records, int resident_ctas,
+// 1 / 2 / 3 of a Netflix-shaped set, runs of <= 1024 by 1.4 % / 0.1 % / 0.2 %; every cleverer merge that was tried
+// (summing, direction-split weights, exchanging q_i inside the run) diverges on the stiff common direction that plain
+// matrix factorisation without biases has. So runs are as long as the launch can balance: the launch hands its runs out
+// longest first, so it lasts about max(records / resident sub-warps, longest run) -- the longest run may be about the
+// per-sub-warp share of the launch (two launches' worth where two stream lanes overlap them, `lanes` = 2).
+// 256 <= run <= 1024, multiple of 32: small launches leave sub-warps idle rather than cut their items into pieces
+// (they are latency-bound anyway: an ML-100K-shaped epoch takes 0.35 ms either way).
+inline int plan_run_length(int hot_chunk_cfg, int lanes, int mu, int rounds, int IB, int64_t run_records, int resident_ctas,
                            int runs_per_warp) {
-    (void)G;
     if (hot_chunk_cfg > 0) return hot_chunk_cfg;
-    const double per_launch = (double)run_records / ((double)mu * rounds * IB);
+    const double per_launch = (double)run_records / ((double)mu * rounds * IB) * (lanes > 1 ? lanes : 1);
     const double want = per_launch / (1.25 * resident_ctas * 8.0 * runs_per_warp);
-    return (int)std::min(1024.0, std::max(64.0, std::ceil(want / 32.0) * 32.0));
+    return (int)std::min(1024.0, std::max(256.0, std::ceil(want / 32.0) * 32.0));
 }
 
 // Merge weight of a run whose slice of its item's bucket was cut into `pieces` runs for one launch: min(1, boost / pieces).

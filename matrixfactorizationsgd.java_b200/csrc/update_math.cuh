@@ -66,6 +66,22 @@ __device__ __forceinline__ float4 new_chunk(float4 o, float4 x, float e, float l
     return upd4(o, x, e, lr, lambda);
 }
 
+// the increment of row chunk `o` alone: new_chunk - o = b * x + (a - 1) * o, with ccoef = a - 1 = -(lr * lambda) exactly.
+// Used where the row is updated in memory by red.global.add (no lost updates between concurrent writers of a row).
+template <bool FAST>
+__device__ __forceinline__ float4 delta_chunk(float4 o, float4 x, float e, float lr, float lambda, float ccoef, float b) {
+    if (FAST) {
+        const uint64_t c2 = pk2(ccoef, ccoef), b2 = pk2(b, b);
+        const uint64_t lo = fma2(b2, pk2(x.x, x.y), mul2(c2, pk2(o.x, o.y)));
+        const uint64_t hi = fma2(b2, pk2(x.z, x.w), mul2(c2, pk2(o.z, o.w)));
+        float4 r;
+        upk2(lo, r.x, r.y);
+        upk2(hi, r.z, r.w);
+        return r;
+    }
+    return delta4(o, x, e, lr, lambda);
+}
+
 struct Coef {
     float lr, lambda, acoef;   // acoef = 1 - lr * lambda (FAST arithmetic)
 };

@@ -12,7 +12,7 @@ from ._capi import Config, EpochStats, LayoutInfo, SynthParams, check, lib, ptr,
 def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_HOGWILD, n_gpus=1,
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
                 world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0,
-                merge_boost=0.0):
+                merge_boost=0.0, p_atomic_threshold=0.0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -22,6 +22,7 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.scatter, cfg.flags, cfg.device = int(scatter), int(flags), int(device)
     cfg.world_size, cfg.rank, cfg.ctas_per_sm, cfg.rounds = int(world_size), int(rank), int(ctas_per_sm), int(rounds)
     cfg.hot_share, cfg.hot_chunk, cfg.merge_boost = float(hot_share), int(hot_chunk), float(merge_boost)
+    cfg.p_atomic_threshold = float(p_atomic_threshold)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg
@@ -34,10 +35,22 @@ def synth_params(n_total, seed=20261018, log2_alpha_user=2, c_user=0.25, log2_al
                        float(c_item), float(amplitude), float(noise_scale))
 
 
+def synth_params_of(w, seed=20261018):
+    """SynthParams of a workloads.Workload (shape, skew, and the signal-dominant variant's amplitude / noise scale)."""
+    return synth_params(w.n_ratings, seed, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item, w.amplitude, w.noise_scale)
+
+
 def device_count():
     n = C.c_int32(0)
     rc = lib.mfsgd_device_count(C.byref(n))
     return n.value if rc == capi.OK else 0
+
+
+def measure_ceilings(device=0, buffer_mb=61.0):
+    """Measured ceilings of the update path's access pattern on `device` (mfsgd_measure_ceilings) as a dict."""
+    out = capi.Ceilings()
+    check(lib.mfsgd_measure_ceilings(int(device), float(buffer_mb), C.byref(out)))
+    return {name: getattr(out, name) for name, _ in capi.Ceilings._fields_ if name != "reserved"}
 
 
 def nccl_unique_id():
@@ -78,6 +91,13 @@ class Engine:
         if not (len(u) == len(i) == len(r)):
             raise ValueError("triplet arrays differ in length")
         check(lib.mfsgd_load_ratings(self._h, ptr(u), ptr(i), ptr(r), len(r)))
+
+    def load_ratings_sharded(self, users, items, ratings):
+        """Multi-process ring: this rank's own slice of the triplets (collective call; see mfsgd_load_ratings_sharded)."""
+        u, i, r = as_i32(users), as_i32(items), as_f32(ratings)
+        if not (len(u) == len(i) == len(r)):
+            raise ValueError("triplet arrays differ in length")
+        check(lib.mfsgd_load_ratings_sharded(self._h, ptr(u), ptr(i), ptr(r), len(r)))
 
     def load_heldout(self, users, items, ratings):
         u, i, r = as_i32(users), as_i32(items), as_f32(ratings)
@@ -156,14 +176,19 @@ class Engine:
         check(lib.mfsgd_get_bounds(self._h, ptr(ub), ptr(ib)))
         return ub, ib
 
-    def records(self, member=0):
+    def records(self, member=0, with_marks=False):
+        """(u, i, r, bucket offsets) of a ring member's current layout; with_marks keeps the heavy-user mark (bit 31 of u:
+        negative values) that the run kernel and its oracle twin read, otherwise u is the plain id."""
         info = self.layout_info()
         n = C.c_int64(0)
         check(lib.mfsgd_get_records(self._h, member, None, None, C.byref(n)))
         recs = np.zeros((n.value, 3), dtype=np.int32)
         off = np.zeros(info.stripes_per_gpu * (info.item_blocks + info.n_hot_items) + 1, dtype=np.int64)
         check(lib.mfsgd_get_records(self._h, member, ptr(recs), ptr(off), C.byref(n)))
-        return recs[:, 0].copy(), recs[:, 1].copy(), recs[:, 2].copy().view(np.float32), off
+        u = recs[:, 0].copy()
+        if not with_marks:
+            u &= 0x7fffffff
+        return u, recs[:, 1].copy(), recs[:, 2].copy().view(np.float32), off
 
     def shuffle_once(self, epoch):
         check(lib.mfsgd_shuffle_once(self._h, int(epoch)))

@@ -1,11 +1,20 @@
 """The five BASELINE.json configs as data (shapes from BASELINE.json `configs`; lr/lambda/epochs and
-the skew parameters are the pins of SURVEY.md section 8d)."""
+the skew parameters are the pins of SURVEY.md section 8d), plus their signal-dominant variants.
+
+This module is pure data: it loads no native library (bench.py's reference arm imports it on its own)."""
 from collections import namedtuple
 
 Workload = namedtuple("Workload", "name n_users n_items n_ratings k epochs lr lambda_ log2_alpha_user c_user "
-                                  "log2_alpha_item c_item gpus")
+                                  "log2_alpha_item c_item gpus amplitude noise_scale",
+                      defaults=(0.0, 0.0))
 
 SEED = 20261018
+
+# planted amplitude / noise scale of the signal-dominant variant (stand-in SIGNAL_AMPLITUDE / SIGNAL_NOISE_SCALE):
+# planted dot of std 1.0 against noise of std 0.07, so that a model which only learns the mean (held-out RMSE ~0.94) is
+# far from the trained one (~0.19-0.5) and RMSE parity at equal epochs is a sharp test. 0 / 0 = the stand-in's defaults
+# (planted std 0.25, noise std 0.29: the throughput workloads, where SGD barely beats the constant predictor's 0.38).
+SIGNAL_AMPLITUDE, SIGNAL_NOISE_SCALE = 1.7320508, 0.125
 
 WORKLOADS = {
     "ml100k": Workload("ml100k-shaped", 943, 1682, 100_000, 32, 20, 0.01, 0.05, 2, 0.25, 3, 0.375, (1,)),
@@ -16,6 +25,20 @@ WORKLOADS = {
     "powerlaw": Workload("power-law-heavy", 10_000_000, 1_000_000, 2_000_000_000, 64, 3, 0.005, 0.05, 2, 0.25, 4, 0.375,
                          (8,)),
 }
+
+
+def signal_variant(w, lr=0.02, lambda_=0.02, epochs=None):
+    return w._replace(name=w.name + "-signal", lr=lr, lambda_=lambda_, epochs=epochs or w.epochs,
+                      amplitude=SIGNAL_AMPLITUDE, noise_scale=SIGNAL_NOISE_SCALE)
+
+
+# Same shapes, signal-dominant ratings, a learning rate under which the sequential oracle gets >= 30 % below the constant
+# predictor within the epoch count (tests/golden/oracle_rmse_*_signal.json hold the curves and the constant predictor's RMSE).
+WORKLOADS.update({
+    "ml100k_signal": signal_variant(WORKLOADS["ml100k"]),
+    "ml20m_signal": signal_variant(WORKLOADS["ml20m"]),
+    "netflix_signal": signal_variant(WORKLOADS["netflix"]),
+})
 
 
 def bytes_per_update(k):

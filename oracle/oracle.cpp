@@ -18,13 +18,14 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
 
 #define ORC_API extern "C" __attribute__((visibility("default")))
 
-enum { ORC_ORDER_SEQ = 0, ORC_ORDER_WARP_TREE = 1, ORC_ORDER_WARP_TREE_FMA = 2 };
+enum { ORC_ORDER_SEQ = 0, ORC_ORDER_WARP_TREE = 1, ORC_ORDER_WARP_TREE_FMA = 2, ORC_ORDER_WARP_TREE_FMA_PDELTA = 3 };
 
 static const uint64_t STREAM_P_INIT = 0, STREAM_Q_INIT = 1, STREAM_SHUFFLE = 2, STREAM_USER = 3,
                       STREAM_ITEM = 4, STREAM_NOISE = 5, STREAM_HELDOUT = 6, STREAM_PSTAR = 7,
@@ -66,6 +67,47 @@ ORC_API void orc_shuffle(uint64_t seed, int epoch, int n, int32_t* order) {
     }
     std::sort(packed.begin(), packed.end());
     for (int j = 0; j < n; j++) order[j] = (int32_t)(packed[j] & 0xFFFFFFFFULL);
+}
+
+/* The same permutation as orc_shuffle, produced by `threads` host threads (the threaded variant may use every core the box
+ * has, also for its per-epoch order): keys are uniform 31-bit values, so the packed words are range-partitioned by their
+ * top bits into 16 * threads buckets (counting pass, scatter pass), and the buckets are sorted side by side. */
+ORC_API void orc_shuffle_mt(uint64_t seed, int epoch, int n, int32_t* order, int threads) {
+    if (threads <= 1 || n < (1 << 16)) { orc_shuffle(seed, epoch, n, order); return; }
+    const int B = 16 * threads;                                  /* buckets by key range */
+    std::vector<uint64_t> packed((size_t)n), sorted((size_t)n);
+    std::vector<std::vector<int64_t>> cnt((size_t)threads, std::vector<int64_t>((size_t)B, 0));
+    auto bucket_of = [B](uint64_t w) { return (int)(((w >> 32) * (uint64_t)B) >> 31); };   /* key < 2^31 */
+    auto run = [&](auto&& f) {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < threads; w++) pool.emplace_back(f, w);
+        for (auto& th : pool) th.join();
+    };
+    run([&](int w) {
+        const int64_t lo = (int64_t)n * w / threads, hi = (int64_t)n * (w + 1) / threads;
+        for (int64_t idx = lo; idx < hi; idx++) {
+            uint64_t key = orc_hash64(seed, STREAM_SHUFFLE, ((uint64_t)(uint32_t)epoch << 32) | (uint64_t)idx) >> 33;
+            packed[(size_t)idx] = (key << 32) | (uint64_t)idx;
+            cnt[(size_t)w][(size_t)bucket_of(packed[(size_t)idx])]++;
+        }
+    });
+    std::vector<int64_t> start((size_t)B + 1, 0);
+    for (int b = 0; b < B; b++) {
+        int64_t c = 0;
+        for (int w = 0; w < threads; w++) { int64_t t = cnt[(size_t)w][(size_t)b]; cnt[(size_t)w][(size_t)b] = start[(size_t)b] + c; c += t; }
+        start[(size_t)b + 1] = start[(size_t)b] + c;
+    }
+    run([&](int w) {
+        const int64_t lo = (int64_t)n * w / threads, hi = (int64_t)n * (w + 1) / threads;
+        for (int64_t idx = lo; idx < hi; idx++) sorted[(size_t)cnt[(size_t)w][(size_t)bucket_of(packed[(size_t)idx])]++] = packed[(size_t)idx];
+    });
+    run([&](int w) {
+        for (int b = w; b < B; b += threads) std::sort(sorted.begin() + start[(size_t)b], sorted.begin() + start[(size_t)b + 1]);
+    });
+    run([&](int w) {
+        const int64_t lo = (int64_t)n * w / threads, hi = (int64_t)n * (w + 1) / threads;
+        for (int64_t j = lo; j < hi; j++) order[j] = (int32_t)(sorted[(size_t)j] & 0xFFFFFFFFULL);
+    });
 }
 
 /* The dot product of MatrixFactorizationSGD.java:91-94 (f ascending, binary32 accumulate). */
@@ -141,13 +183,24 @@ static inline float dot_warp_tree_fma(const float* p, const float* q, int k) {
 }
 
 static inline float dot_ordered(const float* p, const float* q, int k, int order_mode) {
-    if (order_mode == ORC_ORDER_WARP_TREE_FMA) return dot_warp_tree_fma(p, q, k);
+    if (order_mode == ORC_ORDER_WARP_TREE_FMA || order_mode == ORC_ORDER_WARP_TREE_FMA_PDELTA) return dot_warp_tree_fma(p, q, k);
     return order_mode == ORC_ORDER_WARP_TREE ? dot_warp_tree(p, q, k) : dot_seq(p, q, k);
 }
 
 /* MatrixFactorizationSGD.java:89 sgdUpdate */
 ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float lambda, int order_mode) {
     float e = r - dot_ordered(p, q, k, order_mode);
+    if (order_mode == ORC_ORDER_WARP_TREE_FMA_PDELTA) {
+        /* the GPU run kernel with p_u updated in memory by red.global.add (MFSGD_SCATTER_ATOMIC_P): the increment
+         * b * q + c * p (c = -(lr * lambda), one fused multiply-add) is added to the row; q_i, in registers, as in FMA mode */
+        const float a = 1.0f - lr * lambda, b = lr * e, c = -(lr * lambda);
+        for (int f = 0; f < k; f++) {
+            float pf = p[f], qf = q[f];
+            p[f] = pf + std::fmaf(b, qf, c * pf);
+            q[f] = std::fmaf(b, pf, a * qf);
+        }
+        return e;
+    }
     if (order_mode == ORC_ORDER_WARP_TREE_FMA) {
         const float a = 1.0f - lr * lambda, b = lr * e;
         for (int f = 0; f < k; f++) {
@@ -242,7 +295,7 @@ ORC_API int orc_train_hogwild(const int32_t* u, const int32_t* i, const float* r
     std::vector<int32_t> order((size_t)n);
     double total = 0.0;
     for (int epoch = epoch_begin; epoch < epoch_end; epoch++) {
-        if (shuffled) orc_shuffle(seed, epoch, (int)n, order.data());
+        if (shuffled) orc_shuffle_mt(seed, epoch, (int)n, order.data(), threads);
         else for (int64_t j = 0; j < n; j++) order[j] = (int32_t)j;
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> pool;
@@ -455,8 +508,20 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
             if (virt && unit_bn[s.unit] > 1)
                 idx = unit_bstart[s.unit] + (int64_t)orc_block_perm((uint64_t)(pos - unit_bstart[s.unit]), (uint64_t)unit_bn[s.unit], s.key);
             if (idx < 0 || idx >= n_recs) return -2;
-            orc_sgd_update(P + (int64_t)(rec_u[idx] - u_base) * k, s.q.data(), k, rec_r[idx], lr, lambda, order_mode);
+            /* bit 31 of u marks a heavy user (csrc/common.cuh REC_USER_MASK): the kernel adds that row's increment in memory,
+             * which in the FMA arrangement rounds differently from storing the new value (ORC_ORDER_WARP_TREE_FMA_PDELTA) */
+            const int32_t uid = rec_u[idx] & 0x7fffffff;
+            const int mode = (rec_u[idx] < 0 && order_mode == ORC_ORDER_WARP_TREE_FMA) ? ORC_ORDER_WARP_TREE_FMA_PDELTA : order_mode;
+            orc_sgd_update(P + (int64_t)(uid - u_base) * k, s.q.data(), k, rec_r[idx], lr, lambda, mode);
             s.step++;
+            static const char* senv = getenv("ORC_SYNC_EVERY");          /* PROTOTYPE: Hogwild-style exchange inside a run */
+            if (senv && unit_weight[s.unit] < 1.0f && s.step < unit_count[s.unit] && s.step % atoi(senv) == 0) {
+                static const float mstar = getenv("ORC_SYNC_MSTAR") ? (float)atof(getenv("ORC_SYNC_MSTAR")) : 8.0f;
+                const float m = std::nearbyintf(1.25f / unit_weight[s.unit]);
+                const float w = std::min(1.0f, mstar / m);
+                float* qr = Q + (int64_t)(unit_item[s.unit] - i_base) * k;
+                for (int f = 0; f < k; f++) { qr[f] = qr[f] + (s.q[f] - s.q0[f]) * w; s.q[f] = qr[f]; s.q0[f] = qr[f]; }
+            }
         }
         for (int g = 0; g < groups; g++) {                 /* a warp merges its runs when the longest is done, then claims again */
             bool all_done = true, any = false;
@@ -476,6 +541,30 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
                     std::memcpy(qr, s.q.data(), sizeof(float) * k);
                 } else {
                     const float w = planned;               /* the planner's weight: min(1, merge_boost / runs of the slice) */
+                    static const char* senv2 = getenv("ORC_SYNC_EVERY");
+                    if (senv2) {
+                        static const float mstar = getenv("ORC_SYNC_MSTAR") ? (float)atof(getenv("ORC_SYNC_MSTAR")) : 8.0f;
+                        const float m = std::nearbyintf(1.25f / w);
+                        const float ws = std::min(1.0f, mstar / m);
+                        for (int f = 0; f < k; f++) qr[f] = qr[f] + (s.q[f] - s.q0[f]) * ws;
+                        done++;
+                        continue;
+                    }
+                    static const char* kenv = getenv("ORC_MERGE_KAPPA");      /* PROTOTYPE: direction-split merge */
+                    if (kenv) {
+                        const float kappa = (float)atof(kenv);
+                        const float m = std::nearbyintf(1.25f / w);
+                        double n0 = 0, a = 0;
+                        for (int f = 0; f < k; f++) { n0 += (double)s.q0[f] * s.q0[f]; a += (double)(s.q[f] - s.q0[f]) * s.q0[f]; }
+                        const float wperp = std::min(1.0f, kappa / m);
+                        for (int f = 0; f < k; f++) {
+                            const float par = n0 > 0 ? (float)(a / n0) * s.q0[f] : 0.0f;
+                            const float d = s.q[f] - s.q0[f];
+                            qr[f] = qr[f] + par * w + (d - par) * wperp;
+                        }
+                        done++;
+                        continue;
+                    }
                     for (int f = 0; f < k; f++) qr[f] = qr[f] + (s.q[f] - s.q0[f]) * w;
                 }
                 done++;

@@ -12,7 +12,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_DIR, "liboracle.so")
 
-ORDER_SEQ, ORDER_WARP_TREE, ORDER_WARP_TREE_FMA = 0, 1, 2
+ORDER_SEQ, ORDER_WARP_TREE, ORDER_WARP_TREE_FMA, ORDER_WARP_TREE_FMA_PDELTA = 0, 1, 2, 3
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -37,6 +37,8 @@ def _load():
     lib.orc_init_factors.argtypes = [_f32p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_float]
     lib.orc_shuffle.restype = None
     lib.orc_shuffle.argtypes = [C.c_uint64, C.c_int, C.c_int, _i32p]
+    lib.orc_shuffle_mt.restype = None
+    lib.orc_shuffle_mt.argtypes = [C.c_uint64, C.c_int, C.c_int, _i32p, C.c_int]
     lib.orc_sgd_update.restype = C.c_float
     lib.orc_sgd_update.argtypes = [_f32p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.orc_train.restype = C.c_int
@@ -117,9 +119,12 @@ def init_factors(n_rows, k, seed, stream, scale=None):
     return out
 
 
-def shuffle(seed, epoch, n):
+def shuffle(seed, epoch, n, threads=1):
     out = np.empty(n, dtype=np.int32)
-    lib.orc_shuffle(seed, epoch, n, out)
+    if threads > 1:
+        lib.orc_shuffle_mt(seed, epoch, n, out, threads)
+    else:
+        lib.orc_shuffle(seed, epoch, n, out)
     return out
 
 
@@ -215,3 +220,25 @@ def train_runs_launch(rec_u, rec_r, plan, lo, hi, P, Q, lr, lam, order_mode, res
                                    resident, gpw, int(always_add))
     if rc:
         raise ValueError("oracle: bad run plan (%d)" % rc)
+
+
+def balanced_bounds(ids, n_rows, nblocks):
+    """Rating-count-balanced row bounds, as the engine computes them (csrc/kernels_layout.cu balanced_bounds_kernel):
+    bounds[b] = first row whose exclusive cumulative rating count reaches b * total / nblocks; bounds[nblocks] = n_rows."""
+    cnt = np.bincount(ids, minlength=n_rows).astype(np.int64)
+    cum = np.concatenate([[0], np.cumsum(cnt)])
+    total = int(cum[-1])
+    b = [int(np.searchsorted(cum[:-1], (total * j) // nblocks, side="left")) for j in range(nblocks)]
+    b[0] = 0
+    return np.array(b + [n_rows], dtype=np.int32)
+
+
+def dsgd_order(u, i, user_bounds, item_bounds, seed, epoch):
+    """Visiting order of the DSGD schedule for the sequential rule: sub-epoch s = 0..G-1, member g = 0..G-1 trains block
+    (user stripe g, item group (g + s) % G); inside a block the stand-in's shuffled order of the epoch. Returns record indices."""
+    G = len(user_bounds) - 1
+    order = shuffle(seed, epoch, len(u)).astype(np.int64)
+    g = (np.searchsorted(user_bounds, u[order], side="right") - 1).astype(np.int64)
+    grp = (np.searchsorted(item_bounds, i[order], side="right") - 1).astype(np.int64)
+    s = (grp - g) % G
+    return order[np.argsort(s * G + g, kind="stable")]

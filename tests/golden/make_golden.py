@@ -38,6 +38,9 @@ def main():
         g["gen_" + name] = {"u": u.tolist(), "i": i.tolist(), "r": bits(r), "held": held.astype(int).tolist(),
                             "u_at_1e9": u2.tolist(), "i_at_1e9": i2.tolist(), "r_at_1e9": bits(r2),
                             "held_at_1e9": held2.astype(int).tolist()}
+    # the signal-dominant variant: planted amplitude 1.7320508, noise scale 0.125
+    u, i, r, held = npr.generate(SEED, 0, 256, 943, 1682, 2, 0.25, 3, 0.375, 1.7320508, 0.125)
+    g["gen_ml100k_signal"] = {"u": u.tolist(), "i": i.tolist(), "r": bits(r), "held": held.astype(int).tolist()}
     # a small SGD run: 40 users x 60 items, 1000 ratings, k=8, 2 epochs, both summation orders
     nu, ni, k, lr, lam = 40, 60, 8, 0.02, 0.05
     u, i, r, held = npr.generate(SEED, 0, 1000, nu, ni, 2, 0.25, 3, 0.375)

@@ -36,12 +36,27 @@ def main():
     eng.train(3)
     P, Q = ring.assemble_factors(dist, *eng.get_factors())
     eng.close()
+    # 1b. the same through the sharded load: every rank passes only its own (uneven) slice of the triplets; the records travel
+    # to their stripe owners over NCCL (mfsgd_load_ratings_sharded). Same layout bounds, same factors, bit for bit.
+    cuts = [0] + [int(m * (j + 1) ** 2 / world ** 2) for j in range(world)]          # uneven on purpose; the last rank gets most
+    sl = slice(cuts[rank], cuts[rank + 1])
+    eng = ring.create_rank_engine(dist, rank, world, local, n_users=m, n_items=m, k=128, lr=0.02, lambda_=0.03, seed=seed)
+    eng.load_ratings_sharded(cu[sl], ci[sl], cr[sl])
+    info_sh = eng.layout_info()
+    eng.init_factors()
+    eng.train(3)
+    Psh, Qsh = ring.assemble_factors(dist, *eng.get_factors())
+    eng.close()
     if rank == 0:
         Po, Qo = orc.factorize(cu, ci, cr, m, m, 128, 0.02, 0.03, 3, seed, orc.ORDER_WARP_TREE_FMA)
         out["conflict_free_bit_exact"] = bool(np.array_equal(P, Po) and np.array_equal(Q, Qo))
+        out["sharded_load_bit_exact"] = bool(np.array_equal(Psh, Po) and np.array_equal(Qsh, Qo))
+        out["sharded_n_train_total"] = int(info_sh.n_train_total)
     # 2. convergence parity on the mid-size workload
     eng = ring.create_rank_engine(dist, rank, world, local, n_users=nu, n_items=ni, k=k, lr=lr, lambda_=lam, seed=seed)
-    eng.load_ratings(*tr)
+    nt = len(tr[2])
+    mine = slice(nt * rank // world, nt * (rank + 1) // world)
+    eng.load_ratings_sharded(tr[0][mine], tr[1][mine], tr[2][mine])       # each rank uploads 1/world of the set
     eng.load_heldout(*ho)
     eng.init_factors()
     part = eng.partition()
@@ -56,9 +71,16 @@ def main():
     if rank == 0:
         Po, Qo = orc.factorize(*tr, nu, ni, k, lr, lam, epochs, seed)
         want = orc.rmse(Po, Qo, *ho)
-        out.update({"gpu_rmse": got, "oracle_rmse": want, "rel": (got - want) / want,
+        # the sequential rule in this ring's own block order (the schedule's share of any deviation)
+        ub, ib = orc.balanced_bounds(tr[0], nu, world), orc.balanced_bounds(tr[1], ni, world)
+        Pd, Qd = orc.init_factors(nu, k, seed, 0), orc.init_factors(ni, k, seed, 1)
+        for e in range(epochs):
+            o = orc.dsgd_order(tr[0], tr[1], ub, ib, seed, e)
+            orc.train(tr[0][o], tr[1][o], tr[2][o], Pd, Qd, lr, lam, e, e + 1, seed, shuffled=False)
+        out.update({"gpu_rmse": got, "oracle_rmse": want, "oracle_dsgd_order_rmse": orc.rmse(Pd, Qd, *ho), "rel": (got - want) / want,
                     "assembled_rmse": orc.rmse(P, Q, *ho), "partitions": parts, "n_train_total": int(info.n_train_total),
-                    "epoch_ms": [s.epoch_ms for s in stats]})
+                    "n_train": nt, "epoch_ms": [s.epoch_ms for s in stats], "stripes_per_gpu": int(info.stripes_per_gpu),
+                    "shards_per_gpu": int(info.shards_per_gpu), "rounds": int(info.rounds)})
         print("RING_PARITY " + json.dumps(out), flush=True)
     dist.destroy_process_group()
 

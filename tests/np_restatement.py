@@ -137,20 +137,21 @@ def scatter_id(rank, count):
     return np.array([(int(x) * ID_MULT + count // 2) % count for x in np.atleast_1d(rank)], dtype=np.int32)
 
 
-def planted(seed, stream, rows):
+def planted(seed, stream, rows, amplitude=PLANTED_AMPLITUDE):
     """MatrixFactorizationSGD.java:215; returns [len(rows), 16]."""
     rows = np.asarray(rows, dtype=U64)
     ctr = rows[:, None] * U64(PLANTED_RANK) + np.arange(PLANTED_RANK, dtype=U64)[None, :]
-    return (uniform(seed, stream, ctr) - np.float32(0.5)) * PLANTED_AMPLITUDE
+    return (uniform(seed, stream, ctr) - np.float32(0.5)) * np.float32(amplitude)
 
 
-def generate(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci):
-    """MatrixFactorizationSGD.java:220; returns u, i, r, held."""
+def generate(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci, amplitude=PLANTED_AMPLITUDE, noise_scale=0.5):
+    """MatrixFactorizationSGD.java:220; returns u, i, r, held. (amplitude, noise_scale) = (1.7320508, 0.125) is the
+    signal-dominant variant of SURVEY.md 8d."""
     n = np.arange(start, start + count, dtype=U64)
     u = scatter_id(skewed_rank(uniform53(seed, 3, n), n_users, l2au, cu), n_users)
     i = scatter_id(skewed_rank(uniform53(seed, 4, n), n_items, l2ai, ci), n_items)
-    ps = planted(seed, 7, u)
-    qs = planted(seed, 8, i)
+    ps = planted(seed, 7, u, amplitude)
+    qs = planted(seed, 8, i, amplitude)
     dot = np.zeros(count, dtype=np.float32)
     for f in range(PLANTED_RANK):
         dot = (dot + (ps[:, f] * qs[:, f]).astype(np.float32)).astype(np.float32)
@@ -159,7 +160,7 @@ def generate(seed, start, count, n_users, n_items, l2au, cu, l2ai, ci):
         noise = (noise + uniform(seed, 5, U64(4) * n + U64(j))).astype(np.float32)
     noise = noise - np.float32(2.0)
     rating = np.float32(3.5) + dot
-    rating = rating + np.float32(0.5) * noise
+    rating = rating + np.float32(noise_scale) * noise
     rating = np.minimum(np.maximum(rating, np.float32(1.0)), np.float32(5.0)).astype(np.float32)
     held = (hash64(seed, 6, n) % U64(10)) == U64(0)
     return u, i, rating, held

@@ -41,7 +41,7 @@ def test_struct_sizes_match_c_layout():
     assert capi.Config.seed.offset == 24 and capi.Config.nccl_id.offset == 68 and capi.Config.ctas_per_sm.offset == 196
     assert C.sizeof(capi.EpochStats) == 72
     assert C.sizeof(capi.SynthParams) == 48 and capi.SynthParams.planted_amplitude.offset == 40
-    assert C.sizeof(capi.LayoutInfo) == 56
+    assert C.sizeof(capi.LayoutInfo) == 64
     assert C.sizeof(capi.Ratings) == 64 and capi.Ratings.n.offset == 24 and capi.Ratings.user_ids.offset == 40
 
 

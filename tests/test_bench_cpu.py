@@ -34,3 +34,24 @@ def test_product_arm_fails_loudly_without_a_gpu():
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]          # and no number is printed
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """The reference process loads only oracle/ (round-1 review: it used to import the GPU package for WORKLOADS/SEED)."""
+    code = ("import sys, os; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-sample', '100000'];"
+            "import runpy; runpy.run_path(%r, run_name='__main__');"
+            "maps = open('/proc/self/maps').read(); assert 'libmfsgd' not in maps, 'product library mapped'; assert 'liboracle' in maps"
+            % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_cpu_baseline_ml100k_runs_the_oracle_cli():
+    sys.path.insert(0, ROOT)
+    import bench
+    d = bench.cpu_baseline_ml100k()
+    assert d is not None and d["host_cores"] >= 1
+    modes = [(r["mode"], r["threads"]) for r in d["runs"] if "error" not in r]
+    assert ("seq", 1) in modes and any(m == "threads" for m, _ in modes)
+    seq = [r for r in d["runs"] if r.get("mode") == "seq"][0]
+    assert abs(seq["heldout_rmse"] - 0.393763) < 1e-5          # tests/golden/oracle_rmse_ml100k.json, last epoch

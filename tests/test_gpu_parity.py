@@ -22,19 +22,28 @@ RMSE_TOL = 0.005    # north_star: "held-out RMSE within 0.5 %"
 
 
 def assert_rmse_parity(got, want):
-    """The GPU must REACH the reference's held-out RMSE at equal epochs: at most 0.5 % above it. It may land
-    below (the hot-item path averages the item factor over concurrent runs, which lowers its variance), but
-    not absurdly so -- more than 2 % below the oracle would mean the evaluation itself is broken."""
-    assert got <= want * (1 + RMSE_TOL), (got, want)
-    assert got >= want * (1 - 0.02), (got, want)
+    """Two-sided: held-out RMSE within 0.5 % of the sequential oracle's at equal epochs (north_star)."""
+    assert abs(got / want - 1.0) <= RMSE_TOL, (got, want, got / want - 1.0)
 
 
-def train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, lr, lam, e0, e1, order):
+def assert_ring_rmse_parity(got, shuffled, dsgd_ordered):
+    """A DSGD ring is held between two sequential executions of the reference rule on the same data: the stand-in's
+    shuffled order and the DSGD schedule's own block order (pyoracle.dsgd_order: same strata, same sub-epoch sequence,
+    one rating at a time). On noise-dominant sets the two are < 0.3 % apart and this is the 0.5 % bar; on signal-dominant
+    sets the schedule itself costs several per cent at a constant learning rate and the GPU's run path,
+    which averages an item's concurrent runs, lands between the two. Each side gets the 0.5 % tolerance."""
+    lo, hi = min(shuffled, dsgd_ordered), max(shuffled, dsgd_ordered)
+    assert lo * (1 - RMSE_TOL) <= got <= hi * (1 + RMSE_TOL), (got, shuffled, dsgd_ordered)
+
+
+def train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, lr, lam, e0, e1, order, heavy=False):
     """Oracle twin of a layout whose items < n_hot go through the run kernel (orc.run_lanes(k) lanes per rating) and
-    the others through the cold kernel (default lanes). Valid when the two sets share no P or Q row."""
+    the others through the cold kernel (default lanes). Valid when the two sets share no P or Q row.
+    heavy: every user is marked heavy, i.e. the run kernel adds p_u's increment in memory (FMA arrangement: PDELTA rounding)."""
     hot = oi < n_hot
+    run_order = orc.ORDER_WARP_TREE_FMA_PDELTA if heavy and order == orc.ORDER_WARP_TREE_FMA else order
     with orc.tree_lanes(orc.run_lanes(k)):
-        orc.train(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, order, shuffled=False)
+        orc.train(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, run_order, shuffled=False)
     orc.train(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, order, shuffled=False)
 
 
@@ -276,8 +285,15 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         off = before[3]
         assert np.array_equal(off, e0[3])
         moved = 0
-        for b in range(len(off) - 1):
+        nblk = len(off) - 1
+        for b in range(nblk):
             s = slice(off[b], off[b + 1])
+            nb = int(off[b + 1] - off[b])
+            if nb > 0 and b % 7 == 0:        # the materialised order is the oracle's restatement of the permutation, bit for bit
+                for ep, src, got in ((0, before, e0), (1, e0, e1)):      # each materialising pass permutes the current layout
+                    perm = orc.block_perm(nb, SEED, ep, 0 * nblk + b)   # bucket id = member * blocks + block; member 0 here
+                    assert np.array_equal(got[0][s], src[0][s][perm]) and np.array_equal(got[1][s], src[1][s][perm])
+                    assert np.array_equal(got[2][s].view(np.uint32), src[2][s][perm].view(np.uint32))
             kb = rec_keys(before[0][s], before[1][s], before[2][s])
             assert np.array_equal(kb, rec_keys(e0[0][s], e0[1][s], e0[2][s]))
             assert np.array_equal(kb, rec_keys(e1[0][s], e1[1][s], e1[2][s]))
@@ -286,7 +302,8 @@ def test_bucketing_layout_and_shuffle(mode, G, mu, mi):
         assert not np.array_equal(e0[0], e1[0])
 
 
-def test_virtual_reshuffle_visits_the_materialised_order():
+@pytest.mark.parametrize("marks", ["off", "all"])
+def test_virtual_reshuffle_visits_the_materialised_order(marks):
     """The permutation the update kernels apply on the fly is the one block_shuffle_kernel materialises: with one
     run per hot item (sequential, hence order-sensitive) an epoch trained through the virtual reshuffle must equal
     the oracle walking the order that mfsgd_shuffle_once materialises from the same layout."""
@@ -298,16 +315,18 @@ def test_virtual_reshuffle_visits_the_materialised_order():
     u = rng.permutation(n).astype(np.int32)
     r = (1 + 4 * rng.random(n)).astype(np.float32)
     ni, k = n_hot + n_cold, 128
-    cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1, hot_chunk=4096)
+    cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1, hot_chunk=4096,
+                         p_atomic_threshold=-1.0 if marks == "off" else 1e-9)
     with mf.Engine(cfg) as eng:
         eng.load_ratings(u, i, r)                 # bucketing order inside a bucket is arbitrary: stay on this one layout
+        assert eng.layout_info().n_heavy_users == (0 if marks == "off" else n)
         eng.init_factors()
         eng.train(1)                              # epoch 0, records read through the permutation, layout untouched
         P, Q = eng.get_factors()
         eng.shuffle_once(0)                       # now materialise epoch 0's permutation of that same layout
         ou, oi, orr, _ = eng.records()
     Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
-    train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, 0.01, 0.03, 0, 1, orc.ORDER_WARP_TREE_FMA)
+    train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, 0.01, 0.03, 0, 1, orc.ORDER_WARP_TREE_FMA, heavy=marks == "all")
     assert np.array_equal(Q, Qo) and np.array_equal(P, Po)
 
 
@@ -331,14 +350,50 @@ def test_synthetic_on_device_matches_oracle_split():
 # ------------------------------------------------------------------------------------------------
 # Hogwild and DSGD: convergence parity (held-out RMSE within 0.5 % of the oracle at equal epochs)
 # ------------------------------------------------------------------------------------------------
+class MidSet:
+    """ML-20M-shaped scaled 1:10 (13.8K x 2.7K, 2M ratings), k=32: the oracles run in seconds. `signal` selects the
+    signal-dominant variant (workloads.SIGNAL_*; lr 0.02, lambda 0.02, 12 epochs: the sequential oracle ends 77 % below the
+    constant predictor and still moves 50 % between epochs 3 and 12)."""
+
+    def __init__(self, signal):
+        self.nu, self.ni, n, self.k = 13_800, 2_700, 2_000_000, 32
+        self.lr, self.lam, self.epochs = (0.02, 0.02, 12) if signal else (0.005, 0.05, 8)
+        amp, noise = (mf.workloads.SIGNAL_AMPLITUDE, mf.workloads.SIGNAL_NOISE_SCALE) if signal else (0.0, 0.0)
+        self.synth = dict(amplitude=amp, noise_scale=noise)
+        u, i, r, held = orc.generate(SEED, 0, n, self.nu, self.ni, amplitude=amp, noise_scale=noise)
+        self.train, self.held = split(u, i, r, held)
+        P, Q = orc.factorize(*self.train, self.nu, self.ni, self.k, self.lr, self.lam, self.epochs, SEED)
+        self.oracle_rmse = orc.rmse(P, Q, *self.held)
+        self.const_rmse = float(np.sqrt(np.mean((self.held[2] - self.train[2].mean()) ** 2)))
+        self._dsgd = {}
+
+    def __getitem__(self, key):          # the round-1 tests index the fixture like a dict
+        return {"nu": self.nu, "ni": self.ni, "k": self.k, "lr": self.lr, "lam": self.lam, "epochs": self.epochs,
+                "train": self.train, "held": self.held, "oracle_rmse": self.oracle_rmse}[key]
+
+    def dsgd_oracle_rmse(self, user_bounds, item_bounds):
+        """The sequential rule walking the DSGD schedule's block order for these strata (pyoracle.dsgd_order)."""
+        key = (tuple(user_bounds), tuple(item_bounds))
+        if key not in self._dsgd:
+            tu, ti, tr = self.train
+            P, Q = orc.init_factors(self.nu, self.k, SEED, 0), orc.init_factors(self.ni, self.k, SEED, 1)
+            for e in range(self.epochs):
+                o = orc.dsgd_order(tu, ti, np.asarray(user_bounds), np.asarray(item_bounds), SEED, e)
+                orc.train(tu[o], ti[o], tr[o], P, Q, self.lr, self.lam, e, e + 1, SEED, shuffled=False)
+            self._dsgd[key] = orc.rmse(P, Q, *self.held)
+        return self._dsgd[key]
+
+
 @pytest.fixture(scope="module")
 def midsize():
-    """ML-20M-shaped scaled 1:10 (13.8K x 2.7K, 2M ratings), k=32, 8 epochs: oracle runs in seconds."""
-    nu, ni, n, k, lr, lam, epochs = 13_800, 2_700, 2_000_000, 32, 0.005, 0.05, 8
-    u, i, r, held = orc.generate(SEED, 0, n, nu, ni)
-    tr, ho = split(u, i, r, held)
-    P, Q = orc.factorize(*tr, nu, ni, k, lr, lam, epochs, SEED)
-    return dict(nu=nu, ni=ni, k=k, lr=lr, lam=lam, epochs=epochs, train=tr, held=ho, oracle_rmse=orc.rmse(P, Q, *ho))
+    return MidSet(signal=False)
+
+
+@pytest.fixture(scope="module")
+def midsize_signal():
+    m = MidSet(signal=True)
+    assert m.oracle_rmse < 0.7 * m.const_rmse          # the variant's reason to exist: training beats the mean by far
+    return m
 
 
 @pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256, 512])
@@ -374,7 +429,7 @@ def test_hogwild_kernel_bit_exact_on_conflict_free_data(k, arith):
     np.testing.assert_allclose(Q, Qe, rtol=2e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("arith", ["fast", "exact"])
+@pytest.mark.parametrize("arith", ["fast", "exact", "fast-heavy", "exact-heavy", "fast-atomic-p"])
 @pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 200, 256, 512])
 def test_hot_item_kernel_exact_sequential_runs(k, arith):
     """Run path: with one run per item (hot_chunk >= run length) the kernel applies an item's ratings strictly in
@@ -390,19 +445,108 @@ def test_hot_item_kernel_exact_sequential_runs(k, arith):
     u = rng.permutation(n).astype(np.int32)
     r = (1 + 4 * rng.random(n)).astype(np.float32)
     ni = n_hot + n_cold
+    # "-heavy": every user's records carry the heavy mark, "-atomic-p": MFSGD_SCATTER_ATOMIC_P -- both make the run kernel add
+    # p_u's increment in memory (red.global.add) instead of storing the new row; the cold kernel keeps storing.
+    heavy = arith.endswith("-heavy") or arith.endswith("-atomic-p")
+    exact = arith.startswith("exact")
     cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1,
-                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE | (capi.FLAG_EXACT_ARITH if arith == "exact" else 0))
+                         hot_chunk=4096, flags=capi.FLAG_NO_SHUFFLE | (capi.FLAG_EXACT_ARITH if exact else 0),
+                         p_atomic_threshold=1e-9 if arith.endswith("-heavy") else -1.0,
+                         scatter=capi.SCATTER_ATOMIC_P if arith.endswith("-atomic-p") else capi.SCATTER_STORE)
     with mf.Engine(cfg) as eng:
         eng.load_ratings(u, i, r)
         assert eng.layout_info().n_hot_items == n_hot
+        assert eng.layout_info().n_heavy_users == (n if arith.endswith("-heavy") else 0)
+        mu_, _, _, _ = eng.records(with_marks=True)
+        assert np.all((mu_ < 0) == arith.endswith("-heavy")) and np.array_equal(mu_ & 0x7fffffff, eng.records()[0])
         ou, oi, orr, off = eng.records()                  # the order the kernels will see (no reshuffle)
         eng.init_factors()
         eng.train(3)
         P, Q = eng.get_factors()
     Po, Qo = orc.init_factors(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    if arith == "fast-atomic-p":      # the cold kernel's atomic variants add exact-rule increments (a few ulp from the FMA twin)
+        hot = oi < n_hot
+        with orc.tree_lanes(orc.run_lanes(k)):
+            orc.train(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), Po, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE_FMA_PDELTA, shuffled=False)
+        assert np.array_equal(P[ou[hot]], Po[ou[hot]]) and np.array_equal(Q[:n_hot], Qo[:n_hot])
+        return
     train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, 0.01, 0.03, 0, 3,
-                         orc.ORDER_WARP_TREE if arith == "exact" else orc.ORDER_WARP_TREE_FMA)
+                         orc.ORDER_WARP_TREE if exact else orc.ORDER_WARP_TREE_FMA, heavy=heavy)
     assert np.array_equal(P, Po) and np.array_equal(Q, Qo)
+
+
+
+def plan_runs_of(off, n_hot, hot_items, rounds, chunk, boost, mu=1, IB=1, member=0):
+    """The engine's own run plan for a layout (host-only hook mfsgd_plan_runs) as an oracle RunPlan + per-visit unit ranges."""
+    import ctypes as C
+    cap = int(((off[mu * IB + 1:] - off[mu * IB:-1]) // chunk + rounds + 1).sum()) + 16
+    st, ct, it, wt = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+    n = C.c_int64(cap)
+    visits = np.zeros(mu * rounds * IB + 1, np.int32)
+    hbl = np.array([0, n_hot], np.int32) if IB == 1 else None
+    hit = np.ascontiguousarray(hot_items, np.int32)
+    capi.check(capi.lib.mfsgd_plan_runs(capi.ptr(off), mu, n_hot, IB, capi.ptr(hbl), capi.ptr(hit), rounds, chunk, SEED, member, boost,
+                                        capi.ptr(st), capi.ptr(ct), capi.ptr(it), capi.ptr(wt), C.byref(n), capi.ptr(visits)))
+    m = n.value
+    return orc.RunPlan(st[:m], ct[:m], it[:m], wt[:m], off, member=member), visits
+
+
+@pytest.mark.parametrize("boost,marks", [(1.0, "off"), (1.25, "off"), (1.25, "all")])
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("k,rounds", [(128, 1), (32, 1), (128, 2)])
+def test_run_kernel_averaged_merge_matches_its_oracle_twin(k, rounds, shuffle, boost, marks):
+    """The dominant branch of the bench workload: several runs of one item in one launch, merged with
+    red.global.add of weight * (q_run - q_start). Oracle twin = oracle.cpp orc_train_runs_launch fed with the plan the
+    engine itself uses (mfsgd_plan_runs): every run walks its records sequentially from the launch-start q_i, the merge adds
+    the same weighted differences -- the order of the float adds is the only freedom left, hence <= 1e-5 relative.
+    Users are pairwise distinct (P rows commute); every item has 8 equally long runs per launch, which the launch's
+    grid (>= 2 waves: 3 CTAs at k = 128, 1 CTA of 32 sub-warps at k = 32) takes item-aligned wave by wave, so which runs
+    are in flight together does not depend on timing."""
+    n_hot, pieces, chunk, n_cold = 6, 8, 64, 1003
+    per_hot = pieces * chunk * rounds
+    n = n_hot * per_hot + n_cold
+    rng = np.random.default_rng(100 + k + rounds)
+    items = np.concatenate([np.repeat(np.arange(n_hot), per_hot), n_hot + np.arange(n_cold)]).astype(np.int32)
+    i = items[rng.permutation(n)]
+    u = rng.permutation(n).astype(np.int32)
+    nu = n
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    ni, lr, lam, epochs = n_hot + n_cold, 0.01, 0.03, 3
+    # "off": no heavy-user marks (p_u stored); "all": every user marked heavy (red.global.add of p_u's increment, PDELTA rounding)
+    thr = {"off": -1.0, "all": 1e-9}[marks]
+    cfg = mf.make_config(nu, ni, k, lr, lam, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=rounds, hot_chunk=chunk,
+                         merge_boost=boost, flags=0 if shuffle else capi.FLAG_NO_SHUFFLE, p_atomic_threshold=thr)
+    with mf.Engine(cfg) as eng:
+        eng.load_ratings(u, i, r)
+        assert eng.layout_info().n_hot_items == n_hot
+        ou, oi, orr, off = eng.records(with_marks=True)
+        assert eng.layout_info().n_heavy_users == {"off": 0, "all": n}[marks]
+        assert np.all((ou < 0) == (marks == "all"))
+        eng.init_factors()
+        eng.train(epochs)
+        P, Q = eng.get_factors()
+    plan, visits = plan_runs_of(off, n_hot, np.arange(n_hot), rounds, chunk, boost)
+    assert len(plan.start) == n_hot * pieces * rounds and np.all(plan.count == chunk)
+    assert np.allclose(plan.weight, min(1.0, boost / pieces))
+    per_warp = 32 // orc.run_lanes(k)
+    Po, Qo = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    cold = slice(int(off[0]), int(off[1]))
+    for e in range(epochs):
+        for rnd in range(rounds):                      # one sub-stripe: visit = round
+            lo, hi = int(visits[rnd]), int(visits[rnd + 1])
+            grid = max(1, -(-(hi - lo) // (16 * per_warp)))
+            with orc.tree_lanes(orc.run_lanes(k)):
+                orc.train_runs_launch(ou, orr, plan, lo, hi, Po, Qo, lr, lam, orc.ORDER_WARP_TREE_FMA, grid * 8 * per_warp, per_warp,
+                                      virt=shuffle, seed=SEED, epoch=e)
+        # the cold block rides along: distinct users and items, any order
+        orc.train((ou[cold] & 0x7fffffff).copy(), oi[cold].copy(), orr[cold].copy(), Po, Qo, lr, lam, e, e + 1, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+    ou = ou & 0x7fffffff
+    np.testing.assert_allclose(Q, Qo, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(P, Po, rtol=1e-5, atol=1e-7)
+    # and the merge really was an average: a plain sequential walk of each item's bucket ends somewhere else
+    Ps, Qs = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    train_runs_then_cold(ou, oi, orr, n_hot, Ps, Qs, k, lr, lam, 0, epochs, orc.ORDER_WARP_TREE_FMA)
+    assert np.abs(Q[:n_hot] - Qs[:n_hot]).max() > 1e-3
 
 
 def test_hot_item_path_can_be_disabled(midsize):
@@ -419,44 +563,51 @@ def test_hot_item_path_can_be_disabled(midsize):
 
 @pytest.mark.parametrize("flags", [0, capi.FLAG_MATERIALIZE_SHUFFLE])
 @pytest.mark.parametrize("mu", [1, 4])
-def test_hogwild_rmse_parity(midsize, mu, flags):
-    """Default: the update kernels read every bucket through its per-epoch permutation (virtual reshuffle);
-    MFSGD_FLAG_MATERIALIZE_SHUFFLE runs the reshuffle kernel instead. Both must reach the oracle's RMSE."""
-    m = midsize
-    cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_HOGWILD,
-                         stripes_per_gpu=mu, flags=flags)
+@pytest.mark.parametrize("variant", ["default", "signal"])
+def test_hogwild_rmse_parity(midsize, midsize_signal, variant, mu, flags):
+    """Held-out RMSE within 0.5 % of the sequential oracle at equal epochs, BOTH sides, on the noise-dominant set of the
+    throughput workloads and on the signal-dominant one (where a wrong merge weight or lost updates cost whole per cents).
+    Default: the update kernels read every bucket through its per-epoch permutation (virtual reshuffle);
+    MFSGD_FLAG_MATERIALIZE_SHUFFLE runs the reshuffle kernel instead."""
+    m = midsize_signal if variant == "signal" else midsize
+    cfg = mf.make_config(m.nu, m.ni, m.k, m.lr, m.lam, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=mu, flags=flags)
     with mf.Engine(cfg) as eng:
-        eng.load_ratings(*m["train"])
-        eng.load_heldout(*m["held"])
+        eng.load_ratings(*m.train)
+        eng.load_heldout(*m.held)
         eng.init_factors()
         eng.set_eval_every_epoch(True)
-        stats = eng.train(m["epochs"])
-        got = eng.rmse(*m["held"])
+        stats = eng.train(m.epochs)
+        got = eng.rmse(*m.held)
     assert abs(stats[-1].heldout_rmse - got) < 1e-9
     assert stats[0].heldout_rmse > stats[-1].heldout_rmse
-    assert_rmse_parity(got, m["oracle_rmse"])
+    assert_rmse_parity(got, m.oracle_rmse)
 
 
 @pytest.mark.parametrize("G,mu,mi", [(2, 1, 1), (4, 2, 2), (8, 1, 1)])
-def test_dsgd_virtual_ring_rmse_parity(midsize, G, mu, mi):
+@pytest.mark.parametrize("variant", ["default", "signal"])
+def test_dsgd_virtual_ring_rmse_parity(midsize, midsize_signal, variant, G, mu, mi):
     """The DSGD scheduler with G ring members placed on one GPU (streams instead of devices)."""
-    m = midsize
-    cfg = mf.make_config(m["nu"], m["ni"], m["k"], m["lr"], m["lam"], seed=SEED, mode=capi.MODE_DSGD, n_gpus=G,
+    m = midsize_signal if variant == "signal" else midsize
+    cfg = mf.make_config(m.nu, m.ni, m.k, m.lr, m.lam, seed=SEED, mode=capi.MODE_DSGD, n_gpus=G,
                          stripes_per_gpu=mu, shards_per_gpu=mi, flags=capi.FLAG_VIRTUAL_RING | capi.FLAG_TIME_KERNELS)
     with mf.Engine(cfg) as eng:
-        eng.load_ratings(*m["train"])
+        eng.load_ratings(*m.train)
+        ub, ib = eng.bounds()
         eng.init_factors()
         P0, Q0 = eng.get_factors()
-        assert np.array_equal(P0, orc.init_factors(m["nu"], m["k"], SEED, 0))      # stripes reassemble the whole
-        assert np.array_equal(Q0, orc.init_factors(m["ni"], m["k"], SEED, 1))
-        stats = eng.train(m["epochs"])
-        assert all(s.updates == len(m["train"][2]) for s in stats)
+        assert np.array_equal(P0, orc.init_factors(m.nu, m.k, SEED, 0))      # stripes reassemble the whole
+        assert np.array_equal(Q0, orc.init_factors(m.ni, m.k, SEED, 1))
+        stats = eng.train(m.epochs)
+        assert all(s.updates == len(m.train[2]) for s in stats)
         rounds = eng.layout_info().rounds
         assert all(s.update_launches <= 2 * G * mu * rounds and s.update_kernel_ms > 0 for s in stats)   # cold + hot per visit
-        got = eng.rmse(*m["held"])
+        got = eng.rmse(*m.held)
         P, Q = eng.get_factors()
-    assert abs(got - orc.rmse(P, Q, *m["held"])) / got < 1e-6                         # factors came home intact
-    assert_rmse_parity(got, m["oracle_rmse"])
+    assert abs(got - orc.rmse(P, Q, *m.held)) / got < 1e-6                         # factors came home intact
+    # the engine's strata are the oracle's (rating-count-balanced bounds)
+    assert np.array_equal(ub[::mu], orc.balanced_bounds(m.train[0], m.nu, G))
+    assert np.array_equal(ib[::mi], orc.balanced_bounds(m.train[1], m.ni, G))
+    assert_ring_rmse_parity(got, m.oracle_rmse, m.dsgd_oracle_rmse(ub[::mu], ib[::mi]))
 
 
 def test_set_get_factors_roundtrip_and_resume(midsize):

@@ -26,8 +26,7 @@ def test_hogwild_reaches_oracle_rmse_at_equal_epochs(name):
     ref = oracle_curve(name)
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
     with mf.Engine(cfg) as eng:
-        nt, nh = eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user,
-                                                        w.log2_alpha_item, w.c_item))
+        nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
         assert (nt, nh) == (ref["n_train"], ref["n_heldout"])           # identical split
         eng.init_factors()
         eng.set_eval_every_epoch(True)
@@ -51,8 +50,7 @@ def test_ml100k_shaped_hogwild_close_to_oracle():
     ref = oracle_curve("ml100k")
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
     with mf.Engine(cfg) as eng:
-        nt, nh = eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user,
-                                                        w.log2_alpha_item, w.c_item))
+        nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
         assert (nt, nh) == (ref["n_train"], ref["n_heldout"])
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)
@@ -68,8 +66,7 @@ def test_dsgd_virtual_ring_netflix_shaped_reaches_oracle_rmse():
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_DSGD, n_gpus=8,
                          flags=capi.FLAG_VIRTUAL_RING)
     with mf.Engine(cfg) as eng:
-        eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user,
-                                               w.log2_alpha_item, w.c_item))
+        eng.generate_synthetic(mf.synth_params_of(w))
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)
         got = eng.rmse_heldout()[0]
@@ -92,8 +89,7 @@ def test_dsgd_virtual_ring_large_shapes_reach_oracle_rmse(name):
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_DSGD, n_gpus=8,
                          flags=capi.FLAG_VIRTUAL_RING)
     with mf.Engine(cfg) as eng:
-        nt, nh = eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user,
-                                                        w.log2_alpha_item, w.c_item))
+        nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
         assert (nt, nh) == (ref["n_train"], ref["n_heldout"])
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)

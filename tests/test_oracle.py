@@ -225,3 +225,126 @@ def test_tree_lanes_override_matches_numpy(k, lanes):
     assert np.float32(e) == np.float32(want)
     e_default = orc.lib.orc_sgd_update(p.copy(), q.copy(), k, 1.5, 0.01, 0.05, orc.ORDER_WARP_TREE)
     assert np.float32(e_default) == np.float32(np.float32(1.5) - npr.dot_warp_tree(p, q))
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: signal-dominant generator variant, the engine's bucket permutation, the run kernel's twin
+# ------------------------------------------------------------------------------------------------
+SIGNAL = dict(amplitude=1.7320508, noise_scale=0.125)
+
+
+def test_signal_variant_generator_golden_and_numpy(golden):
+    g = golden["gen_ml100k_signal"]
+    u, i, r, held = orc.generate(SEED, 0, 256, 943, 1682, **SIGNAL)
+    assert u.tolist() == g["u"] and i.tolist() == g["i"] and r.view(np.uint32).tolist() == g["r"]
+    assert held.astype(int).tolist() == g["held"]
+    nu, ni, nr, nh = npr.generate(SEED, 5000, 300, 480_000, 17_800, 2, 0.25, 3, 0.375, 1.7320508, 0.125)
+    ou, oi, orr, oh = orc.generate(SEED, 5000, 300, 480_000, 17_800, **SIGNAL)
+    assert np.array_equal(nu, ou) and np.array_equal(ni, oi) and np.array_equal(nr.view(np.uint32), orr.view(np.uint32))
+    # same users, items and split as the default variant: only the ratings differ
+    du, di, dr, dh = orc.generate(SEED, 5000, 300, 480_000, 17_800)
+    assert np.array_equal(du, ou) and np.array_equal(di, oi) and np.array_equal(dh, oh) and not np.array_equal(dr, orr)
+
+
+def test_signal_variant_is_signal_dominant():
+    """The variant exists so that RMSE parity bites: the planted signal (std ~1) dwarfs the noise (std 0.07), and a
+    factorisation that only learns the mean scores ~0.94 while the sequential oracle gets far below it."""
+    nu, ni, n, k = 2000, 800, 300_000, 16
+    u, i, r, held = orc.generate(SEED, 0, n, nu, ni, **SIGNAL)
+    tr = (u[~held].copy(), i[~held].copy(), r[~held].copy())
+    ho = (u[held].copy(), i[held].copy(), r[held].copy())
+    const = float(np.sqrt(np.mean((ho[2] - tr[2].mean()) ** 2)))
+    assert 0.85 < const < 1.05
+    P, Q = orc.factorize(*tr, nu, ni, k, 0.02, 0.02, 12, SEED)
+    assert orc.rmse(P, Q, *ho) < 0.5 * const
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 33, 63, 64, 65, 100, 1000, 4097, 70_001])
+def test_block_perm_is_a_tile_coherent_bijection(n):
+    p0 = orc.block_perm(n, SEED, 0, 17)
+    assert sorted(p0.tolist()) == list(range(n))
+    full = (n // 32) * 32
+    # positions of one aligned group of 32 read one aligned group of 32 records (whole sectors); the tail stays the tail
+    assert np.all((p0[:full].reshape(-1, 32) // 32) == (p0[:full:32] // 32)[:, None])
+    assert np.all(p0[full:] >= full)
+    if n >= 64:
+        p1, pb = orc.block_perm(n, SEED, 1, 17), orc.block_perm(n, SEED, 0, 18)
+        assert not np.array_equal(p0, p1) and not np.array_equal(p0, pb)      # keyed by epoch and by bucket
+        assert np.mean(p0 != np.arange(n)) > 0.5
+
+
+def _run_plan_one_bucket_per_item(counts, chunk, weights=None):
+    """Units of a launch over consecutive per-item buckets of the given sizes, each cut into ceil(n / chunk) equal runs."""
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    start, count, item, weight = [], [], [], []
+    for it, n in enumerate(counts):
+        pieces = -(-n // chunk)
+        for pc in range(pieces):
+            lo, hi = off[it] + n * pc // pieces, off[it] + n * (pc + 1) // pieces
+            start.append(lo); count.append(hi - lo); item.append(it)
+            weight.append((weights or {}).get(pieces, 1.0 / pieces))
+    return orc.RunPlan(start, count, item, weight, off), off
+
+
+@pytest.mark.parametrize("k,order", [(8, orc.ORDER_SEQ), (32, orc.ORDER_WARP_TREE), (128, orc.ORDER_WARP_TREE_FMA)])
+def test_run_twin_with_one_run_per_item_is_the_sequential_rule(k, order):
+    rng = np.random.default_rng(k)
+    counts = [40, 1, 300, 17, 64]
+    n = sum(counts)
+    u = rng.permutation(n).astype(np.int32)                    # pairwise distinct users: runs commute exactly
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    plan, off = _run_plan_one_bucket_per_item(counts, 4096)
+    items = np.repeat(np.arange(len(counts)), counts).astype(np.int32)
+    P, Q = orc.init_factors(n, k, SEED, 0), orc.init_factors(len(counts), k, SEED, 1)
+    Ps, Qs = P.copy(), Q.copy()
+    orc.train_runs_launch(u, r, plan, 0, len(counts), P, Q, 0.02, 0.03, order, resident=2)
+    orc.train(u, items, r, Ps, Qs, 0.02, 0.03, 0, 1, SEED, order, shuffled=False)
+    assert np.array_equal(P, Ps) and np.array_equal(Q, Qs)
+
+
+@pytest.mark.parametrize("resident,gpw", [(64, 1), (4, 1), (8, 4)])
+def test_run_twin_weighted_merge_by_hand(resident, gpw):
+    """Runs of an item that are in flight together all start from the launch-start q_i and add weight * (q_run - q_start);
+    with fewer sub-warps than runs, later runs start from what the earlier ones merged."""
+    k, lr, lam, chunk = 16, 0.02, 0.03, 32
+    rng = np.random.default_rng(3)
+    counts = [128, 96]
+    n = sum(counts)
+    u = rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    plan, off = _run_plan_one_bucket_per_item(counts, chunk, weights={4: 0.3125, 3: 0.4})
+    P0, Q0 = orc.init_factors(n, k, SEED, 0), orc.init_factors(2, k, SEED, 1)
+    P, Q = P0.copy(), Q0.copy()
+    orc.train_runs_launch(u, r, plan, 0, len(plan.start), P, Q, lr, lam, orc.ORDER_SEQ, resident=resident, gpw=gpw)
+    # by hand: waves of `resident` units in claim order (all runs equally long here except item 1's: 32 each too)
+    Ph, Qh = P0.copy(), Q0.copy()
+    units = list(range(len(plan.start)))
+    while units:
+        wave, units = units[:resident], units[resident:]
+        start_q = Qh.copy()
+        for j in wave:
+            it = int(plan.item[j])
+            q = start_q[it].copy()
+            for t in range(int(plan.start[j]), int(plan.start[j] + plan.count[j])):
+                orc.lib.orc_sgd_update(Ph[u[t]], q, k, float(r[t]), lr, lam, orc.ORDER_SEQ)
+            Qh[it] = Qh[it] + (q - start_q[it]) * np.float32(plan.weight[j])
+    assert np.array_equal(P, Ph)
+    np.testing.assert_allclose(Q, Qh, rtol=1e-6, atol=1e-8)      # the adds of one wave come in slot order on both sides
+    assert not np.allclose(Q, Q0)
+
+
+def test_run_twin_reads_buckets_through_the_permutation():
+    k = 8
+    rng = np.random.default_rng(5)
+    counts = [200, 70]
+    n = sum(counts)
+    u = rng.permutation(n).astype(np.int32)
+    r = (1 + 4 * rng.random(n)).astype(np.float32)
+    plan, off = _run_plan_one_bucket_per_item(counts, 4096)
+    P, Q = orc.init_factors(n, k, SEED, 0), orc.init_factors(2, k, SEED, 1)
+    orc.train_runs_launch(u, r, plan, 0, 2, P, Q, 0.02, 0.03, orc.ORDER_SEQ, resident=2, virt=True, seed=SEED, epoch=4)
+    order = np.concatenate([off[b] + orc.block_perm(counts[b], SEED, 4, int(plan.bid[b])) for b in range(2)])
+    items = np.repeat(np.arange(2), counts).astype(np.int32)
+    Ps, Qs = orc.init_factors(n, k, SEED, 0), orc.init_factors(2, k, SEED, 1)
+    orc.train(u[order].copy(), items, r[order].copy(), Ps, Qs, 0.02, 0.03, 0, 1, SEED, orc.ORDER_SEQ, shuffled=False)
+    assert np.array_equal(P, Ps) and np.array_equal(Q, Qs)

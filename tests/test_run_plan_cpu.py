@@ -110,17 +110,19 @@ def test_layout_of_the_baseline_shapes():
     # sub-warp's share of the launch (round 2: long runs, few merges per item)
     assert layout("netflix") == (4, 1, 4, 960) and layout("netflix", resident_ctas=444) == (4, 1, 4, 1024)
     # one process per GPU: the rotation is pipelined over 2 item sub-shards, runs shorten with the launches
-    assert layout("netflix", G=2, world=2) == (2, 2, 4, 256)
-    assert layout("netflix", G=4, world=4) == (1, 2, 2, 256)
-    assert layout("netflix", G=8, world=8) == (1, 2, 1, 128)
+    # (two stream lanes overlap the sub-shards' launches, so a run may be as long as a sub-warp's share of two launches)
+    assert layout("netflix", G=2, world=2) == (2, 2, 4, 480)
+    assert layout("netflix", G=4, world=4) == (1, 2, 2, 480)
+    assert layout("netflix", G=8, world=8) == (1, 2, 1, 256) and layout("netflix", G=8, world=8, resident_ctas=444) == (1, 2, 1, 320)
     # a single process driving 8 devices (peer copies, no pipelining): one shard group per member
     assert layout("netflix", G=8, world=1) == (1, 1, 1, 256)
     assert layout("ml20m") == (2, 1, 4, 384)
-    # 90 K ratings: one sub-stripe, but still 4 launches per epoch of >= 16 K records each; shortest runs
-    assert layout("ml100k") == (1, 1, 4, 64)
+    # 90 K ratings: one sub-stripe, but still 4 launches per epoch of >= 16 K records each; shortest runs (256: small
+    # launches leave sub-warps idle rather than cut their items into pieces)
+    assert layout("ml100k") == (1, 1, 4, 256)
     # the large shapes on their own configuration (8 GPUs) and squeezed onto one
-    assert layout("yahoo", G=8, world=8) == (2, 2, 2, 224) and layout("powerlaw", G=8, world=8) == (7, 2, 1, 192)
-    assert layout("yahoo") == (70, 1, 4, 384) and layout("powerlaw") == (193, 1, 4, 224)
+    assert layout("yahoo", G=8, world=8) == (2, 2, 2, 416) and layout("powerlaw", G=8, world=8) == (7, 2, 1, 352)
+    assert layout("yahoo") == (70, 1, 4, 384) and layout("powerlaw") == (193, 1, 4, 256)
 
 
 def test_layout_overrides_and_modes():

@@ -37,7 +37,7 @@ def conv():
 
 def sweep(wname):
     w = mf.WORKLOADS[wname]
-    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     for scatter in (0, 1, 2, 3):
         for stripes, rounds in ((1, 1), (7, 1), (7, 0), (7, 32), (14, 0)):
             cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD,
@@ -53,7 +53,7 @@ def sweep(wname):
 
 def curve(wname, stripes=0, rounds=0, scatter=0, hot=0.0, chunk=0):
     w = mf.WORKLOADS[wname]
-    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=stripes, rounds=rounds, scatter=scatter, hot_share=hot, hot_chunk=chunk)
     with mf.Engine(cfg) as eng:
         eng.generate_synthetic(sp); eng.init_factors(); eng.set_eval_every_epoch(True)
@@ -89,7 +89,7 @@ def smallblocks(wname):
     """Proxy for the per-GPU work of an 8-member ring on one GPU: 64 user sub-stripes, rounds 1 -> every launch
     holds 1/64 of the ratings, like one (member, sub-epoch) block at G = 8."""
     w = mf.WORKLOADS[wname]
-    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     for mw in (128, 32, 8):
         os.environ["MFSGD_MIN_WINDOWS"] = str(mw)
         for chunk in (256, 128):
@@ -110,7 +110,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "smallblocks":
 
 def stripes_sweep(wname):
     w = mf.WORKLOADS[wname]
-    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     for stripes in (2, 3, 4, 5, 7):
         for rounds in (1, 2, 4):
             cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_HOGWILD,
@@ -130,7 +130,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "stripes":
 def ringcurve(wname, G, chunk, shards=0):
     """Held-out RMSE per epoch of the G-member DSGD schedule (virtual ring on one GPU) for a given run length."""
     w = mf.WORKLOADS[wname]
-    sp = mf.synth_params(w.n_ratings, SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item)
+    sp = mf.synth_params_of(w)
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=SEED, mode=capi.MODE_DSGD, n_gpus=G, hot_chunk=chunk,
                          shards_per_gpu=shards, flags=capi.FLAG_VIRTUAL_RING)
     with mf.Engine(cfg) as eng:

@@ -10,7 +10,7 @@ w = mf.WORKLOADS["netflix"]
 cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=mf.capi.MODE_HOGWILD,
                      stripes_per_gpu=64, rounds=1, hot_chunk=chunk)
 with mf.Engine(cfg) as eng:
-    eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
+    eng.generate_synthetic(mf.synth_params_of(w))
     eng.init_factors()
     st = eng.train(epochs)
     print("epoch_ms", [round(s.epoch_ms, 2) for s in st], "launches/epoch", st[-1].update_launches)

@@ -12,7 +12,7 @@ import bench
 epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 w = mf.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "netflix"]
 eng = mf.Engine(mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD, flags=capi.FLAG_TIME_KERNELS))
-eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
+eng.generate_synthetic(mf.synth_params_of(w))
 eng.init_factors()
 eng.train(3)
 hu, hi, hr, pins = bench.host_training_set(mf, w, 0, pinned=True)

@@ -28,6 +28,7 @@ SEED = 20261018
 MIN_RUN = 16
 L2_BYTES = 126 << 20
 SMS, CTAS_PER_SM = 148, 3
+HOT_OFF = False
 
 SHAPES = {  # n_users, n_items, n_ratings, k, epochs, log2_alpha_item
     "ml100k": (943, 1682, 100_000, 32, 20, 3),
@@ -65,7 +66,7 @@ def build_layout(u, i, r, nu, ni, k, G, mu_cfg, mi_cfg, rounds_cfg, chunk_cfg, m
     ub, ib = balanced_bounds(ucnt, UB), balanced_bounds(icnt, IB)
     owner_u = (np.searchsorted(ub, np.arange(nu), side="right") - 1).astype(np.int32)
     owner_i = (np.searchsorted(ib, np.arange(ni), side="right") - 1).astype(np.int32)
-    thr = max(1e-6 * len(r), MIN_RUN * mu * G)
+    thr = max(1e-6 * len(r), MIN_RUN * mu * G) if not HOT_OFF else 1e18
     hot_items = np.flatnonzero(icnt >= thr).astype(np.int32)
     H = len(hot_items)
     hot_index = np.full(ni, -1, np.int64)
@@ -149,10 +150,12 @@ def main():
     ap.add_argument("--lr", type=float, default=0.0)
     ap.add_argument("--lam", type=float, default=-1.0)
     ap.add_argument("--multi-process", action="store_true")
+    ap.add_argument("--hot-off", action="store_true", help="no run path: every block is walked sequentially in arrival order")
     ap.add_argument("--sms", type=int, default=148, help="simulated SM count (scale the machine with the data)")
     a = ap.parse_args()
-    global SMS
+    global SMS, HOT_OFF
     SMS = a.sms
+    HOT_OFF = a.hot_off
     nu, ni, n, k, epochs, l2ai = SHAPES[a.shape]
     amp, noise, vlr, vlam = VARIANTS[a.variant]
     lr = a.lr or vlr or (0.01 if a.shape == "ml100k" else 0.005)
@@ -173,7 +176,7 @@ def main():
         want.append(orc.rmse(Po, Qo, hu, hi, hr))
         nl = train_epoch(members, info, Ps, Qs, lr, lam, e, SEED, orc.ORDER_WARP_TREE_FMA, a.always_add)
         got.append(orc.rmse(Ps, Qs, hu, hi, hr))
-        print(json.dumps({"shape": a.shape, "variant": a.variant, "lr": lr, "lambda": lam, "layout": info, "boost": a.boost,
+    print(json.dumps({"shape": a.shape, "variant": a.variant, "lr": lr, "lambda": lam, "layout": info, "boost": a.boost,
                       "launches_per_epoch": nl, "units": len(members[0].plan.start),
                       "records_in_multi_run_slices": float((members[0].plan.count[members[0].plan.weight < 1.0]).sum() / max(1, members[0].plan.count.sum())),
                       "const_predictor_rmse": const, "oracle": want, "sim": got,

@@ -14,7 +14,7 @@ G = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 w = mf.WORKLOADS[name]
 epochs = int(sys.argv[3]) if len(sys.argv) > 3 else w.epochs
 kw = dict(seed=mf.SEED, flags=capi.FLAG_TIME_KERNELS)
-for env, key, conv in (("RW_ROUNDS", "rounds", int), ("RW_HOT_SHARE", "hot_share", float), ("RW_STRIPES", "stripes_per_gpu", int),
+for env, key, conv in (("RW_SCATTER", "scatter", int), ("RW_BOOST", "merge_boost", float), ("RW_ROUNDS", "rounds", int), ("RW_HOT_SHARE", "hot_share", float), ("RW_STRIPES", "stripes_per_gpu", int),
                        ("RW_HOT_CHUNK", "hot_chunk", int), ("RW_SHARDS", "shards_per_gpu", int)):
     if os.environ.get(env):
         kw[key] = conv(os.environ[env])
@@ -26,7 +26,7 @@ cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, **kw)
 out = {"workload": w.name, "members": G, "k": w.k, "epochs": epochs}
 with mf.Engine(cfg) as eng:
     t0 = time.time()
-    nt, nh = eng.generate_synthetic(mf.synth_params(w.n_ratings, mf.SEED, w.log2_alpha_user, w.c_user, w.log2_alpha_item, w.c_item))
+    nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
     out["setup_s"] = time.time() - t0
     info = eng.layout_info()
     eng.init_factors()
@@ -41,8 +41,12 @@ out["gupdates_per_s"] = nt / ms / 1e6
 out["roofline_frac_measured_peak"] = nt / (ms * 1e-3) * mf.bytes_per_update(w.k) / 6552.6e9
 ref = os.path.join(ROOT, "tests", "golden", "oracle_rmse_%s.json" % name)
 if os.path.exists(ref):
-    want = json.load(open(ref))["heldout_rmse_per_epoch"]
+    fixture = json.load(open(ref))
+    want = fixture.get("heldout_rmse_per_epoch", [])
     out["oracle_rmse_per_epoch"] = want
+    out["constant_predictor_rmse"] = fixture.get("constant_predictor_rmse")
+    if "dsgd%d" % G in fixture:      # the sequential rule in this ring's own block order (tools/oracle_reference_rmse.py --dsgd)
+        out["oracle_dsgd_order_rmse_per_epoch"] = fixture["dsgd%d" % G]["heldout_rmse_per_epoch"]
     m = min(len(want), epochs)
     out["rel_diff_at_equal_epochs"] = [out["heldout_rmse_per_epoch"][e] / want[e] - 1 for e in range(m)]
 line = json.dumps(out)
