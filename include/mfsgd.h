@@ -266,6 +266,10 @@ typedef struct mfsgd_ceilings {
 } mfsgd_ceilings;
 MFSGD_API int  mfsgd_measure_ceilings(int32_t device, double buffer_mb, mfsgd_ceilings* out);
 
+/* Device buffers of destroyed handles are kept in a process-wide cache and reused by later handles (cudaFree of gigabytes
+ * costs up to a second and synchronises the device); this returns them to the driver. MFSGD_NO_CACHE=1 disables the cache. */
+MFSGD_API int  mfsgd_release_cached_memory(void);
+
 /* Pinned host staging helpers (optional; plain host memory works too, at lower H2D bandwidth). */
 MFSGD_API int  mfsgd_host_alloc(void** out, int64_t bytes);
 MFSGD_API int  mfsgd_host_free(void* p);

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mfsgd_generate_to_host": (C.c_int, [_i32, C.POINTER(SynthParams), _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mfsgd_nccl_unique_id": (C.c_int, [_vp]),
     "mfsgd_measure_ceilings": (C.c_int, [_i32, C.c_double, C.POINTER(Ceilings)]),
+    "mfsgd_release_cached_memory": (C.c_int, []),
     "mfsgd_host_alloc": (C.c_int, [C.POINTER(_vp), _i64]),
     "mfsgd_host_free": (C.c_int, [_vp]),
 }

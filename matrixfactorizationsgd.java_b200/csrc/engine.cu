@@ -14,6 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -239,16 +242,105 @@ struct mfsgd_handle {
 static inline int group_lo(const mfsgd_handle* h, int grp) { return h->item_bounds[(size_t)grp * h->mi]; }
 static inline int group_hi(const mfsgd_handle* h, int grp) { return h->item_bounds[(size_t)(grp + 1) * h->mi]; }
 
+// ------------------------------------------------------------------------------------------------
+// device memory: a process-wide cache of freed blocks
+// ------------------------------------------------------------------------------------------------
+// cudaFree of multi-gigabyte buffers synchronises the device and unmaps the pages: measured 0.06-0.9 s inside mfsgd_destroy of
+// a Netflix-shaped handle (round-2 e2e trace: the "first-call stall" of round 1), and cudaMalloc pays again on the next
+// handle. A resident caller (the JVM) creates and destroys handles repeatedly, so freed blocks are kept per device and
+// handed out again (first block of >= the requested size and <= 1.25 x + 1 MB); on an allocation failure the cache is
+// emptied and the allocation retried. mfsgd_release_cached_memory() returns everything to the driver.
+struct DeviceBlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;      // (device, bytes) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> live;        // blocks handed out
+    size_t cached_bytes = 0;
+
+    cudaError_t alloc(void** out, size_t bytes) {
+        *out = nullptr;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        bytes = (bytes + 511) & ~(size_t)511;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = free_blocks.lower_bound({dev, bytes});
+            if (it != free_blocks.end() && it->first.first == dev && it->first.second <= bytes + bytes / 4 + ((size_t)1 << 20)) {
+                *out = it->second;
+                live[*out] = it->first;
+                cached_bytes -= it->first.second;
+                free_blocks.erase(it);
+                return cudaSuccess;
+            }
+        }
+        e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            release_all();
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(mu);
+            live[*out] = {dev, bytes};
+        }
+        return e;
+    }
+    void free(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = live.find(p);
+        if (it == live.end()) {      // not ours (never happens): hand it to the driver
+            cudaFree(p);
+            return;
+        }
+        free_blocks.insert({it->second, p});
+        cached_bytes += it->second.second;
+        live.erase(it);
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> lock(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& kv : free_blocks) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+        cudaSetDevice(cur);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+static DeviceBlockCache g_cache;
+static inline bool cache_enabled() {
+    static int on = -1;
+    if (on < 0) on = (getenv("MFSGD_NO_CACHE") == nullptr) ? 1 : 0;
+    return on == 1;
+}
+static cudaError_t raw_alloc(void** p, size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    return cache_enabled() ? g_cache.alloc(p, bytes) : cudaMalloc(p, bytes);
+}
+static void raw_free(void* p) {
+    if (!p) return;
+    if (cache_enabled()) g_cache.free(p);
+    else cudaFree(p);
+}
+
 template <typename T>
 static cudaError_t dev_alloc(T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    return cudaMalloc((void**)p, count * sizeof(T));
+    return raw_alloc((void**)p, count * sizeof(T));
 }
 template <typename T>
 static void dev_free(T*& p) {
-    if (p) cudaFree(p);
+    if (p) raw_free(p);
     p = nullptr;
+}
+
+extern "C" int mfsgd_release_cached_memory(void) {
+    g_cache.release_all();
+    return MFSGD_OK;
 }
 
 static void free_eval(EvalSet& e) {
@@ -404,11 +496,14 @@ static inline bool run_p_red(const mfsgd_config& c) { return c.scatter == MFSGD_
 
 static int member_setup(mfsgd_handle* h, Member& m) {
     CK(cudaSetDevice(m.device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, m.device));
-    if (prop.major < 10) return fail(MFSGD_E_CUDA, "device %d is sm_%d%d; libmfsgd.so carries sm_100a code only", m.device, prop.major, prop.minor);
-    m.n_sms = prop.multiProcessorCount;
-    m.l2_bytes = (size_t)prop.l2CacheSize;
+    int cc_major = 0, cc_minor = 0, n_sms = 0, l2 = 0;     // three attributes instead of cudaGetDeviceProperties (milliseconds per call)
+    CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, m.device));
+    CK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, m.device));
+    CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, m.device));
+    CK(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m.device));
+    if (cc_major < 10) return fail(MFSGD_E_CUDA, "device %d is sm_%d%d; libmfsgd.so carries sm_100a code only", m.device, cc_major, cc_minor);
+    m.n_sms = n_sms;
+    m.l2_bytes = (size_t)l2;
     CK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m.hot_stream, cudaStreamNonBlocking));
@@ -549,6 +644,35 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
             mfsgd_destroy(h);
             return rc2;
         }
+        // NCCL connects two ranks lazily, on their first exchange (tens of milliseconds per pair): do it now, as part of
+        // the ring's bootstrap, for every pair the engine will use -- ring neighbours (Q rotation) and all pairs (record
+        // exchange of mfsgd_load_ratings_sharded, all-reduce of the row counts).
+        {
+            Member& m = h->members[0];
+            uint32_t* warm = nullptr;
+            cudaError_t e = dev_alloc(&warm, (size_t)2 * cfg->world_size + 2);
+            ncclResult_t nr = ncclSuccess;
+            if (e == cudaSuccess) e = cudaMemsetAsync(warm, 0, ((size_t)2 * cfg->world_size + 2) * 4, m.stream);
+            if (e == cudaSuccess) {
+                nr = g_nccl.AllReduce(warm, warm, 1, ncclUint32, ncclSum, h->comm, m.stream);
+                if (nr == ncclSuccess) nr = g_nccl.GroupStart();
+                for (int p = 0; p < cfg->world_size && nr == ncclSuccess; p++) {
+                    if (p == cfg->rank) continue;
+                    nr = g_nccl.Send(warm + 1, 1, ncclUint32, p, h->comm, m.stream);
+                    if (nr == ncclSuccess) nr = g_nccl.Recv(warm + 2 + p, 1, ncclUint32, p, h->comm, m.stream);
+                }
+                ncclResult_t ne = g_nccl.GroupEnd();
+                if (nr == ncclSuccess) nr = ne;
+                if (nr == ncclSuccess) e = cudaStreamSynchronize(m.stream);
+            }
+            dev_free(warm);
+            if (e != cudaSuccess || nr != ncclSuccess) {
+                int rc2 = nr != ncclSuccess ? fail(MFSGD_E_NCCL, "ring warm-up: %s", g_nccl.GetErrorString(nr))
+                                            : fail(MFSGD_E_CUDA, "ring warm-up: %s", cudaGetErrorString(e));
+                mfsgd_destroy(h);
+                return rc2;
+            }
+        }
     }
     *out = h;
     return MFSGD_OK;
@@ -603,7 +727,7 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     int rc = MFSGD_OK;
     auto cleanup = [&]() {
         dev_free(ucnt); dev_free(icnt); dev_free(ucum); dev_free(icum); dev_free(ub); dev_free(ib); dev_free(bad);
-        if (temp) cudaFree(temp);
+        if (temp) raw_free(temp);
     };
 #define CKC(call)                                                                                           \
     do {                                                                                                    \
@@ -646,7 +770,7 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     CKC(exclusive_cumsum_u32(ucnt, ucum, c.n_users, nullptr, &tb_u, m.stream, nullptr));
     CKC(exclusive_cumsum_u32(icnt, icum, c.n_items, nullptr, &tb_i, m.stream, nullptr));
     size_t tb = std::max(tb_u, tb_i);
-    CKC(cudaMalloc(&temp, tb ? tb : 1));
+    CKC(raw_alloc(&temp, tb ? tb : 1));
     CKC(exclusive_cumsum_u32(ucnt, ucum, c.n_users, temp, &tb, m.stream, &m.launches));
     CKC(launch_balanced_bounds(ucum, c.n_users, h->UB, ub, m.stream, &m.launches));
     CKC(exclusive_cumsum_u32(icnt, icum, c.n_items, temp, &tb, m.stream, &m.launches));
@@ -746,7 +870,7 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, h->item_bounds.data(), ((size_t)h->IB + 1) * 4, cudaMemcpyHostToDevice, m.stream);
     if (e == cudaSuccess) e = launch_fill_owner(d_b, h->IB, c.n_items, m.d_owner_i, m.stream, &m.launches);
     if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
-    cudaFree(d_b);
+    raw_free(d_b);
     CK(e);
     // hot-item lookup table and the per-group ranges of the (ascending) hot list
     h->hot_block_lo.assign((size_t)h->IB + 1, 0);
@@ -833,9 +957,9 @@ static int bucket_with(Member& m, const Source& src, Chunk& ch, BucketArgs b, Re
         }
         if (rc == MFSGD_OK && e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
     }
-    cudaFree(d_cnt);
+    raw_free(d_cnt);
     if (rc != MFSGD_OK || e != cudaSuccess) {
-        if (recs) cudaFree(recs);
+        if (recs) raw_free(recs);
         if (rc != MFSGD_OK) return rc;
         CK(e);
     }
@@ -893,12 +1017,12 @@ static int exchange_slices(mfsgd_handle* h, Member& m, const Source& src, Chunk&
         else e = cudaStreamSynchronize(m.stream);
         m.launches += 1;
     }
-    cudaFree(d_cnt);
-    cudaFree(d_all);
-    cudaFree(send);
+    raw_free(d_cnt);
+    raw_free(d_all);
+    raw_free(send);
     if (rc == MFSGD_OK && e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "record exchange: %s", cudaGetErrorString(e));
     if (rc != MFSGD_OK) {
-        if (*recv) cudaFree(*recv);
+        if (*recv) raw_free(*recv);
         *recv = nullptr;
         return rc;
     }
@@ -981,7 +1105,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
                 if (e == cudaSuccess) e = dev_alloc(&m.keys_b, (size_t)src.total);
                 if (e == cudaSuccess) e = launch_pack_records(ch.u, ch.i, ch.r, src.total, m.recs_orig, m.stream, &m.launches);
                 if (e == cudaSuccess) e = deterministic_order_gather(nullptr, nullptr, (int32_t)src.total, 0, 0, m.keys_a, m.keys_b, nullptr, &m.sort_temp_bytes, m.stream, nullptr);
-                if (e == cudaSuccess) e = cudaMalloc(&m.sort_temp, m.sort_temp_bytes ? m.sort_temp_bytes : 1);
+                if (e == cudaSuccess) e = raw_alloc(&m.sort_temp, m.sort_temp_bytes ? m.sort_temp_bytes : 1);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
                 if (rc == MFSGD_OK && e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? MFSGD_E_OOM : MFSGD_E_CUDA, "deterministic staging: %s", cudaGetErrorString(e));
             }
@@ -1002,7 +1126,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
                     if (rc == MFSGD_OK) { PhaseTimer pt("load: bucketing (histogram + scatter)"); rc = bucket_member(h, m, own, ch2, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off); }
                     chunk_free(ch2);
                 }
-                if (mine) cudaFree(mine);
+                if (mine) raw_free(mine);
             } else
             { PhaseTimer pt("load: bucketing (histogram + scatter)"); rc = bucket_member(h, m, src, ch, 0, 1, 1, h->IB, true, &m.recs[0], m.block_off); }
             if (rc == MFSGD_OK) {
@@ -1433,9 +1557,10 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
             a.first = 0;
             a.n = m.n_recs;
             if (m.counter_next >= m.n_counters * COUNTER_EPOCHS) return fail(MFSGD_E_STATE, "run launch counters exhausted");
+            const int sub_warp_cap = (int)std::min<int64_t>(1 << 30, (int64_t)(m.u_hi - m.u_lo) / (4 * h->mu));   // a quarter of the sub-stripe's users
             auto overlaps = [&](const Visit& w) {
                 return hot_launch_overlaps(c.k, w.unit_hi - w.unit_lo, m.unit_recs_cum[(size_t)w.unit_hi] - m.unit_recs_cum[(size_t)w.unit_lo],
-                                           m.run_chunk, m.hot_grid);
+                                           m.run_chunk, m.hot_grid, sub_warp_cap);
             };
             bool next_overlaps = false;    // will the next run launch of this chain overlap this one's tail?
             for (size_t vj = vi + 1; vj < visits.size(); vj++)
@@ -1444,7 +1569,7 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
                     break;
                 }
             CK(launch_sgd_update_hot(a, m.d_units + v.unit_lo, v.unit_hi - v.unit_lo, m.d_counters + m.counter_next++, fast_arith,
-                                     run_p_red(c), m.hot_grid, hot_chained && overlaps(v), next_overlaps, hot_s, &m.launches));
+                                     run_p_red(c), m.hot_grid, sub_warp_cap, hot_chained && overlaps(v), next_overlaps, hot_s, &m.launches));
             hot_chained = true;
             m.update_launches++;
             *any_hot = true;
@@ -1474,7 +1599,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         ~TraceBuf() {
             if (p) {
                 cudaSetDevice(device);
-                cudaFree(p);
+                raw_free(p);
             }
         }
     } trace;
@@ -2055,7 +2180,7 @@ static int mfsgd_apply_updates_forced_body(int32_t device, int32_t k, float lr, 
     if (e == cudaSuccess) e = cudaMemcpy(post_p, op, rows * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(post_q, oq, rows * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(err, de, (size_t)n * 4, cudaMemcpyDeviceToHost);
-    cudaFree(dp); cudaFree(dq); cudaFree(dr); cudaFree(op); cudaFree(oq); cudaFree(de);
+    raw_free(dp); raw_free(dq); raw_free(dr); raw_free(op); raw_free(oq); raw_free(de);
     CK(e);
     return MFSGD_OK;
 }
@@ -2090,7 +2215,7 @@ static int mfsgd_generate_to_host_body(int32_t device, const mfsgd_synth_params*
     if (e == cudaSuccess) e = cudaMemcpy(items, di, (size_t)count * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(ratings, dr, (size_t)count * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(held, dh, (size_t)count, cudaMemcpyDeviceToHost);
-    cudaFree(du); cudaFree(di); cudaFree(dr); cudaFree(dh);
+    raw_free(du); raw_free(di); raw_free(dr); raw_free(dh);
     CK(e);
     return MFSGD_OK;
 }

@@ -95,8 +95,9 @@ struct HotUnit {
 // hot_launch_overlaps says so); overlapped_by_next: the NEXT launch on the chain will overlap this one's tail.
 // p_red: p_u is updated in memory by red.global.add of its increment (no lost updates between concurrent writers of a row).
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast, bool p_red,
-                                  int grid, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream, int* launches);
-bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid);
+                                  int grid, int max_sub_warps, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream,
+                                  int* launches);
+bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid, int max_sub_warps);
 
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.

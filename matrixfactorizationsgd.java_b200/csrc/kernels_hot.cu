@@ -193,10 +193,14 @@ Geometry run_geometry_for(int k) {
 
 int run_kernel_lanes(int k) { return run_geometry_for(k).lanes; }
 
-// MFSGD_HDEPTH = 2 | 4: slots of the register ring of gathered rows (depth - 1 gathers in flight per run).
+// MFSGD_HDEPTH = 2 | 4: slots of the register ring of gathered rows (depth - 1 gathers in flight per run). Default 2 since
+// round 2: between the gather of p_u and its scatter another sub-warp's update of the same row is lost (store) or applied to
+// a stale row (red.add); gathering one step ahead instead of three halves that window. On the signal-dominant Netflix-shaped
+// set the held-out RMSE after epochs 1 / 2 / 3 is 10.8 / 3.1 / 1.2 % above the sequential oracle with depth 2 against
+// 27.5 / 8.5 / 4.0 % with depth 4, for 2.5 % of the epoch time (profiles/r02_experiments.md).
 static int run_depth() {
     static int dep = 0;
-    if (dep == 0) dep = env_int("MFSGD_HDEPTH", 4) == 2 ? 2 : 4;
+    if (dep == 0) dep = env_int("MFSGD_HDEPTH", 2) == 4 ? 4 : 2;
     return dep;
 }
 // MFSGD_PDL = 0: plain stream order between the run launches of consecutive visits. Default: programmatic
@@ -256,16 +260,18 @@ static cudaError_t launch_runs(Kernel kernel, int grid, cudaStream_t stream, boo
 // whole launches co-resident, which diverges: round-2 experiment, NaN in the first epoch) and its longest run is no longer
 // than twice a sub-warp's share of the launch (runs are handed out longest first, so long runs end well before the launch
 // does; a launch whose hot-item runs outlast everything else would still be merging when the next launch reads q_i).
-bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid) {
+bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid, int max_sub_warps) {
     const int per_warp = 32 / run_geometry_for(k).lanes;
     if (run_pdl() == 2) return true;                       // tuning aid: force it
     if (run_pdl() == 0 || env_int("MFSGD_HOT_CTAS", 0) > 0) return false;
     const int64_t sub_warps = (int64_t)full_grid * 8 * per_warp;
+    if (max_sub_warps > 0 && max_sub_warps < sub_warps) return false;      // a capped grid leaves SM slots free: no co-resident launches
     return (int64_t)n_units >= 2 * sub_warps && (int64_t)longest_run * sub_warps <= 2 * n_records;
 }
 
 cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int n_units, unsigned int* counter, bool fast, bool p_red,
-                                  int grid, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream, int* launches) {
+                                  int grid, int max_sub_warps, bool overlaps_previous, bool overlapped_by_next, cudaStream_t stream,
+                                  int* launches) {
     if (n_units <= 0) return cudaSuccess;
     const Geometry g = run_geometry_for(a.k);
     const int per_warp = 32 / g.lanes;            // runs a warp walks side by side
@@ -274,6 +280,10 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     // start from the same q_i and are averaged, the next wave builds on their result.
     const int max_grid = (n_units + 16 * per_warp - 1) / (16 * per_warp);
     if (grid > max_grid) grid = max_grid;
+    // ... and no more sub-warps than the stripe has users to spare: with more ratings in flight than half the users of the P
+    // sub-stripe, every row has concurrent writers all the time and parallel SGD stops resembling the sequential rule
+    // (the engine passes a quarter of the sub-stripe's users: at most ~2 ratings in flight per 4 users)
+    if (max_sub_warps > 0 && grid > max_sub_warps / (8 * per_warp)) grid = max_sub_warps / (8 * per_warp);
     if (grid < 1) grid = 1;
     // Overlap with the previous visit's launch only where it is a tail effect: both launches fill the machine (this
     // one offers >= 2 runs per resident sub-warp), so this grid's CTAs become resident as the other's retire. Letting

@@ -36,7 +36,7 @@ def signal_variant(w, lr=0.02, lambda_=0.02, epochs=None):
 # predictor within the epoch count (tests/golden/oracle_rmse_*_signal.json hold the curves and the constant predictor's RMSE).
 WORKLOADS.update({
     "ml100k_signal": signal_variant(WORKLOADS["ml100k"]),
-    "ml20m_signal": signal_variant(WORKLOADS["ml20m"]),
+    "ml20m_signal": signal_variant(WORKLOADS["ml20m"], epochs=20),
     "netflix_signal": signal_variant(WORKLOADS["netflix"]),
 })
 

@@ -20,10 +20,21 @@ def oracle_curve(name):
     return json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_rmse_%s.json" % name)))
 
 
-@pytest.mark.parametrize("name", ["ml20m", "netflix"])
+def assert_two_sided(got, want, what=""):
+    assert abs(got / want - 1.0) <= RMSE_TOL, (what, got, want, got / want - 1.0)
+
+
+@pytest.mark.parametrize("name", ["ml20m", "netflix", "ml20m_signal", "netflix_signal"])
 def test_hogwild_reaches_oracle_rmse_at_equal_epochs(name):
+    """BASELINE.json configs[1] and [2] on one GPU, on the throughput (noise-dominant) data and on the signal-dominant variant
+    (workloads.py: the constant predictor is at 0.94 there, the oracle ends 75-80 % below it): final held-out RMSE within
+    0.5 % of the sequential oracle's, both sides."""
     w = mf.WORKLOADS[name]
     ref = oracle_curve(name)
+    if len(ref["heldout_rmse_per_epoch"]) < w.epochs:
+        pytest.skip("oracle curve for %s is still incomplete" % name)
+    if name.endswith("_signal"):
+        assert ref["heldout_rmse_per_epoch"][w.epochs - 1] < 0.7 * ref["constant_predictor_rmse"]
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
     with mf.Engine(cfg) as eng:
         nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
@@ -32,22 +43,25 @@ def test_hogwild_reaches_oracle_rmse_at_equal_epochs(name):
         eng.set_eval_every_epoch(True)
         stats = eng.train(w.epochs)
     curve = [s.heldout_rmse for s in stats]
-    want = ref["heldout_rmse_per_epoch"]
-    assert len(want) == w.epochs
-    assert curve[-1] <= want[-1] * (1 + RMSE_TOL), (curve, want)
-    assert curve[-1] >= want[-1] * (1 - 0.02), (curve, want)
-    # and it gets there at a comparable pace: from the 3rd epoch on never more than 1 % behind the oracle
+    want = ref["heldout_rmse_per_epoch"][:w.epochs]
+    assert_two_sided(curve[-1], want[-1], (curve, want))
+    # and it gets there at a comparable pace: on the throughput data never more than 1 % from the oracle from the 3rd epoch on;
+    # on the signal-dominant data (a steep curve: every epoch is worth 3-20 %) never more than half an epoch behind
     for e in range(2, w.epochs):
-        assert curve[e] <= want[e] * 1.01, (e, curve[e], want[e])
+        if name.endswith("_signal"):
+            assert curve[e] <= 0.5 * (want[e] + want[e - 1]) * (1 + RMSE_TOL), (e, curve[e], want[e - 1], want[e])
+        else:
+            assert abs(curve[e] / want[e] - 1.0) <= 0.01, (e, curve[e], want[e])
 
 
-def test_ml100k_shaped_hogwild_close_to_oracle():
-    """configs[0] (the reference's own CPU-sized case) through the full-grid Hogwild path. 90 K ratings are far fewer than
-    the ratings a B200 keeps in flight, so parallel SGD trails the sequential oracle in the first epochs; after the
-    workload's 20 epochs it is within 1 % (measured +0.4 %). The 0.5 % bar of the north star is held on the ML-20M- and
-    Netflix-shaped workloads above; bit-level parity on this config is the deterministic mode's job (test_gpu_parity.py)."""
-    w = mf.WORKLOADS["ml100k"]
-    ref = oracle_curve("ml100k")
+@pytest.mark.parametrize("name", ["ml100k", "ml100k_signal"])
+def test_ml100k_shaped_hogwild_within_half_a_percent(name):
+    """configs[0] (the reference's own CPU-sized case) through the full-grid Hogwild path, both data variants: 0.5 %, two-sided,
+    after the workload's 20 epochs. 90 K ratings are far fewer than the ratings a B200 can keep in flight, so the launch
+    leaves most of the machine idle (no more sub-warps than half the users, runs of 256) and every user's row is updated with
+    red.global.add; bit-level parity on this config is the deterministic mode's job (test_gpu_parity.py)."""
+    w = mf.WORKLOADS[name]
+    ref = oracle_curve(name)
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_HOGWILD)
     with mf.Engine(cfg) as eng:
         nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
@@ -55,14 +69,28 @@ def test_ml100k_shaped_hogwild_close_to_oracle():
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)
         got = eng.rmse_heldout()[0]
-    want = ref["heldout_rmse_per_epoch"][-1]
-    assert np.isfinite(got) and got <= want * 1.01 and got >= want * 0.98, (got, want)
+    want = ref["heldout_rmse_per_epoch"][w.epochs - 1]
+    assert np.isfinite(got)
+    assert_two_sided(got, want, name)
 
 
-def test_dsgd_virtual_ring_netflix_shaped_reaches_oracle_rmse():
-    """The 8-member DSGD schedule (virtual ring on one GPU) on the full Netflix-shaped workload."""
-    w = mf.WORKLOADS["netflix"]
-    ref = oracle_curve("netflix")
+def assert_ring(got, ref, G, epochs):
+    """A ring is held between the two sequential executions of the reference rule: the stand-in's shuffled order and the DSGD
+    schedule's own block order (fixture key dsgd<G>, tools/oracle_reference_rmse.py --dsgd); 0.5 % on each side."""
+    shuffled = ref["heldout_rmse_per_epoch"][epochs - 1]
+    key = "dsgd%d" % G
+    ordered = ref[key]["heldout_rmse_per_epoch"][epochs - 1] if key in ref and len(ref[key]["heldout_rmse_per_epoch"]) >= epochs else shuffled
+    lo, hi = min(shuffled, ordered), max(shuffled, ordered)
+    assert lo * (1 - RMSE_TOL) <= got <= hi * (1 + RMSE_TOL), (got, shuffled, ordered)
+
+
+@pytest.mark.parametrize("name", ["netflix", "netflix_signal"])
+def test_dsgd_virtual_ring_netflix_shaped_reaches_oracle_rmse(name):
+    """The 8-member DSGD schedule (virtual ring on one GPU) on the full Netflix-shaped workload, both data variants."""
+    w = mf.WORKLOADS[name]
+    ref = oracle_curve(name)
+    if len(ref["heldout_rmse_per_epoch"]) < w.epochs:
+        pytest.skip("oracle curve for %s is still incomplete" % name)
     cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, seed=mf.SEED, mode=capi.MODE_DSGD, n_gpus=8,
                          flags=capi.FLAG_VIRTUAL_RING)
     with mf.Engine(cfg) as eng:
@@ -70,8 +98,7 @@ def test_dsgd_virtual_ring_netflix_shaped_reaches_oracle_rmse():
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)
         got = eng.rmse_heldout()[0]
-    want = ref["heldout_rmse_per_epoch"][-1]
-    assert got <= want * (1 + RMSE_TOL) and got >= want * (1 - 0.02), (got, want)
+    assert_ring(got, ref, 8, w.epochs)
 
 
 @pytest.mark.parametrize("name", ["yahoo", "powerlaw"])
@@ -94,8 +121,7 @@ def test_dsgd_virtual_ring_large_shapes_reach_oracle_rmse(name):
         eng.init_factors()
         eng.train(w.epochs, want_stats=False)
         got = eng.rmse_heldout()[0]
-    want = ref["heldout_rmse_per_epoch"][w.epochs - 1]
-    assert got <= want * (1 + RMSE_TOL) and got >= want * (1 - 0.02), (got, want)
+    assert_ring(got, ref, 8, w.epochs)
 
 
 def test_heavy_skew_does_not_collapse_throughput():

@@ -14,7 +14,7 @@ G = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 w = mf.WORKLOADS[name]
 epochs = int(sys.argv[3]) if len(sys.argv) > 3 else w.epochs
 kw = dict(seed=mf.SEED, flags=capi.FLAG_TIME_KERNELS)
-for env, key, conv in (("RW_SCATTER", "scatter", int), ("RW_BOOST", "merge_boost", float), ("RW_ROUNDS", "rounds", int), ("RW_HOT_SHARE", "hot_share", float), ("RW_STRIPES", "stripes_per_gpu", int),
+for env, key, conv in (("RW_PAT", "p_atomic_threshold", float), ("RW_SCATTER", "scatter", int), ("RW_BOOST", "merge_boost", float), ("RW_ROUNDS", "rounds", int), ("RW_HOT_SHARE", "hot_share", float), ("RW_STRIPES", "stripes_per_gpu", int),
                        ("RW_HOT_CHUNK", "hot_chunk", int), ("RW_SHARDS", "shards_per_gpu", int)):
     if os.environ.get(env):
         kw[key] = conv(os.environ[env])
@@ -33,7 +33,7 @@ with mf.Engine(cfg) as eng:
     eng.set_eval_every_epoch(True)
     st = eng.train(epochs)
 out.update(n_train=int(nt), n_heldout=int(nh), stripes_per_gpu=int(info.stripes_per_gpu), shards_per_gpu=int(info.shards_per_gpu),
-           rounds=int(info.rounds), hot_items=int(info.n_hot_items),
+           rounds=int(info.rounds), hot_items=int(info.n_hot_items), heavy_users=int(info.n_heavy_users), run_length=int(info.run_length),
            epoch_ms=[s.epoch_ms for s in st], heldout_rmse_per_epoch=[s.heldout_rmse for s in st],
            cold_ms=[s.cold_ms for s in st], hot_ms=[s.hot_ms for s in st], launches=[s.update_launches for s in st])
 ms = float(np.median(out["epoch_ms"]))
