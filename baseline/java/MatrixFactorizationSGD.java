@@ -248,6 +248,98 @@ public final class MatrixFactorizationSGD {
         return Long.remainderUnsigned(hash64(seed, STREAM_HELDOUT, n), 10L) == 0L;
     }
 
+    /* ------------------------------------------------------------------------------------------
+     * Model extension (SURVEY.md 8f.4): global mean and user / item biases. Same loop, same order;
+     * prediction mu + b_u + b_i + p_u.q_i. With both switches off this is factorize().
+     * ------------------------------------------------------------------------------------------ */
+
+    /** Factors plus the extension's terms. */
+    public static final class Model {
+        public final float[] P, Q, userBias, itemBias;
+        public final float globalMean;
+        public final int nUsers, nItems, k;
+        Model(float[] P, float[] Q, float[] bu, float[] bi, float mu, int nUsers, int nItems, int k) {
+            this.P = P; this.Q = Q; this.userBias = bu; this.itemBias = bi; this.globalMean = mu;
+            this.nUsers = nUsers; this.nItems = nItems; this.k = k;
+        }
+    }
+
+    /**
+     * Training mean, defined on exact integers so that every implementation (sequential, threaded, GPU) gets the same
+     * binary32 value whatever its summation order: S = sum floor(r * 2^20) (the product is exact in binary64),
+     * mu = (float) (S / n / 2^20).
+     */
+    public static float globalMean(float[] ratings) {
+        long s = 0L;
+        for (float r : ratings) s += (long) Math.floor((double) r * 1048576.0);
+        return ratings.length == 0 ? 0.0f : (float) ((double) s / (double) ratings.length / 1048576.0);
+    }
+
+    /**
+     * One update of the extended model on the CENTRED rating rc = r - mu. pred = (dot + b_u) + b_i, e = rc - pred;
+     * biases (when present): b <- b + lr * (e - lambda * b), from the pre-update values; factors as in sgdUpdate.
+     */
+    public static float sgdUpdateModel(float[] P, int pOff, float[] Q, int qOff, int k, float[] bu, int u, float[] bi, int i,
+                                       float rc, float lr, float lambda) {
+        float dot = 0.0f;
+        for (int f = 0; f < k; f++) dot = dot + P[pOff + f] * Q[qOff + f];
+        float e;
+        if (bu != null) {
+            float pred = dot + bu[u];
+            pred = pred + bi[i];
+            e = rc - pred;
+            float b0 = bu[u], b1 = bi[i];
+            bu[u] = b0 + lr * (e - lambda * b0);
+            bi[i] = b1 + lr * (e - lambda * b1);
+        } else {
+            e = rc - dot;
+        }
+        for (int f = 0; f < k; f++) {
+            float pf = P[pOff + f], qf = Q[qOff + f];
+            P[pOff + f] = pf + lr * (e * qf - lambda * pf);
+            Q[qOff + f] = qf + lr * (e * pf - lambda * qf);
+        }
+        return e;
+    }
+
+    public static Model factorizeModel(int[] users, int[] items, float[] ratings, int nUsers, int nItems, int k,
+                                       float lr, float lambda, int epochs, long seed, boolean useGlobalMean, boolean useBiases) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || nUsers <= 0 || nItems <= 0 || epochs < 0) throw new IllegalArgumentException("bad shape");
+        final int n = ratings.length;
+        float[] P = new float[nUsers * k], Q = new float[nItems * k];
+        float scale = defaultInitScale(k);
+        initFactors(P, nUsers, k, seed, STREAM_P_INIT, scale);
+        initFactors(Q, nItems, k, seed, STREAM_Q_INIT, scale);
+        float[] bu = useBiases ? new float[nUsers] : null, bi = useBiases ? new float[nItems] : null;    // biases start at 0
+        final float mu = useGlobalMean ? globalMean(ratings) : 0.0f;
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            int[] order = shuffle(seed, epoch, n);
+            for (int j = 0; j < n; j++) {
+                int t = order[j];
+                sgdUpdateModel(P, users[t] * k, Q, items[t] * k, k, bu, users[t], bi, items[t], ratings[t] - mu, lr, lambda);
+            }
+        }
+        return new Model(P, Q, bu, bi, mu, nUsers, nItems, k);
+    }
+
+    /** RMSE of the extended model: e = (r - mu) - ((dot + b_u) + b_i). */
+    public static double rmseModel(Model m, int[] users, int[] items, float[] ratings) {
+        double sse = 0.0;
+        final int n = ratings.length, k = m.k;
+        for (int t = 0; t < n; t++) {
+            int pOff = users[t] * k, qOff = items[t] * k;
+            float dot = 0.0f;
+            for (int f = 0; f < k; f++) dot = dot + m.P[pOff + f] * m.Q[qOff + f];
+            float pred = dot;
+            if (m.userBias != null) { pred = pred + m.userBias[users[t]]; pred = pred + m.itemBias[items[t]]; }
+            float e = (ratings[t] - m.globalMean) - pred;
+            sse += (double) e * (double) e;
+        }
+        return n == 0 ? 0.0 : Math.sqrt(sse / (double) n);
+    }
+
     /** ML-100K-shaped demo: sequential and threaded, updates/s and held-out RMSE. */
     public static void main(String[] args) throws Exception {
         final long seed = 20261018L;

@@ -374,6 +374,19 @@ def run_ours(args):
                                                "hot_kernels": sum(s.hot_ms for s in stats) / args.steps,
                                                "q_rotation": sum(s.exchange_ms for s in stats) / args.steps,
                                                "note": "cold and hot overlap (two streams); spans start at the sub-epoch fork"}}
+        # the sequential oracle's held-out RMSE at the same epoch count, when the committed curve reaches that far
+        try:
+            fx = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_rmse_%s.json" % args.workload)))
+            ep = args.warmup + args.steps
+            if len(fx.get("heldout_rmse_per_epoch", [])) >= ep:
+                want = fx["heldout_rmse_per_epoch"][ep - 1]
+                out["rmse_vs_oracle"] = {"epochs": ep, "gpu": heldout_rmse, "oracle_sequential": want, "rel": heldout_rmse / want - 1.0,
+                                         "constant_predictor_rmse": fx.get("constant_predictor_rmse")}
+                key = "dsgd%d" % world
+                if key in fx and len(fx[key]["heldout_rmse_per_epoch"]) >= ep:
+                    out["rmse_vs_oracle"]["oracle_dsgd_order"] = fx[key]["heldout_rmse_per_epoch"][ep - 1]
+        except Exception:      # noqa: BLE001  (no fixture for this workload)
+            pass
         if cpu is not None:
             out["cpu_baseline"] = cpu
         if cpu_ml100k is not None:

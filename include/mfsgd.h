@@ -49,6 +49,11 @@ extern "C" {
 #define MFSGD_SCATTER_ATOMIC_Q 2 /* store p_u, red q_i */
 #define MFSGD_SCATTER_ATOMIC_P 3 /* red p_u, store q_i */
 
+/* mfsgd_config.model -- model extension (stand-in factorizeModel :305): r ~ mu + b_u + b_i + p_u . q_i */
+#define MFSGD_MODEL_GLOBAL_MEAN 1u /* mu = mean of the training ratings (stand-in globalMean :272), subtracted from every
+                                      rating as it is loaded; mfsgd_get_model returns it                               */
+#define MFSGD_MODEL_BIASES      2u /* user and item biases, b <- b + lr * (e - lambda * b), initialised to 0            */
+
 /* mfsgd_config.flags */
 #define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
 #define MFSGD_FLAG_VIRTUAL_RING   2u /* place all n_gpus ring members on one device (scheduler test mode) */
@@ -92,11 +97,12 @@ typedef struct mfsgd_config {
                                   64..1024                                                                  */
     float    merge_boost;      /* runs of one item that share a launch are merged with weight min(1, merge_boost / runs);
                                   0 = default 1.25, 1 = plain model averaging; must be < 2                      */
+    uint32_t model;            /* MFSGD_MODEL_* : 0 = the reference model r ~ p_u . q_i                          */
     float    p_atomic_threshold; /* run kernel: a user expected to have >= this many ratings in flight at once (its share of a
                                   launch's records x the ratings the resident sub-warps hold in flight) is a HEAVY user: its row is
                                   updated in memory with red.global.add instead of a store, so concurrent updates are not lost.
                                   0 = default 0.25, < 0 = never (round-1 behaviour); MFSGD_SCATTER_ATOMIC_P = every user       */
-    int32_t  reserved[2];
+    int32_t  reserved[1];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
@@ -171,6 +177,10 @@ MFSGD_API int  mfsgd_generate_synthetic(mfsgd_handle* h, const mfsgd_synth_param
 MFSGD_API int  mfsgd_init_factors(mfsgd_handle* h);                        /* MatrixFactorizationSGD.java:53 */
 MFSGD_API int  mfsgd_set_factors(mfsgd_handle* h, const float* P, const float* Q);  /* full nU*k, nI*k host arrays */
 MFSGD_API int  mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q);     /* multi-process: only this rank's rows are written */
+/* Model extension: the global mean (0 when off) and the biases (full n_users / n_items host arrays, nullable; multi-process:
+ * only this rank's rows are written). MFSGD_E_STATE for the bias arrays when MFSGD_MODEL_BIASES is off. */
+MFSGD_API int  mfsgd_get_model(mfsgd_handle* h, float* global_mean, float* user_bias, float* item_bias);
+MFSGD_API int  mfsgd_set_biases(mfsgd_handle* h, const float* user_bias, const float* item_bias);
 /* Row ranges this process owns (users [u_lo,u_hi), items [i_lo,i_hi)) -- whole matrices when world_size==1. */
 MFSGD_API int  mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi);
 

@@ -173,6 +173,8 @@ struct Member {              // one ring member ("GPU g")
     int32_t u_lo = 0, u_hi = 0;      // owned P rows
     float* P = nullptr;
     float* Q[2] = {nullptr, nullptr};
+    float* BU = nullptr;              // model extension: biases of the owned users ...
+    float* BQ[2] = {nullptr, nullptr}; // ... and of the held item group (travels with Q)
     int64_t q_cap_rows = 0;
     int cur = 0;             // Q buffer holding the current shard group
     int held_group = 0;      // which shard group that is
@@ -227,6 +229,8 @@ struct mfsgd_handle {
     int H = 0;
     std::vector<uint32_t> heavy_bits;   // bit u set: heavy user (empty: none)
     int n_heavy = 0;
+    float center = 0.f;      // model extension: global mean, subtracted from every rating at load (0 when off)
+    bool biases = false;
     float scale = 0.f;
     std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
     std::vector<Member> members;                    // the ring members this process drives
@@ -356,6 +360,9 @@ static void free_member_data(Member& m) {
     dev_free(m.P);
     dev_free(m.Q[0]);
     dev_free(m.Q[1]);
+    dev_free(m.BU);
+    dev_free(m.BQ[0]);
+    dev_free(m.BQ[1]);
     dev_free(m.recs[0]);
     dev_free(m.recs[1]);
     dev_free(m.d_block_off);
@@ -484,6 +491,7 @@ static int validate_config(const mfsgd_config* c) {
         return fail(MFSGD_E_INVALID_ARG, "DETERMINISTIC mode keeps the caller's record order: no blocking");
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
     if (c->hot_chunk < 0 || c->hot_chunk > 65536) return fail(MFSGD_E_INVALID_ARG, "hot_chunk=%d out of range (0..65536)", c->hot_chunk);
+    if (c->model & ~(MFSGD_MODEL_GLOBAL_MEAN | MFSGD_MODEL_BIASES)) return fail(MFSGD_E_INVALID_ARG, "unknown model bits 0x%x", c->model);
     if (c->p_atomic_threshold != c->p_atomic_threshold) return fail(MFSGD_E_INVALID_ARG, "p_atomic_threshold is NaN");
     if (!(c->merge_boost >= 0.f) || c->merge_boost >= 2.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
     if (c->merge_boost > 0.f && c->merge_boost < 1.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
@@ -592,6 +600,7 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     h->multi_process = cfg->world_size > 1;
     if (const char* mw = getenv("MFSGD_MIN_WINDOWS")) h->min_windows = std::max(1, atoi(mw));
     h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
+    h->biases = (cfg->model & MFSGD_MODEL_BIASES) != 0;
     const bool virtual_ring = (cfg->flags & MFSGD_FLAG_VIRTUAL_RING) != 0;
     const int n_local = h->multi_process ? 1 : h->G;
     if (!virtual_ring && !h->multi_process && cfg->device + h->G > ndev) {
@@ -723,10 +732,12 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     uint64_t *ucum = nullptr, *icum = nullptr;
     int32_t *ub = nullptr, *ib = nullptr;
     int* bad = nullptr;
+    unsigned long long* rsum = nullptr;
     void* temp = nullptr;
     int rc = MFSGD_OK;
+    const bool want_mean = (c.model & MFSGD_MODEL_GLOBAL_MEAN) != 0;
     auto cleanup = [&]() {
-        dev_free(ucnt); dev_free(icnt); dev_free(ucum); dev_free(icum); dev_free(ub); dev_free(ib); dev_free(bad);
+        dev_free(ucnt); dev_free(icnt); dev_free(ucum); dev_free(icum); dev_free(ub); dev_free(ib); dev_free(bad); dev_free(rsum);
         if (temp) raw_free(temp);
     };
 #define CKC(call)                                                                                           \
@@ -746,6 +757,8 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     CKC(dev_alloc(&ub, (size_t)h->UB + 1));
     CKC(dev_alloc(&ib, (size_t)h->IB + 1));
     CKC(dev_alloc(&bad, 1));
+    CKC(dev_alloc(&rsum, 1));
+    CKC(cudaMemsetAsync(rsum, 0, sizeof(unsigned long long), m.stream));
     CKC(cudaMemsetAsync(ucnt, 0, ((size_t)c.n_users + 1) * 4, m.stream));
     CKC(cudaMemsetAsync(icnt, 0, ((size_t)c.n_items + 1) * 4, m.stream));
     CKC(cudaMemsetAsync(bad, 0, sizeof(int), m.stream));
@@ -754,12 +767,13 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
         rc = chunk_stage(ch, src, start, count, m.stream, &m.launches);
         if (rc != MFSGD_OK) { cleanup(); return rc; }
         CKC(launch_count_rows(ch.u, ch.i, src.synthetic ? ch.held : nullptr, count, ucnt, icnt, c.n_users, c.n_items, bad,
-                              m.stream, &m.launches));
+                              ch.r, want_mean ? rsum : nullptr, m.stream, &m.launches));
     }
     if (src.sharded) {     // every rank counted its own slice: sum the per-row counts (and the bad-id flag) over the ring
         ncclResult_t r1 = g_nccl.AllReduce(ucnt, ucnt, (size_t)c.n_users, ncclUint32, ncclSum, h->comm, m.stream);
         ncclResult_t r2 = r1 == ncclSuccess ? g_nccl.AllReduce(icnt, icnt, (size_t)c.n_items, ncclUint32, ncclSum, h->comm, m.stream) : r1;
         ncclResult_t r3 = r2 == ncclSuccess ? g_nccl.AllReduce(bad, bad, 1, ncclInt32, ncclMax, h->comm, m.stream) : r2;
+        if (r3 == ncclSuccess) r3 = g_nccl.AllReduce(rsum, rsum, 1, ncclUint64, ncclSum, h->comm, m.stream);
         if (r3 != ncclSuccess) {
             cleanup();
             return fail(MFSGD_E_NCCL, "all-reduce of the row counts: %s", g_nccl.GetErrorString(r3));
@@ -779,6 +793,8 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
     h->item_bounds.assign((size_t)h->IB + 1, 0);
     int bad_host = 0;
     uint64_t total_train = 0;
+    unsigned long long rsum_host = 0;
+    CKC(cudaMemcpyAsync(&rsum_host, rsum, sizeof(rsum_host), cudaMemcpyDeviceToHost, m.stream));
     CKC(cudaMemcpyAsync(h->user_bounds.data(), ub, ((size_t)h->UB + 1) * 4, cudaMemcpyDeviceToHost, m.stream));
     CKC(cudaMemcpyAsync(h->item_bounds.data(), ib, ((size_t)h->IB + 1) * 4, cudaMemcpyDeviceToHost, m.stream));
     CKC(cudaMemcpyAsync(&bad_host, bad, sizeof(int), cudaMemcpyDeviceToHost, m.stream));
@@ -809,6 +825,8 @@ static int compute_bounds(mfsgd_handle* h, const Source& src, Chunk& ch) {
         std::sort(h->hot_items.begin(), h->hot_items.end());
     }
     h->H = (int)h->hot_items.size();
+    // model extension: the training mean from the exact integer sum (MatrixFactorizationSGD.java:272 globalMean)
+    h->center = (want_mean && total_train > 0) ? (float)((double)(long long)rsum_host / (double)total_train / 1048576.0) : 0.f;
     // heavy users: expected ratings in flight at once >= p_atomic_threshold. A launch of the run kernel walks one P sub-stripe
     // (1 / (G * mu) of the ratings, evenly over the rounds) with every resident sub-warp holding ~2 ratings between the
     // gather of p_u and its scatter, so user u has about cnt_u * G * mu / total * (2 * resident sub-warps) ratings in flight.
@@ -840,6 +858,7 @@ static void uniform_bounds(mfsgd_handle* h) {
     h->H = 0;
     h->heavy_bits.clear();
     h->n_heavy = 0;
+    h->center = 0.f;
     h->user_bounds.resize((size_t)h->UB + 1);
     h->item_bounds.resize((size_t)h->IB + 1);
     for (int b = 0; b <= h->UB; b++) h->user_bounds[(size_t)b] = (int32_t)((int64_t)h->cfg.n_users * b / h->UB);
@@ -859,6 +878,12 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     CK(dev_alloc(&m.P, (size_t)(m.u_hi - m.u_lo) * c.k));
     CK(dev_alloc(&m.Q[0], (size_t)cap * c.k));
     if (h->G > 1) CK(dev_alloc(&m.Q[1], (size_t)cap * c.k));
+    dev_free(m.BU); dev_free(m.BQ[0]); dev_free(m.BQ[1]);
+    if (h->biases) {
+        CK(dev_alloc(&m.BU, (size_t)(m.u_hi - m.u_lo)));
+        CK(dev_alloc(&m.BQ[0], (size_t)cap));
+        if (h->G > 1) CK(dev_alloc(&m.BQ[1], (size_t)cap));
+    }
     m.cur = 0;
     m.held_group = m.g;
     CK(dev_alloc(&m.d_owner_u, (size_t)c.n_users));
@@ -908,6 +933,7 @@ static int bucket_member(mfsgd_handle* h, Member& m, const Source& src, Chunk& c
     b.col_div = col_div;
     b.n_cols = n_cols;
     b.want_held = want_held;
+    b.center = h->center;          // model extension: ratings are stored centred (training and held-out sets alike)
     if (split_hot && h->H > 0) {
         b.hot_index = m.d_hot_index;
         b.n_hot = h->H;
@@ -1103,7 +1129,7 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
                 if (e == cudaSuccess) e = dev_alloc(&m.recs[0], (size_t)src.total);
                 if (e == cudaSuccess) e = dev_alloc(&m.keys_a, (size_t)src.total);
                 if (e == cudaSuccess) e = dev_alloc(&m.keys_b, (size_t)src.total);
-                if (e == cudaSuccess) e = launch_pack_records(ch.u, ch.i, ch.r, src.total, m.recs_orig, m.stream, &m.launches);
+                if (e == cudaSuccess) e = launch_pack_records(ch.u, ch.i, ch.r, src.total, h->center, m.recs_orig, m.stream, &m.launches);
                 if (e == cudaSuccess) e = deterministic_order_gather(nullptr, nullptr, (int32_t)src.total, 0, 0, m.keys_a, m.keys_b, nullptr, &m.sort_temp_bytes, m.stream, nullptr);
                 if (e == cudaSuccess) e = raw_alloc(&m.sort_temp, m.sort_temp_bytes ? m.sort_temp_bytes : 1);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
@@ -1271,6 +1297,10 @@ static int mfsgd_init_factors_body(mfsgd_handle* h) {
         CK(launch_init_factors(m.P, m.u_hi - m.u_lo, h->cfg.k, m.u_lo, h->cfg.seed, STREAM_P_INIT, h->scale, m.stream, &m.launches));
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
         CK(launch_init_factors(m.Q[m.cur], hi - lo, h->cfg.k, lo, h->cfg.seed, STREAM_Q_INIT, h->scale, m.stream, &m.launches));
+        if (h->biases) {          // MatrixFactorizationSGD.java:305: biases start at 0
+            CK(cudaMemsetAsync(m.BU, 0, (size_t)(m.u_hi - m.u_lo) * 4, m.stream));
+            CK(cudaMemsetAsync(m.BQ[m.cur], 0, (size_t)(hi - lo) * 4, m.stream));
+        }
     }
     for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
     h->factors_ready = true;
@@ -1290,6 +1320,10 @@ static int mfsgd_set_factors_body(mfsgd_handle* h, const float* P, const float* 
         CK(cudaMemcpyAsync(m.P, P + (size_t)m.u_lo * k, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
         CK(cudaMemcpyAsync(m.Q[m.cur], Q + (size_t)lo * k, (size_t)(hi - lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
+        if (h->biases && !h->factors_ready) {      // fresh factors: biases start at 0 (mfsgd_set_biases overrides)
+            CK(cudaMemsetAsync(m.BU, 0, (size_t)(m.u_hi - m.u_lo) * 4, m.stream));
+            CK(cudaMemsetAsync(m.BQ[m.cur], 0, (size_t)(hi - lo) * 4, m.stream));
+        }
     }
     for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
     h->factors_ready = true;
@@ -1309,6 +1343,45 @@ static int mfsgd_get_factors_body(mfsgd_handle* h, float* P, float* Q) {
         CK(cudaMemcpyAsync(P + (size_t)m.u_lo * k, m.P, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
         CK(cudaMemcpyAsync(Q + (size_t)lo * k, m.Q[m.cur], (size_t)(hi - lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
+    }
+    for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
+    return MFSGD_OK;
+}
+
+static int mfsgd_get_model_body(mfsgd_handle* h, float* global_mean, float* user_bias, float* item_bias);
+extern "C" int mfsgd_get_model(mfsgd_handle* h, float* global_mean, float* user_bias, float* item_bias) {
+    return guarded([&]() { return mfsgd_get_model_body(h, global_mean, user_bias, item_bias); });
+}
+static int mfsgd_get_model_body(mfsgd_handle* h, float* global_mean, float* user_bias, float* item_bias) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "no ratings loaded (the global mean is the training set's)");
+    if (global_mean) *global_mean = h->center;
+    if (!user_bias && !item_bias) return MFSGD_OK;
+    if (!h->biases) return fail(MFSGD_E_STATE, "MFSGD_MODEL_BIASES is off");
+    if (!h->factors_ready) return fail(MFSGD_E_STATE, "factors are not initialised");
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        if (user_bias) CK(cudaMemcpyAsync(user_bias + m.u_lo, m.BU, (size_t)(m.u_hi - m.u_lo) * 4, cudaMemcpyDeviceToHost, m.stream));
+        const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
+        if (item_bias) CK(cudaMemcpyAsync(item_bias + lo, m.BQ[m.cur], (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, m.stream));
+    }
+    for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
+    return MFSGD_OK;
+}
+
+static int mfsgd_set_biases_body(mfsgd_handle* h, const float* user_bias, const float* item_bias);
+extern "C" int mfsgd_set_biases(mfsgd_handle* h, const float* user_bias, const float* item_bias) {
+    return guarded([&]() { return mfsgd_set_biases_body(h, user_bias, item_bias); });
+}
+static int mfsgd_set_biases_body(mfsgd_handle* h, const float* user_bias, const float* item_bias) {
+    if (!h || !user_bias || !item_bias) return fail(MFSGD_E_INVALID_ARG, "null argument");
+    if (!h->biases) return fail(MFSGD_E_STATE, "MFSGD_MODEL_BIASES is off");
+    if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before setting biases");
+    for (Member& m : h->members) {
+        CK(cudaSetDevice(m.device));
+        CK(cudaMemcpyAsync(m.BU, user_bias + m.u_lo, (size_t)(m.u_hi - m.u_lo) * 4, cudaMemcpyHostToDevice, m.stream));
+        const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
+        CK(cudaMemcpyAsync(m.BQ[m.cur], item_bias + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, m.stream));
     }
     for (Member& m : h->members) { CK(cudaSetDevice(m.device)); CK(cudaStreamSynchronize(m.stream)); }
     return MFSGD_OK;
@@ -1364,6 +1437,10 @@ static int rotate_part(mfsgd_handle* h, Member& m, int part, cudaStream_t after)
     CKN(g_nccl.GroupStart());
     CKN(g_nccl.Send(sptr, (size_t)(s_hi - s_lo) * k, ncclFloat, to, h->comm, m.copy_stream));
     CKN(g_nccl.Recv(rptr, (size_t)(r_hi - r_lo) * k, ncclFloat, from, h->comm, m.copy_stream));
+    if (h->biases) {         // the slice's item biases travel with it
+        CKN(g_nccl.Send(m.BQ[m.cur] + (s_lo - group_lo(h, send_grp)), (size_t)(s_hi - s_lo), ncclFloat, to, h->comm, m.copy_stream));
+        CKN(g_nccl.Recv(m.BQ[m.cur ^ 1] + (r_lo - group_lo(h, recv_grp)), (size_t)(r_hi - r_lo), ncclFloat, from, h->comm, m.copy_stream));
+    }
     CKN(g_nccl.GroupEnd());
     CK(cudaEventRecord(m.ev_part_recv[(size_t)part], m.copy_stream));
     m.part_recv_pending[(size_t)part] = 1;
@@ -1391,6 +1468,10 @@ static int rotate_q(mfsgd_handle* h) {
         CKN(g_nccl.GroupStart());
         CKN(g_nccl.Send(m.Q[m.cur], send_n, ncclFloat, to, h->comm, m.stream));
         CKN(g_nccl.Recv(m.Q[m.cur ^ 1], recv_n, ncclFloat, from, h->comm, m.stream));
+        if (h->biases) {
+            CKN(g_nccl.Send(m.BQ[m.cur], send_n / k, ncclFloat, to, h->comm, m.stream));
+            CKN(g_nccl.Recv(m.BQ[m.cur ^ 1], recv_n / k, ncclFloat, from, h->comm, m.stream));
+        }
         CKN(g_nccl.GroupEnd());
         m.launches += 1;
         m.cur ^= 1;
@@ -1413,6 +1494,12 @@ static int rotate_q(mfsgd_handle* h) {
             CK(cudaMemcpyAsync(dst.Q[dst.cur ^ 1], m.Q[m.cur], bytes, cudaMemcpyDeviceToDevice, m.copy_stream));
         else
             CK(cudaMemcpyPeerAsync(dst.Q[dst.cur ^ 1], dst.device, m.Q[m.cur], m.device, bytes, m.copy_stream));
+        if (h->biases) {
+            if (dst.device == m.device)
+                CK(cudaMemcpyAsync(dst.BQ[dst.cur ^ 1], m.BQ[m.cur], bytes / k, cudaMemcpyDeviceToDevice, m.copy_stream));
+            else
+                CK(cudaMemcpyPeerAsync(dst.BQ[dst.cur ^ 1], dst.device, m.BQ[m.cur], m.device, bytes / k, m.copy_stream));
+        }
         CK(cudaEventRecord(m.ev_sent, m.copy_stream));   // also the receiver's "data arrived" signal
     }
     for (Member& m : h->members) {
@@ -1715,6 +1802,8 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 a.seed = c.seed;
                 a.epoch = (uint32_t)h->epoch;
                 a.virt = h->virtual_shuffle ? 1 : 0;
+                a.BU = h->biases ? m.BU : nullptr;
+                a.BI = h->biases ? m.BQ[m.cur] : nullptr;
                 if (c.mode == MFSGD_MODE_DETERMINISTIC) {
                     a.recs = m.recs[0];
                     a.first = 0;
@@ -1861,20 +1950,20 @@ static int rmse_sets(mfsgd_handle* h, std::vector<EvalSet*>& sets, bool train_se
                 for (int sa = 0; sa < h->mu; sa++) {
                     const int64_t lo = m.block_off[(size_t)sa * h->IB + (size_t)grp * h->mi];
                     const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
-                    CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                    CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                        m.d_sse, m.n_sms, m.stream, &m.launches));
                     if (h->H > 0) {   // the hot buckets of (sa, grp) are contiguous too
                         const size_t hb = (size_t)h->mu * h->IB + (size_t)sa * h->H;
                         const int64_t hlo = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)grp * h->mi]];
                         const int64_t hhi = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)(grp + 1) * h->mi]];
-                        CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                        CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                            m.d_sse, m.n_sms, m.stream, &m.launches));
                     }
                 }
             } else {
                 EvalSet* e = sets[j];
                 const int64_t lo = e->group_off[(size_t)grp], hi = e->group_off[(size_t)grp + 1];
-                CK(launch_rmse_sse(e->recs + lo, hi - lo, m.P, m.Q[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch, m.d_sse,
+                CK(launch_rmse_sse(e->recs + lo, hi - lo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch, m.d_sse,
                                    m.n_sms, m.stream, &m.launches));
             }
         }
@@ -1938,7 +2027,7 @@ static int mfsgd_rmse_train_body(mfsgd_handle* h, double* rmse_out, double* sse_
         Member& m = h->members[0];
         CK(cudaSetDevice(m.device));
         CK(cudaMemsetAsync(m.d_sse, 0, sizeof(double), m.stream));
-        CK(launch_rmse_sse(m.recs_orig, m.n_recs, m.P, m.Q[m.cur], h->cfg.k, m.u_lo, 0, m.d_scratch, m.d_sse, m.n_sms, m.stream, &m.launches));
+        CK(launch_rmse_sse(m.recs_orig, m.n_recs, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], h->cfg.k, m.u_lo, 0, m.d_scratch, m.d_sse, m.n_sms, m.stream, &m.launches));
         double sse = 0.0;
         CK(cudaMemcpyAsync(&sse, m.d_sse, sizeof(double), cudaMemcpyDeviceToHost, m.stream));
         CK(cudaStreamSynchronize(m.stream));

@@ -58,6 +58,9 @@ struct UpdateArgs {
     uint32_t epoch, blk_id;
     uint64_t seed;
     int64_t blk_start, blk_n;
+    // model extension (MatrixFactorizationSGD.java:282 sgdUpdateModel): user / item biases, indexed like P / Q; both null = off
+    float* BU;
+    float* BI;
 };
 
 // (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
@@ -102,8 +105,9 @@ bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run,
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
 int rmse_scratch_doubles();
-cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, int32_t k, int32_t u_base,
-                            int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
+// BU / BI: biases of the model extension (nullable together), indexed like P / Q.
+cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, const float* BU, const float* BI, int32_t k,
+                            int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
                             int* launches);
 
 // factor init (MatrixFactorizationSGD.java:53) for local rows [row_lo, row_lo + n_rows).
@@ -122,9 +126,10 @@ cudaError_t launch_generate(const SynthArgs& s, int64_t start, int64_t count, in
 
 // (1) bucketing + shuffle
 // per-row rating counts of the training records (held != 0 records are skipped when held != nullptr)
+// r / rating_sum (nullable together): *rating_sum += sum floor(r * 2^20) over the counted records (MatrixFactorizationSGD.java:272)
 cudaError_t launch_count_rows(const int32_t* u, const int32_t* i, const uint8_t* held, int64_t n, uint32_t* user_cnt,
-                              uint32_t* item_cnt, int32_t n_users, int32_t n_items, int* bad_flag, cudaStream_t stream,
-                              int* launches);
+                              uint32_t* item_cnt, int32_t n_users, int32_t n_items, int* bad_flag, const float* r,
+                              unsigned long long* rating_sum, cudaStream_t stream, int* launches);
 // bounds[b] = first row whose exclusive cumulative count reaches b * total / nblocks; bounds[nblocks] = n_rows.
 // cum = exclusive prefix sums of the counts (n_rows + 1 entries, cum[n_rows] = total).
 cudaError_t launch_balanced_bounds(const uint64_t* cum, int32_t n_rows, int32_t nblocks, int32_t* bounds,
@@ -152,6 +157,7 @@ struct BucketArgs {
     const int32_t* hot_index;
     int32_t hot_base, n_hot;
     const uint32_t* heavy_bits;   // nullable: bit u set -> the scattered record carries the heavy-user mark (common.cuh REC_USER_MASK)
+    float center;                 // subtracted from every rating as it is scattered (the model extension's global mean; else 0)
 };
 inline int bucket_rows(const BucketArgs& b) { return (b.ub_hi - b.ub_lo + b.row_div - 1) / b.row_div; }
 inline int bucket_block_count(const BucketArgs& b) {
@@ -168,7 +174,7 @@ cudaError_t launch_block_scatter(const BucketArgs& b, unsigned long long* cursor
 cudaError_t launch_block_shuffle(const Rec* in, Rec* out, const int64_t* block_off, int32_t nblocks, int64_t n,
                                  uint64_t seed, uint32_t epoch, uint32_t block_id_base, cudaStream_t stream, int* launches);
 // SoA -> AoS in input order (deterministic mode keeps the caller's record order).
-cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, Rec* out,
+cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, float center, Rec* out,
                                 cudaStream_t stream, int* launches);
 // AoS -> SoA
 cudaError_t launch_unpack_records(const Rec* in, int64_t n, int32_t* u, int32_t* i, float* r, cudaStream_t stream, int* launches);

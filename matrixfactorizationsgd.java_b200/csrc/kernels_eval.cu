@@ -15,7 +15,8 @@ constexpr int RMSE_MAX_CTAS = 148 * 8;
 template <int LANES, int VEC, bool FULL>
 __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __restrict__ recs, int64_t n,
                                                                 const float* __restrict__ P,
-                                                                const float* __restrict__ Q, int k, int u_base,
+                                                                const float* __restrict__ Q, const float* __restrict__ BU,
+                                                                const float* __restrict__ BI, int k, int u_base,
                                                                 int i_base, double* __restrict__ partial) {
     constexpr int GPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __res
                 if (act && (FULL || c < chunks)) s = dot4_acc(s, ld_row4(prow + 4 * c), ld_row4(qrow + 4 * c));
             }
             s = group_sum<LANES>(s);
+            if (BU != nullptr && act) s = __fadd_rn(__fadd_rn(s, __ldcg(BU + (u - u_base))), __ldcg(BI + (i - i_base)));   // rmseModel :328
             const float e = __fsub_rn(r, s);
             if (act && gl == 0) acc += (double)e * (double)e;
         }
@@ -167,8 +169,8 @@ inline int grid_for(int64_t n, int threads, int max_ctas) {
 
 int rmse_scratch_doubles() { return RMSE_MAX_CTAS; }
 
-cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, int32_t k, int32_t u_base,
-                            int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
+cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, const float* BU, const float* BI, int32_t k,
+                            int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
                             int* launches) {
     if (n <= 0) return cudaSuccess;
     const Geometry g = geometry_for(k);
@@ -178,7 +180,7 @@ cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const fl
     if (grid > (tiles + 7) / 8) grid = (int)((tiles + 7) / 8);
     if (grid < 1) grid = 1;
 #define CALL(L, V, F) \
-    rmse_sse_kernel<L, V, F><<<grid, RMSE_THREADS, 0, stream>>>(recs, n, P, Q, k, u_base, i_base, scratch)
+    rmse_sse_kernel<L, V, F><<<grid, RMSE_THREADS, 0, stream>>>(recs, n, P, Q, BU, BI, k, u_base, i_base, scratch)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     cudaError_t err = cudaGetLastError();

@@ -45,7 +45,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Every thread therefore waits for the prerequisite grid as its last action (a no-op without the launch attribute).
 __device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int LANES, int VEC, bool FULL, bool FAST, int D, bool PRED>
+template <int LANES, int VEC, bool FULL, bool FAST, int D, bool PRED, bool BIAS>
 __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
                                                                                  unsigned int* __restrict__ counter, int always_add) {
     constexpr int GPW = 32 / LANES;                   // runs walked side by side by one warp
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
     const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;
     const int chunks = (int)(k >> 2);
     float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;
+    float* const BUl = BIAS ? a.BU - a.u_base : nullptr;     // model extension: user biases by global id
     const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
     const float ccoef = -__fmul_rn(a.lr, a.lambda);   // PRED: p_u += b * q_i + ccoef * p_u, added in memory
     const int32_t* __restrict__ words = reinterpret_cast<const int32_t*>(a.recs);
@@ -87,6 +88,9 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
             q[v] = (has && (FULL || gl + v * LANES < chunks)) ? ld_row4(qrow + 4 * v * LANES) : zero4;
             sq0[v][wic][lane] = q[v];
         }
+        float* const birow = BIAS ? a.BI + (hu.item - a.i_base) : nullptr;
+        float bi = (BIAS && has) ? __ldcg(birow) : 0.0f;          // the run's private b_i, merged like q_i at the end
+        const float bi0 = bi;
         auto stage_tile = [&](int tile) {               // lane gl copies (u, r) of record LANES*tile + gl of its run
             const int j = tile * LANES + gl;
             if (j < count) {
@@ -97,9 +101,11 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
             }
             cp_async_commit();
         };
-        auto gather = [&](float4 (&slot)[VEC], int t) {   // p_u of step t -> a ring slot (nothing past the run's end)
+        auto gather = [&](float4 (&slot)[VEC], float& bslot, int t) {   // p_u (and b_u) of step t -> a ring slot (nothing past the run's end)
             if (t < count) {
-                const float* xp = Pl + (int64_t)(recs[t & (RING - 1)].x & REC_USER_MASK) * k;
+                const int32_t uu = recs[t & (RING - 1)].x & REC_USER_MASK;
+                if (BIAS) bslot = __ldcg(BUl + uu);
+                const float* xp = Pl + (int64_t)uu * k;
 #pragma unroll
                 for (int v = 0; v < VEC; v++)
                     if (FULL || gl + v * LANES < chunks) slot[v] = ld_row4(xp + 4 * v * LANES);
@@ -111,12 +117,15 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
         cp_async_wait<0>();
         __syncwarp();
         float4 ring[D][VEC];
+        float bring[D];
 #pragma unroll
-        for (int d = 0; d < D; d++)
+        for (int d = 0; d < D; d++) {
+            bring[d] = 0.0f;
 #pragma unroll
             for (int v = 0; v < VEC; v++) ring[d][v] = zero4;
+        }
 #pragma unroll
-        for (int d = 0; d < D - 1; d++) gather(ring[d], d);
+        for (int d = 0; d < D - 1; d++) gather(ring[d], bring[d], d);
         for (int t0 = 0; t0 < steps; t0 += D) {
             if ((t0 & (S - 1)) == 0) {                  // warp-uniform: a tile opens
                 stage_tile(t0 / S + 2);
@@ -127,13 +136,23 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
             for (int d = 0; d < D; d++) {
                 const int t = t0 + d;
                 if (t >= steps) break;                  // warp-uniform
-                gather(ring[(d + D - 1) & (D - 1)], t + D - 1);   // into the slot step t - 1 has just released
+                gather(ring[(d + D - 1) & (D - 1)], bring[(d + D - 1) & (D - 1)], t + D - 1);   // into the slot step t - 1 has just released
                 const int2 rec = recs[t & (RING - 1)];
-                const float e = __fsub_rn(__int_as_float(rec.y), rows_dot<LANES, VEC, FAST>(ring[d], q));
+                float pred = rows_dot<LANES, VEC, FAST>(ring[d], q);
+                if (BIAS) pred = __fadd_rn(__fadd_rn(pred, bring[d]), bi);
+                const float e = __fsub_rn(__int_as_float(rec.y), pred);
                 const float b = __fmul_rn(cf.lr, e);
                 if (t < count) {
                     float* const cp = Pl + (int64_t)(rec.x & REC_USER_MASK) * k;
                     const bool p_red = PRED || rec.x < 0;       // heavy user (or every user): add the increment in memory
+                    if (BIAS) {
+                        const float du = bias_delta(bring[d], e, cf.lr, cf.lambda);
+                        if (gl == 0) {
+                            if (p_red) atomicAdd(BUl + (rec.x & REC_USER_MASK), du);
+                            else __stcg(BUl + (rec.x & REC_USER_MASK), __fadd_rn(bring[d], du));
+                        }
+                        bi = __fadd_rn(bi, bias_delta(bi, e, cf.lr, cf.lambda));
+                    }
 #pragma unroll
                     for (int v = 0; v < VEC; v++) {
                         if (FULL || gl + v * LANES < chunks) {
@@ -147,6 +166,10 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
         }
         cp_async_wait<0>();
         __syncwarp();                                   // every lane is done with the runs' record tiles
+        if (BIAS && has && gl == 0) {
+            if (hu.weight == 1.0f && !always_add) __stcg(birow, bi);
+            else atomicAdd(birow, __fmul_rn(__fsub_rn(bi, bi0), hu.weight));
+        }
         if (has) {
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
@@ -296,14 +319,19 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     // a launch that overlaps a neighbour (either side) never overwrites an item row: its weight-1 runs add their net change too
     const int always_add = (pdl || overlapped_by_next) ? 1 : 0;
     const bool d2 = run_depth() == 2;
+    const bool bias = a.BU != nullptr;            // model extension: biases (always one gather ahead)
     cudaError_t err = cudaSuccess;
 #define CALL(L, V, F)                                                                                                        \
-    err = (fast && p_red && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-          : (fast && p_red)     ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-          : (fast && d2)        ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-          : fast                ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-          : p_red               ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 4, true>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-                                : launch_runs(sgd_update_runs_kernel<L, V, F, false, 4, false>, grid, stream, pdl, always_add, a, units, n_units, counter)
+    err = bias ? ((fast && p_red) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true, true>, grid, stream, pdl, always_add, a, units, n_units, counter)   \
+                  : fast          ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+                  : p_red         ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, true, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+                                  : launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, false, true>, grid, stream, pdl, always_add, a, units, n_units, counter)) \
+        : (fast && p_red && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+          : (fast && p_red)     ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
+          : (fast && d2)        ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+          : fast                ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+          : p_red               ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
+                                : launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;
@@ -315,12 +343,12 @@ cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, int* ctas) {
     const bool d2 = run_depth() == 2;
     cudaError_t err = cudaSuccess;
 #define CALL(L, V, F)                                                                                                              \
-    err = (fast && p_red && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, true>, 256, 0)   \
-          : (fast && p_red)     ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, true>, 256, 0)   \
-          : (fast && d2)        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, false>, 256, 0)  \
-          : fast                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, false>, 256, 0)  \
-          : p_red               ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4, true>, 256, 0)  \
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 4, false>, 256, 0)
+    err = (fast && p_red && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, true, false>, 256, 0)   \
+          : (fast && p_red)     ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, true, false>, 256, 0)   \
+          : (fast && d2)        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, false, false>, 256, 0)  \
+          : fast                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, false, false>, 256, 0)  \
+          : p_red               ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 2, true, false>, 256, 0)  \
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 2, false, false>, 256, 0)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
     const int cap = env_int("MFSGD_HOT_CTAS", 0);    // tuning aid: resident run-kernel CTAs per SM

@@ -27,8 +27,10 @@ inline int grid_for(int64_t n, int threads, int max_ctas) {
 __global__ void __launch_bounds__(256) count_rows_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i,
                                                          const uint8_t* __restrict__ held, int64_t n,
                                                          uint32_t* __restrict__ user_cnt, uint32_t* __restrict__ item_cnt,
-                                                         int32_t n_users, int32_t n_items, int* __restrict__ bad_flag) {
+                                                         int32_t n_users, int32_t n_items, int* __restrict__ bad_flag,
+                                                         const float* __restrict__ r, unsigned long long* __restrict__ rating_sum) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    long long fixed = 0;      // sum floor(r * 2^20): exact integers, so the training mean does not depend on the summation order
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         const int32_t uu = u[t], ii = i[t];
         if (uu < 0 || uu >= n_users || ii < 0 || ii >= n_items) {
@@ -38,6 +40,12 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const int32_t* __restri
         if (held != nullptr && held[t] != 0) continue;
         atomicAdd(user_cnt + uu, 1u);
         atomicAdd(item_cnt + ii, 1u);
+        if (r != nullptr) fixed += __double2ll_rd(__dmul_rn((double)r[t], 1048576.0));
+    }
+    if (rating_sum != nullptr) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) fixed += __shfl_xor_sync(0xffffffffu, fixed, m);
+        if ((threadIdx.x & 31) == 0 && fixed != 0) atomicAdd(rating_sum, (unsigned long long)fixed);
     }
 }
 
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) block_scatter_kernel(BucketArg
                 Rec rec;
                 rec.u = marked_user(b, b.u[t]);
                 rec.i = b.i[t];
-                rec.r = b.r[t];
+                rec.r = __fsub_rn(b.r[t], b.center);
                 out[base[blk[it]] + slot[it]] = rec;
             }
         }
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(256) block_scatter_global_kernel(BucketArgs b,
             Rec rec;
             rec.u = marked_user(b, b.u[t]);
             rec.i = b.i[t];
-            rec.r = b.r[t];
+            rec.r = __fsub_rn(b.r[t], b.center);
             out[base + (unsigned long long)__popc(peers & ((1u << lane) - 1u))] = rec;
         }
     }
@@ -238,13 +246,13 @@ __global__ void __launch_bounds__(256) block_shuffle_kernel(const Rec* __restric
 }
 
 __global__ void __launch_bounds__(256) pack_records_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i,
-                                                           const float* __restrict__ r, int64_t n, Rec* __restrict__ out) {
+                                                           const float* __restrict__ r, int64_t n, float center, Rec* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         Rec rec;
         rec.u = u[t];
         rec.i = i[t];
-        rec.r = r[t];
+        rec.r = __fsub_rn(r[t], center);
         out[t] = rec;
     }
 }
@@ -279,11 +287,11 @@ __global__ void __launch_bounds__(256) order_gather_kernel(const Rec* __restrict
 }  // namespace
 
 cudaError_t launch_count_rows(const int32_t* u, const int32_t* i, const uint8_t* held, int64_t n, uint32_t* user_cnt,
-                              uint32_t* item_cnt, int32_t n_users, int32_t n_items, int* bad_flag, cudaStream_t stream,
-                              int* launches) {
+                              uint32_t* item_cnt, int32_t n_users, int32_t n_items, int* bad_flag, const float* r,
+                              unsigned long long* rating_sum, cudaStream_t stream, int* launches) {
     if (n <= 0) return cudaSuccess;
     count_rows_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, stream>>>(u, i, held, n, user_cnt, item_cnt, n_users, n_items,
-                                                                    bad_flag);
+                                                                    bad_flag, rating_sum ? r : nullptr, rating_sum);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -362,10 +370,10 @@ cudaError_t launch_block_shuffle(const Rec* in, Rec* out, const int64_t* block_o
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, Rec* out,
+cudaError_t launch_pack_records(const int32_t* u, const int32_t* i, const float* r, int64_t n, float center, Rec* out,
                                 cudaStream_t stream, int* launches) {
     if (n <= 0) return cudaSuccess;
-    pack_records_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, stream>>>(u, i, r, n, out);
+    pack_records_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, stream>>>(u, i, r, n, center, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -66,13 +66,19 @@ __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, floa
 template <int VEC>
 struct Slot {          // only the gathered rows live in registers; ids and rating are re-read from the tile (one LDS)
     float4 p[VEC], q[VEC];
+    float bu, bi;      // biases of the model extension (BIAS instantiations only; never touched otherwise)
 };
 
-template <int LANES, int VEC, bool FULL, bool FULLTILE>
+template <int LANES, int VEC, bool FULL, bool FULLTILE, bool BIAS>
 __device__ __forceinline__ void slot_load(Slot<VEC>& sl, const int4* __restrict__ tile, int j, int cnt, const float* __restrict__ Pl,
-                                          const float* __restrict__ Ql, int64_t k, int lane_chunk, int chunks) {
+                                          const float* __restrict__ Ql, int64_t k, int lane_chunk, int chunks,
+                                          const float* __restrict__ BUl, const float* __restrict__ BIl) {
     const int4 rec = tile[j & 31];
     const bool act = FULLTILE || j < cnt;
+    if (BIAS) {
+        sl.bu = act ? __ldcg(BUl + rec.x) : 0.0f;
+        sl.bi = act ? __ldcg(BIl + rec.y) : 0.0f;
+    }
     const float* pp = Pl + (int64_t)rec.x * k;
     const float* qq = Ql + (int64_t)rec.y * k;
 #pragma unroll
@@ -83,16 +89,17 @@ __device__ __forceinline__ void slot_load(Slot<VEC>& sl, const int4* __restrict_
     }
 }
 
-template <int LANES, int VEC, bool FULL, int SC, bool FAST, bool FULLTILE, int DEPTH>
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, bool FULLTILE, int DEPTH, bool BIAS>
 __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt, float* __restrict__ Pl,
-                                          float* __restrict__ Ql, int64_t k, int grp, int lane_chunk, int chunks, Coef cf) {
+                                          float* __restrict__ Ql, int64_t k, int grp, int lane_chunk, int chunks, Coef cf,
+                                          float* __restrict__ BUl, float* __restrict__ BIl) {
     constexpr int GPW = 32 / LANES;
     constexpr int FULL_STEPS = 32 / GPW;
     const int steps = FULLTILE ? FULL_STEPS : (cnt + GPW - 1) / GPW;
     Slot<VEC> ring[DEPTH];
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; d++)
-        slot_load<LANES, VEC, FULL, FULLTILE>(ring[d], tile, d * GPW + grp, cnt, Pl, Ql, k, lane_chunk, chunks);
+        slot_load<LANES, VEC, FULL, FULLTILE, BIAS>(ring[d], tile, d * GPW + grp, cnt, Pl, Ql, k, lane_chunk, chunks, BUl, BIl);
     for (int t0 = 0; t0 < steps; t0 += DEPTH) {
 #pragma unroll
         for (int d = 0; d < DEPTH; d++) {
@@ -102,16 +109,24 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
             // a partial tile slot_load sees j >= cnt and loads nothing; a full tile has no such predicate, so the look-ahead
             // itself is skipped there (warp-uniform) -- it would gather rows of wrapped records that are never used.
             if (!FULLTILE || t + DEPTH - 1 < FULL_STEPS)
-                slot_load<LANES, VEC, FULL, FULLTILE>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp, cnt, Pl, Ql, k,
-                                                      lane_chunk, chunks);
+                slot_load<LANES, VEC, FULL, FULLTILE, BIAS>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp, cnt, Pl, Ql, k,
+                                                      lane_chunk, chunks, BUl, BIl);
             const int j = t * GPW + grp;
             const int4 rec = tile[j & 31];
             const bool act = FULLTILE ? true : j < cnt;
             float* const cp = Pl + (int64_t)rec.x * k;
             float* const cq = Ql + (int64_t)rec.y * k;
             const Slot<VEC>& c = ring[d];
-            const float e = __fsub_rn(__int_as_float(rec.z), rows_dot<LANES, VEC, FAST>(c.p, c.q));
+            float pred = rows_dot<LANES, VEC, FAST>(c.p, c.q);
+            if (BIAS) pred = __fadd_rn(__fadd_rn(pred, c.bu), c.bi);
+            const float e = __fsub_rn(__int_as_float(rec.z), pred);
             const float b = __fmul_rn(cf.lr, e);
+            if (BIAS && act && lane_chunk == 0) {      // one lane of the sub-warp owns the two bias entries
+                if (SC == 1 || SC == 3) atomicAdd(BUl + rec.x, bias_delta(c.bu, e, cf.lr, cf.lambda));
+                else __stcg(BUl + rec.x, __fadd_rn(c.bu, bias_delta(c.bu, e, cf.lr, cf.lambda)));
+                if (SC == 1 || SC == 2) atomicAdd(BIl + rec.y, bias_delta(c.bi, e, cf.lr, cf.lambda));
+                else __stcg(BIl + rec.y, __fadd_rn(c.bi, bias_delta(c.bi, e, cf.lr, cf.lambda)));
+            }
             if (act) {
 #pragma unroll
                 for (int v = 0; v < VEC; v++) {
@@ -130,7 +145,7 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
 // Hogwild kernel (cold records). Work unit = tile of 32 consecutive records per warp: lane l streams record l
 // (12 B, past L1, evict-first) one tile ahead and parks it in the warp's shared-memory slot, from where every
 // step reads its (u, i, r) with one broadcast LDS.128 instead of three shuffles.
-template <int LANES, int VEC, bool FULL, int SC, bool FAST, int DEPTH>
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, int DEPTH, bool BIAS>
 __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_update_hogwild_kernel(UpdateArgs a) {
     __shared__ int4 srec[8][2][32];
     const int lane = threadIdx.x & 31;
@@ -141,6 +156,8 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
     const int chunks = (int)(k >> 2);
     float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;               // lane-adjusted bases, indexed by global ids
     float* const Ql = a.Q - (int64_t)a.i_base * k + 4 * gl;
+    float* const BUl = BIAS ? a.BU - a.u_base : nullptr;                  // biases of the model extension, indexed by global ids
+    float* const BIl = BIAS ? a.BI - a.i_base : nullptr;
     const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -183,8 +200,8 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
                 nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
             }
         }
-        if (cnt == 32) walk_tile<LANES, VEC, FULL, SC, FAST, true, DEPTH>(srec[wic][buf], 32, Pl, Ql, k, grp, gl, chunks, cf);
-        else walk_tile<LANES, VEC, FULL, SC, FAST, false, DEPTH>(srec[wic][buf], cnt, Pl, Ql, k, grp, gl, chunks, cf);
+        if (cnt == 32) walk_tile<LANES, VEC, FULL, SC, FAST, true, DEPTH, BIAS>(srec[wic][buf], 32, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl);
+        else walk_tile<LANES, VEC, FULL, SC, FAST, false, DEPTH, BIAS>(srec[wic][buf], cnt, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl);
         buf ^= 1;
         srec[wic][buf][lane] = nrec;
         __syncwarp();
@@ -206,7 +223,20 @@ __global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs
         float* qrow = a.Q + (int64_t)(rec.i - a.i_base) * a.k;
         RowPair<LANES, VEC> rp;
         load_rows<LANES, VEC, FULL>(rp, prow, qrow, gl, chunks, act);
-        const float e = __fsub_rn(rec.r, row_dot<LANES, VEC>(rp));
+        float pred = row_dot<LANES, VEC>(rp);
+        float bu = 0.0f, bi = 0.0f;
+        if (a.BU != nullptr) {                 // model extension: every lane reads the two entries, lane 0 writes them
+            bu = __ldcg(a.BU + (rec.u - a.u_base));
+            bi = __ldcg(a.BI + (rec.i - a.i_base));
+            pred = __fadd_rn(__fadd_rn(pred, bu), bi);
+        }
+        const float e = __fsub_rn(rec.r, pred);
+        __syncwarp();                          // all lanes have read the biases before lane 0 overwrites them
+        if (a.BU != nullptr && lane == 0) {
+            __stcg(a.BU + (rec.u - a.u_base), __fadd_rn(bu, bias_delta(bu, e, a.lr, a.lambda)));
+            __stcg(a.BI + (rec.i - a.i_base), __fadd_rn(bi, bias_delta(bi, e, a.lr, a.lambda)));
+        }
+        __syncwarp();
         if (act) scatter_rows<LANES, VEC, FULL, 0>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
         if (err_trace != nullptr && lane == 0) err_trace[j] = e;
     }
@@ -268,14 +298,22 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fas
     if (grid < 1) grid = 1;
     if (scatter != 0) fast = false;           // the atomic scatter variants add exact-rule deltas
     const bool deep = pipeline_depth() == 4 && g.vec == 1;
-#define CALL(L, V, F)                                                                                    \
-    if (fast && deep) sgd_update_hogwild_kernel<L, V, F, 0, true, 4><<<grid, 256, 0, stream>>>(a);       \
-    else if (fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2><<<grid, 256, 0, stream>>>(a);          \
-    else switch (scatter) {                                                                              \
-        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
-        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
-        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2><<<grid, 256, 0, stream>>>(a); break;     \
-        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2><<<grid, 256, 0, stream>>>(a); break;    \
+    const bool bias = a.BU != nullptr;        // model extension: its own instantiations (one gather ahead), none of its registers otherwise
+#define CALL(L, V, F)                                                                                          \
+    if (bias && fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2, true><<<grid, 256, 0, stream>>>(a);       \
+    else if (bias) switch (scatter) {                                                                          \
+        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
+        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
+        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
+        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2, true><<<grid, 256, 0, stream>>>(a); break;    \
+    }                                                                                                          \
+    else if (fast && deep) sgd_update_hogwild_kernel<L, V, F, 0, true, 4, false><<<grid, 256, 0, stream>>>(a); \
+    else if (fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false><<<grid, 256, 0, stream>>>(a);         \
+    else switch (scatter) {                                                                                    \
+        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
+        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
+        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
+        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2, false><<<grid, 256, 0, stream>>>(a); break;   \
     }
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
@@ -289,9 +327,9 @@ cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas) {
     if (scatter != 0) fast = false;
     const bool deep = pipeline_depth() == 4 && g.vec == 1;
 #define CALL(L, V, F)                                                                                                          \
-    err = (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 4>, 256, 0) \
-          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2>, 256, 0)       \
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, false, 2>, 256, 0)
+    err = (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 4, false>, 256, 0) \
+          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false>, 256, 0)       \
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, false, 2, false>, 256, 0)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     return err;

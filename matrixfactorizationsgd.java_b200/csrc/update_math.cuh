@@ -82,6 +82,12 @@ __device__ __forceinline__ float4 delta_chunk(float4 o, float4 x, float e, float
     return delta4(o, x, e, lr, lambda);
 }
 
+// Model extension (MatrixFactorizationSGD.java:282 sgdUpdateModel): the increment of a bias, lr * (e - lambda * b),
+// one rounding per operation in every arithmetic.
+__device__ __forceinline__ float bias_delta(float b, float e, float lr, float lambda) {
+    return __fmul_rn(lr, __fsub_rn(e, __fmul_rn(lambda, b)));
+}
+
 struct Coef {
     float lr, lambda, acoef;   // acoef = 1 - lr * lambda (FAST arithmetic)
 };

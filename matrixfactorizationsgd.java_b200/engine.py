@@ -12,7 +12,7 @@ from ._capi import Config, EpochStats, LayoutInfo, SynthParams, check, lib, ptr,
 def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_HOGWILD, n_gpus=1,
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
                 world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0,
-                merge_boost=0.0, p_atomic_threshold=0.0):
+                merge_boost=0.0, p_atomic_threshold=0.0, model=0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -23,6 +23,7 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.world_size, cfg.rank, cfg.ctas_per_sm, cfg.rounds = int(world_size), int(rank), int(ctas_per_sm), int(rounds)
     cfg.hot_share, cfg.hot_chunk, cfg.merge_boost = float(hot_share), int(hot_chunk), float(merge_boost)
     cfg.p_atomic_threshold = float(p_atomic_threshold)
+    cfg.model = int(model)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg
@@ -119,6 +120,23 @@ class Engine:
         if P.shape != (self.cfg.n_users, self.cfg.k) or Q.shape != (self.cfg.n_items, self.cfg.k):
             raise ValueError("P/Q shapes do not match the configuration")
         check(lib.mfsgd_set_factors(self._h, ptr(P), ptr(Q)))
+
+    def get_model(self):
+        """(global mean, user biases, item biases) of the model extension; biases are None when MFSGD_MODEL_BIASES is off."""
+        mu = C.c_float(0.0)
+        if self.cfg.model & capi.MODEL_BIASES:
+            bu = np.zeros(self.cfg.n_users, dtype=np.float32)
+            bi = np.zeros(self.cfg.n_items, dtype=np.float32)
+            check(lib.mfsgd_get_model(self._h, C.byref(mu), ptr(bu), ptr(bi)))
+            return mu.value, bu, bi
+        check(lib.mfsgd_get_model(self._h, C.byref(mu), None, None))
+        return mu.value, None, None
+
+    def set_biases(self, user_bias, item_bias):
+        bu, bi = as_f32(user_bias), as_f32(item_bias)
+        if bu.shape != (self.cfg.n_users,) or bi.shape != (self.cfg.n_items,):
+            raise ValueError("bias arrays must be [n_users] and [n_items]")
+        check(lib.mfsgd_set_biases(self._h, ptr(bu), ptr(bi)))
 
     def get_factors(self):
         P = np.zeros((self.cfg.n_users, self.cfg.k), dtype=np.float32)

@@ -17,6 +17,8 @@ from . import _capi as capi
 from .engine import Engine, make_config
 
 Factors = namedtuple("Factors", ["P", "Q", "nUsers", "nItems", "k"])
+#: the model extension's result (stand-in Model :257): userBias / itemBias are None when the biases are off
+Model = namedtuple("Model", ["P", "Q", "userBias", "itemBias", "globalMean", "nUsers", "nItems", "k"])
 #: a parsed ratings file: dense triplets + the file ids of every row (RatingsFile.userIds[u] is the file's id of row u)
 RatingsFile = namedtuple("RatingsFile", ["users", "items", "ratings", "nUsers", "nItems", "userIds", "itemIds", "format"])
 
@@ -60,6 +62,38 @@ class MatrixFactorizationSGD:
         capi.check(capi.lib.mfsgd_factorize(capi.ptr(u), capi.ptr(i), capi.ptr(r), len(r), C.byref(cfg), int(epochs),
                                             capi.ptr(P), capi.ptr(Q)))
         return Factors(P, Q, nUsers, nItems, k)
+
+    @staticmethod
+    def factorizeModel(users, items, ratings, nUsers, nItems, k, lr, lambda_, epochs, seed, useGlobalMean, useBiases,
+                       mode=capi.MODE_HOGWILD, n_gpus=1, device=0, **cfg_kw):
+        """Stand-in factorizeModel (:305): r ~ mu + b_u + b_i + p_u . q_i. The mean is taken on the device while the ratings are
+        counted, ratings are stored centred, the biases ride through the update kernels beside their rows."""
+        MatrixFactorizationSGD._check(users, items, ratings, nUsers, nItems, k, epochs)
+        bits = (capi.MODEL_GLOBAL_MEAN if useGlobalMean else 0) | (capi.MODEL_BIASES if useBiases else 0)
+        cfg = make_config(nUsers, nItems, k, lr, lambda_, seed=seed, mode=mode, n_gpus=n_gpus, device=device, model=bits, **cfg_kw)
+        with Engine(cfg) as eng:
+            eng.load_ratings(users, items, ratings)
+            eng.init_factors()
+            if epochs > 0:
+                eng.train(epochs, want_stats=False)
+            P, Q = eng.get_factors()
+            mu, bu, bi = eng.get_model()
+        return Model(P, Q, bu, bi, mu, nUsers, nItems, k)
+
+    @staticmethod
+    def rmseModel(model, users, items, ratings, device=0):
+        """Stand-in rmseModel (:328): e = (r - mu) - ((p_u . q_i + b_u) + b_i), evaluated by the RMSE kernel."""
+        P, Q = capi.as_f32(model.P), capi.as_f32(model.Q)
+        biased = model.userBias is not None
+        cfg = make_config(P.shape[0], Q.shape[0], model.k, 1e-3, 0.0, mode=capi.MODE_HOGWILD, device=device, stripes_per_gpu=1,
+                          model=capi.MODEL_BIASES if biased else 0)
+        rc = (capi.as_f32(ratings) - np.float32(model.globalMean)).astype(np.float32)      # one binary32 subtraction, as :335
+        with Engine(cfg) as eng:
+            eng.load_ratings(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32))
+            eng.set_factors(P, Q)
+            if biased:
+                eng.set_biases(model.userBias, model.itemBias)
+            return eng.rmse(users, items, rc)
 
     @staticmethod
     def rmse(P, Q, k, users, items, ratings, device=0):

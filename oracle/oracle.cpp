@@ -218,6 +218,49 @@ ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float
     return e;
 }
 
+/* MatrixFactorizationSGD.java:272 globalMean: exact integer sum, hence order-independent */
+ORC_API float orc_global_mean(const float* r, int64_t n) {
+    int64_t s = 0;
+    for (int64_t t = 0; t < n; t++) s += (int64_t)std::floor((double)r[t] * 1048576.0);
+    return n == 0 ? 0.0f : (float)((double)s / (double)n / 1048576.0);
+}
+
+/* MatrixFactorizationSGD.java:282 sgdUpdateModel on the centred rating rc; bu / bi point at the two bias entries (or are null).
+ * The factor part is orc_sgd_update in any order mode; the bias part is the plain rule, one rounding per operation, in every mode. */
+ORC_API float orc_sgd_update_model(float* p, float* q, int k, float* bu, float* bi, float rc, float lr, float lambda, int order_mode) {
+    if (!bu) return orc_sgd_update(p, q, k, rc, lr, lambda, order_mode);
+    const float b0 = *bu, b1 = *bi;
+    /* e = rc - ((dot + b_u) + b_i): feed the factor update with the rating reduced by the biases -- algebraically the same, but
+     * NOT the same roundings; so restate: compute the dot in the requested order, then the error exactly as the stand-in does */
+    float pred = dot_ordered(p, q, k, order_mode) + b0;
+    pred = pred + b1;
+    const float e = rc - pred;
+    *bu = b0 + lr * (e - lambda * b0);
+    *bi = b1 + lr * (e - lambda * b1);
+    if (order_mode == ORC_ORDER_WARP_TREE_FMA_PDELTA) {
+        const float a = 1.0f - lr * lambda, b = lr * e, c = -(lr * lambda);
+        for (int f = 0; f < k; f++) {
+            float pf = p[f], qf = q[f];
+            p[f] = pf + std::fmaf(b, qf, c * pf);
+            q[f] = std::fmaf(b, pf, a * qf);
+        }
+    } else if (order_mode == ORC_ORDER_WARP_TREE_FMA) {
+        const float a = 1.0f - lr * lambda, b = lr * e;
+        for (int f = 0; f < k; f++) {
+            float pf = p[f], qf = q[f];
+            p[f] = std::fmaf(b, qf, a * pf);
+            q[f] = std::fmaf(b, pf, a * qf);
+        }
+    } else {
+        for (int f = 0; f < k; f++) {
+            float pf = p[f], qf = q[f];
+            p[f] = pf + lr * (e * qf - lambda * pf);
+            q[f] = qf + lr * (e * pf - lambda * qf);
+        }
+    }
+    return e;
+}
+
 static int check_triplets(const int32_t* u, const int32_t* i, int64_t n, int nU, int nI) {
     for (int64_t t = 0; t < n; t++)
         if (u[t] < 0 || u[t] >= nU || i[t] < 0 || i[t] >= nI) return -1;
@@ -245,6 +288,37 @@ ORC_API int orc_train(const int32_t* u, const int32_t* i, const float* r, int64_
         }
     }
     return 0;
+}
+
+/* MatrixFactorizationSGD.java:305 factorizeModel's loop on existing P, Q, biases (bu, bi nullable together); rc = centred ratings. */
+ORC_API int orc_train_model(const int32_t* u, const int32_t* i, const float* rc, int64_t n, float* P, float* Q, float* bu, float* bi,
+                            int nU, int nI, int k, float lr, float lambda, int epoch_begin, int epoch_end, uint64_t seed,
+                            int order_mode, int shuffled) {
+    if (n > 0x7fffffffLL || check_triplets(u, i, n, nU, nI)) return -1;
+    std::vector<int32_t> order((size_t)n);
+    for (int epoch = epoch_begin; epoch < epoch_end; epoch++) {
+        if (shuffled) orc_shuffle(seed, epoch, (int)n, order.data());
+        else for (int64_t j = 0; j < n; j++) order[j] = (int32_t)j;
+        for (int64_t j = 0; j < n; j++) {
+            int32_t t = order[j];
+            orc_sgd_update_model(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, bu ? bu + u[t] : nullptr, bi ? bi + i[t] : nullptr,
+                                 rc[t], lr, lambda, order_mode);
+        }
+    }
+    return 0;
+}
+
+/* MatrixFactorizationSGD.java:328 rmseModel on centred ratings */
+ORC_API double orc_rmse_model(const float* P, const float* Q, const float* bu, const float* bi, int k, const int32_t* u, const int32_t* i,
+                              const float* rc, int64_t n, int order_mode) {
+    double sse = 0.0;
+    for (int64_t t = 0; t < n; t++) {
+        float pred = dot_ordered(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, order_mode);
+        if (bu) { pred = pred + bu[u[t]]; pred = pred + bi[i[t]]; }
+        float e = rc[t] - pred;
+        sse += (double)e * (double)e;
+    }
+    return n == 0 ? 0.0 : std::sqrt(sse / (double)n);
 }
 
 /*
@@ -479,9 +553,9 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
                                   const float* unit_weight, const int64_t* unit_bstart, const int32_t* unit_bn,
                                   const uint32_t* unit_bid, int64_t n_units, int virt, uint64_t seed, uint32_t epoch,
                                   float* P, int32_t u_base, float* Q, int32_t i_base, int k, float lr, float lambda,
-                                  int order_mode, int resident, int gpw, int always_add) {
+                                  int order_mode, int resident, int gpw, int always_add, float* BU, float* BI) {
     if (resident < 1 || gpw < 1 || resident % gpw) return -1;
-    struct Slot { int64_t unit; int step; std::vector<float> q, q0; uint64_t key; };
+    struct Slot { int64_t unit; int step; std::vector<float> q, q0; uint64_t key; float b = 0.f, b0 = 0.f; };   /* b: the run's private b_i */
     std::vector<Slot> slots((size_t)resident);
     for (auto& s : slots) { s.unit = -1; s.step = 0; s.q.resize((size_t)k); s.q0.resize((size_t)k); s.key = 0; }
     int64_t next = 0, done = 0;
@@ -495,6 +569,7 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
                 const float* qr = Q + (int64_t)(unit_item[s.unit] - i_base) * k;
                 std::memcpy(s.q.data(), qr, sizeof(float) * k);
                 std::memcpy(s.q0.data(), qr, sizeof(float) * k);
+                if (BI) s.b = s.b0 = BI[unit_item[s.unit] - i_base];
                 s.key = (virt && unit_bn[s.unit] > 1) ? orc_bucket_perm_key(seed, epoch, unit_bid[s.unit]) : 0;
             } else s.unit = -1;
         }
@@ -512,7 +587,8 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
              * which in the FMA arrangement rounds differently from storing the new value (ORC_ORDER_WARP_TREE_FMA_PDELTA) */
             const int32_t uid = rec_u[idx] & 0x7fffffff;
             const int mode = (rec_u[idx] < 0 && order_mode == ORC_ORDER_WARP_TREE_FMA) ? ORC_ORDER_WARP_TREE_FMA_PDELTA : order_mode;
-            orc_sgd_update(P + (int64_t)(uid - u_base) * k, s.q.data(), k, rec_r[idx], lr, lambda, mode);
+            orc_sgd_update_model(P + (int64_t)(uid - u_base) * k, s.q.data(), k, BU ? BU + (uid - u_base) : nullptr, BI ? &s.b : nullptr,
+                                 rec_r[idx], lr, lambda, mode);
             s.step++;
             static const char* senv = getenv("ORC_SYNC_EVERY");          /* PROTOTYPE: Hogwild-style exchange inside a run */
             if (senv && unit_weight[s.unit] < 1.0f && s.step < unit_count[s.unit] && s.step % atoi(senv) == 0) {
@@ -537,6 +613,11 @@ ORC_API int orc_train_runs_launch(const int32_t* rec_u, const float* rec_r, int6
                 if (s.unit < 0) continue;
                 float* qr = Q + (int64_t)(unit_item[s.unit] - i_base) * k;
                 const float planned = unit_weight[s.unit];
+                if (BI) {        /* the run's b_i merges exactly like its q_i */
+                    float* br = BI + (unit_item[s.unit] - i_base);
+                    if (planned == 1.0f && !always_add) *br = s.b;
+                    else *br = *br + (s.b - s.b0) * planned;
+                }
                 if (planned == 1.0f && !always_add) {
                     std::memcpy(qr, s.q.data(), sizeof(float) * k);
                 } else {

@@ -79,7 +79,16 @@ def _load():
     lib.orc_train_runs_launch.restype = C.c_int
     lib.orc_train_runs_launch.argtypes = [_i32p, _f32p, C.c_int64, _i64p, _i32p, _i32p, _f32p, _i64p, _i32p, _u32p, C.c_int64,
                                           C.c_int, C.c_uint64, C.c_uint32, _f32p, C.c_int32, _f32p, C.c_int32, C.c_int,
-                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
+                                          C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.orc_global_mean.restype = C.c_float
+    lib.orc_global_mean.argtypes = [_f32p, C.c_int64]
+    lib.orc_train_model.restype = C.c_int
+    lib.orc_train_model.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int]
+    lib.orc_sgd_update_model.restype = C.c_float
+    lib.orc_sgd_update_model.argtypes = [_f32p, _f32p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
+    lib.orc_rmse_model.restype = C.c_double
+    lib.orc_rmse_model.argtypes = [_f32p, _f32p, C.c_void_p, C.c_void_p, C.c_int, _i32p, _i32p, _f32p, C.c_int64, C.c_int]
     lib.orc_set_tree_lanes.restype = None
     lib.orc_set_tree_lanes.argtypes = [C.c_int]
     return lib
@@ -210,14 +219,33 @@ class RunPlan:
         self.bid = np.ascontiguousarray(member * (len(off) - 1) + blk, np.uint32)
 
 
+def global_mean(r):
+    """Training mean of the model extension (stand-in globalMean: exact integer sum -> the same binary32 everywhere)."""
+    return float(lib.orc_global_mean(np.ascontiguousarray(r, np.float32), len(r)))
+
+
+def train_model(u, i, rc, P, Q, bu, bi, lr, lam, epoch_begin, epoch_end, seed, order_mode=ORDER_SEQ, shuffled=True):
+    """factorizeModel's loop on CENTRED ratings rc = r - mu; bu / bi = bias arrays (float32, updated in place) or None."""
+    rc_ = lib.orc_train_model(u, i, rc, len(rc), P, Q, None if bu is None else bu.ctypes.data, None if bi is None else bi.ctypes.data,
+                              P.shape[0], Q.shape[0], P.shape[1], lr, lam, epoch_begin, epoch_end, seed, order_mode, int(shuffled))
+    if rc_:
+        raise ValueError("oracle: bad triplets")
+
+
+def rmse_model(P, Q, bu, bi, u, i, rc, order_mode=ORDER_SEQ):
+    return float(lib.orc_rmse_model(P, Q, None if bu is None else bu.ctypes.data, None if bi is None else bi.ctypes.data, P.shape[1],
+                                    u, i, rc, len(rc), order_mode))
+
+
 def train_runs_launch(rec_u, rec_r, plan, lo, hi, P, Q, lr, lam, order_mode, resident, gpw=1, virt=False, seed=0, epoch=0,
-                      u_base=0, i_base=0, always_add=False):
+                      u_base=0, i_base=0, always_add=False, bu=None, bi=None):
     """Twin of one sgd_update_runs_kernel launch over units [lo, hi) of `plan` (oracle.cpp orc_train_runs_launch)."""
     sl = slice(lo, hi)
     rc = lib.orc_train_runs_launch(rec_u, rec_r, len(rec_r), plan.start[sl].copy(), plan.count[sl].copy(), plan.item[sl].copy(),
                                    plan.weight[sl].copy(), plan.bstart[sl].copy(), plan.bn[sl].copy(), plan.bid[sl].copy(),
                                    hi - lo, int(virt), seed, epoch, P, u_base, Q, i_base, P.shape[1], lr, lam, order_mode,
-                                   resident, gpw, int(always_add))
+                                   resident, gpw, int(always_add), None if bu is None else bu.ctypes.data,
+                                   None if bi is None else bi.ctypes.data)
     if rc:
         raise ValueError("oracle: bad run plan (%d)" % rc)
 

@@ -52,3 +52,25 @@ def test_multi_process_ring_nccl(G):
     lo = [p[0] for p in res["partitions"]]
     hi = [p[1] for p in res["partitions"]]
     assert lo[0] == 0 and hi[-1] == 13_800 and lo[1:] == hi[:-1]            # user stripes tile [0, nU)
+
+
+@pytest.mark.parametrize("name", ["yahoo", "powerlaw"])
+def test_large_shapes_on_eight_real_gpus(name):
+    """BASELINE.json configs[3] and [4] on their own configuration: 8 real B200s, one process per GPU, NCCL ring (700 M / 2 B ratings
+    generated on the devices). Held-out RMSE after the config's epoch count between the two sequential executions of the rule
+    (shuffled oracle; DSGD-ordered where the fixture has it), 0.5 % on each side; identical split."""
+    if n_gpus() < 8:
+        pytest.skip("needs 8 GPUs")
+    w = mf.WORKLOADS[name]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "8", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "tests", "mp", "ring_workload.py"), name]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RING_WORKLOAD ")][-1]
+    res = json.loads(line[len("RING_WORKLOAD "):])
+    assert res["n_train"] == res["n_train_oracle"]
+    got = res["heldout_rmse_per_epoch"][w.epochs - 1]
+    shuffled = res["oracle_rmse_per_epoch"][w.epochs - 1]
+    ordered = res.get("oracle_dsgd_order_rmse_per_epoch", [shuffled] * w.epochs)[w.epochs - 1]
+    lo, hi = min(shuffled, ordered), max(shuffled, ordered)
+    assert lo * 0.995 <= got <= hi * 1.005, (got, shuffled, ordered)

@@ -348,3 +348,111 @@ def test_run_twin_reads_buckets_through_the_permutation():
     Ps, Qs = orc.init_factors(n, k, SEED, 0), orc.init_factors(2, k, SEED, 1)
     orc.train(u[order].copy(), items, r[order].copy(), Ps, Qs, 0.02, 0.03, 0, 1, SEED, orc.ORDER_SEQ, shuffled=False)
     assert np.array_equal(P, Ps) and np.array_equal(Q, Qs)
+
+
+# ------------------------------------------------------------------------------------------------
+# model extension: global mean + biases -- stand-in factorizeModel :305, sgdUpdateModel :282
+# ------------------------------------------------------------------------------------------------
+def _np_model_epochs(u, i, rc, P, Q, bu, bi, lr, lam, epochs, seed):
+    """Independent NumPy float32 restatement of factorizeModel's loop (sequential dot, one rounding per operation)."""
+    f = np.float32
+    lr, lam = f(lr), f(lam)
+    for ep in range(epochs):
+        for t in npr.shuffle(seed, ep, len(rc)):
+            p, q = P[u[t]], Q[i[t]]
+            dot = f(0)
+            for a, b in zip(p, q):
+                dot = f(dot + f(a * b))
+            if bu is not None:
+                pred = f(f(dot + bu[u[t]]) + bi[i[t]])
+                e = f(rc[t] - pred)
+                b0, b1 = bu[u[t]], bi[i[t]]
+                bu[u[t]] = f(b0 + f(lr * f(e - f(lam * b0))))
+                bi[i[t]] = f(b1 + f(lr * f(e - f(lam * b1))))
+            else:
+                e = f(rc[t] - dot)
+            pn = (p + lr * (e * q - lam * p).astype(f)).astype(f)
+            qn = (q + lr * (e * p - lam * q).astype(f)).astype(f)
+            P[u[t]], Q[i[t]] = pn, qn
+
+
+def test_global_mean_is_an_exact_integer_sum():
+    rng = np.random.default_rng(1)
+    r = (1 + 4 * rng.random(100_001)).astype(np.float32)
+    mu = orc.global_mean(r)
+    s = int(np.floor(r.astype(np.float64) * 1048576.0).astype(np.int64).sum())
+    assert mu == np.float32(s / len(r) / 1048576.0)
+    assert orc.global_mean(r[::-1].copy()) == mu and orc.global_mean(rng.permutation(r)) == mu     # any order
+    assert abs(mu - r.astype(np.float64).mean()) < 1e-6
+    assert orc.global_mean(r[:0]) == 0.0
+
+
+@pytest.mark.parametrize("use_mean,use_bias", [(True, True), (False, True), (True, False)])
+def test_model_extension_matches_numpy(use_mean, use_bias):
+    nu, ni, n, k = 30, 40, 400, 8
+    u, i, r, _ = orc.generate(SEED, 0, n, nu, ni)
+    mu = orc.global_mean(r) if use_mean else 0.0
+    rc = (r - np.float32(mu)).astype(np.float32)
+    P, Q = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    bu = np.zeros(nu, np.float32) if use_bias else None
+    bi = np.zeros(ni, np.float32) if use_bias else None
+    Pn, Qn = P.copy(), Q.copy()
+    bun, bin_ = (bu.copy(), bi.copy()) if use_bias else (None, None)
+    orc.train_model(u, i, rc, P, Q, bu, bi, 0.02, 0.05, 0, 2, SEED)
+    _np_model_epochs(u, i, rc, Pn, Qn, bun, bin_, 0.02, 0.05, 2, SEED)
+    assert np.array_equal(P, Pn) and np.array_equal(Q, Qn)
+    if use_bias:
+        assert np.array_equal(bu, bun) and np.array_equal(bi, bin_) and np.abs(bu).max() > 0
+    # without biases the extension is the reference rule on centred ratings
+    if not use_bias:
+        Pr, Qr = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+        orc.train(u, i, rc, Pr, Qr, 0.02, 0.05, 0, 2, SEED)
+        assert np.array_equal(P, Pr) and np.array_equal(Q, Qr)
+    want = np.sqrt(np.mean([(float(rc[t]) - float(np.float32(np.float32(np.dot(P[u[t]].astype(np.float64), Q[i[t]].astype(np.float64))) +
+                                                  (bu[u[t]] if use_bias else 0) + (bi[i[t]] if use_bias else 0)))) ** 2 for t in range(n)]))
+    assert abs(orc.rmse_model(P, Q, bu, bi, u, i, rc) - want) / want < 1e-5
+
+
+def test_model_extension_learns_past_the_mean_on_the_default_data():
+    """Why the extension matters (round-1 review): on the noise-dominant sets plain MF ends above the constant predictor;
+    with the global mean and biases the same rule, same epochs, ends below it."""
+    nu, ni, n, k = 2000, 800, 300_000, 16
+    u, i, r, held = orc.generate(SEED, 0, n, nu, ni)
+    tr = (u[~held].copy(), i[~held].copy(), r[~held].copy())
+    ho = (u[held].copy(), i[held].copy(), r[held].copy())
+    mu = orc.global_mean(tr[2])
+    const = float(np.sqrt(np.mean((ho[2] - np.float32(mu)) ** 2)))
+    P, Q = orc.factorize(*tr, nu, ni, k, 0.005, 0.05, 10, SEED)
+    plain = orc.rmse(P, Q, *ho)
+    P, Q = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    bu, bi = np.zeros(nu, np.float32), np.zeros(ni, np.float32)
+    orc.train_model(tr[0], tr[1], (tr[2] - np.float32(mu)).astype(np.float32), P, Q, bu, bi, 0.005, 0.05, 0, 10, SEED)
+    ext = orc.rmse_model(P, Q, bu, bi, ho[0], ho[1], (ho[2] - np.float32(mu)).astype(np.float32))
+    assert plain > const and ext < plain, (const, plain, ext)
+
+
+def test_run_twin_carries_biases_like_q():
+    k, lr, lam, chunk = 8, 0.02, 0.03, 32
+    rng = np.random.default_rng(9)
+    counts = [128, 64]
+    n = sum(counts)
+    u = rng.permutation(n).astype(np.int32)
+    r = (rng.random(n) - 0.5).astype(np.float32)
+    plan, off = _run_plan_one_bucket_per_item(counts, chunk, weights={4: 0.3125, 2: 0.625})
+    P0, Q0 = orc.init_factors(n, k, SEED, 0), orc.init_factors(2, k, SEED, 1)
+    P, Q, bu, bi = P0.copy(), Q0.copy(), np.zeros(n, np.float32), np.full(2, 0.25, np.float32)
+    orc.train_runs_launch(u, r, plan, 0, len(plan.start), P, Q, lr, lam, orc.ORDER_SEQ, resident=64, bu=bu, bi=bi)
+    # by hand: one wave, every run from the launch-start q_i and b_i
+    Ph, Qh, buh, bih = P0.copy(), Q0.copy(), np.zeros(n, np.float32), np.full(2, 0.25, np.float32)
+    bi_start = bih.copy()
+    for j in range(len(plan.start)):
+        it = int(plan.item[j])
+        q, b = Q0[it].copy(), np.array([bi_start[it]], np.float32)
+        for t in range(int(plan.start[j]), int(plan.start[j] + plan.count[j])):
+            orc.lib.orc_sgd_update_model(Ph[u[t]], q, k, buh[u[t]:u[t] + 1].ctypes.data, b.ctypes.data, float(r[t]), lr, lam, orc.ORDER_SEQ)
+        Qh[it] = Qh[it] + (q - Q0[it]) * np.float32(plan.weight[j])
+        bih[it] = bih[it] + (b[0] - bi_start[it]) * np.float32(plan.weight[j])
+    assert np.array_equal(P, Ph) and np.array_equal(bu, buh)
+    np.testing.assert_allclose(Q, Qh, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(bi, bih, rtol=1e-6, atol=1e-8)
+    assert np.abs(bu).max() > 0 and not np.allclose(bi, 0.25)
