@@ -324,6 +324,67 @@ public final class MatrixFactorizationSGD {
         return new Model(P, Q, bu, bi, mu, nUsers, nItems, k);
     }
 
+    /**
+     * Learning-rate schedule of the extension: lr_0 = lr, lr_(e+1) = lr_e * decay, one binary32 multiply per epoch
+     * (so every implementation gets the same rate; Math.pow would not be bit-reproducible). decay = 1: the constant rate.
+     */
+    public static float learningRate(float lr, float decay, int epoch) {
+        float l = lr;
+        for (int e = 0; e < epoch; e++) l = l * decay;
+        return l;
+    }
+
+    /** Result of factorizeEarlyStop: the model after the last epoch run, the epochs run and the validation curve. */
+    public static final class EarlyStopResult {
+        public final Model model;
+        public final int epochsRun;
+        public final double[] validationRmse;
+        EarlyStopResult(Model model, int epochsRun, double[] curve) { this.model = model; this.epochsRun = epochsRun; this.validationRmse = curve; }
+    }
+
+    /**
+     * factorizeModel with the schedule and early stopping: after every epoch the RMSE v on the validation triplets is
+     * taken; v < best * (1 - minDelta) makes it the new best and clears the strike count, anything else is a strike, and
+     * `patience` strikes in a row end the training (patience = 0: never). The model returned is the one after the last epoch run.
+     */
+    public static EarlyStopResult factorizeEarlyStop(int[] users, int[] items, float[] ratings, int[] vUsers, int[] vItems, float[] vRatings,
+                                                     int nUsers, int nItems, int k, float lr, float lambda, int maxEpochs, long seed,
+                                                     boolean useGlobalMean, boolean useBiases, float lrDecay, int patience, float minDelta) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || nUsers <= 0 || nItems <= 0 || maxEpochs < 0) throw new IllegalArgumentException("bad shape");
+        if (!(lrDecay > 0.0f) || lrDecay > 1.0f || patience < 0 || !(minDelta >= 0.0f) || minDelta >= 1.0f)
+            throw new IllegalArgumentException("bad schedule");
+        final int n = ratings.length;
+        float[] P = new float[nUsers * k], Q = new float[nItems * k];
+        float scale = defaultInitScale(k);
+        initFactors(P, nUsers, k, seed, STREAM_P_INIT, scale);
+        initFactors(Q, nItems, k, seed, STREAM_Q_INIT, scale);
+        float[] bu = useBiases ? new float[nUsers] : null, bi = useBiases ? new float[nItems] : null;
+        final float mu = useGlobalMean ? globalMean(ratings) : 0.0f;
+        Model m = new Model(P, Q, bu, bi, mu, nUsers, nItems, k);
+        double[] curve = new double[maxEpochs];
+        double best = Double.POSITIVE_INFINITY;
+        int strikes = 0, ran = 0;
+        float lrNow = lr;
+        for (int epoch = 0; epoch < maxEpochs; epoch++) {
+            int[] order = shuffle(seed, epoch, n);
+            for (int j = 0; j < n; j++) {
+                int t = order[j];
+                sgdUpdateModel(P, users[t] * k, Q, items[t] * k, k, bu, users[t], bi, items[t], ratings[t] - mu, lrNow, lambda);
+            }
+            lrNow = lrNow * lrDecay;
+            ran = epoch + 1;
+            double v = rmseModel(m, vUsers, vItems, vRatings);
+            curve[epoch] = v;
+            if (patience > 0) {
+                if (v < best * (1.0 - (double) minDelta)) { best = v; strikes = 0; }
+                else if (++strikes >= patience) break;
+            }
+        }
+        return new EarlyStopResult(m, ran, java.util.Arrays.copyOf(curve, ran));
+    }
+
     /** RMSE of the extended model: e = (r - mu) - ((dot + b_u) + b_i). */
     public static double rmseModel(Model m, int[] users, int[] items, float[] ratings) {
         double sse = 0.0;

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MFSGD_ABI_VERSION 2
+#define MFSGD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MFSGD_API __attribute__((visibility("default")))
@@ -102,7 +102,14 @@ typedef struct mfsgd_config {
                                   launch's records x the ratings the resident sub-warps hold in flight) is a HEAVY user: its row is
                                   updated in memory with red.global.add instead of a store, so concurrent updates are not lost.
                                   0 = default 0.25, < 0 = never (round-1 behaviour); MFSGD_SCATTER_ATOMIC_P = every user       */
-    int32_t  reserved[1];
+    /* model extension, all off at 0 */
+    float    lr_decay;         /* learning-rate schedule: epoch e runs at lr_e, lr_0 = lr, lr_(e+1) = lr_e * lr_decay (one binary32
+                                  multiply per epoch: MatrixFactorizationSGD.java learningRate); 0 = constant rate, else in (0, 1] */
+    int32_t  early_stop_patience; /* > 0: mfsgd_train evaluates the held-out set after every epoch and returns once its RMSE has
+                                  failed `patience` times in a row to fall below best * (1 - early_stop_min_delta)
+                                  (MatrixFactorizationSGD.java factorizeEarlyStop); needs a held-out set; mfsgd_get_progress reports */
+    float    early_stop_min_delta; /* relative improvement that counts, in [0, 1)                                 */
+    int32_t  reserved[3];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA
@@ -181,6 +188,9 @@ MFSGD_API int  mfsgd_get_factors(mfsgd_handle* h, float* P, float* Q);     /* mu
  * only this rank's rows are written). MFSGD_E_STATE for the bias arrays when MFSGD_MODEL_BIASES is off. */
 MFSGD_API int  mfsgd_get_model(mfsgd_handle* h, float* global_mean, float* user_bias, float* item_bias);
 MFSGD_API int  mfsgd_set_biases(mfsgd_handle* h, const float* user_bias, const float* item_bias);
+/* Epochs trained since the ratings were loaded, the learning rate the next epoch would use (lr_decay), and whether the last
+ * mfsgd_train call returned on the early-stopping rule. Every out pointer is nullable. */
+MFSGD_API int  mfsgd_get_progress(mfsgd_handle* h, int32_t* epochs_done, float* next_lr, int32_t* stopped_early);
 /* Row ranges this process owns (users [u_lo,u_hi), items [i_lo,i_hi)) -- whole matrices when world_size==1. */
 MFSGD_API int  mfsgd_get_partition(mfsgd_handle* h, int32_t* u_lo, int32_t* u_hi, int32_t* i_lo, int32_t* i_hi);
 

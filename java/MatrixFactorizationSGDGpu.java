@@ -34,7 +34,7 @@ public final class MatrixFactorizationSGDGpu {
 
     public static final int MODE_DETERMINISTIC = 0, MODE_HOGWILD = 1, MODE_DSGD = 2;
 
-    /** struct mfsgd_config (include/mfsgd.h), 232 bytes; field order and padding as laid out by the C compiler. */
+    /** struct mfsgd_config (include/mfsgd.h, ABI 3), 248 bytes; field order and padding as laid out by the C compiler. */
     static final StructLayout CONFIG = MemoryLayout.structLayout(
             JAVA_INT.withName("n_users"), JAVA_INT.withName("n_items"), JAVA_INT.withName("k"),
             JAVA_FLOAT.withName("lr"), JAVA_FLOAT.withName("lambda"), JAVA_FLOAT.withName("init_scale"),
@@ -45,8 +45,10 @@ public final class MatrixFactorizationSGDGpu {
             MemoryLayout.sequenceLayout(128, JAVA_BYTE).withName("nccl_id"),   /* offset 68 */
             JAVA_INT.withName("ctas_per_sm"),                             /* offset 196 */
             JAVA_INT.withName("rounds"), JAVA_FLOAT.withName("hot_share"), JAVA_INT.withName("hot_chunk"),
-            MemoryLayout.sequenceLayout(4, JAVA_INT).withName("reserved"),
-            MemoryLayout.paddingLayout(4));                              /* tail padding to 232 */
+            JAVA_FLOAT.withName("merge_boost"), JAVA_INT.withName("model"),  /* offsets 212, 216 */
+            JAVA_FLOAT.withName("p_atomic_threshold"), JAVA_FLOAT.withName("lr_decay"),
+            JAVA_INT.withName("early_stop_patience"), JAVA_FLOAT.withName("early_stop_min_delta"),   /* offsets 228, 232 */
+            MemoryLayout.sequenceLayout(3, JAVA_INT).withName("reserved"));  /* 248 bytes, no tail padding */
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB = SymbolLookup.libraryLookup(

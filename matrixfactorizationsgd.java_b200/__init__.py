@@ -10,7 +10,7 @@ from . import _capi as capi  # noqa: F401  (loads libmfsgd.so or raises)
 from ._capi import MfsgdError  # noqa: F401
 from .engine import (Engine, apply_updates_forced, device_count, generate_to_host, make_config, measure_ceilings,  # noqa: F401
                      nccl_unique_id, synth_params, synth_params_of)
-from .host import Factors, MatrixFactorizationSGD, Model, RatingsFile, read_ratings  # noqa: F401
+from .host import EarlyStopResult, Factors, MatrixFactorizationSGD, Model, RatingsFile, read_ratings  # noqa: F401
 from .workloads import SEED, WORKLOADS, bytes_per_update  # noqa: F401
 
 __all__ = ["MatrixFactorizationSGD", "Factors", "Engine", "MfsgdError", "make_config", "synth_params", "synth_params_of",

@@ -16,7 +16,7 @@ SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
 FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE, FLAG_EXACT_ARITH, FLAG_SPLIT_SHARDS = 1, 2, 4, 8, 16
 FLAG_MATERIALIZE_SHUFFLE = 32
 MODEL_GLOBAL_MEAN, MODEL_BIASES = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Config(C.Structure):
@@ -26,7 +26,8 @@ class Config(C.Structure):
                 ("scatter", C.c_int32), ("flags", C.c_uint32), ("device", C.c_int32), ("world_size", C.c_int32),
                 ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
                 ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("merge_boost", C.c_float),
-                ("model", C.c_uint32), ("p_atomic_threshold", C.c_float), ("reserved", C.c_int32 * 1)]
+                ("model", C.c_uint32), ("p_atomic_threshold", C.c_float), ("lr_decay", C.c_float),
+                ("early_stop_patience", C.c_int32), ("early_stop_min_delta", C.c_float), ("reserved", C.c_int32 * 3)]
 
 
 class EpochStats(C.Structure):
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mfsgd_get_factors": (C.c_int, [_vp, _vp, _vp]),
     "mfsgd_get_model": (C.c_int, [_vp, C.POINTER(C.c_float), _vp, _vp]),
     "mfsgd_set_biases": (C.c_int, [_vp, _vp, _vp]),
+    "mfsgd_get_progress": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(C.c_float), C.POINTER(_i32)]),
     "mfsgd_get_partition": (C.c_int, [_vp] + [C.POINTER(_i32)] * 4),
     "mfsgd_train": (C.c_int, [_vp, _i32, C.POINTER(EpochStats)]),
     "mfsgd_train_traced": (C.c_int, [_vp, _i32, C.POINTER(EpochStats), _vp]),

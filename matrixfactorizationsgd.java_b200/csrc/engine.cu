@@ -237,10 +237,20 @@ struct mfsgd_handle {
     bool loaded = false, factors_ready = false;
     int epoch = 0;
     int eval_every = 0;
+    // model extension: learning-rate schedule and early stopping
+    float lr_decay = 1.f;    // lr of epoch e+1 = lr of epoch e * lr_decay, one binary32 multiply (MatrixFactorizationSGD.java learningRate)
+    float lr_now = 0.f;      // lr of the next epoch to run
+    int es_patience = 0;     // 0 = off
+    float es_min_delta = 0.f;
+    double es_best = std::numeric_limits<double>::infinity();
+    int es_bad = 0;
+    bool es_stopped = false; // the last mfsgd_train call ended on the early-stopping rule
+    double* d_allreduce = nullptr;   // 2 doubles on member 0's device: (sse, n) summed over a multi-process ring
     int64_t n_train_total = 0;
     ncclComm_t comm = nullptr;
     bool multi_process = false;
     int min_windows = 128;   // MFSGD_MIN_WINDOWS overrides (tuning aid)
+    int sub_warp_div = 4;    // run kernel: at most (users of a P sub-stripe) / sub_warp_div runs in flight; MFSGD_SUBWARP_DIV overrides
 };
 
 static inline int group_lo(const mfsgd_handle* h, int grp) { return h->item_bounds[(size_t)grp * h->mi]; }
@@ -492,6 +502,9 @@ static int validate_config(const mfsgd_config* c) {
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
     if (c->hot_chunk < 0 || c->hot_chunk > 65536) return fail(MFSGD_E_INVALID_ARG, "hot_chunk=%d out of range (0..65536)", c->hot_chunk);
     if (c->model & ~(MFSGD_MODEL_GLOBAL_MEAN | MFSGD_MODEL_BIASES)) return fail(MFSGD_E_INVALID_ARG, "unknown model bits 0x%x", c->model);
+    if (!(c->lr_decay >= 0.f) || c->lr_decay > 1.f) return fail(MFSGD_E_INVALID_ARG, "lr_decay must be 0 (constant rate) or in (0, 1]");
+    if (c->early_stop_patience < 0) return fail(MFSGD_E_INVALID_ARG, "early_stop_patience < 0");
+    if (!(c->early_stop_min_delta >= 0.f) || c->early_stop_min_delta >= 1.f) return fail(MFSGD_E_INVALID_ARG, "early_stop_min_delta must be in [0, 1)");
     if (c->p_atomic_threshold != c->p_atomic_threshold) return fail(MFSGD_E_INVALID_ARG, "p_atomic_threshold is NaN");
     if (!(c->merge_boost >= 0.f) || c->merge_boost >= 2.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
     if (c->merge_boost > 0.f && c->merge_boost < 1.f) return fail(MFSGD_E_INVALID_ARG, "merge_boost must be 0 (default) or in [1, 2)");
@@ -555,6 +568,10 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         }
     }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->d_allreduce && !h->members.empty()) {
+        cudaSetDevice(h->members[0].device);
+        dev_free(h->d_allreduce);
+    }
     for (Member& m : h->members) {
         free_member_data(m);
         dev_free(m.d_scratch);
@@ -599,8 +616,13 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     h->G = cfg->n_gpus;
     h->multi_process = cfg->world_size > 1;
     if (const char* mw = getenv("MFSGD_MIN_WINDOWS")) h->min_windows = std::max(1, atoi(mw));
+    if (const char* sd = getenv("MFSGD_SUBWARP_DIV")) h->sub_warp_div = std::max(1, atoi(sd));
     h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
     h->biases = (cfg->model & MFSGD_MODEL_BIASES) != 0;
+    h->lr_decay = cfg->lr_decay > 0.f ? cfg->lr_decay : 1.f;
+    h->lr_now = cfg->lr;
+    h->es_patience = cfg->early_stop_patience;
+    h->es_min_delta = cfg->early_stop_min_delta;
     const bool virtual_ring = (cfg->flags & MFSGD_FLAG_VIRTUAL_RING) != 0;
     const int n_local = h->multi_process ? 1 : h->G;
     if (!virtual_ring && !h->multi_process && cfg->device + h->G > ndev) {
@@ -1102,6 +1124,10 @@ static int load_training(mfsgd_handle* h, const Source& src, bool with_heldout) 
     h->loaded = false;
     h->factors_ready = false;
     h->epoch = 0;
+    h->lr_now = c.lr;
+    h->es_best = std::numeric_limits<double>::infinity();
+    h->es_bad = 0;
+    h->es_stopped = false;
     choose_blocking(h);
     if (h->UB > 65535 || h->IB > 65535) return fail(MFSGD_E_INVALID_ARG, "too many blocks");
     if (c.mode == MFSGD_MODE_DETERMINISTIC && src.total > CHUNK_MAX)     // staged and sorted as one chunk (one warp walks it anyway)
@@ -1644,7 +1670,7 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
             a.first = 0;
             a.n = m.n_recs;
             if (m.counter_next >= m.n_counters * COUNTER_EPOCHS) return fail(MFSGD_E_STATE, "run launch counters exhausted");
-            const int sub_warp_cap = (int)std::min<int64_t>(1 << 30, (int64_t)(m.u_hi - m.u_lo) / (4 * h->mu));   // a quarter of the sub-stripe's users
+            const int sub_warp_cap = (int)std::min<int64_t>(1 << 30, (int64_t)(m.u_hi - m.u_lo) / ((int64_t)h->sub_warp_div * h->mu));   // a fraction of the sub-stripe's users
             auto overlaps = [&](const Visit& w) {
                 return hot_launch_overlaps(c.k, w.unit_hi - w.unit_lo, m.unit_recs_cum[(size_t)w.unit_hi] - m.unit_recs_cum[(size_t)w.unit_lo],
                                            m.run_chunk, m.hot_grid, sub_warp_cap);
@@ -1668,6 +1694,23 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
         CK(cudaEventRecord(ev_join, hot_s));
         CK(cudaStreamWaitEvent(cold_s, ev_join, 0));
     }
+    return MFSGD_OK;
+}
+
+// Multi-process ring: (sse, n) of a held-out pass summed over the ranks (ncclAllReduce of two doubles on member 0's stream).
+// Collective: every rank evaluates in the same epochs (same configuration), so every rank gets here together.
+static int allreduce_sse(mfsgd_handle* h, double* sse, int64_t* n) {
+    Member& m = h->members[0];
+    CK(cudaSetDevice(m.device));
+    if (!h->d_allreduce) CK(dev_alloc(&h->d_allreduce, 2));
+    double v[2] = {*sse, (double)*n};
+    CK(cudaMemcpyAsync(h->d_allreduce, v, sizeof(v), cudaMemcpyHostToDevice, m.stream));
+    ncclResult_t r = g_nccl.AllReduce(h->d_allreduce, h->d_allreduce, 2, ncclFloat64, ncclSum, h->comm, m.stream);
+    if (r != ncclSuccess) return fail(MFSGD_E_NCCL, "all-reduce of the held-out error: %s", g_nccl.GetErrorString(r));
+    CK(cudaMemcpyAsync(v, h->d_allreduce, sizeof(v), cudaMemcpyDeviceToHost, m.stream));
+    CK(cudaStreamSynchronize(m.stream));
+    *sse = v[0];
+    *n = (int64_t)(v[1] + 0.5);
     return MFSGD_OK;
 }
 
@@ -1754,7 +1797,12 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         resolved = upto;
         return MFSGD_OK;
     };
-    const bool want_eval = h->eval_every && !h->members[0].heldout.group_off.empty();
+    const bool have_heldout = !h->members[0].heldout.group_off.empty();
+    if (h->es_patience > 0 && !have_heldout) return fail(MFSGD_E_STATE, "early stopping needs a held-out set (mfsgd_load_heldout / mfsgd_generate_synthetic)");
+    const bool want_eval = (h->eval_every || h->es_patience > 0) && have_heldout;
+    h->es_bad = 0;
+    h->es_stopped = false;
+    int ran = epochs;        // epochs this call actually runs (early stopping may cut it short)
     for (int ep = 0; ep < epochs && rc == MFSGD_OK; ep++) {
         for (Member& m : h->members) {
             m.launches = 0;
@@ -1797,7 +1845,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 a.k = c.k;
                 a.u_base = m.u_lo;
                 a.i_base = group_lo(h, grp);
-                a.lr = c.lr;
+                a.lr = h->lr_now;
                 a.lambda = c.lambda;
                 a.seed = c.seed;
                 a.epoch = (uint32_t)h->epoch;
@@ -1907,15 +1955,33 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             er.update_launches = m.update_launches;
         }
         h->epoch++;
+        h->lr_now = h->lr_now * h->lr_decay;          // binary32 multiply, epoch by epoch: the same value on every host
         if (want_eval) {
             CKRC(resolve(ep + 1));
             double sse = 0.0;
             int64_t n = 0;
             rc = rmse_pass(h, true, &sse, &n);
-            if (rc == MFSGD_OK && stats) stats[ep].heldout_rmse = n > 0 ? std::sqrt(sse / (double)n) : 0.0;
+            if (rc == MFSGD_OK && h->multi_process) rc = allreduce_sse(h, &sse, &n);   // every rank sees the ring's RMSE
+            const double v = n > 0 ? std::sqrt(sse / (double)n) : 0.0;
+            if (rc == MFSGD_OK && stats) stats[ep].heldout_rmse = v;
+            if (rc == MFSGD_OK && h->es_patience > 0) {     // MatrixFactorizationSGD.java factorizeEarlyStop: the rule, verbatim
+                if (v < h->es_best * (1.0 - (double)h->es_min_delta)) {
+                    h->es_best = v;
+                    h->es_bad = 0;
+                } else if (++h->es_bad >= h->es_patience) {
+                    h->es_stopped = true;
+                    ran = ep + 1;
+                    break;
+                }
+            }
         }
     }
-    if (rc == MFSGD_OK) rc = resolve(epochs);
+    if (rc == MFSGD_OK) rc = resolve(ran);
+    if (rc == MFSGD_OK && stats)
+        for (int ep = ran; ep < epochs; ep++) {       // epochs the early-stopping rule skipped: updates == 0
+            stats[ep] = mfsgd_epoch_stats{};
+            stats[ep].heldout_rmse = std::numeric_limits<double>::quiet_NaN();
+        }
     return rc;
 }
 
@@ -1925,6 +1991,13 @@ extern "C" int mfsgd_train(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* s
 extern "C" int mfsgd_train_traced(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats, float* err_trace) {
     if (!err_trace) return fail(MFSGD_E_INVALID_ARG, "err_trace is null");
     return guarded([&]() { return train_impl(h, epochs, stats, err_trace); });
+}
+extern "C" int mfsgd_get_progress(mfsgd_handle* h, int32_t* epochs_done, float* next_lr, int32_t* stopped_early) {
+    if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");
+    if (epochs_done) *epochs_done = (int32_t)h->epoch;
+    if (next_lr) *next_lr = h->lr_now;
+    if (stopped_early) *stopped_early = h->es_stopped ? 1 : 0;
+    return MFSGD_OK;
 }
 extern "C" int mfsgd_set_eval_every_epoch(mfsgd_handle* h, int32_t on) {
     if (!h) return fail(MFSGD_E_INVALID_ARG, "handle is null");

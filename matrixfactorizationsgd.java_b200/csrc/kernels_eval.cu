@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __res
                 if (act && (FULL || c < chunks)) s = dot4_acc(s, ld_row4(prow + 4 * c), ld_row4(qrow + 4 * c));
             }
             s = group_sum<LANES>(s);
-            if (BU != nullptr && act) s = __fadd_rn(__fadd_rn(s, __ldcg(BU + (u - u_base))), __ldcg(BI + (i - i_base)));   // rmseModel :328
+            if (BU != nullptr && act) s = __fadd_rn(__fadd_rn(s, __ldcg(BU + (u - u_base))), __ldcg(BI + (i - i_base)));   // rmseModel :389
             const float e = __fsub_rn(r, s);
             if (act && gl == 0) acc += (double)e * (double)e;
         }

@@ -12,7 +12,8 @@ from ._capi import Config, EpochStats, LayoutInfo, SynthParams, check, lib, ptr,
 def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_HOGWILD, n_gpus=1,
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
                 world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0,
-                merge_boost=0.0, p_atomic_threshold=0.0, model=0):
+                merge_boost=0.0, p_atomic_threshold=0.0, model=0, lr_decay=0.0, early_stop_patience=0,
+                early_stop_min_delta=0.0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -24,6 +25,7 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.hot_share, cfg.hot_chunk, cfg.merge_boost = float(hot_share), int(hot_chunk), float(merge_boost)
     cfg.p_atomic_threshold = float(p_atomic_threshold)
     cfg.model = int(model)
+    cfg.lr_decay, cfg.early_stop_patience, cfg.early_stop_min_delta = float(lr_decay), int(early_stop_patience), float(early_stop_min_delta)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg
@@ -131,6 +133,12 @@ class Engine:
             return mu.value, bu, bi
         check(lib.mfsgd_get_model(self._h, C.byref(mu), None, None))
         return mu.value, None, None
+
+    def progress(self):
+        """(epochs trained since the load, learning rate of the next epoch, last train() ended on the early-stopping rule)."""
+        ep, lr, stopped = C.c_int32(0), C.c_float(0.0), C.c_int32(0)
+        check(lib.mfsgd_get_progress(self._h, C.byref(ep), C.byref(lr), C.byref(stopped)))
+        return ep.value, lr.value, bool(stopped.value)
 
     def set_biases(self, user_bias, item_bias):
         bu, bi = as_f32(user_bias), as_f32(item_bias)

@@ -19,6 +19,8 @@ from .engine import Engine, make_config
 Factors = namedtuple("Factors", ["P", "Q", "nUsers", "nItems", "k"])
 #: the model extension's result (stand-in Model :257): userBias / itemBias are None when the biases are off
 Model = namedtuple("Model", ["P", "Q", "userBias", "itemBias", "globalMean", "nUsers", "nItems", "k"])
+#: stand-in EarlyStopResult (:339)
+EarlyStopResult = namedtuple("EarlyStopResult", ["model", "epochsRun", "validationRmse"])
 #: a parsed ratings file: dense triplets + the file ids of every row (RatingsFile.userIds[u] is the file's id of row u)
 RatingsFile = namedtuple("RatingsFile", ["users", "items", "ratings", "nUsers", "nItems", "userIds", "itemIds", "format"])
 
@@ -81,13 +83,35 @@ class MatrixFactorizationSGD:
         return Model(P, Q, bu, bi, mu, nUsers, nItems, k)
 
     @staticmethod
+    def factorizeEarlyStop(users, items, ratings, vUsers, vItems, vRatings, nUsers, nItems, k, lr, lambda_, maxEpochs, seed,
+                           useGlobalMean, useBiases, lrDecay, patience, minDelta, mode=capi.MODE_HOGWILD, n_gpus=1, device=0, **cfg_kw):
+        """Stand-in factorizeEarlyStop (:350): the learning-rate schedule lr_(e+1) = lr_e * lrDecay and the early-stopping rule
+        on the validation RMSE, both evaluated inside mfsgd_train (the validation set lives on the device)."""
+        MatrixFactorizationSGD._check(users, items, ratings, nUsers, nItems, k, maxEpochs)
+        if not (0.0 < lrDecay <= 1.0) or patience < 0 or not (0.0 <= minDelta < 1.0):
+            raise ValueError("bad schedule")                                  # stand-in line 356-357
+        bits = (capi.MODEL_GLOBAL_MEAN if useGlobalMean else 0) | (capi.MODEL_BIASES if useBiases else 0)
+        cfg = make_config(nUsers, nItems, k, lr, lambda_, seed=seed, mode=mode, n_gpus=n_gpus, device=device, model=bits,
+                          lr_decay=lrDecay, early_stop_patience=patience, early_stop_min_delta=minDelta, **cfg_kw)
+        with Engine(cfg) as eng:
+            eng.load_ratings(users, items, ratings)
+            eng.load_heldout(vUsers, vItems, vRatings)
+            eng.init_factors()
+            eng.set_eval_every_epoch(True)
+            stats = eng.train(maxEpochs) if maxEpochs > 0 else []
+            ran = eng.progress()[0]
+            P, Q = eng.get_factors()
+            mu, bu, bi = eng.get_model()
+        return EarlyStopResult(Model(P, Q, bu, bi, mu, nUsers, nItems, k), ran, [s.heldout_rmse for s in stats[:ran]])
+
+    @staticmethod
     def rmseModel(model, users, items, ratings, device=0):
-        """Stand-in rmseModel (:328): e = (r - mu) - ((p_u . q_i + b_u) + b_i), evaluated by the RMSE kernel."""
+        """Stand-in rmseModel (:389): e = (r - mu) - ((p_u . q_i + b_u) + b_i), evaluated by the RMSE kernel."""
         P, Q = capi.as_f32(model.P), capi.as_f32(model.Q)
         biased = model.userBias is not None
         cfg = make_config(P.shape[0], Q.shape[0], model.k, 1e-3, 0.0, mode=capi.MODE_HOGWILD, device=device, stripes_per_gpu=1,
                           model=capi.MODEL_BIASES if biased else 0)
-        rc = (capi.as_f32(ratings) - np.float32(model.globalMean)).astype(np.float32)      # one binary32 subtraction, as :335
+        rc = (capi.as_f32(ratings) - np.float32(model.globalMean)).astype(np.float32)      # one binary32 subtraction, as :399
         with Engine(cfg) as eng:
             eng.load_ratings(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.float32))
             eng.set_factors(P, Q)

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <limits>
 #include <vector>
 
 #define ORC_API extern "C" __attribute__((visibility("default")))
@@ -308,7 +309,7 @@ ORC_API int orc_train_model(const int32_t* u, const int32_t* i, const float* rc,
     return 0;
 }
 
-/* MatrixFactorizationSGD.java:328 rmseModel on centred ratings */
+/* MatrixFactorizationSGD.java:389 rmseModel on centred ratings */
 ORC_API double orc_rmse_model(const float* P, const float* Q, const float* bu, const float* bi, int k, const int32_t* u, const int32_t* i,
                               const float* rc, int64_t n, int order_mode) {
     double sse = 0.0;
@@ -319,6 +320,43 @@ ORC_API double orc_rmse_model(const float* P, const float* Q, const float* bu, c
         sse += (double)e * (double)e;
     }
     return n == 0 ? 0.0 : std::sqrt(sse / (double)n);
+}
+
+/* MatrixFactorizationSGD.java:331 learningRate: lr_0 = lr, lr_(e+1) = lr_e * decay, one binary32 multiply per epoch */
+ORC_API float orc_learning_rate(float lr, float decay, int epoch) {
+    float l = lr;
+    for (int e = 0; e < epoch; e++) l = l * decay;
+    return l;
+}
+
+/* MatrixFactorizationSGD.java:350 factorizeEarlyStop's loop on existing P, Q, biases; rc / vrc = centred training / validation ratings.
+ * curve[e] = validation RMSE after epoch e (max_epochs entries). Returns the epochs run, or -1 on bad triplets. */
+ORC_API int orc_train_early_stop(const int32_t* u, const int32_t* i, const float* rc, int64_t n, const int32_t* vu, const int32_t* vi,
+                                 const float* vrc, int64_t vn, float* P, float* Q, float* bu, float* bi, int nU, int nI, int k, float lr,
+                                 float lambda, float lr_decay, int patience, float min_delta, int max_epochs, uint64_t seed,
+                                 int order_mode, double* curve) {
+    if (n > 0x7fffffffLL || check_triplets(u, i, n, nU, nI) || check_triplets(vu, vi, vn, nU, nI)) return -1;
+    std::vector<int32_t> order((size_t)n);
+    double best = std::numeric_limits<double>::infinity();
+    int strikes = 0, ran = 0;
+    float lr_now = lr;
+    for (int epoch = 0; epoch < max_epochs; epoch++) {
+        orc_shuffle(seed, epoch, (int)n, order.data());
+        for (int64_t j = 0; j < n; j++) {
+            int32_t t = order[j];
+            orc_sgd_update_model(P + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, bu ? bu + u[t] : nullptr, bi ? bi + i[t] : nullptr,
+                                 rc[t], lr_now, lambda, order_mode);
+        }
+        lr_now = lr_now * lr_decay;
+        ran = epoch + 1;
+        const double v = orc_rmse_model(P, Q, bu, bi, k, vu, vi, vrc, vn, order_mode);
+        if (curve) curve[epoch] = v;
+        if (patience > 0) {
+            if (v < best * (1.0 - (double)min_delta)) { best = v; strikes = 0; }
+            else if (++strikes >= patience) break;
+        }
+    }
+    return ran;
 }
 
 /*

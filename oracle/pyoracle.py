@@ -89,6 +89,12 @@ def _load():
     lib.orc_sgd_update_model.argtypes = [_f32p, _f32p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
     lib.orc_rmse_model.restype = C.c_double
     lib.orc_rmse_model.argtypes = [_f32p, _f32p, C.c_void_p, C.c_void_p, C.c_int, _i32p, _i32p, _f32p, C.c_int64, C.c_int]
+    lib.orc_learning_rate.restype = C.c_float
+    lib.orc_learning_rate.argtypes = [C.c_float, C.c_float, C.c_int]
+    lib.orc_train_early_stop.restype = C.c_int
+    lib.orc_train_early_stop.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_uint64,
+                                         C.c_int, C.POINTER(C.c_double)]
     lib.orc_set_tree_lanes.restype = None
     lib.orc_set_tree_lanes.argtypes = [C.c_int]
     return lib
@@ -230,6 +236,22 @@ def train_model(u, i, rc, P, Q, bu, bi, lr, lam, epoch_begin, epoch_end, seed, o
                               P.shape[0], Q.shape[0], P.shape[1], lr, lam, epoch_begin, epoch_end, seed, order_mode, int(shuffled))
     if rc_:
         raise ValueError("oracle: bad triplets")
+
+
+def learning_rate(lr, decay, epoch):
+    """Stand-in learningRate: lr * decay^epoch by repeated binary32 multiplication."""
+    return float(lib.orc_learning_rate(lr, decay, epoch))
+
+
+def train_early_stop(u, i, rc, vu, vi, vrc, P, Q, bu, bi, lr, lam, lr_decay, patience, min_delta, max_epochs, seed, order_mode=ORDER_SEQ):
+    """Stand-in factorizeEarlyStop's loop on centred ratings; returns (epochs run, validation RMSE per epoch run)."""
+    curve = (C.c_double * max(max_epochs, 1))()
+    ran = lib.orc_train_early_stop(u, i, rc, len(rc), vu, vi, vrc, len(vrc), P, Q, None if bu is None else bu.ctypes.data,
+                                   None if bi is None else bi.ctypes.data, P.shape[0], Q.shape[0], P.shape[1], lr, lam, lr_decay, patience,
+                                   min_delta, max_epochs, seed, order_mode, curve)
+    if ran < 0:
+        raise ValueError("oracle: bad triplets")
+    return ran, [curve[e] for e in range(ran)]
 
 
 def rmse_model(P, Q, bu, bi, u, i, rc, order_mode=ORDER_SEQ):

@@ -21,7 +21,7 @@ static const char* SYMBOLS[] = {
     "mfsgd_apply_updates_forced", "mfsgd_generate_to_host", "mfsgd_nccl_unique_id", "mfsgd_host_alloc",
     "mfsgd_host_free", "mfsgd_read_ratings", "mfsgd_free_ratings", "mfsgd_plan_runs", "mfsgd_plan_layout",
     "mfsgd_measure_ceilings", "mfsgd_load_ratings_sharded",
-    "mfsgd_release_cached_memory", "mfsgd_get_model", "mfsgd_set_biases"};
+    "mfsgd_release_cached_memory", "mfsgd_get_model", "mfsgd_set_biases", "mfsgd_get_progress"};
 
 #define EXPECT(cond, msg)                                 \
     do {                                                  \

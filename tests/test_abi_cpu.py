@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_c_layout():
     # offsets the Java FFM layout (java/MatrixFactorizationSGDGpu.java) also hard-codes
-    assert C.sizeof(capi.Config) == 232
+    assert C.sizeof(capi.Config) == 248 and capi.Config.model.offset == 216 and capi.Config.lr_decay.offset == 224
+    assert capi.Config.early_stop_min_delta.offset == 232
     assert capi.Config.seed.offset == 24 and capi.Config.nccl_id.offset == 68 and capi.Config.ctas_per_sm.offset == 196
     assert C.sizeof(capi.EpochStats) == 72
     assert C.sizeof(capi.SynthParams) == 48 and capi.SynthParams.planted_amplitude.offset == 40

@@ -456,3 +456,62 @@ def test_run_twin_carries_biases_like_q():
     np.testing.assert_allclose(Q, Qh, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(bi, bih, rtol=1e-6, atol=1e-8)
     assert np.abs(bu).max() > 0 and not np.allclose(bi, 0.25)
+
+
+# ------------------------------------------------------------------------------------------------
+# model extension: learning-rate schedule and early stopping -- stand-in learningRate :331, factorizeEarlyStop :350
+# ------------------------------------------------------------------------------------------------
+def test_learning_rate_schedule_is_repeated_binary32_multiplication():
+    lr, d = np.float32(0.02), np.float32(0.9)
+    want = lr
+    for e in range(12):
+        assert np.float32(orc.learning_rate(float(lr), float(d), e)) == want
+        want = np.float32(want * d)
+    assert orc.learning_rate(0.005, 1.0, 1000) == float(np.float32(0.005))
+
+
+def _model_set(nu=60, ni=40, n=3000, k=8):
+    u, i, r, held = orc.generate(SEED, 0, n, nu, ni)
+    mu = np.float32(orc.global_mean(r[~held].copy()))
+    tr = (u[~held].copy(), i[~held].copy(), (r[~held] - mu).astype(np.float32))
+    va = (u[held].copy(), i[held].copy(), (r[held] - mu).astype(np.float32))
+    return nu, ni, k, tr, va
+
+
+def test_early_stop_loop_is_the_model_loop_with_a_schedule():
+    nu, ni, k, tr, va = _model_set()
+    for decay in (1.0, 0.8):
+        P, Q = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+        bu, bi = np.zeros(nu, np.float32), np.zeros(ni, np.float32)
+        ran, curve = orc.train_early_stop(*tr, *va, P, Q, bu, bi, 0.02, 0.05, decay, 0, 0.0, 5, SEED)
+        assert ran == 5 and len(curve) == 5
+        Pm, Qm = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+        bum, bim = np.zeros(nu, np.float32), np.zeros(ni, np.float32)
+        for e in range(5):
+            orc.train_model(*tr, Pm, Qm, bum, bim, orc.learning_rate(0.02, decay, e), 0.05, e, e + 1, SEED)
+            assert curve[e] == orc.rmse_model(Pm, Qm, bum, bim, *va)
+        assert np.array_equal(P, Pm) and np.array_equal(Q, Qm) and np.array_equal(bu, bum) and np.array_equal(bi, bim)
+
+
+def test_early_stop_rule():
+    nu, ni, k, tr, va = _model_set()
+    fresh = lambda: (orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1), np.zeros(nu, np.float32), np.zeros(ni, np.float32))
+    # an improvement of 50 % per epoch never happens after the first epoch: 1 + patience epochs run
+    for patience in (1, 3):
+        ran, curve = orc.train_early_stop(*tr, *va, *fresh(), 0.02, 0.05, 1.0, patience, 0.5, 20, SEED)
+        assert ran == 1 + patience and len(curve) == ran
+    # min_delta 0: stops `patience` epochs after the validation curve's first non-improvement, if it has one
+    full_ran, full = orc.train_early_stop(*tr, *va, *fresh(), 0.1, 0.0, 1.0, 0, 0.0, 40, SEED)
+    assert full_ran == 40
+    best, strikes, want = float("inf"), 0, 40
+    for e, v in enumerate(full):
+        if v < best:
+            best, strikes = v, 0
+        else:
+            strikes += 1
+            if strikes >= 2:
+                want = e + 1
+                break
+    ran, curve = orc.train_early_stop(*tr, *va, *fresh(), 0.1, 0.0, 1.0, 2, 0.0, 40, SEED)
+    assert ran == want and curve == full[:ran]
+    assert want < 40          # lr 0.1 without regularisation overfits this set within 40 epochs

@@ -1,0 +1,47 @@
+"""Run-to-run spread of the mid-size RMSE parity cases (tests/test_gpu_parity.py fixtures): Hogwild is nondeterministic, so a
+case that sits near the 0.5 % bar fails now and then. Prints rel = got / oracle - 1 per repetition.
+  python tools/rmse_spread.py [reps]"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import matrixfactorizationsgd.java_b200 as mf   # noqa: E402
+from matrixfactorizationsgd.java_b200 import _capi as capi   # noqa: E402
+from test_gpu_parity import SEED, MidSet   # noqa: E402
+
+
+def main():
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    extra = json.loads(sys.argv[2]) if len(sys.argv) > 2 else {}
+    for signal in ((True,) if os.environ.get('SPREAD_SIGNAL_ONLY') else (True, False)):
+        m = MidSet(signal)
+        for mode, G, mu, mi, flags in ((capi.MODE_HOGWILD, 1, 1, 0, 0), (capi.MODE_HOGWILD, 1, 4, 0, 0), (capi.MODE_HOGWILD, 1, 1, 0, 32),
+                                       (capi.MODE_HOGWILD, 1, 4, 0, 32), (capi.MODE_DSGD, 2, 1, 1, 2), (capi.MODE_DSGD, 4, 2, 2, 2),
+                                       (capi.MODE_DSGD, 8, 1, 1, 2)):
+            rels, info = [], None
+            for _ in range(reps):
+                cfg = mf.make_config(m.nu, m.ni, m.k, m.lr, m.lam, seed=SEED, mode=mode, n_gpus=G, stripes_per_gpu=mu, shards_per_gpu=mi,
+                                     flags=flags, **extra)
+                with mf.Engine(cfg) as eng:
+                    eng.load_ratings(*m.train)
+                    eng.init_factors()
+                    eng.train(m.epochs, want_stats=False)
+                    got = eng.rmse(*m.held)
+                    li = eng.layout_info()
+                    info = (li.n_hot_items, li.n_heavy_users, li.run_length, li.rounds)
+                    ub, ib = eng.bounds()
+                rels.append(got / m.oracle_rmse - 1.0)
+            line = {"signal": signal, "mode": mode, "G": G, "mu": mu, "mi": mi, "flags": flags, "layout": info,
+                    "rel_pct": [round(100 * x, 3) for x in rels], "max_abs_pct": round(100 * max(abs(x) for x in rels), 3)}
+            if mode == capi.MODE_DSGD:
+                line["dsgd_oracle_rel_pct"] = round(100 * (m.dsgd_oracle_rmse(ub[::mu], ib[::mi]) / m.oracle_rmse - 1.0), 3)
+            print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
