@@ -219,6 +219,97 @@ ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float
     return e;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Mixed-precision factor storage (stand-in section "Mixed-precision storage"): P rows are KEPT as binary16,
+ * every operation of the update rule stays binary32. A row is widened exactly on load and narrowed on store with
+ * stochastic rounding driven by a counter hash of (seed, epoch, u, i, chunk) -- no state, any visiting order.
+ * ------------------------------------------------------------------------------------------------ */
+static inline uint32_t f32_bits(float v) { uint32_t b; std::memcpy(&b, &v, 4); return b; }
+static inline float bits_f32(uint32_t b) { float v; std::memcpy(&v, &b, 4); return v; }
+
+/* binary16 -> binary32, exact (stand-in Float.float16ToFloat) */
+ORC_API float orc_f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, ex = (h >> 10) & 0x1Fu, man = h & 0x3FFu;
+    if (ex == 0) {
+        if (man == 0) return bits_f32(sign);
+        float v = (float)man * 0x1.0p-24f;                   /* subnormal: man * 2^-24, exact */
+        return sign ? -v : v;
+    }
+    if (ex == 31) return bits_f32(sign | 0x7F800000u | (man << 13));
+    return bits_f32(sign | ((ex + 112u) << 23) | (man << 13));
+}
+
+/* binary32 -> binary16, round to nearest even (stand-in Float.floatToFloat16; GPU cvt.rn.f16.f32) */
+ORC_API uint16_t orc_f32_to_f16_rn(float v) {
+    const uint32_t b = f32_bits(v), sign = (b >> 16) & 0x8000u, a = b & 0x7FFFFFFFu;
+    if (a >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (a > 0x7F800000u ? 0x200u : 0u));   /* inf / nan */
+    if (a >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                                        /* rounds to inf (>= 65520) */
+    if (a < 0x33000001u) return (uint16_t)sign;                                                    /* <= 2^-25: rounds to 0 */
+    int ex = (int)(a >> 23) - 127;
+    uint32_t man = (a & 0x7FFFFFu) | 0x800000u;               /* 24-bit significand */
+    int shift;                                                /* bits to drop */
+    uint32_t base;
+    if (ex < -14) { shift = 13 + (-14 - ex); base = 0; }      /* subnormal result */
+    else { shift = 13; base = (uint32_t)(ex + 15) << 10; man &= 0x7FFFFFu; }
+    uint32_t q = man >> shift, rem = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (q & 1u))) q++;
+    return (uint16_t)(sign | (base + q));                     /* a carry out of the mantissa bumps the exponent: intended */
+}
+
+/* the 32 random bits of one float4 chunk c of row u at the update (u, i) of `epoch` (lowbias32 finaliser) */
+ORC_API uint32_t orc_sr_word(uint64_t seed, uint32_t epoch, uint32_t u, uint32_t i, uint32_t c) {
+    uint32_t x = (uint32_t)(seed ^ (seed >> 32)) + u * 0x9E3779B1u + i * 0x85EBCA77u + (epoch * 0x10001u + c) * 0xC2B2AE3Du;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+
+/* narrow element j (0..3) of a chunk with stochastic rounding: 8 random bits decide among the 13 dropped mantissa bits */
+ORC_API uint16_t orc_store_f16_sr(float v, uint32_t word, int j) {
+    const uint32_t rho = (((word >> (8 * j)) & 0xFFu) << 5) | 0x10u;
+    return orc_f32_to_f16_rn(bits_f32((f32_bits(v) + rho) & 0xFFFFE000u));
+}
+
+ORC_API void orc_init_factors_f16(uint16_t* rows, int64_t n_rows, int k, uint64_t seed, uint64_t stream, float scale) {
+    for (int64_t e = 0; e < n_rows * (int64_t)k; e++) rows[e] = orc_f32_to_f16_rn(orc_uniform(seed, stream, (uint64_t)e) * scale);
+}
+
+/* sgdUpdate on a binary16 p_u: widen, the rule in `order_mode`, narrow (sr != 0: stochastic, else round to nearest even) */
+ORC_API float orc_sgd_update_mixed(uint16_t* p16, float* q, int k, float r, float lr, float lambda, int order_mode, uint64_t seed,
+                                   uint32_t epoch, int32_t u, int32_t i, int sr) {
+    std::vector<float> p((size_t)k);
+    for (int f = 0; f < k; f++) p[(size_t)f] = orc_f16_to_f32(p16[f]);
+    const float e = orc_sgd_update(p.data(), q, k, r, lr, lambda, order_mode);
+    for (int c = 0; c < k / 4; c++) {
+        const uint32_t w = orc_sr_word(seed, epoch, (uint32_t)u, (uint32_t)i, (uint32_t)c);
+        for (int j = 0; j < 4; j++)
+            p16[4 * c + j] = sr ? orc_store_f16_sr(p[(size_t)(4 * c + j)], w, j) : orc_f32_to_f16_rn(p[(size_t)(4 * c + j)]);
+    }
+    return e;
+}
+
+ORC_API int orc_train_mixed(const int32_t* u, const int32_t* i, const float* r, int64_t n, uint16_t* P16, float* Q, int nU, int nI,
+                            int k, float lr, float lambda, int epoch_begin, int epoch_end, uint64_t seed, int order_mode, int shuffled,
+                            int sr) {
+    if (n > 0x7fffffffLL) return -1;
+    for (int64_t t = 0; t < n; t++)
+        if (u[t] < 0 || u[t] >= nU || i[t] < 0 || i[t] >= nI) return -1;
+    std::vector<int32_t> order((size_t)n);
+    for (int epoch = epoch_begin; epoch < epoch_end; epoch++) {
+        if (shuffled) orc_shuffle(seed, epoch, (int)n, order.data());
+        else for (int64_t j = 0; j < n; j++) order[(size_t)j] = (int32_t)j;
+        for (int64_t j = 0; j < n; j++) {
+            const int32_t t = order[(size_t)j];
+            orc_sgd_update_mixed(P16 + (int64_t)u[t] * k, Q + (int64_t)i[t] * k, k, r[t], lr, lambda, order_mode, seed, (uint32_t)epoch,
+                                 u[t], i[t], sr);
+        }
+    }
+    return 0;
+}
+
+ORC_API void orc_widen_f16(const uint16_t* in, int64_t n, float* out) {
+    for (int64_t e = 0; e < n; e++) out[e] = orc_f16_to_f32(in[e]);
+}
+
 /* MatrixFactorizationSGD.java:272 globalMean: exact integer sum, hence order-independent */
 ORC_API float orc_global_mean(const float* r, int64_t n) {
     int64_t s = 0;

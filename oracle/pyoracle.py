@@ -95,6 +95,25 @@ def _load():
     lib.orc_train_early_stop.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _i32p, _i32p, _f32p, C.c_int64, _f32p, _f32p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_uint64,
                                          C.c_int, C.POINTER(C.c_double)]
+    _u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    lib.orc_f16_to_f32.restype = C.c_float
+    lib.orc_f16_to_f32.argtypes = [C.c_uint16]
+    lib.orc_f32_to_f16_rn.restype = C.c_uint16
+    lib.orc_f32_to_f16_rn.argtypes = [C.c_float]
+    lib.orc_sr_word.restype = C.c_uint32
+    lib.orc_sr_word.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.orc_store_f16_sr.restype = C.c_uint16
+    lib.orc_store_f16_sr.argtypes = [C.c_float, C.c_uint32, C.c_int]
+    lib.orc_init_factors_f16.restype = None
+    lib.orc_init_factors_f16.argtypes = [_u16p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_float]
+    lib.orc_sgd_update_mixed.restype = C.c_float
+    lib.orc_sgd_update_mixed.argtypes = [_u16p, _f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_uint32,
+                                         C.c_int32, C.c_int32, C.c_int]
+    lib.orc_train_mixed.restype = C.c_int
+    lib.orc_train_mixed.argtypes = [_i32p, _i32p, _f32p, C.c_int64, _u16p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                    C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    lib.orc_widen_f16.restype = None
+    lib.orc_widen_f16.argtypes = [_u16p, C.c_int64, _f32p]
     lib.orc_set_tree_lanes.restype = None
     lib.orc_set_tree_lanes.argtypes = [C.c_int]
     return lib
@@ -235,6 +254,28 @@ def train_model(u, i, rc, P, Q, bu, bi, lr, lam, epoch_begin, epoch_end, seed, o
     rc_ = lib.orc_train_model(u, i, rc, len(rc), P, Q, None if bu is None else bu.ctypes.data, None if bi is None else bi.ctypes.data,
                               P.shape[0], Q.shape[0], P.shape[1], lr, lam, epoch_begin, epoch_end, seed, order_mode, int(shuffled))
     if rc_:
+        raise ValueError("oracle: bad triplets")
+
+
+def init_factors_f16(n_rows, k, seed, stream, scale=None):
+    """initFactors narrowed to binary16 (round to nearest even): the mixed-precision storage of P."""
+    rows = np.zeros((n_rows, k), np.uint16)
+    lib.orc_init_factors_f16(rows, n_rows, k, seed, stream, lib.orc_default_init_scale(k) if scale is None else scale)
+    return rows
+
+
+def widen(P16):
+    """binary16 bit patterns -> float32 (exact)."""
+    out = np.zeros(P16.shape, np.float32)
+    lib.orc_widen_f16(np.ascontiguousarray(P16), P16.size, out)
+    return out
+
+
+def train_mixed(u, i, r, P16, Q, lr, lam, epoch_begin, epoch_end, seed, order_mode=ORDER_SEQ, shuffled=True, sr=True):
+    """The stand-in's loop with P kept in binary16 (oracle.cpp orc_train_mixed); sr=False rounds to nearest even instead."""
+    rc = lib.orc_train_mixed(u, i, r, len(r), P16, Q, P16.shape[0], Q.shape[0], Q.shape[1], lr, lam, epoch_begin, epoch_end, seed,
+                             order_mode, int(shuffled), int(sr))
+    if rc:
         raise ValueError("oracle: bad triplets")
 
 

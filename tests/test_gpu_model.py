@@ -8,7 +8,8 @@ import pytest
 import matrixfactorizationsgd.java_b200 as mf
 from matrixfactorizationsgd.java_b200 import _capi as capi
 import pyoracle as orc
-from test_gpu_parity import (SEED, MidSet, assert_ring_rmse_parity, assert_rmse_parity, plan_runs_of, split)  # noqa: F401
+from test_gpu_parity import (SEED, MidSet, assert_curve_parity, assert_ring_rmse_parity, assert_rmse_parity, plan_runs_of,  # noqa: F401
+                             split)
 
 pytestmark = pytest.mark.gpu
 
@@ -188,26 +189,14 @@ def test_model_run_kernel_averaged_merge_matches_its_oracle_twin(k, rounds, shuf
 class ModelMidSet(MidSet):
     """The mid-size sets under the extended model. Noise-dominant: the mean and the biases take the stiff common direction out of
     the factors and the sequential oracle ends below plain MF (which ends ~2 % ABOVE the constant predictor there).
-    Signal-dominant: the sharp case -- the oracle ends 77 % below the constant predictor and still moves per cents per epoch."""
+    Signal-dominant: the sharp case -- the oracle ends 79 % below the constant predictor."""
+    MODEL = "model"
 
     def __init__(self, signal):
         super().__init__(signal=signal)
         self.mu, self.rc = centred(self.train[2], MEAN)
-        P, Q = orc.init_factors(self.nu, self.k, SEED, 0), orc.init_factors(self.ni, self.k, SEED, 1)
-        bu, bi = np.zeros(self.nu, np.float32), np.zeros(self.ni, np.float32)
-        orc.train_model(self.train[0], self.train[1], self.rc, P, Q, bu, bi, self.lr, self.lam, 0, self.epochs, SEED)
         self.hc = (self.held[2] - self.mu).astype(np.float32)
-        self.plain_rmse = self.oracle_rmse
-        self.oracle_rmse = orc.rmse_model(P, Q, bu, bi, self.held[0], self.held[1], self.hc)
-
-    def dsgd_oracle_rmse(self, user_bounds, item_bounds):
-        tu, ti, _ = self.train
-        P, Q = orc.init_factors(self.nu, self.k, SEED, 0), orc.init_factors(self.ni, self.k, SEED, 1)
-        bu, bi = np.zeros(self.nu, np.float32), np.zeros(self.ni, np.float32)
-        for e in range(self.epochs):
-            o = orc.dsgd_order(tu, ti, np.asarray(user_bounds), np.asarray(item_bounds), SEED, e)
-            orc.train_model(tu[o], ti[o], self.rc[o], P, Q, bu, bi, self.lr, self.lam, e, e + 1, SEED, shuffled=False)
-        return orc.rmse_model(P, Q, bu, bi, self.held[0], self.held[1], self.hc)
+        self.plain_rmse = self.fx["plain"]["shuffled"][-1]
 
 
 @pytest.fixture(scope="module")
@@ -241,7 +230,7 @@ def test_model_hogwild_rmse_parity(model_midsize, model_midsize_signal, variant,
     assert np.float32(mu) == m.mu
     assert abs(stats[-1].heldout_rmse - got) < 1e-9
     assert abs(got - orc.rmse_model(P, Q, bu, bi, m.held[0], m.held[1], m.hc)) / got < 1e-6
-    assert_rmse_parity(got, m.oracle_rmse)
+    assert_curve_parity([s.heldout_rmse for s in stats], m.curve)
 
 
 @pytest.mark.parametrize("G,mu_,mi", [(2, 1, 1), (4, 2, 2), (8, 1, 1)])

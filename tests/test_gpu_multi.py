@@ -68,6 +68,9 @@ def test_large_shapes_on_eight_real_gpus(name):
     assert out.returncode == 0, out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RING_WORKLOAD ")][-1]
     res = json.loads(line[len("RING_WORKLOAD "):])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)       # the measured curve and epoch times, for profiles/
+    with open(os.path.join(ROOT, "gpurun_out", "ring_workload_%s_g8.json" % name), "w") as f:
+        json.dump(res, f)
     assert res["n_train"] == res["n_train_oracle"]
     got = res["heldout_rmse_per_epoch"][w.epochs - 1]
     shuffled = res["oracle_rmse_per_epoch"][w.epochs - 1]

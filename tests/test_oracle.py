@@ -515,3 +515,35 @@ def test_early_stop_rule():
     ran, curve = orc.train_early_stop(*tr, *va, *fresh(), 0.1, 0.0, 1.0, 2, 0.0, 40, SEED)
     assert ran == want and curve == full[:ran]
     assert want < 40          # lr 0.1 without regularisation overfits this set within 40 epochs
+
+
+def test_midsize_fixture_is_the_oracles():
+    """tests/golden/oracle_rmse_midsize.json (the GPU parity tests' reference curves) re-derived here for its first epochs:
+    shuffled order, plain and extended model, and the DSGD block order with 4 x 4 strata."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rmse_midsize.json")))
+    nu, ni, n, k = fx["n_users"], fx["n_items"], fx["n_ratings"], fx["k"]
+    assert fx["seed"] == SEED
+    for variant, model, G, epochs in (("default", False, 0, 2), ("signal", True, 0, 1), ("signal", False, 4, 1)):
+        par = fx["params"][variant]
+        u, i, r, held = orc.generate(SEED, 0, n, nu, ni, amplitude=par["amplitude"], noise_scale=par["noise_scale"])
+        tu, ti, tr = u[~held].copy(), i[~held].copy(), r[~held].copy()
+        hu, hi, hr = u[held].copy(), i[held].copy(), r[held].copy()
+        assert (len(tr), len(hr)) == (fx[variant]["n_train"], fx[variant]["n_heldout"])
+        mu = np.float32(orc.global_mean(tr)) if model else np.float32(0)
+        rc, hc = (tr - mu).astype(np.float32), (hr - mu).astype(np.float32)
+        P, Q = orc.init_factors(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+        bu, bi = (np.zeros(nu, np.float32), np.zeros(ni, np.float32)) if model else (None, None)
+        want = fx[variant]["model" if model else "plain"]["dsgd%d" % G if G else "shuffled"]
+        assert len(want) == par["epochs"]
+        for e in range(epochs):
+            if G:
+                o = orc.dsgd_order(tu, ti, orc.balanced_bounds(tu, nu, G), orc.balanced_bounds(ti, ni, G), SEED, e)
+                orc.train_model(tu[o], ti[o], rc[o], P, Q, bu, bi, par["lr"], par["lam"], e, e + 1, SEED, shuffled=False)
+            else:
+                orc.train_model(tu, ti, rc, P, Q, bu, bi, par["lr"], par["lam"], e, e + 1, SEED)
+            assert orc.rmse_model(P, Q, bu, bi, hu, hi, hc) == want[e]
+        if not model and not G:        # orc_train_model without biases is orc_train: the plain curves are factorize()'s
+            Pf, Qf = orc.factorize(tu, ti, tr, nu, ni, k, par["lr"], par["lam"], epochs, SEED)
+            assert np.array_equal(P, Pf) and np.array_equal(Q, Qf)

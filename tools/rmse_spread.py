@@ -23,21 +23,26 @@ def main():
         for mode, G, mu, mi, flags in ((capi.MODE_HOGWILD, 1, 1, 0, 0), (capi.MODE_HOGWILD, 1, 4, 0, 0), (capi.MODE_HOGWILD, 1, 1, 0, 32),
                                        (capi.MODE_HOGWILD, 1, 4, 0, 32), (capi.MODE_DSGD, 2, 1, 1, 2), (capi.MODE_DSGD, 4, 2, 2, 2),
                                        (capi.MODE_DSGD, 8, 1, 1, 2)):
-            rels, info = [], None
+            rels, lags, info = [], [], None
             for _ in range(reps):
                 cfg = mf.make_config(m.nu, m.ni, m.k, m.lr, m.lam, seed=SEED, mode=mode, n_gpus=G, stripes_per_gpu=mu, shards_per_gpu=mi,
                                      flags=flags, **extra)
                 with mf.Engine(cfg) as eng:
                     eng.load_ratings(*m.train)
+                    eng.load_heldout(*m.held)
                     eng.init_factors()
-                    eng.train(m.epochs, want_stats=False)
+                    eng.set_eval_every_epoch(True)
+                    curve = [s.heldout_rmse for s in eng.train(m.epochs)]
                     got = eng.rmse(*m.held)
                     li = eng.layout_info()
                     info = (li.n_hot_items, li.n_heavy_users, li.run_length, li.rounds)
                     ub, ib = eng.bounds()
                 rels.append(got / m.oracle_rmse - 1.0)
+                want = m.curve       # worst margin against the half-epoch-lag bound of assert_curve_parity (negative = inside)
+                lags.append(max(curve[e] / max(want[e], 0.5 * (want[e] + want[e - 1])) - 1.0 for e in range(2, len(want))))
             line = {"signal": signal, "mode": mode, "G": G, "mu": mu, "mi": mi, "flags": flags, "layout": info,
-                    "rel_pct": [round(100 * x, 3) for x in rels], "max_abs_pct": round(100 * max(abs(x) for x in rels), 3)}
+                    "rel_pct": [round(100 * x, 3) for x in rels], "max_abs_pct": round(100 * max(abs(x) for x in rels), 3),
+                    "lag_bound_excess_pct": [round(100 * x, 3) for x in lags]}
             if mode == capi.MODE_DSGD:
                 line["dsgd_oracle_rel_pct"] = round(100 * (m.dsgd_oracle_rmse(ub[::mu], ib[::mi]) / m.oracle_rmse - 1.0), 3)
             print(json.dumps(line), flush=True)
