@@ -401,6 +401,64 @@ public final class MatrixFactorizationSGD {
         return n == 0 ? 0.0 : Math.sqrt(sse / (double) n);
     }
 
+    /* ------------------------------------------------------------------------------------------
+     * Mixed-precision storage (SURVEY.md 8f.3): the rows of P are KEPT as binary16 (short bit patterns), every
+     * operation of the update rule stays binary32. A row is widened exactly before an update and narrowed after it with
+     * stochastic rounding: 8 random bits per value decide among the 13 mantissa bits binary16 drops; they come from a
+     * counter hash of (seed, epoch, u, i, chunk of 4 values) -- no state, the same bits in any visiting order.
+     * Q stays binary32. (Float.float16ToFloat / floatToFloat16: JDK 20+, round to nearest even.)
+     * ------------------------------------------------------------------------------------------ */
+
+    /** The 32 random bits of chunk c (values 4c .. 4c+3) of row u at the update (u, i) of `epoch`: lowbias32 finaliser. */
+    public static int srWord(long seed, int epoch, int u, int i, int c) {
+        int x = (int) (seed ^ (seed >>> 32)) + u * 0x9E3779B1 + i * 0x85EBCA77 + (epoch * 0x10001 + c) * 0xC2B2AE3D;
+        x ^= x >>> 16; x *= 0x7FEB352D; x ^= x >>> 15; x *= 0x846CA68B; x ^= x >>> 16;
+        return x;
+    }
+
+    /** Narrow value j (0..3) of a chunk: push the magnitude up by (byte j of word) * 32 + 16, cut the 13 low mantissa bits, convert. */
+    public static short storeF16Sr(float v, int word, int j) {
+        int rho = (((word >>> (8 * j)) & 0xFF) << 5) | 0x10;
+        return Float.floatToFloat16(Float.intBitsToFloat((Float.floatToRawIntBits(v) + rho) & 0xFFFFE000));
+    }
+
+    /** sgdUpdate on a binary16 p_u (P16 holds bit patterns); returns the error. */
+    public static float sgdUpdateMixed(short[] P16, int pOff, float[] Q, int qOff, int k, float r, float lr, float lambda,
+                                       long seed, int epoch, int u, int i) {
+        float[] p = new float[k];
+        for (int f = 0; f < k; f++) p[f] = Float.float16ToFloat(P16[pOff + f]);
+        float e = sgdUpdate(p, 0, Q, qOff, k, r, lr, lambda);
+        for (int c = 0; c < k / 4; c++) {
+            int w = srWord(seed, epoch, u, i, c);
+            for (int j = 0; j < 4; j++) P16[pOff + 4 * c + j] = storeF16Sr(p[4 * c + j], w, j);
+        }
+        return e;
+    }
+
+    /** factorize with P kept in binary16 (k a multiple of 4); P comes back widened (exactly). */
+    public static Factors factorizeMixed(int[] users, int[] items, float[] ratings, int nUsers, int nItems, int k,
+                                         float lr, float lambda, int epochs, long seed) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || k % 4 != 0 || nUsers <= 0 || nItems <= 0 || epochs < 0) throw new IllegalArgumentException("bad shape");
+        final int n = ratings.length;
+        float[] P = new float[nUsers * k], Q = new float[nItems * k];
+        float scale = defaultInitScale(k);
+        initFactors(P, nUsers, k, seed, STREAM_P_INIT, scale);
+        initFactors(Q, nItems, k, seed, STREAM_Q_INIT, scale);
+        short[] P16 = new short[nUsers * k];
+        for (int e = 0; e < P16.length; e++) P16[e] = Float.floatToFloat16(P[e]);      // round to nearest even, once
+        for (int epoch = 0; epoch < epochs; epoch++) {
+            int[] order = shuffle(seed, epoch, n);
+            for (int j = 0; j < n; j++) {
+                int t = order[j];
+                sgdUpdateMixed(P16, users[t] * k, Q, items[t] * k, k, ratings[t], lr, lambda, seed, epoch, users[t], items[t]);
+            }
+        }
+        for (int e = 0; e < P16.length; e++) P[e] = Float.float16ToFloat(P16[e]);
+        return new Factors(P, Q, nUsers, nItems, k);
+    }
+
     /** ML-100K-shaped demo: sequential and threaded, updates/s and held-out RMSE. */
     public static void main(String[] args) throws Exception {
         final long seed = 20261018L;

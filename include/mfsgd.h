@@ -54,6 +54,13 @@ extern "C" {
                                       rating as it is loaded; mfsgd_get_model returns it                               */
 #define MFSGD_MODEL_BIASES      2u /* user and item biases, b <- b + lr * (e - lambda * b), initialised to 0            */
 
+/* mfsgd_config.p_storage -- mixed-precision factor storage: how the rows of P are KEPT in device memory.
+ * Arithmetic is binary32 either way; P, Q cross this interface as binary32 (get: widened exactly; set: rounded to nearest). */
+#define MFSGD_STORAGE_F32 0      /* the reference's: binary32                                                              */
+#define MFSGD_STORAGE_F16 1      /* binary16 rows, narrowed with stochastic rounding from a counter hash of (seed, epoch, u, i,
+                                    chunk): half the bytes of the update's dominant stream. Needs MFSGD_SCATTER_STORE and, outside
+                                    DETERMINISTIC mode, the FMA arrangement (no MFSGD_FLAG_EXACT_ARITH). Q stays binary32.    */
+
 /* mfsgd_config.flags */
 #define MFSGD_FLAG_TIME_KERNELS   1u /* bracket every update launch with events -> stats.update_kernel_ms */
 #define MFSGD_FLAG_VIRTUAL_RING   2u /* place all n_gpus ring members on one device (scheduler test mode) */
@@ -109,7 +116,8 @@ typedef struct mfsgd_config {
                                   failed `patience` times in a row to fall below best * (1 - early_stop_min_delta)
                                   (MatrixFactorizationSGD.java factorizeEarlyStop); needs a held-out set; mfsgd_get_progress reports */
     float    early_stop_min_delta; /* relative improvement that counts, in [0, 1)                                 */
-    int32_t  reserved[3];
+    int32_t  p_storage;        /* MFSGD_STORAGE_*                                                                  */
+    int32_t  reserved[2];
 } mfsgd_config;
 
 /* One entry per epoch, filled by mfsgd_train when `stats` is non-null. Times are device times (CUDA

@@ -48,7 +48,8 @@ public final class MatrixFactorizationSGDGpu {
             JAVA_FLOAT.withName("merge_boost"), JAVA_INT.withName("model"),  /* offsets 212, 216 */
             JAVA_FLOAT.withName("p_atomic_threshold"), JAVA_FLOAT.withName("lr_decay"),
             JAVA_INT.withName("early_stop_patience"), JAVA_FLOAT.withName("early_stop_min_delta"),   /* offsets 228, 232 */
-            MemoryLayout.sequenceLayout(3, JAVA_INT).withName("reserved"));  /* 248 bytes, no tail padding */
+            JAVA_INT.withName("p_storage"),                                /* offset 236 */
+            MemoryLayout.sequenceLayout(2, JAVA_INT).withName("reserved"));  /* 248 bytes, no tail padding */
 
     private static final Linker LINKER = Linker.nativeLinker();
     private static final SymbolLookup LIB = SymbolLookup.libraryLookup(

@@ -16,6 +16,7 @@ SCATTER_STORE, SCATTER_ATOMIC, SCATTER_ATOMIC_Q, SCATTER_ATOMIC_P = 0, 1, 2, 3
 FLAG_TIME_KERNELS, FLAG_VIRTUAL_RING, FLAG_NO_SHUFFLE, FLAG_EXACT_ARITH, FLAG_SPLIT_SHARDS = 1, 2, 4, 8, 16
 FLAG_MATERIALIZE_SHUFFLE = 32
 MODEL_GLOBAL_MEAN, MODEL_BIASES = 1, 2
+STORAGE_F32, STORAGE_F16 = 0, 1
 ABI_VERSION = 3
 
 
@@ -27,7 +28,8 @@ class Config(C.Structure):
                 ("rank", C.c_int32), ("nccl_id", C.c_uint8 * 128), ("ctas_per_sm", C.c_int32),
                 ("rounds", C.c_int32), ("hot_share", C.c_float), ("hot_chunk", C.c_int32), ("merge_boost", C.c_float),
                 ("model", C.c_uint32), ("p_atomic_threshold", C.c_float), ("lr_decay", C.c_float),
-                ("early_stop_patience", C.c_int32), ("early_stop_min_delta", C.c_float), ("reserved", C.c_int32 * 3)]
+                ("early_stop_patience", C.c_int32), ("early_stop_min_delta", C.c_float), ("p_storage", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class EpochStats(C.Structure):

@@ -4,6 +4,7 @@
 // nearest intrinsic (__fmul_rn/__fadd_rn/__fsub_rn), so nvcc can never contract a*b+c into an FMA;
 // this mirrors the strict binary32 semantics of baseline/java/MatrixFactorizationSGD.java:89-105.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,6 +56,71 @@ __device__ __forceinline__ void st_row4_cs(float* p, float4 v) { __stcs(reinterp
 __device__ __forceinline__ void red_add_row4(float* p, float4 d) {
     // sm_90+: vectorised fire-and-forget float atomic add, resolved in L2.
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                 : "memory");
+}
+
+// ---- mixed-precision factor storage ---------------------------
+// mfsgd_config.p_storage = MFSGD_STORAGE_F16: the rows of P are KEPT as binary16 (half the L2 / HBM bytes of the update's
+// dominant stream), every operation of the rule stays binary32. A chunk of 4 values is widened exactly on load and narrowed on
+// store with stochastic rounding: 8 random bits per value decide among the 13 dropped mantissa bits, drawn from a counter hash
+// of (seed, epoch, u, i, chunk) -- stateless, the same bits in any visiting order, restated by the oracle bit for bit.
+template <bool PH> struct PChunk { using type = float4; };     // what one lane holds of a P row: 4 consecutive values
+template <> struct PChunk<true> { using type = uint2; };       // ... as 4 binary16
+template <bool PH> __host__ __device__ constexpr int p_elem_bytes() { return PH ? 2 : 4; }
+
+__device__ __forceinline__ float4 widen4(float4 v) { return v; }
+__device__ __forceinline__ float4 widen4(uint2 h) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <bool PH>
+__device__ __forceinline__ typename PChunk<PH>::type ld_pchunk(const char* p) {
+    return __ldcg(reinterpret_cast<const typename PChunk<PH>::type*>(p));
+}
+template <bool PH>
+__device__ __forceinline__ typename PChunk<PH>::type zero_pchunk() {
+    if constexpr (PH) return make_uint2(0u, 0u);
+    else return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__host__ __device__ __forceinline__ uint32_t sr_seed32(uint64_t seed) { return (uint32_t)(seed ^ (seed >> 32)); }
+// the 32 random bits of chunk c of row u at the update (u, i) of `epoch` (lowbias32 finaliser)
+__host__ __device__ __forceinline__ uint32_t sr_word(uint32_t s32, uint32_t epoch, uint32_t u, uint32_t i, uint32_t c) {
+    uint32_t x = s32 + u * 0x9E3779B1u + i * 0x85EBCA77u + (epoch * 0x10001u + c) * 0xC2B2AE3Du;
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+// value j of a chunk, pushed up by its random offset and cut to the 10 mantissa bits binary16 keeps;
+// the conversion that follows is exact for normal results and rounds to nearest in binary16's subnormal range
+__device__ __forceinline__ float sr_prepare(float v, uint32_t w, int j) {
+    const uint32_t rho = (((w >> (8 * j)) & 0xFFu) << 5) | 0x10u;
+    return __uint_as_float((__float_as_uint(v) + rho) & 0xFFFFE000u);
+}
+__device__ __forceinline__ uint2 narrow4_sr(float4 v, uint32_t w) {
+    const __half2 lo = __floats2half2_rn(sr_prepare(v.x, w, 0), sr_prepare(v.y, w, 1));
+    const __half2 hi = __floats2half2_rn(sr_prepare(v.z, w, 2), sr_prepare(v.w, w, 3));
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+__device__ __forceinline__ uint2 narrow4_rn(float4 v) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+// store the new value of a P chunk (binary32: as is; binary16: stochastic rounding with the update's random word)
+__device__ __forceinline__ void st_pchunk(char* p, float4 v, float4, uint32_t) { __stcg(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st_pchunk(char* p, float4 v, uint2, uint32_t w) { __stcg(reinterpret_cast<uint2*>(p), narrow4_sr(v, w)); }
+// heavy users, binary16: the row in memory moves by (narrowed new value - the binary16 value this update started from) -- an
+// exact binary16 difference (neighbouring values), added in L2 by one vector red; with no concurrent writer the row ends on
+// the narrowed new value exactly, like the store
+__device__ __forceinline__ void red_pchunk_f16(char* p, float4 newv, uint2 old, uint32_t w) {
+    const uint2 nv = narrow4_sr(newv, w);
+    const __half2 dlo = __hsub2(*reinterpret_cast<const __half2*>(&nv.x), *reinterpret_cast<const __half2*>(&old.x));
+    const __half2 dhi = __hsub2(*reinterpret_cast<const __half2*>(&nv.y), *reinterpret_cast<const __half2*>(&old.y));
+    asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t*>(&dlo)),
+                 "r"(*reinterpret_cast<const uint32_t*>(&dhi))
                  : "memory");
 }
 

@@ -231,6 +231,7 @@ struct mfsgd_handle {
     int n_heavy = 0;
     float center = 0.f;      // model extension: global mean, subtracted from every rating at load (0 when off)
     bool biases = false;
+    bool p_half = false;     // mixed-precision factor storage: P rows kept as binary16 (mfsgd_config.p_storage)
     float scale = 0.f;
     std::vector<int32_t> user_bounds, item_bounds;  // [UB + 1], [IB + 1]
     std::vector<Member> members;                    // the ring members this process drives
@@ -250,6 +251,8 @@ struct mfsgd_handle {
     ncclComm_t comm = nullptr;
     bool multi_process = false;
     int min_windows = 128;   // MFSGD_MIN_WINDOWS overrides (tuning aid)
+    int reserve_sms = 0;     // multi-process ring: SMs the run kernel leaves to the rotation's NCCL kernels (MFSGD_RESERVE_SMS)
+    int n_lanes = 2;         // stream lanes of the pipelined rotation (MFSGD_LANES = 1 | 2)
     int sub_warp_div = 4;    // run kernel: at most (users of a P sub-stripe) / sub_warp_div runs in flight; MFSGD_SUBWARP_DIV overrides
 };
 
@@ -502,6 +505,11 @@ static int validate_config(const mfsgd_config* c) {
     if (c->device < 0) return fail(MFSGD_E_INVALID_ARG, "bad device %d", c->device);
     if (c->hot_chunk < 0 || c->hot_chunk > 65536) return fail(MFSGD_E_INVALID_ARG, "hot_chunk=%d out of range (0..65536)", c->hot_chunk);
     if (c->model & ~(MFSGD_MODEL_GLOBAL_MEAN | MFSGD_MODEL_BIASES)) return fail(MFSGD_E_INVALID_ARG, "unknown model bits 0x%x", c->model);
+    if (c->p_storage != MFSGD_STORAGE_F32 && c->p_storage != MFSGD_STORAGE_F16) return fail(MFSGD_E_INVALID_ARG, "bad p_storage %d", c->p_storage);
+    if (c->p_storage == MFSGD_STORAGE_F16 && c->scatter != MFSGD_SCATTER_STORE)
+        return fail(MFSGD_E_INVALID_ARG, "binary16 P storage needs scatter = MFSGD_SCATTER_STORE");
+    if (c->p_storage == MFSGD_STORAGE_F16 && c->mode != MFSGD_MODE_DETERMINISTIC && (c->flags & MFSGD_FLAG_EXACT_ARITH))
+        return fail(MFSGD_E_INVALID_ARG, "binary16 P storage runs the FMA arrangement (MFSGD_FLAG_EXACT_ARITH: DETERMINISTIC mode only)");
     if (!(c->lr_decay >= 0.f) || c->lr_decay > 1.f) return fail(MFSGD_E_INVALID_ARG, "lr_decay must be 0 (constant rate) or in (0, 1]");
     if (c->early_stop_patience < 0) return fail(MFSGD_E_INVALID_ARG, "early_stop_patience < 0");
     if (!(c->early_stop_min_delta >= 0.f) || c->early_stop_min_delta >= 1.f) return fail(MFSGD_E_INVALID_ARG, "early_stop_min_delta must be in [0, 1)");
@@ -544,12 +552,13 @@ static int member_setup(mfsgd_handle* h, Member& m) {
     m.d_sse = m.d_scratch + rmse_scratch_doubles();
     int ctas = 0;
     const bool fast = !(h->cfg.flags & MFSGD_FLAG_EXACT_ARITH);
-    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter, fast, &ctas));
+    const bool p_half = h->cfg.p_storage == MFSGD_STORAGE_F16;
+    CK(hogwild_max_ctas_per_sm(h->cfg.k, h->cfg.scatter, fast, p_half, &ctas));
     if (ctas < 1) ctas = 1;
     if (h->cfg.ctas_per_sm > 0 && h->cfg.ctas_per_sm < ctas) ctas = h->cfg.ctas_per_sm;
     m.grid = m.n_sms * ctas;
     int hot_ctas = 0;
-    CK(hot_max_ctas_per_sm(h->cfg.k, fast, run_p_red(h->cfg), &hot_ctas));
+    CK(hot_max_ctas_per_sm(h->cfg.k, fast, run_p_red(h->cfg), p_half, &hot_ctas));
     m.hot_grid = m.n_sms * std::max(1, hot_ctas);
     return MFSGD_OK;
 }
@@ -617,8 +626,11 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     h->multi_process = cfg->world_size > 1;
     if (const char* mw = getenv("MFSGD_MIN_WINDOWS")) h->min_windows = std::max(1, atoi(mw));
     if (const char* sd = getenv("MFSGD_SUBWARP_DIV")) h->sub_warp_div = std::max(1, atoi(sd));
+    if (const char* rs = getenv("MFSGD_RESERVE_SMS")) h->reserve_sms = std::max(0, std::min(32, atoi(rs)));
+    if (const char* nl = getenv("MFSGD_LANES")) h->n_lanes = atoi(nl) == 1 ? 1 : 2;
     h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
     h->biases = (cfg->model & MFSGD_MODEL_BIASES) != 0;
+    h->p_half = cfg->p_storage == MFSGD_STORAGE_F16;
     h->lr_decay = cfg->lr_decay > 0.f ? cfg->lr_decay : 1.f;
     h->lr_now = cfg->lr;
     h->es_patience = cfg->early_stop_patience;
@@ -897,7 +909,7 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     for (int grp = 0; grp < h->G; grp++) cap = std::max<int64_t>(cap, group_hi(h, grp) - group_lo(h, grp));
     m.q_cap_rows = cap;
     dev_free(m.P); dev_free(m.Q[0]); dev_free(m.Q[1]); dev_free(m.d_owner_u); dev_free(m.d_owner_i);
-    CK(dev_alloc(&m.P, (size_t)(m.u_hi - m.u_lo) * c.k));
+    CK(dev_alloc(&m.P, h->p_half ? ((size_t)(m.u_hi - m.u_lo) * c.k + 1) / 2 : (size_t)(m.u_hi - m.u_lo) * c.k));   // binary16 rows: half the bytes
     CK(dev_alloc(&m.Q[0], (size_t)cap * c.k));
     if (h->G > 1) CK(dev_alloc(&m.Q[1], (size_t)cap * c.k));
     dev_free(m.BU); dev_free(m.BQ[0]); dev_free(m.BQ[1]);
@@ -1320,9 +1332,9 @@ static int mfsgd_init_factors_body(mfsgd_handle* h) {
     if (!h->loaded) return fail(MFSGD_E_STATE, "load ratings before initialising factors");
     for (Member& m : h->members) {
         CK(cudaSetDevice(m.device));
-        CK(launch_init_factors(m.P, m.u_hi - m.u_lo, h->cfg.k, m.u_lo, h->cfg.seed, STREAM_P_INIT, h->scale, m.stream, &m.launches));
+        CK(launch_init_factors(m.P, h->p_half, m.u_hi - m.u_lo, h->cfg.k, m.u_lo, h->cfg.seed, STREAM_P_INIT, h->scale, m.stream, &m.launches));
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
-        CK(launch_init_factors(m.Q[m.cur], hi - lo, h->cfg.k, lo, h->cfg.seed, STREAM_Q_INIT, h->scale, m.stream, &m.launches));
+        CK(launch_init_factors(m.Q[m.cur], false, hi - lo, h->cfg.k, lo, h->cfg.seed, STREAM_Q_INIT, h->scale, m.stream, &m.launches));
         if (h->biases) {          // MatrixFactorizationSGD.java:305: biases start at 0
             CK(cudaMemsetAsync(m.BU, 0, (size_t)(m.u_hi - m.u_lo) * 4, m.stream));
             CK(cudaMemsetAsync(m.BQ[m.cur], 0, (size_t)(hi - lo) * 4, m.stream));
@@ -1343,7 +1355,18 @@ static int mfsgd_set_factors_body(mfsgd_handle* h, const float* P, const float* 
     const int k = h->cfg.k;
     for (Member& m : h->members) {
         CK(cudaSetDevice(m.device));
-        CK(cudaMemcpyAsync(m.P, P + (size_t)m.u_lo * k, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
+        const size_t pn = (size_t)(m.u_hi - m.u_lo) * k;
+        if (h->p_half) {           // binary16 rows: stage the caller's binary32 rows, narrow (round to nearest even) on the device
+            float* tmp = nullptr;
+            CK(dev_alloc(&tmp, std::max<size_t>(pn, 1)));
+            cudaError_t e = cudaMemcpyAsync(tmp, P + (size_t)m.u_lo * k, pn * 4, cudaMemcpyHostToDevice, m.stream);
+            if (e == cudaSuccess) e = launch_narrow_rows(tmp, (int64_t)pn, m.P, m.stream, &m.launches);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+            dev_free(tmp);
+            CK(e);
+        } else {
+            CK(cudaMemcpyAsync(m.P, P + (size_t)m.u_lo * k, pn * 4, cudaMemcpyHostToDevice, m.stream));
+        }
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
         CK(cudaMemcpyAsync(m.Q[m.cur], Q + (size_t)lo * k, (size_t)(hi - lo) * k * 4, cudaMemcpyHostToDevice, m.stream));
         if (h->biases && !h->factors_ready) {      // fresh factors: biases start at 0 (mfsgd_set_biases overrides)
@@ -1366,7 +1389,18 @@ static int mfsgd_get_factors_body(mfsgd_handle* h, float* P, float* Q) {
     const int k = h->cfg.k;
     for (Member& m : h->members) {
         CK(cudaSetDevice(m.device));
-        CK(cudaMemcpyAsync(P + (size_t)m.u_lo * k, m.P, (size_t)(m.u_hi - m.u_lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
+        const size_t pn = (size_t)(m.u_hi - m.u_lo) * k;
+        if (h->p_half) {           // binary16 rows come back widened (exact)
+            float* tmp = nullptr;
+            CK(dev_alloc(&tmp, std::max<size_t>(pn, 1)));
+            cudaError_t e = launch_widen_rows(m.P, (int64_t)pn, tmp, m.stream, &m.launches);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(P + (size_t)m.u_lo * k, tmp, pn * 4, cudaMemcpyDeviceToHost, m.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(m.stream);
+            dev_free(tmp);
+            CK(e);
+        } else {
+            CK(cudaMemcpyAsync(P + (size_t)m.u_lo * k, m.P, pn * 4, cudaMemcpyDeviceToHost, m.stream));
+        }
         const int lo = group_lo(h, m.held_group), hi = group_hi(h, m.held_group);
         CK(cudaMemcpyAsync(Q + (size_t)lo * k, m.Q[m.cur], (size_t)(hi - lo) * k * 4, cudaMemcpyDeviceToHost, m.stream));
     }
@@ -1598,8 +1632,8 @@ static int rmse_pass(mfsgd_handle* h, bool heldout, double* sse_out, int64_t* n_
 // which cost ~25 % of an 8-GPU epoch in launch tails (profiles/r01_bench.md).
 static const int N_LANES = 2;
 
-static int ensure_lanes(Member& m) {
-    while ((int)m.lanes.size() < N_LANES) {
+static int ensure_lanes(Member& m, int n_lanes) {
+    while ((int)m.lanes.size() < n_lanes) {
         Lane l;
         CK(cudaStreamCreateWithFlags(&l.cold, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&l.hot, cudaStreamNonBlocking));
@@ -1797,6 +1831,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         resolved = upto;
         return MFSGD_OK;
     };
+    const double t_train0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     const bool have_heldout = !h->members[0].heldout.group_off.empty();
     if (h->es_patience > 0 && !have_heldout) return fail(MFSGD_E_STATE, "early stopping needs a held-out set (mfsgd_load_heldout / mfsgd_generate_synthetic)");
     const bool want_eval = (h->eval_every || h->es_patience > 0) && have_heldout;
@@ -1809,7 +1844,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             m.update_launches = 0;
             Member::EpochRec er{};
             CK(cudaSetDevice(m.device));
-            if (lane_mode) CKRC(ensure_lanes(m));
+            if (lane_mode) CKRC(ensure_lanes(m, h->n_lanes));
             CKRC(timing_event(m, &er.start));
             CKRC(timing_event(m, &er.shuffled));
             CKRC(timing_event(m, &er.end));
@@ -1852,6 +1887,8 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 a.virt = h->virtual_shuffle ? 1 : 0;
                 a.BU = h->biases ? m.BU : nullptr;
                 a.BI = h->biases ? m.BQ[m.cur] : nullptr;
+                a.p_half = h->p_half ? 1 : 0;
+                a.sm_limit = (pipelined && h->reserve_sms > 0 && h->reserve_sms < m.n_sms) ? m.n_sms - h->reserve_sms : 0;
                 if (c.mode == MFSGD_MODE_DETERMINISTIC) {
                     a.recs = m.recs[0];
                     a.first = 0;
@@ -1883,7 +1920,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                 } else {
                     if (pipelined) CKRC(ensure_part_events(h, m));
                     for (int part = 0; part < parts; part++) {
-                        Lane& l = m.lanes[(size_t)(part % N_LANES)];
+                        Lane& l = m.lanes[(size_t)(part % h->n_lanes)];
                         if (pipelined && m.part_recv_pending[(size_t)part]) {      // this slice of the group has to have arrived
                             CK(cudaStreamWaitEvent(l.cold, m.ev_part_recv[(size_t)part], 0));
                             m.part_recv_pending[(size_t)part] = 0;
@@ -1976,7 +2013,13 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             }
         }
     }
+    const double t_enq = trace_on() ? std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0.0;
     if (rc == MFSGD_OK) rc = resolve(ran);
+    if (trace_on()) {
+        const double t_end = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        fprintf(stderr, "[mfsgd] train: %d epochs, host enqueue %.3f ms per epoch, enqueue + drain %.3f ms per epoch\n", ran,
+                (t_enq - t_train0) * 1e3 / std::max(1, ran), (t_end - t_train0) * 1e3 / std::max(1, ran));
+    }
     if (rc == MFSGD_OK && stats)
         for (int ep = ran; ep < epochs; ep++) {       // epochs the early-stopping rule skipped: updates == 0
             stats[ep] = mfsgd_epoch_stats{};
@@ -2023,20 +2066,20 @@ static int rmse_sets(mfsgd_handle* h, std::vector<EvalSet*>& sets, bool train_se
                 for (int sa = 0; sa < h->mu; sa++) {
                     const int64_t lo = m.block_off[(size_t)sa * h->IB + (size_t)grp * h->mi];
                     const int64_t hi = m.block_off[(size_t)sa * h->IB + (size_t)(grp + 1) * h->mi];
-                    CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                    CK(launch_rmse_sse(m.recs[m.rcur] + lo, hi - lo, m.P, h->p_half, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                        m.d_sse, m.n_sms, m.stream, &m.launches));
                     if (h->H > 0) {   // the hot buckets of (sa, grp) are contiguous too
                         const size_t hb = (size_t)h->mu * h->IB + (size_t)sa * h->H;
                         const int64_t hlo = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)grp * h->mi]];
                         const int64_t hhi = m.block_off[hb + (size_t)h->hot_block_lo[(size_t)(grp + 1) * h->mi]];
-                        CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
+                        CK(launch_rmse_sse(m.recs[m.rcur] + hlo, hhi - hlo, m.P, h->p_half, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch,
                                            m.d_sse, m.n_sms, m.stream, &m.launches));
                     }
                 }
             } else {
                 EvalSet* e = sets[j];
                 const int64_t lo = e->group_off[(size_t)grp], hi = e->group_off[(size_t)grp + 1];
-                CK(launch_rmse_sse(e->recs + lo, hi - lo, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch, m.d_sse,
+                CK(launch_rmse_sse(e->recs + lo, hi - lo, m.P, h->p_half, m.Q[m.cur], m.BU, m.BQ[m.cur], k, m.u_lo, group_lo(h, grp), m.d_scratch, m.d_sse,
                                    m.n_sms, m.stream, &m.launches));
             }
         }
@@ -2100,7 +2143,7 @@ static int mfsgd_rmse_train_body(mfsgd_handle* h, double* rmse_out, double* sse_
         Member& m = h->members[0];
         CK(cudaSetDevice(m.device));
         CK(cudaMemsetAsync(m.d_sse, 0, sizeof(double), m.stream));
-        CK(launch_rmse_sse(m.recs_orig, m.n_recs, m.P, m.Q[m.cur], m.BU, m.BQ[m.cur], h->cfg.k, m.u_lo, 0, m.d_scratch, m.d_sse, m.n_sms, m.stream, &m.launches));
+        CK(launch_rmse_sse(m.recs_orig, m.n_recs, m.P, h->p_half, m.Q[m.cur], m.BU, m.BQ[m.cur], h->cfg.k, m.u_lo, 0, m.d_scratch, m.d_sse, m.n_sms, m.stream, &m.launches));
         double sse = 0.0;
         CK(cudaMemcpyAsync(&sse, m.d_sse, sizeof(double), cudaMemcpyDeviceToHost, m.stream));
         CK(cudaStreamSynchronize(m.stream));

@@ -61,6 +61,11 @@ struct UpdateArgs {
     // model extension (MatrixFactorizationSGD.java:282 sgdUpdateModel): user / item biases, indexed like P / Q; both null = off
     float* BU;
     float* BI;
+    // mixed-precision factor storage (mfsgd_config.p_storage): != 0 -> P points at binary16 rows (common.cuh)
+    int32_t p_half;
+    // run kernel: CTAs that land on an SM with %smid >= sm_limit leave at once (their runs are claimed by the others), which keeps
+    // those SMs free for the NCCL kernels of the pipelined Q rotation; 0 = use every SM
+    int32_t sm_limit;
 };
 
 // (2) the SGD update kernel, Hogwild: full grid, one sub-warp per rating, software-pipelined gathers.
@@ -69,8 +74,8 @@ struct UpdateArgs {
 cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fast, int grid, int min_windows,
                                       cudaStream_t stream, int* launches);
 // Resident CTAs per SM of the Hogwild kernel for rank k (occupancy query; sizes the grid).
-cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas);
-cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, int* ctas);
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, bool p_half, int* ctas);
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, bool p_half, int* ctas);
 // Lanes per rating of the run kernel at rank k (kernels_hot.cu): a warp walks 32 / lanes runs side by side.
 int run_kernel_lanes(int k);
 // Deterministic parity mode: one warp, records strictly in order; err_trace nullable (n floats).
@@ -106,13 +111,18 @@ bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run,
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
 int rmse_scratch_doubles();
 // BU / BI: biases of the model extension (nullable together), indexed like P / Q.
-cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, const float* BU, const float* BI, int32_t k,
-                            int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
-                            int* launches);
+// p_half: P points at binary16 rows (mfsgd_config.p_storage).
+cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, bool p_half, const float* Q, const float* BU, const float* BI,
+                            int32_t k, int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms,
+                            cudaStream_t stream, int* launches);
 
 // factor init (MatrixFactorizationSGD.java:53) for local rows [row_lo, row_lo + n_rows).
-cudaError_t launch_init_factors(float* rows, int64_t n_rows, int32_t k, int64_t row_lo, uint64_t seed, uint64_t stream_id,
+// half: the rows are binary16 (the binary32 value rounded to nearest even).
+cudaError_t launch_init_factors(void* rows, bool half, int64_t n_rows, int32_t k, int64_t row_lo, uint64_t seed, uint64_t stream_id,
                                 float scale, cudaStream_t stream, int* launches);
+// binary16 rows <-> binary32 rows (n values): exact / round to nearest even
+cudaError_t launch_widen_rows(const void* half_rows, int64_t n, float* out, cudaStream_t stream, int* launches);
+cudaError_t launch_narrow_rows(const float* rows, int64_t n, void* half_out, cudaStream_t stream, int* launches);
 
 // synthetic records [start, start+count) -> SoA + held flag (MatrixFactorizationSGD.java:220).
 struct SynthArgs {

@@ -12,7 +12,7 @@ constexpr int RMSE_MAX_CTAS = 148 * 8;
 // sub-warp tree as the update kernel), squared error accumulated in binary64 per sub-warp, then a
 // warp shuffle reduction, a shared-memory block reduction and one partial per CTA (fixed order ->
 // the result is reproducible for a given grid).
-template <int LANES, int VEC, bool FULL>
+template <int LANES, int VEC, bool FULL, bool PH>
 __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __restrict__ recs, int64_t n,
                                                                 const float* __restrict__ P,
                                                                 const float* __restrict__ Q, const float* __restrict__ BU,
@@ -46,13 +46,14 @@ __global__ void __launch_bounds__(RMSE_THREADS) rmse_sse_kernel(const Rec* __res
             const int32_t i = __shfl_sync(0xffffffffu, ri, j);
             const float r = __int_as_float(__shfl_sync(0xffffffffu, rr, j));
             const bool act = j < cnt;
-            const float* prow = P + (int64_t)(u - u_base) * k;
+            const char* prow = reinterpret_cast<const char*>(P) + (int64_t)(u - u_base) * k * p_elem_bytes<PH>();   // PH: binary16 rows
             const float* qrow = Q + (int64_t)(i - i_base) * k;
             float s = 0.0f;
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 const int c = gl + v * LANES;
-                if (act && (FULL || c < chunks)) s = dot4_acc(s, ld_row4(prow + 4 * c), ld_row4(qrow + 4 * c));
+                if (act && (FULL || c < chunks))
+                    s = dot4_acc(s, widen4(ld_pchunk<PH>(prow + 4 * c * p_elem_bytes<PH>())), ld_row4(qrow + 4 * c));
             }
             s = group_sum<LANES>(s);
             if (BU != nullptr && act) s = __fadd_rn(__fadd_rn(s, __ldcg(BU + (u - u_base))), __ldcg(BI + (i - i_base)));   // rmseModel :389
@@ -90,14 +91,29 @@ __global__ void __launch_bounds__(256) rmse_finalize_kernel(const double* __rest
 }
 
 // MatrixFactorizationSGD.java:53 initFactors; counters are GLOBAL row ids so stripes agree with the whole.
-__global__ void __launch_bounds__(256) init_factors_kernel(float* __restrict__ rows, int64_t n_elems, int k,
+// HALF: the rows are kept as binary16 -- the same values, rounded to nearest even once.
+template <bool HALF>
+__global__ void __launch_bounds__(256) init_factors_kernel(void* __restrict__ rows, int64_t n_elems, int k,
                                                            int64_t row_lo, uint64_t seed, uint64_t stream_id,
                                                            float scale) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += stride) {
         const uint64_t ctr = (uint64_t)(row_lo * k + e);
-        rows[e] = __fmul_rn(uniform24(seed, stream_id, ctr), scale);
+        const float v = __fmul_rn(uniform24(seed, stream_id, ctr), scale);
+        if (HALF) static_cast<__half*>(rows)[e] = __float2half_rn(v);
+        else static_cast<float*>(rows)[e] = v;
     }
+}
+
+// binary16 rows <-> binary32 (mfsgd_get_factors / mfsgd_set_factors under MFSGD_STORAGE_F16): widening is exact, narrowing
+// rounds to nearest even
+__global__ void __launch_bounds__(256) widen_rows_kernel(const __half* __restrict__ in, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) out[e] = __half2float(in[e]);
+}
+__global__ void __launch_bounds__(256) narrow_rows_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) out[e] = __float2half_rn(in[e]);
 }
 
 // ---- synthetic records: MatrixFactorizationSGD.java:186-239, binary64/binary32 ops spelled out ----
@@ -169,9 +185,9 @@ inline int grid_for(int64_t n, int threads, int max_ctas) {
 
 int rmse_scratch_doubles() { return RMSE_MAX_CTAS; }
 
-cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const float* Q, const float* BU, const float* BI, int32_t k,
-                            int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms, cudaStream_t stream,
-                            int* launches) {
+cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, bool p_half, const float* Q, const float* BU, const float* BI,
+                            int32_t k, int32_t u_base, int32_t i_base, double* scratch, double* sse_accum, int n_sms,
+                            cudaStream_t stream, int* launches) {
     if (n <= 0) return cudaSuccess;
     const Geometry g = geometry_for(k);
     int64_t tiles = (n + 31) / 32;
@@ -179,8 +195,9 @@ cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const fl
     if (grid > RMSE_MAX_CTAS) grid = RMSE_MAX_CTAS;
     if (grid > (tiles + 7) / 8) grid = (int)((tiles + 7) / 8);
     if (grid < 1) grid = 1;
-#define CALL(L, V, F) \
-    rmse_sse_kernel<L, V, F><<<grid, RMSE_THREADS, 0, stream>>>(recs, n, P, Q, BU, BI, k, u_base, i_base, scratch)
+#define CALL(L, V, F)                                                                                                          \
+    if (p_half) rmse_sse_kernel<L, V, F, true><<<grid, RMSE_THREADS, 0, stream>>>(recs, n, P, Q, BU, BI, k, u_base, i_base, scratch); \
+    else rmse_sse_kernel<L, V, F, false><<<grid, RMSE_THREADS, 0, stream>>>(recs, n, P, Q, BU, BI, k, u_base, i_base, scratch)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     cudaError_t err = cudaGetLastError();
@@ -190,11 +207,26 @@ cudaError_t launch_rmse_sse(const Rec* recs, int64_t n, const float* P, const fl
     return cudaGetLastError();
 }
 
-cudaError_t launch_init_factors(float* rows, int64_t n_rows, int32_t k, int64_t row_lo, uint64_t seed, uint64_t stream_id,
+cudaError_t launch_init_factors(void* rows, bool half, int64_t n_rows, int32_t k, int64_t row_lo, uint64_t seed, uint64_t stream_id,
                                 float scale, cudaStream_t stream, int* launches) {
     const int64_t n = n_rows * k;
     if (n <= 0) return cudaSuccess;
-    init_factors_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(rows, n, k, row_lo, seed, stream_id, scale);
+    if (half) init_factors_kernel<true><<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(rows, n, k, row_lo, seed, stream_id, scale);
+    else init_factors_kernel<false><<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(rows, n, k, row_lo, seed, stream_id, scale);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_widen_rows(const void* half_rows, int64_t n, float* out, cudaStream_t stream, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    widen_rows_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(static_cast<const __half*>(half_rows), n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_rows(const float* rows, int64_t n, void* half_out, cudaStream_t stream, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    narrow_rows_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(rows, n, static_cast<__half*>(half_out));
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -45,7 +45,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // Every thread therefore waits for the prerequisite grid as its last action (a no-op without the launch attribute).
 __device__ __forceinline__ void pdl_wait_prerequisites() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int LANES, int VEC, bool FULL, bool FAST, int D, bool PRED, bool BIAS>
+// PH: P rows kept as binary16 (mfsgd_config.p_storage; common.cuh "mixed-precision factor storage"): a.P then points at binary16
+// rows, a lane's chunk is 8 bytes, the ring holds the raw chunks and widens them at use, the scatter narrows with stochastic
+// rounding (heavy users: the narrowed difference, one f16x4 red).
+template <int LANES, int VEC, bool FULL, bool FAST, int D, bool PRED, bool BIAS, bool PH>
 __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(UpdateArgs a, const HotUnit* __restrict__ units, int n_units,
                                                                                  unsigned int* __restrict__ counter, int always_add) {
     constexpr int GPW = 32 / LANES;                   // runs walked side by side by one warp
@@ -55,13 +58,25 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
     __shared__ int2 srec[8][GPW][RING];               // per sub-warp: (u, r bits), record j of the run at j % RING
     __shared__ __align__(16) float4 sq0[VEC][8][32];  // q_i as the run found it (only the merge needs it again)
     pdl_launch_dependents();
+    if (a.sm_limit > 0) {                             // SMs kept free for the rotation's NCCL kernels (engine.cu reserve_sms)
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid >= (unsigned int)a.sm_limit) {
+            pdl_wait_prerequisites();
+            return;
+        }
+    }
     const int lane = threadIdx.x & 31;
     const int wic = threadIdx.x >> 5;
     const int gl = lane & (LANES - 1);
     const int grp = lane / LANES;
     const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;
     const int chunks = (int)(k >> 2);
-    float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;
+    using pchunk_t = typename PChunk<PH>::type;
+    constexpr int ES = p_elem_bytes<PH>();                // bytes per stored value of P
+    const int64_t prow_bytes = k * ES;
+    char* const Pl = reinterpret_cast<char*>(a.P) + ((int64_t)4 * gl - (int64_t)a.u_base * k) * ES;   // lane-adjusted, indexed by global user id
+    const uint32_t s32 = sr_seed32(a.seed);
     float* const BUl = BIAS ? a.BU - a.u_base : nullptr;     // model extension: user biases by global id
     const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
     const float ccoef = -__fmul_rn(a.lr, a.lambda);   // PRED: p_u += b * q_i + ccoef * p_u, added in memory
@@ -101,14 +116,14 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
             }
             cp_async_commit();
         };
-        auto gather = [&](float4 (&slot)[VEC], float& bslot, int t) {   // p_u (and b_u) of step t -> a ring slot (nothing past the run's end)
+        auto gather = [&](pchunk_t (&slot)[VEC], float& bslot, int t) {   // p_u (and b_u) of step t -> a ring slot (nothing past the run's end)
             if (t < count) {
                 const int32_t uu = recs[t & (RING - 1)].x & REC_USER_MASK;
                 if (BIAS) bslot = __ldcg(BUl + uu);
-                const float* xp = Pl + (int64_t)uu * k;
+                const char* xp = Pl + (int64_t)uu * prow_bytes;
 #pragma unroll
                 for (int v = 0; v < VEC; v++)
-                    if (FULL || gl + v * LANES < chunks) slot[v] = ld_row4(xp + 4 * v * LANES);
+                    if (FULL || gl + v * LANES < chunks) slot[v] = ld_pchunk<PH>(xp + 4 * v * LANES * ES);
             }
         };
         // prologue: tiles 0 and 1 staged and visible, D-1 gathers in flight
@@ -116,13 +131,13 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
         stage_tile(1);
         cp_async_wait<0>();
         __syncwarp();
-        float4 ring[D][VEC];
+        pchunk_t ring[D][VEC];
         float bring[D];
 #pragma unroll
         for (int d = 0; d < D; d++) {
             bring[d] = 0.0f;
 #pragma unroll
-            for (int v = 0; v < VEC; v++) ring[d][v] = zero4;
+            for (int v = 0; v < VEC; v++) ring[d][v] = zero_pchunk<PH>();
         }
 #pragma unroll
         for (int d = 0; d < D - 1; d++) gather(ring[d], bring[d], d);
@@ -138,12 +153,15 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
                 if (t >= steps) break;                  // warp-uniform
                 gather(ring[(d + D - 1) & (D - 1)], bring[(d + D - 1) & (D - 1)], t + D - 1);   // into the slot step t - 1 has just released
                 const int2 rec = recs[t & (RING - 1)];
-                float pred = rows_dot<LANES, VEC, FAST>(ring[d], q);
+                float4 pw[VEC];                          // the gathered row in binary32 (PH: widened here, exactly)
+#pragma unroll
+                for (int v = 0; v < VEC; v++) pw[v] = widen4(ring[d][v]);
+                float pred = rows_dot<LANES, VEC, FAST>(pw, q);
                 if (BIAS) pred = __fadd_rn(__fadd_rn(pred, bring[d]), bi);
                 const float e = __fsub_rn(__int_as_float(rec.y), pred);
                 const float b = __fmul_rn(cf.lr, e);
                 if (t < count) {
-                    float* const cp = Pl + (int64_t)(rec.x & REC_USER_MASK) * k;
+                    char* const cp = Pl + (int64_t)(rec.x & REC_USER_MASK) * prow_bytes;
                     const bool p_red = PRED || rec.x < 0;       // heavy user (or every user): add the increment in memory
                     if (BIAS) {
                         const float du = bias_delta(bring[d], e, cf.lr, cf.lambda);
@@ -156,9 +174,17 @@ __global__ void __launch_bounds__(256, VEC >= 3 ? 2 : 3) sgd_update_runs_kernel(
 #pragma unroll
                     for (int v = 0; v < VEC; v++) {
                         if (FULL || gl + v * LANES < chunks) {
-                            if (p_red) red_add_row4(cp + 4 * v * LANES, delta_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, ccoef, b));
-                            else st_row4(cp + 4 * v * LANES, new_chunk<FAST>(ring[d][v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
-                            q[v] = new_chunk<FAST>(q[v], ring[d][v], e, cf.lr, cf.lambda, cf.acoef, b);
+                            char* const dst = cp + 4 * v * LANES * ES;
+                            if constexpr (PH) {
+                                const uint32_t w = sr_word(s32, a.epoch, (uint32_t)(rec.x & REC_USER_MASK), (uint32_t)hu.item, (uint32_t)(gl + v * LANES));
+                                const float4 np = new_chunk<FAST>(pw[v], q[v], e, cf.lr, cf.lambda, cf.acoef, b);
+                                if (p_red) red_pchunk_f16(dst, np, ring[d][v], w);
+                                else st_pchunk(dst, np, ring[d][v], w);
+                            } else {
+                                if (p_red) red_add_row4(reinterpret_cast<float*>(dst), delta_chunk<FAST>(pw[v], q[v], e, cf.lr, cf.lambda, ccoef, b));
+                                else st_row4(reinterpret_cast<float*>(dst), new_chunk<FAST>(pw[v], q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                            }
+                            q[v] = new_chunk<FAST>(q[v], pw[v], e, cf.lr, cf.lambda, cf.acoef, b);
                         }
                     }
                 }
@@ -320,37 +346,45 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
     const int always_add = (pdl || overlapped_by_next) ? 1 : 0;
     const bool d2 = run_depth() == 2;
     const bool bias = a.BU != nullptr;            // model extension: biases (always one gather ahead)
+    const bool p_half = a.p_half != 0;
+    if (p_half && (!fast || p_red)) return cudaErrorInvalidValue;      // binary16 P: FMA arrangement, scatter = store (validate_config)
     cudaError_t err = cudaSuccess;
-#define CALL(L, V, F)                                                                                                        \
-    err = bias ? ((fast && p_red) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true, true>, grid, stream, pdl, always_add, a, units, n_units, counter)   \
-                  : fast          ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-                  : p_red         ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, true, true>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-                                  : launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, false, true>, grid, stream, pdl, always_add, a, units, n_units, counter)) \
-        : (fast && p_red && d2) ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-          : (fast && p_red)     ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter)  \
-          : (fast && d2)        ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 2, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-          : fast                ? launch_runs(sgd_update_runs_kernel<L, V, F, true, 4, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-          : p_red               ? launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, true, false>, grid, stream, pdl, always_add, a, units, n_units, counter) \
-                                : launch_runs(sgd_update_runs_kernel<L, V, F, false, 2, false, false>, grid, stream, pdl, always_add, a, units, n_units, counter)
+#define RK(L_, V_, F_, FAST_, D_, PRED_, BIAS_, PH_) launch_runs(sgd_update_runs_kernel<L_, V_, F_, FAST_, D_, PRED_, BIAS_, PH_>, grid, stream, pdl, always_add, a, units, n_units, counter)
+#define CALL(L, V, F)                                                            \
+    err = p_half ? (bias ? RK(L, V, F, true, 2, false, true, true) : RK(L, V, F, true, 2, false, false, true))   \
+        : bias ? ((fast && p_red) ? RK(L, V, F, true, 2, true, true, false)               \
+                  : fast          ? RK(L, V, F, true, 2, false, true, false)              \
+                  : p_red         ? RK(L, V, F, false, 2, true, true, false)              \
+                                  : RK(L, V, F, false, 2, false, true, false))            \
+        : (fast && p_red && d2) ? RK(L, V, F, true, 2, true, false, false)                \
+          : (fast && p_red)     ? RK(L, V, F, true, 4, true, false, false)                \
+          : (fast && d2)        ? RK(L, V, F, true, 2, false, false, false)               \
+          : fast                ? RK(L, V, F, true, 4, false, false, false)               \
+          : p_red               ? RK(L, V, F, false, 2, true, false, false)               \
+                                : RK(L, V, F, false, 2, false, false, false)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
+#undef RK
     if (launches) *launches += 1;
     return err != cudaSuccess ? err : cudaGetLastError();
 }
 
-cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, int* ctas) {
+cudaError_t hot_max_ctas_per_sm(int k, bool fast, bool p_red, bool p_half, int* ctas) {
     const Geometry g = run_geometry_for(k);
     const bool d2 = run_depth() == 2;
     cudaError_t err = cudaSuccess;
-#define CALL(L, V, F)                                                                                                              \
-    err = (fast && p_red && d2) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, true, false>, 256, 0)   \
-          : (fast && p_red)     ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, true, false>, 256, 0)   \
-          : (fast && d2)        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 2, false, false>, 256, 0)  \
-          : fast                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, true, 4, false, false>, 256, 0)  \
-          : p_red               ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 2, true, false>, 256, 0)  \
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L, V, F, false, 2, false, false>, 256, 0)
+#define OCC(L_, V_, F_, FAST_, D_, PRED_, PH_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_runs_kernel<L_, V_, F_, FAST_, D_, PRED_, false, PH_>, 256, 0)
+#define CALL(L, V, F)                                                \
+    err = p_half                ? OCC(L, V, F, true, 2, false, true)          \
+          : (fast && p_red && d2) ? OCC(L, V, F, true, 2, true, false)        \
+          : (fast && p_red)     ? OCC(L, V, F, true, 4, true, false)          \
+          : (fast && d2)        ? OCC(L, V, F, true, 2, false, false)         \
+          : fast                ? OCC(L, V, F, true, 4, false, false)         \
+          : p_red               ? OCC(L, V, F, false, 2, true, false)         \
+                                : OCC(L, V, F, false, 2, false, false)
     MFSGD_DISPATCH_RUN_GEOMETRY(g, CALL);
 #undef CALL
+#undef OCC
     const int cap = env_int("MFSGD_HOT_CTAS", 0);    // tuning aid: resident run-kernel CTAs per SM
     if (err == cudaSuccess && cap > 0 && *ctas > cap) *ctas = cap;
     return err;

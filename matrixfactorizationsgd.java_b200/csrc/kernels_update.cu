@@ -63,43 +63,48 @@ __device__ __forceinline__ void scatter_rows(const RowPair<LANES, VEC>& rp, floa
 // sub-warps with a DEPTH-deep software pipeline: the row gathers of the next DEPTH-1 ratings are in flight while
 // the current one is reduced and scattered. FULLTILE: all 32 records present -> no activity predicates.
 // SC: 0 = st/st, 1 = red/red, 2 = st P + red Q, 3 = red P + st Q  (mfsgd.h MFSGD_SCATTER_*; FAST needs SC == 0)
-template <int VEC>
+// PH: P rows kept as binary16 (mfsgd_config.p_storage; common.cuh): the slot holds the raw 8-byte chunks of p_u.
+template <int VEC, bool PH>
 struct Slot {          // only the gathered rows live in registers; ids and rating are re-read from the tile (one LDS)
-    float4 p[VEC], q[VEC];
+    typename PChunk<PH>::type p[VEC];
+    float4 q[VEC];
     float bu, bi;      // biases of the model extension (BIAS instantiations only; never touched otherwise)
 };
 
-template <int LANES, int VEC, bool FULL, bool FULLTILE, bool BIAS>
-__device__ __forceinline__ void slot_load(Slot<VEC>& sl, const int4* __restrict__ tile, int j, int cnt, const float* __restrict__ Pl,
+template <int LANES, int VEC, bool FULL, bool FULLTILE, bool BIAS, bool PH>
+__device__ __forceinline__ void slot_load(Slot<VEC, PH>& sl, const int4* __restrict__ tile, int j, int cnt, const char* __restrict__ Pl,
                                           const float* __restrict__ Ql, int64_t k, int lane_chunk, int chunks,
                                           const float* __restrict__ BUl, const float* __restrict__ BIl) {
+    constexpr int ES = p_elem_bytes<PH>();
     const int4 rec = tile[j & 31];
     const bool act = FULLTILE || j < cnt;
     if (BIAS) {
         sl.bu = act ? __ldcg(BUl + rec.x) : 0.0f;
         sl.bi = act ? __ldcg(BIl + rec.y) : 0.0f;
     }
-    const float* pp = Pl + (int64_t)rec.x * k;
+    const char* pp = Pl + (int64_t)rec.x * k * ES;
     const float* qq = Ql + (int64_t)rec.y * k;
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
         const bool on = act && (FULL || lane_chunk + v * LANES < chunks);
-        sl.p[v] = on ? ld_row4(pp + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sl.p[v] = on ? ld_pchunk<PH>(pp + 4 * v * LANES * ES) : zero_pchunk<PH>();
         sl.q[v] = on ? ld_row4(qq + 4 * v * LANES) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-template <int LANES, int VEC, bool FULL, int SC, bool FAST, bool FULLTILE, int DEPTH, bool BIAS>
-__device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt, float* __restrict__ Pl,
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, bool FULLTILE, int DEPTH, bool BIAS, bool PH>
+__device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt, char* __restrict__ Pl,
                                           float* __restrict__ Ql, int64_t k, int grp, int lane_chunk, int chunks, Coef cf,
-                                          float* __restrict__ BUl, float* __restrict__ BIl) {
+                                          float* __restrict__ BUl, float* __restrict__ BIl, uint32_t s32, uint32_t epoch) {
+    static_assert(!PH || (SC == 0 && FAST), "binary16 P: FMA arrangement, scatter = store");
     constexpr int GPW = 32 / LANES;
     constexpr int FULL_STEPS = 32 / GPW;
+    constexpr int ES = p_elem_bytes<PH>();
     const int steps = FULLTILE ? FULL_STEPS : (cnt + GPW - 1) / GPW;
-    Slot<VEC> ring[DEPTH];
+    Slot<VEC, PH> ring[DEPTH];
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; d++)
-        slot_load<LANES, VEC, FULL, FULLTILE, BIAS>(ring[d], tile, d * GPW + grp, cnt, Pl, Ql, k, lane_chunk, chunks, BUl, BIl);
+        slot_load<LANES, VEC, FULL, FULLTILE, BIAS, PH>(ring[d], tile, d * GPW + grp, cnt, Pl, Ql, k, lane_chunk, chunks, BUl, BIl);
     for (int t0 = 0; t0 < steps; t0 += DEPTH) {
 #pragma unroll
         for (int d = 0; d < DEPTH; d++) {
@@ -109,15 +114,18 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
             // a partial tile slot_load sees j >= cnt and loads nothing; a full tile has no such predicate, so the look-ahead
             // itself is skipped there (warp-uniform) -- it would gather rows of wrapped records that are never used.
             if (!FULLTILE || t + DEPTH - 1 < FULL_STEPS)
-                slot_load<LANES, VEC, FULL, FULLTILE, BIAS>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp, cnt, Pl, Ql, k,
+                slot_load<LANES, VEC, FULL, FULLTILE, BIAS, PH>(ring[(d + DEPTH - 1) % DEPTH], tile, (t + DEPTH - 1) * GPW + grp, cnt, Pl, Ql, k,
                                                       lane_chunk, chunks, BUl, BIl);
             const int j = t * GPW + grp;
             const int4 rec = tile[j & 31];
             const bool act = FULLTILE ? true : j < cnt;
-            float* const cp = Pl + (int64_t)rec.x * k;
+            char* const cp = Pl + (int64_t)rec.x * k * ES;
             float* const cq = Ql + (int64_t)rec.y * k;
-            const Slot<VEC>& c = ring[d];
-            float pred = rows_dot<LANES, VEC, FAST>(c.p, c.q);
+            const Slot<VEC, PH>& c = ring[d];
+            float4 pw[VEC];                        // p_u in binary32 (PH: widened here, exactly)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) pw[v] = widen4(c.p[v]);
+            float pred = rows_dot<LANES, VEC, FAST>(pw, c.q);
             if (BIAS) pred = __fadd_rn(__fadd_rn(pred, c.bu), c.bi);
             const float e = __fsub_rn(__int_as_float(rec.z), pred);
             const float b = __fmul_rn(cf.lr, e);
@@ -131,10 +139,16 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
 #pragma unroll
                 for (int v = 0; v < VEC; v++) {
                     if (FULL || lane_chunk + v * LANES < chunks) {
-                        if (SC == 1 || SC == 3) red_add_row4(cp + 4 * v * LANES, delta4(c.p[v], c.q[v], e, cf.lr, cf.lambda));
-                        else st_row4(cp + 4 * v * LANES, new_chunk<FAST>(c.p[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b));
-                        if (SC == 1 || SC == 2) red_add_row4(cq + 4 * v * LANES, delta4(c.q[v], c.p[v], e, cf.lr, cf.lambda));
-                        else st_row4(cq + 4 * v * LANES, new_chunk<FAST>(c.q[v], c.p[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                        char* const dst = cp + 4 * v * LANES * ES;
+                        if constexpr (PH) {
+                            st_pchunk(dst, new_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b), c.p[v],
+                                      sr_word(s32, epoch, (uint32_t)rec.x, (uint32_t)rec.y, (uint32_t)(lane_chunk + v * LANES)));
+                        } else {
+                            if (SC == 1 || SC == 3) red_add_row4(reinterpret_cast<float*>(dst), delta4(pw[v], c.q[v], e, cf.lr, cf.lambda));
+                            else st_row4(reinterpret_cast<float*>(dst), new_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b));
+                        }
+                        if (SC == 1 || SC == 2) red_add_row4(cq + 4 * v * LANES, delta4(c.q[v], pw[v], e, cf.lr, cf.lambda));
+                        else st_row4(cq + 4 * v * LANES, new_chunk<FAST>(c.q[v], pw[v], e, cf.lr, cf.lambda, cf.acoef, b));
                     }
                 }
             }
@@ -145,7 +159,7 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
 // Hogwild kernel (cold records). Work unit = tile of 32 consecutive records per warp: lane l streams record l
 // (12 B, past L1, evict-first) one tile ahead and parks it in the warp's shared-memory slot, from where every
 // step reads its (u, i, r) with one broadcast LDS.128 instead of three shuffles.
-template <int LANES, int VEC, bool FULL, int SC, bool FAST, int DEPTH, bool BIAS>
+template <int LANES, int VEC, bool FULL, int SC, bool FAST, int DEPTH, bool BIAS, bool PH>
 __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_update_hogwild_kernel(UpdateArgs a) {
     __shared__ int4 srec[8][2][32];
     const int lane = threadIdx.x & 31;
@@ -154,8 +168,9 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
     const int grp = lane / LANES;
     const int64_t k = FULL ? (int64_t)(4 * LANES * VEC) : (int64_t)a.k;   // compile-time row length for the common ranks
     const int chunks = (int)(k >> 2);
-    float* const Pl = a.P - (int64_t)a.u_base * k + 4 * gl;               // lane-adjusted bases, indexed by global ids
-    float* const Ql = a.Q - (int64_t)a.i_base * k + 4 * gl;
+    char* const Pl = reinterpret_cast<char*>(a.P) + ((int64_t)4 * gl - (int64_t)a.u_base * k) * p_elem_bytes<PH>();   // lane-adjusted bases,
+    float* const Ql = a.Q - (int64_t)a.i_base * k + 4 * gl;                                                              // indexed by global ids
+    const uint32_t s32 = sr_seed32(a.seed);
     float* const BUl = BIAS ? a.BU - a.u_base : nullptr;                  // biases of the model extension, indexed by global ids
     float* const BIl = BIAS ? a.BI - a.i_base : nullptr;
     const Coef cf = {a.lr, a.lambda, __fsub_rn(1.0f, __fmul_rn(a.lr, a.lambda))};
@@ -200,8 +215,8 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
                 nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
             }
         }
-        if (cnt == 32) walk_tile<LANES, VEC, FULL, SC, FAST, true, DEPTH, BIAS>(srec[wic][buf], 32, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl);
-        else walk_tile<LANES, VEC, FULL, SC, FAST, false, DEPTH, BIAS>(srec[wic][buf], cnt, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl);
+        if (cnt == 32) walk_tile<LANES, VEC, FULL, SC, FAST, true, DEPTH, BIAS, PH>(srec[wic][buf], 32, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl, s32, a.epoch);
+        else walk_tile<LANES, VEC, FULL, SC, FAST, false, DEPTH, BIAS, PH>(srec[wic][buf], cnt, Pl, Ql, k, grp, gl, chunks, cf, BUl, BIl, s32, a.epoch);
         buf ^= 1;
         srec[wic][buf][lane] = nrec;
         __syncwarp();
@@ -211,18 +226,30 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
 // Deterministic parity mode: a single warp applies the records strictly in array order; sub-warp 0
 // holds the rows (the other lanes carry zeros through the shuffles). Each lane re-reads only
 // addresses it wrote itself, so program order makes every update see its predecessor's result.
-template <int LANES, int VEC, bool FULL>
+template <int LANES, int VEC, bool FULL, bool PH>
 __global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs a, float* __restrict__ err_trace) {
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LANES - 1);
     const bool act = lane < LANES;
     const int chunks = a.k >> 2;
+    const uint32_t s32 = sr_seed32(a.seed);
     for (int64_t j = 0; j < a.n; j++) {
         const Rec rec = a.recs[a.first + j];
         float* prow = a.P + (int64_t)(rec.u - a.u_base) * a.k;
         float* qrow = a.Q + (int64_t)(rec.i - a.i_base) * a.k;
         RowPair<LANES, VEC> rp;
-        load_rows<LANES, VEC, FULL>(rp, prow, qrow, gl, chunks, act);
+        if constexpr (PH) {              // binary16 P: widen p_u, the exact rule in binary32, narrow with the update's random words
+            const char* ph = reinterpret_cast<const char*>(a.P) + (int64_t)(rec.u - a.u_base) * a.k * 2;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const int c = gl + v * LANES;
+                const bool on = act && (FULL || c < chunks);
+                rp.p[v] = on ? widen4(ld_pchunk<true>(ph + 8 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rp.q[v] = on ? ld_row4(qrow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            load_rows<LANES, VEC, FULL>(rp, prow, qrow, gl, chunks, act);
+        }
         float pred = row_dot<LANES, VEC>(rp);
         float bu = 0.0f, bi = 0.0f;
         if (a.BU != nullptr) {                 // model extension: every lane reads the two entries, lane 0 writes them
@@ -237,7 +264,20 @@ __global__ void __launch_bounds__(32) sgd_update_deterministic_kernel(UpdateArgs
             __stcg(a.BI + (rec.i - a.i_base), __fadd_rn(bi, bias_delta(bi, e, a.lr, a.lambda)));
         }
         __syncwarp();
-        if (act) scatter_rows<LANES, VEC, FULL, 0>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
+        if constexpr (PH) {
+            char* ph = reinterpret_cast<char*>(a.P) + (int64_t)(rec.u - a.u_base) * a.k * 2;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const int c = gl + v * LANES;
+                if (act && (FULL || c < chunks)) {
+                    st_pchunk(ph + 8 * c, upd4(rp.p[v], rp.q[v], e, a.lr, a.lambda), make_uint2(0u, 0u),
+                              sr_word(s32, a.epoch, (uint32_t)rec.u, (uint32_t)rec.i, (uint32_t)c));
+                    st_row4(qrow + 4 * c, upd4(rp.q[v], rp.p[v], e, a.lr, a.lambda));
+                }
+            }
+        } else {
+            if (act) scatter_rows<LANES, VEC, FULL, 0>(rp, prow, qrow, gl, chunks, e, a.lr, a.lambda);
+        }
         if (err_trace != nullptr && lane == 0) err_trace[j] = e;
     }
 }
@@ -299,37 +339,43 @@ cudaError_t launch_sgd_update_hogwild(const UpdateArgs& a, int scatter, bool fas
     if (scatter != 0) fast = false;           // the atomic scatter variants add exact-rule deltas
     const bool deep = pipeline_depth() == 4 && g.vec == 1;
     const bool bias = a.BU != nullptr;        // model extension: its own instantiations (one gather ahead), none of its registers otherwise
-#define CALL(L, V, F)                                                                                          \
-    if (bias && fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2, true><<<grid, 256, 0, stream>>>(a);       \
-    else if (bias) switch (scatter) {                                                                          \
-        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
-        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
-        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2, true><<<grid, 256, 0, stream>>>(a); break;     \
-        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2, true><<<grid, 256, 0, stream>>>(a); break;    \
-    }                                                                                                          \
-    else if (fast && deep) sgd_update_hogwild_kernel<L, V, F, 0, true, 4, false><<<grid, 256, 0, stream>>>(a); \
-    else if (fast) sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false><<<grid, 256, 0, stream>>>(a);         \
-    else switch (scatter) {                                                                                    \
-        case 1: sgd_update_hogwild_kernel<L, V, F, 1, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
-        case 2: sgd_update_hogwild_kernel<L, V, F, 2, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
-        case 3: sgd_update_hogwild_kernel<L, V, F, 3, false, 2, false><<<grid, 256, 0, stream>>>(a); break;    \
-        default: sgd_update_hogwild_kernel<L, V, F, 0, false, 2, false><<<grid, 256, 0, stream>>>(a); break;   \
+    const bool p_half = a.p_half != 0;        // binary16 P rows: FMA arrangement and plain stores only (validate_config)
+    if (p_half && (!fast || scatter != 0)) return cudaErrorInvalidValue;
+#define HK(L_, V_, F_, SC_, FAST_, D_, BIAS_, PH_) sgd_update_hogwild_kernel<L_, V_, F_, SC_, FAST_, D_, BIAS_, PH_><<<grid, 256, 0, stream>>>(a)
+#define CALL(L, V, F)                                                  \
+    if (p_half) { if (bias) HK(L, V, F, 0, true, 2, true, true); else HK(L, V, F, 0, true, 2, false, true); }   \
+    else if (bias && fast) HK(L, V, F, 0, true, 2, true, false);                \
+    else if (bias) switch (scatter) {                                  \
+        case 1: HK(L, V, F, 1, false, 2, true, false); break;                   \
+        case 2: HK(L, V, F, 2, false, 2, true, false); break;                   \
+        case 3: HK(L, V, F, 3, false, 2, true, false); break;                   \
+        default: HK(L, V, F, 0, false, 2, true, false); break;                  \
+    }                                                                  \
+    else if (fast && deep) HK(L, V, F, 0, true, 4, false, false);               \
+    else if (fast) HK(L, V, F, 0, true, 2, false, false);                       \
+    else switch (scatter) {                                            \
+        case 1: HK(L, V, F, 1, false, 2, false, false); break;                  \
+        case 2: HK(L, V, F, 2, false, 2, false, false); break;                  \
+        case 3: HK(L, V, F, 3, false, 2, false, false); break;                  \
+        default: HK(L, V, F, 0, false, 2, false, false); break;                 \
     }
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
+#undef HK
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
-cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas) {
+cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, bool p_half, int* ctas) {
     const Geometry g = geometry_for(k);
     cudaError_t err = cudaSuccess;
     if (scatter != 0) fast = false;
     const bool deep = pipeline_depth() == 4 && g.vec == 1;
 #define CALL(L, V, F)                                                                                                          \
-    err = (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 4, false>, 256, 0) \
-          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false>, 256, 0)       \
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, false, 2, false>, 256, 0)
+    err = p_half ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false, true>, 256, 0)         \
+          : (fast && deep) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 4, false, false>, 256, 0) \
+          : fast ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, true, 2, false, false>, 256, 0)       \
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, sgd_update_hogwild_kernel<L, V, F, 0, false, 2, false, false>, 256, 0)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     return err;
@@ -338,7 +384,9 @@ cudaError_t hogwild_max_ctas_per_sm(int k, int scatter, bool fast, int* ctas) {
 cudaError_t launch_sgd_update_deterministic(const UpdateArgs& a, float* err_trace, cudaStream_t stream, int* launches) {
     if (a.n <= 0) return cudaSuccess;
     const Geometry g = geometry_for(a.k);
-#define CALL(L, V, F) sgd_update_deterministic_kernel<L, V, F><<<1, 32, 0, stream>>>(a, err_trace)
+#define CALL(L, V, F)                                                                                  \
+    if (a.p_half) sgd_update_deterministic_kernel<L, V, F, true><<<1, 32, 0, stream>>>(a, err_trace);  \
+    else sgd_update_deterministic_kernel<L, V, F, false><<<1, 32, 0, stream>>>(a, err_trace)
     MFSGD_DISPATCH_GEOMETRY(g, CALL);
 #undef CALL
     if (launches) *launches += 1;

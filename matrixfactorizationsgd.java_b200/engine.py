@@ -13,7 +13,7 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
                 stripes_per_gpu=0, shards_per_gpu=0, scatter=capi.SCATTER_STORE, flags=0, device=0,
                 world_size=1, rank=0, nccl_id=None, init_scale=0.0, ctas_per_sm=0, rounds=0, hot_share=0.0, hot_chunk=0,
                 merge_boost=0.0, p_atomic_threshold=0.0, model=0, lr_decay=0.0, early_stop_patience=0,
-                early_stop_min_delta=0.0):
+                early_stop_min_delta=0.0, p_storage=0):
     cfg = Config()
     check(lib.mfsgd_config_default(C.byref(cfg)))
     cfg.n_users, cfg.n_items, cfg.k = int(n_users), int(n_items), int(k)
@@ -26,6 +26,7 @@ def make_config(n_users, n_items, k, lr, lambda_, seed=20261018, mode=capi.MODE_
     cfg.p_atomic_threshold = float(p_atomic_threshold)
     cfg.model = int(model)
     cfg.lr_decay, cfg.early_stop_patience, cfg.early_stop_min_delta = float(lr_decay), int(early_stop_patience), float(early_stop_min_delta)
+    cfg.p_storage = int(p_storage)
     if nccl_id is not None:
         C.memmove(cfg.nccl_id, bytes(nccl_id), 128)
     return cfg

@@ -66,6 +66,16 @@ class MatrixFactorizationSGD:
         return Factors(P, Q, nUsers, nItems, k)
 
     @staticmethod
+    def factorizeMixed(users, items, ratings, nUsers, nItems, k, lr, lambda_, epochs, seed, mode=capi.MODE_HOGWILD, n_gpus=1, device=0,
+                       **cfg_kw):
+        """Stand-in factorizeMixed (:439): the rows of P kept as binary16 on the device (stochastic rounding from a counter hash),
+        arithmetic in binary32; P comes back widened exactly."""
+        if k % 4 != 0:
+            raise ValueError("bad shape")                                # stand-in line 443
+        return MatrixFactorizationSGD.factorize(users, items, ratings, nUsers, nItems, k, lr, lambda_, epochs, seed, mode=mode,
+                                                n_gpus=n_gpus, device=device, p_storage=capi.STORAGE_F16, **cfg_kw)
+
+    @staticmethod
     def factorizeModel(users, items, ratings, nUsers, nItems, k, lr, lambda_, epochs, seed, useGlobalMean, useBiases,
                        mode=capi.MODE_HOGWILD, n_gpus=1, device=0, **cfg_kw):
         """Stand-in factorizeModel (:305): r ~ mu + b_u + b_i + p_u . q_i. The mean is taken on the device while the ratings are

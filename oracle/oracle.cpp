@@ -220,7 +220,8 @@ ORC_API float orc_sgd_update(float* p, float* q, int k, float r, float lr, float
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Mixed-precision factor storage (stand-in section "Mixed-precision storage"): P rows are KEPT as binary16,
+ * Mixed-precision factor storage (MatrixFactorizationSGD.java:403-460: srWord :413, storeF16Sr :420,
+ * sgdUpdateMixed :426, factorizeMixed :439): P rows are KEPT as binary16,
  * every operation of the update rule stays binary32. A row is widened exactly on load and narrowed on store with
  * stochastic rounding driven by a counter hash of (seed, epoch, u, i, chunk) -- no state, any visiting order.
  * ------------------------------------------------------------------------------------------------ */

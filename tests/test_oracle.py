@@ -547,3 +547,78 @@ def test_midsize_fixture_is_the_oracles():
         if not model and not G:        # orc_train_model without biases is orc_train: the plain curves are factorize()'s
             Pf, Qf = orc.factorize(tu, ti, tr, nu, ni, k, par["lr"], par["lam"], epochs, SEED)
             assert np.array_equal(P, Pf) and np.array_equal(Q, Qf)
+
+
+# ------------------------------------------------------------------------------------------------
+# mixed-precision factor storage -- stand-in srWord :413, storeF16Sr :420, sgdUpdateMixed :426, factorizeMixed :439
+# ------------------------------------------------------------------------------------------------
+def test_binary16_conversions_are_ieee():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([(rng.standard_normal(50_000) * 0.2).astype(np.float32), (rng.standard_normal(5_000) * 1e-5).astype(np.float32),
+                        np.array([0, -0.0, 65504, 65519.9, 65520, 1e-8, 2.98e-8, 2.9802322e-8, 6.1e-5, 6.0e-5, 1.0, -1.0], np.float32)])
+    with np.errstate(over="ignore"):
+        want = x.astype(np.float16).view(np.uint16)
+    got = np.array([orc.lib.orc_f32_to_f16_rn(float(v)) for v in x], np.uint16)
+    assert np.array_equal(got, want)                                         # round to nearest even, subnormals, overflow to inf
+    h = np.arange(65536, dtype=np.uint16)
+    w = orc.widen(h.reshape(1, -1)).ravel()
+    ww = h.view(np.float16).astype(np.float32)
+    ok = ~np.isnan(ww)
+    assert np.array_equal(w.view(np.uint32)[ok], ww.view(np.uint32)[ok])     # widening is exact for every bit pattern
+
+
+def test_stochastic_rounding_is_unbiased_and_picks_a_neighbour():
+    rng = np.random.default_rng(1)
+    for v in (np.float32(0.1234567), np.float32(-0.0312345), np.float32(0.9999)):
+        lo = np.float32(np.float16(v))                                       # a neighbour; the other one is one binary16 ulp away
+        words = rng.integers(0, 2 ** 32, 40_000, dtype=np.uint64)
+        vals = np.array([orc.lib.orc_f16_to_f32(orc.lib.orc_store_f16_sr(float(v), int(w), int(w) % 4)) for w in words])
+        uniq = np.unique(vals)
+        assert len(uniq) == 2 and uniq[0] < v < uniq[1] and lo in uniq
+        ulp = float(uniq[1] - uniq[0])
+        assert abs(vals.mean() - float(v)) < 0.01 * ulp                      # unbiased to a hundredth of an ulp (8 random bits + sampling)
+    # values binary16 holds exactly are never moved
+    for v in (0.5, -0.25, 0.0999755859375):
+        for w in (0, 0xFFFFFFFF, 0x12345678):
+            assert orc.lib.orc_f16_to_f32(orc.lib.orc_store_f16_sr(v, w, 1)) == v
+
+
+def test_sr_word_known_values_and_independence_of_order():
+    # the hash is a pure function of (seed, epoch, u, i, c): restated here in Python integers
+    def word(seed, epoch, u, i, c):
+        m = 0xFFFFFFFF
+        x = ((seed ^ (seed >> 32)) + u * 0x9E3779B1 + i * 0x85EBCA77 + (epoch * 0x10001 + c) * 0xC2B2AE3D) & m
+        x ^= x >> 16
+        x = (x * 0x7FEB352D) & m
+        x ^= x >> 15
+        x = (x * 0x846CA68B) & m
+        x ^= x >> 16
+        return x
+    for args in ((SEED, 0, 0, 0, 0), (SEED, 3, 479_999, 17_799, 31), (2 ** 63 + 5, 19, 9_999_999, 999_999, 127)):
+        assert orc.lib.orc_sr_word(*args) == word(*args)
+    # two conflict-free updates give the same rows whichever comes first
+    k = 8
+    P16 = orc.init_factors_f16(2, k, SEED, 0)
+    Q = orc.init_factors(2, k, SEED, 1)
+    a, b = (P16.copy(), Q.copy()), (P16.copy(), Q.copy())
+    for (P_, Q_), order in ((a, (0, 1)), (b, (1, 0))):
+        for t in order:
+            orc.lib.orc_sgd_update_mixed(P_[t], Q_[t], k, 3.0 + t, 0.02, 0.05, orc.ORDER_SEQ, SEED, 4, t, t, 1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_mixed_storage_tracks_binary32_training():
+    """P kept in binary16 with stochastic rounding ends within 0.3 % of the binary32 oracle's held-out RMSE (noise-dominant and
+    signal-dominant data)."""
+    nu, ni, n, k = 2000, 800, 300_000, 16
+    for amp, ns, lr, lam, ep in ((0.0, 0.0, 0.005, 0.05, 6), (1.7320508, 0.125, 0.02, 0.02, 10)):
+        u, i, r, held = orc.generate(SEED, 0, n, nu, ni, amplitude=amp, noise_scale=ns)
+        tr = (u[~held].copy(), i[~held].copy(), r[~held].copy())
+        ho = (u[held].copy(), i[held].copy(), r[held].copy())
+        P, Q = orc.factorize(*tr, nu, ni, k, lr, lam, ep, SEED)
+        base = orc.rmse(P, Q, *ho)
+        P16, Qm = orc.init_factors_f16(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+        assert np.array_equal(P16, orc.init_factors(nu, k, SEED, 0).astype(np.float16).view(np.uint16))
+        orc.train_mixed(*tr, P16, Qm, lr, lam, 0, ep, SEED)
+        got = orc.rmse(orc.widen(P16), Qm, *ho)
+        assert abs(got / base - 1.0) < 3e-3, (got, base)

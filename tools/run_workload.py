@@ -18,8 +18,10 @@ for env, key, conv in (("RW_PAT", "p_atomic_threshold", float), ("RW_SCATTER", "
                        ("RW_HOT_CHUNK", "hot_chunk", int), ("RW_SHARDS", "shards_per_gpu", int)):
     if os.environ.get(env):
         kw[key] = conv(os.environ[env])
+extra = int(os.environ.get("RW_FLAGS", "0"))      # e.g. 16 = MFSGD_FLAG_SPLIT_SHARDS: the item sub-shards on stream lanes, as a real ring runs them
+kw["flags"] |= extra
 if G > 1:
-    kw.update(mode=capi.MODE_DSGD, n_gpus=G, flags=capi.FLAG_TIME_KERNELS | capi.FLAG_VIRTUAL_RING)
+    kw.update(mode=capi.MODE_DSGD, n_gpus=G, flags=capi.FLAG_TIME_KERNELS | capi.FLAG_VIRTUAL_RING | extra)
 else:
     kw.update(mode=capi.MODE_HOGWILD)
 cfg = mf.make_config(w.n_users, w.n_items, w.k, w.lr, w.lambda_, **kw)
