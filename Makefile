@@ -6,7 +6,7 @@ PKG       := matrixfactorizationsgd.java_b200
 CSRC      := $(PKG)/csrc
 OBJDIR    := build/obj
 LIB       := $(PKG)/lib/libmfsgd.so
-OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o $(OBJDIR)/kernels_diag.o $(OBJDIR)/ratings_io.o
+OBJS      := $(OBJDIR)/engine.o $(OBJDIR)/kernels_update.o $(OBJDIR)/kernels_hot.o $(OBJDIR)/kernels_layout.o $(OBJDIR)/kernels_eval.o $(OBJDIR)/kernels_diag.o $(OBJDIR)/kernels_ring.o $(OBJDIR)/ratings_io.o
 
 all: $(LIB) oracle harness host tools/l2_peak
 

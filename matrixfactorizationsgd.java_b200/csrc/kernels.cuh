@@ -107,6 +107,9 @@ cudaError_t launch_sgd_update_hot(const UpdateArgs& a, const HotUnit* units, int
                                   int* launches);
 bool hot_launch_overlaps(int k, int n_units, int64_t n_records, int longest_run, int full_grid, int max_sub_warps);
 
+// (4) ring window: wait on `stream` until *flag >= value (cyclic); fallback of the stream memory operation (kernels_ring.cu)
+cudaError_t launch_ring_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream, int* launches);
+
 // (3) held-out RMSE: adds sum (r - p_u.q_i)^2 over the records to *sse_accum (double, device).
 // scratch: >= rmse_scratch_doubles() doubles of device memory owned by the caller.
 int rmse_scratch_doubles();

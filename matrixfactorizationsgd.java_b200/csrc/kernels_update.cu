@@ -77,12 +77,13 @@ __device__ __forceinline__ void slot_load(Slot<VEC, PH>& sl, const int4* __restr
                                           const float* __restrict__ BUl, const float* __restrict__ BIl) {
     constexpr int ES = p_elem_bytes<PH>();
     const int4 rec = tile[j & 31];
+    const int32_t uu = rec.x & REC_USER_MASK;          // bit 31 is the heavy-user mark
     const bool act = FULLTILE || j < cnt;
     if (BIAS) {
-        sl.bu = act ? __ldcg(BUl + rec.x) : 0.0f;
+        sl.bu = act ? __ldcg(BUl + uu) : 0.0f;
         sl.bi = act ? __ldcg(BIl + rec.y) : 0.0f;
     }
-    const char* pp = Pl + (int64_t)rec.x * k * ES;
+    const char* pp = Pl + (int64_t)uu * k * ES;
     const float* qq = Ql + (int64_t)rec.y * k;
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
@@ -101,6 +102,7 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
     constexpr int FULL_STEPS = 32 / GPW;
     constexpr int ES = p_elem_bytes<PH>();
     const int steps = FULLTILE ? FULL_STEPS : (cnt + GPW - 1) / GPW;
+    const float ccoef = -__fmul_rn(cf.lr, cf.lambda);      // heavy users: p_u += b * q_i + ccoef * p_u, added in memory
     Slot<VEC, PH> ring[DEPTH];
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; d++)
@@ -119,7 +121,12 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
             const int j = t * GPW + grp;
             const int4 rec = tile[j & 31];
             const bool act = FULLTILE ? true : j < cnt;
-            char* const cp = Pl + (int64_t)rec.x * k * ES;
+            const int32_t uu = rec.x & REC_USER_MASK;
+            // heavy user (common.cuh REC_USER_MASK): p_u moves by its increment, added in memory, as in the run kernel -- a plain
+            // store here would wipe out the run kernel's concurrent red.adds on the same row (ML-100K-shaped signal set: the third
+            // of the items that take this path cost 0.3 % of held-out RMSE that way, profiles/r02_experiments.md section 10)
+            const bool p_red = SC == 1 || SC == 3 || rec.x < 0;
+            char* const cp = Pl + (int64_t)uu * k * ES;
             float* const cq = Ql + (int64_t)rec.y * k;
             const Slot<VEC, PH>& c = ring[d];
             float4 pw[VEC];                        // p_u in binary32 (PH: widened here, exactly)
@@ -130,8 +137,8 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
             const float e = __fsub_rn(__int_as_float(rec.z), pred);
             const float b = __fmul_rn(cf.lr, e);
             if (BIAS && act && lane_chunk == 0) {      // one lane of the sub-warp owns the two bias entries
-                if (SC == 1 || SC == 3) atomicAdd(BUl + rec.x, bias_delta(c.bu, e, cf.lr, cf.lambda));
-                else __stcg(BUl + rec.x, __fadd_rn(c.bu, bias_delta(c.bu, e, cf.lr, cf.lambda)));
+                if (p_red) atomicAdd(BUl + uu, bias_delta(c.bu, e, cf.lr, cf.lambda));
+                else __stcg(BUl + uu, __fadd_rn(c.bu, bias_delta(c.bu, e, cf.lr, cf.lambda)));
                 if (SC == 1 || SC == 2) atomicAdd(BIl + rec.y, bias_delta(c.bi, e, cf.lr, cf.lambda));
                 else __stcg(BIl + rec.y, __fadd_rn(c.bi, bias_delta(c.bi, e, cf.lr, cf.lambda)));
             }
@@ -141,10 +148,12 @@ __device__ __forceinline__ void walk_tile(const int4* __restrict__ tile, int cnt
                     if (FULL || lane_chunk + v * LANES < chunks) {
                         char* const dst = cp + 4 * v * LANES * ES;
                         if constexpr (PH) {
-                            st_pchunk(dst, new_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b), c.p[v],
-                                      sr_word(s32, epoch, (uint32_t)rec.x, (uint32_t)rec.y, (uint32_t)(lane_chunk + v * LANES)));
+                            const uint32_t w = sr_word(s32, epoch, (uint32_t)uu, (uint32_t)rec.y, (uint32_t)(lane_chunk + v * LANES));
+                            const float4 np = new_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b);
+                            if (p_red) red_pchunk_f16(dst, np, c.p[v], w);
+                            else st_pchunk(dst, np, c.p[v], w);
                         } else {
-                            if (SC == 1 || SC == 3) red_add_row4(reinterpret_cast<float*>(dst), delta4(pw[v], c.q[v], e, cf.lr, cf.lambda));
+                            if (p_red) red_add_row4(reinterpret_cast<float*>(dst), delta_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, ccoef, b));
                             else st_row4(reinterpret_cast<float*>(dst), new_chunk<FAST>(pw[v], c.q[v], e, cf.lr, cf.lambda, cf.acoef, b));
                         }
                         if (SC == 1 || SC == 2) red_add_row4(cq + 4 * v * LANES, delta4(c.q[v], pw[v], e, cf.lr, cf.lambda));
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
         int4 rec = make_int4(0, 0, 0, 0);
         if (j < a.n) {
             const int64_t idx = record_index(j);
-            rec.x = ld_stream_i32(words + 3 * idx, pol) & REC_USER_MASK;
+            rec.x = ld_stream_i32(words + 3 * idx, pol);                    // with the heavy-user mark (bit 31)
             rec.y = ld_stream_i32(words + 3 * idx + 1, pol);
             rec.z = ld_stream_i32(words + 3 * idx + 2, pol);
         }
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(256, VEC == 1 ? 4 : (VEC == 2 ? 2 : 1)) sgd_up
             const int64_t j = (tile + n_warps) * 32 + lane;
             if (j < a.n) {
                 const int64_t idx = record_index(j);
-                nrec.x = ld_stream_i32(words + 3 * idx, pol) & REC_USER_MASK;
+                nrec.x = ld_stream_i32(words + 3 * idx, pol);
                 nrec.y = ld_stream_i32(words + 3 * idx + 1, pol);
                 nrec.z = ld_stream_i32(words + 3 * idx + 2, pol);
             }

@@ -270,11 +270,40 @@ ORC_API uint16_t orc_store_f16_sr(float v, uint32_t word, int j) {
     return orc_f32_to_f16_rn(bits_f32((f32_bits(v) + rho) & 0xFFFFE000u));
 }
 
+/* binary16 a + b (sub != 0: a - b), one rounding to nearest even -- the GPU's HSUB2 / red.global.add.noftz.f16x2 on finite values.
+ * Every finite binary16 value is an integer multiple of 2^-24, so the exact result is an integer in that unit: round it to 11
+ * significant bits (or to the subnormal grid, which is that unit itself). Engine-side twin, not in the stand-in. */
+static inline int64_t f16_scaled(uint16_t h) {
+    const int ex = (h >> 10) & 0x1F, man = h & 0x3FF;
+    const int64_t mag = ex == 0 ? (int64_t)man : ((int64_t)(man | 0x400) << (ex - 1));
+    return (h & 0x8000u) ? -mag : mag;
+}
+ORC_API uint16_t orc_f16_add_rn(uint16_t a, uint16_t b, int sub) {
+    int64_t v = f16_scaled(a) + (sub ? -f16_scaled(b) : f16_scaled(b));
+    if (v == 0) return (uint16_t)((a & (sub ? (b ^ 0x8000u) : b)) & 0x8000u);        /* -0 only from (-0) + (-0); x - x = +0 */
+    const uint16_t sign = v < 0 ? 0x8000u : 0u;
+    uint64_t m = (uint64_t)(v < 0 ? -v : v);
+    int top = 63;
+    while (!((m >> top) & 1u)) top--;                      /* position of the leading bit: value = m * 2^-24 */
+    if (top <= 10) return (uint16_t)(sign | m);            /* subnormal, or the first normal binades: exact (ex = 1 when bit 10 is set) */
+    const int shift = top - 10;
+    uint64_t q = m >> shift;
+    const uint64_t rem = m & ((1ULL << shift) - 1ULL), half = 1ULL << (shift - 1);
+    if (rem > half || (rem == half && (q & 1ULL))) q++;
+    int ex = shift + 1;
+    if (q == 0x800ULL) { q = 0x400ULL; ex++; }
+    if (ex >= 31) return (uint16_t)(sign | 0x7C00u);
+    return (uint16_t)(sign | ((uint16_t)ex << 10) | (uint16_t)(q & 0x3FFULL));
+}
+
 ORC_API void orc_init_factors_f16(uint16_t* rows, int64_t n_rows, int k, uint64_t seed, uint64_t stream, float scale) {
     for (int64_t e = 0; e < n_rows * (int64_t)k; e++) rows[e] = orc_f32_to_f16_rn(orc_uniform(seed, stream, (uint64_t)e) * scale);
 }
 
-/* sgdUpdate on a binary16 p_u: widen, the rule in `order_mode`, narrow (sr != 0: stochastic, else round to nearest even) */
+/* sgdUpdate on a binary16 p_u: widen, the rule in `order_mode`, narrow (sr != 0: stochastic, else round to nearest even).
+ * sr == 2: the engine's heavy-user rows (kernels_hot.cu red_pchunk_f16) -- the row in memory moves by the binary16 difference
+ * between the narrowed new value and the value the update started from, two binary16 roundings (equal to the plain store
+ * whenever that difference is exact, i.e. almost always; small values that more than double are the exception). */
 ORC_API float orc_sgd_update_mixed(uint16_t* p16, float* q, int k, float r, float lr, float lambda, int order_mode, uint64_t seed,
                                    uint32_t epoch, int32_t u, int32_t i, int sr) {
     std::vector<float> p((size_t)k);
@@ -282,8 +311,10 @@ ORC_API float orc_sgd_update_mixed(uint16_t* p16, float* q, int k, float r, floa
     const float e = orc_sgd_update(p.data(), q, k, r, lr, lambda, order_mode);
     for (int c = 0; c < k / 4; c++) {
         const uint32_t w = orc_sr_word(seed, epoch, (uint32_t)u, (uint32_t)i, (uint32_t)c);
-        for (int j = 0; j < 4; j++)
-            p16[4 * c + j] = sr ? orc_store_f16_sr(p[(size_t)(4 * c + j)], w, j) : orc_f32_to_f16_rn(p[(size_t)(4 * c + j)]);
+        for (int j = 0; j < 4; j++) {
+            const uint16_t nv = sr ? orc_store_f16_sr(p[(size_t)(4 * c + j)], w, j) : orc_f32_to_f16_rn(p[(size_t)(4 * c + j)]);
+            p16[4 * c + j] = sr == 2 ? orc_f16_add_rn(p16[4 * c + j], orc_f16_add_rn(nv, p16[4 * c + j], 1), 0) : nv;
+        }
     }
     return e;
 }

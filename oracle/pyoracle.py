@@ -104,6 +104,8 @@ def _load():
     lib.orc_sr_word.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.orc_store_f16_sr.restype = C.c_uint16
     lib.orc_store_f16_sr.argtypes = [C.c_float, C.c_uint32, C.c_int]
+    lib.orc_f16_add_rn.restype = C.c_uint16
+    lib.orc_f16_add_rn.argtypes = [C.c_uint16, C.c_uint16, C.c_int]
     lib.orc_init_factors_f16.restype = None
     lib.orc_init_factors_f16.argtypes = [_u16p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_float]
     lib.orc_sgd_update_mixed.restype = C.c_float
@@ -272,7 +274,8 @@ def widen(P16):
 
 
 def train_mixed(u, i, r, P16, Q, lr, lam, epoch_begin, epoch_end, seed, order_mode=ORDER_SEQ, shuffled=True, sr=True):
-    """The stand-in's loop with P kept in binary16 (oracle.cpp orc_train_mixed); sr=False rounds to nearest even instead."""
+    """The stand-in's loop with P kept in binary16 (oracle.cpp orc_train_mixed); sr=False rounds to nearest even instead;
+    sr=2: rows moved by the binary16 difference (the engine's heavy-user red, two binary16 roundings)."""
     rc = lib.orc_train_mixed(u, i, r, len(r), P16, Q, P16.shape[0], Q.shape[0], Q.shape[1], lr, lam, epoch_begin, epoch_end, seed,
                              order_mode, int(shuffled), int(sr))
     if rc:

@@ -46,7 +46,7 @@ def test_mixed_deterministic_mode_bit_exact(k):
     assert np.array_equal(got.P, orc.widen(P16)) and np.array_equal(got.Q, Q)
     # the binary32 run of the same rule is a different trajectory, a rounding step away
     Pf, Qf = orc.factorize(u, i, r, nu, ni, k, 0.02, 0.03, 3, SEED, orc.ORDER_WARP_TREE)
-    assert not np.array_equal(got.Q, Qf) and np.abs(got.Q - Qf).max() < 5e-3
+    assert not np.array_equal(got.Q, Qf) and np.abs(got.Q - Qf).max() < 0.02 * np.abs(Qf).max()   # (binary16 ulp at 1.0 is 1e-3)
 
 
 @pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256, 512])
@@ -72,7 +72,8 @@ def test_mixed_hogwild_kernel_bit_exact_on_conflict_free_data(k):
 @pytest.mark.parametrize("k", [8, 32, 64, 100, 128, 256])
 def test_mixed_run_kernel_exact_sequential_runs(k, arith):
     """Run path with binary16 P rows, one run per item: gathers widen, stores narrow with the update's random word; a heavy user's
-    row moves by the exact binary16 difference (one f16x4 red), which lands on the same value when nobody else writes the row."""
+    row moves by the binary16 difference between the narrowed new value and the value the update read (one f16x4 red; the oracle
+    restates its two binary16 roundings, orc_f16_add_rn -- the difference is exact unless a small value more than doubles)."""
     n_hot, per_hot, n_cold = 5, 3000, 5003
     n = n_hot * per_hot + n_cold
     rng = np.random.default_rng(7)
@@ -94,8 +95,10 @@ def test_mixed_run_kernel_exact_sequential_runs(k, arith):
     P16, Qo = orc.init_factors_f16(n, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
     hot = oi < n_hot
     with orc.tree_lanes(orc.run_lanes(k)):
-        orc.train_mixed(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), P16, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
-    orc.train_mixed(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), P16, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False)
+        orc.train_mixed(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), P16, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False,
+                        sr=2 if arith == "heavy" else 1)      # heavy rows: moved by the binary16 difference (two binary16 roundings)
+    orc.train_mixed(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), P16, Qo, 0.01, 0.03, 0, 3, SEED, orc.ORDER_WARP_TREE_FMA, shuffled=False,
+                    sr=2 if arith == "heavy" else 1)
     assert np.array_equal(P, orc.widen(P16)) and np.array_equal(Q, Qo)
 
 

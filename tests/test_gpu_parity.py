@@ -39,12 +39,12 @@ def assert_ring_rmse_parity(got, shuffled, dsgd_ordered):
 def train_runs_then_cold(ou, oi, orr, n_hot, Po, Qo, k, lr, lam, e0, e1, order, heavy=False):
     """Oracle twin of a layout whose items < n_hot go through the run kernel (orc.run_lanes(k) lanes per rating) and
     the others through the cold kernel (default lanes). Valid when the two sets share no P or Q row.
-    heavy: every user is marked heavy, i.e. the run kernel adds p_u's increment in memory (FMA arrangement: PDELTA rounding)."""
+    heavy: every user is marked heavy, i.e. both kernels add p_u's increment in memory (FMA arrangement: PDELTA rounding)."""
     hot = oi < n_hot
     run_order = orc.ORDER_WARP_TREE_FMA_PDELTA if heavy and order == orc.ORDER_WARP_TREE_FMA else order
     with orc.tree_lanes(orc.run_lanes(k)):
         orc.train(ou[hot].copy(), oi[hot].copy(), orr[hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, run_order, shuffled=False)
-    orc.train(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, order, shuffled=False)
+    orc.train(ou[~hot].copy(), oi[~hot].copy(), orr[~hot].copy(), Po, Qo, lr, lam, e0, e1, SEED, run_order, shuffled=False)
 
 
 def split(u, i, r, held):
@@ -464,7 +464,7 @@ def test_hot_item_kernel_exact_sequential_runs(k, arith):
     r = (1 + 4 * rng.random(n)).astype(np.float32)
     ni = n_hot + n_cold
     # "-heavy": every user's records carry the heavy mark, "-atomic-p": MFSGD_SCATTER_ATOMIC_P -- both make the run kernel add
-    # p_u's increment in memory (red.global.add) instead of storing the new row; the cold kernel keeps storing.
+    # p_u's increment in memory (red.global.add) instead of storing the new row; the cold kernel does the same for marked records.
     heavy = arith.endswith("-heavy") or arith.endswith("-atomic-p")
     exact = arith.startswith("exact")
     cfg = mf.make_config(n, ni, k, 0.01, 0.03, seed=SEED, mode=capi.MODE_HOGWILD, stripes_per_gpu=1, rounds=1,

@@ -567,6 +567,32 @@ def test_binary16_conversions_are_ieee():
     assert np.array_equal(w.view(np.uint32)[ok], ww.view(np.uint32)[ok])     # widening is exact for every bit pattern
 
 
+def test_binary16_add_twin_is_ieee():
+    """orc_f16_add_rn (twin of the engine's HSUB2 + red.add.f16x2 on heavy users' binary16 rows): one rounding to nearest even of the
+    exact sum / difference, signed zeros, subnormals, overflow -- against NumPy through float64 (exact for binary16 operands)."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2 ** 16, 60_000).astype(np.uint16)
+    b = rng.integers(0, 2 ** 16, 60_000).astype(np.uint16)
+    near = rng.random(60_000) < 0.5                       # half the pairs are neighbours-ish, as in an SGD step
+    b[near] = (a[near].astype(np.int32) + rng.integers(-40, 41, int(near.sum()))).clip(0, 65535).astype(np.uint16)
+    fa, fb = a.view(np.float16), b.view(np.float16)
+    ok = np.isfinite(fa) & np.isfinite(fb)
+    a, b, fa, fb = a[ok], b[ok], fa[ok].astype(np.float64), fb[ok].astype(np.float64)
+    for sub in (0, 1):
+        with np.errstate(over="ignore"):
+            want = (fa - fb if sub else fa + fb).astype(np.float16).view(np.uint16)
+        got = np.array([orc.lib.orc_f16_add_rn(int(x), int(y), sub) for x, y in zip(a, b)], np.uint16)
+        assert np.array_equal(got, want)
+    # the heavy-row rule lands on the plain stochastic store whenever the binary16 difference is exact
+    nu, ni, n, k = 300, 200, 6000, 16
+    u, i, r, _ = orc.generate(SEED, 0, n, nu, ni)
+    Pa, Qa = orc.init_factors_f16(nu, k, SEED, 0), orc.init_factors(ni, k, SEED, 1)
+    Pb, Qb = Pa.copy(), Qa.copy()
+    orc.train_mixed(u, i, r, Pa, Qa, 0.01, 0.03, 0, 1, SEED, sr=1)
+    orc.train_mixed(u, i, r, Pb, Qb, 0.01, 0.03, 0, 1, SEED, sr=2)
+    assert (Pa != Pb).mean() < 0.02 and np.abs(orc.widen(Pa) - orc.widen(Pb)).max() < 2e-3
+
+
 def test_stochastic_rounding_is_unbiased_and_picks_a_neighbour():
     rng = np.random.default_rng(1)
     for v in (np.float32(0.1234567), np.float32(-0.0312345), np.float32(0.9999)):
