@@ -202,7 +202,7 @@ def run_ours(args):
     flags = capi.FLAG_TIME_KERNELS
     common = dict(n_users=w.n_users, n_items=w.n_items, k=w.k, lr=w.lr, lambda_=w.lambda_, seed=mf.SEED,
                   stripes_per_gpu=args.stripes, shards_per_gpu=args.shards, scatter=args.scatter, flags=flags,
-                  ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share)
+                  ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share, hot_chunk=args.hot_chunk)
     if world > 1:
         with stdout_to_stderr():
             eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
@@ -359,7 +359,9 @@ def run_ours(args):
                               w.name, w.n_users, w.n_items, w.n_ratings, int(info.n_train_total), w.k, w.lr, w.lambda_),
                           "parallelism": "hogwild-1gpu" if world == 1 else "dsgd-ring%d" % world,
                           "stripes_per_gpu": int(info.stripes_per_gpu), "shards_per_gpu": int(info.shards_per_gpu),
-                          "rounds": int(info.rounds), "hot_items": int(info.n_hot_items),
+                          "rounds": int(info.rounds), "hot_items": int(info.n_hot_items), "run_length": int(info.run_length),
+                          "rotation": ("ring window: copy-engine writes into the neighbour's memory over NVLink + sequence flags, pipelined over item sub-shards"
+                                       if os.environ.get("MFSGD_RING_TRANSPORT", "window") != "nccl" else "ncclSend/ncclRecv, pipelined over item sub-shards") if world > 1 else "none",
                           "scatter": "store" if args.scatter == 0 else "atomic",
                           "arith": "fma (FFMA2 arrangement of the update rule, a few ulp per update from the stand-in's unfused rule; "
                                    "MFSGD_FLAG_EXACT_ARITH selects the unfused one)",
@@ -503,6 +505,7 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--rounds", type=int, default=0)
     ap.add_argument("--hot-share", type=float, default=0.0)
+    ap.add_argument("--hot-chunk", type=int, default=0, help="longest run of the run kernel (0 = planned from the launch size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=12_000_000)

@@ -3,6 +3,7 @@
 //
 // Replaces the loop of baseline/java/MatrixFactorizationSGD.java:109-135 (factorize). C ABI in
 // include/mfsgd.h. No CPU fallback: every compute entry point needs an sm_100 device.
+#include <cuda.h>      // types of the stream memory operations only; libcuda is reached through cudaGetDriverEntryPoint
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -93,6 +94,12 @@ struct PhaseTimer {
     }
 };
 
+// The engine keeps up to ten streams per ring member busy (main, copy, two lanes of two, reshuffle, ...) and orders them with
+// events and flag waits. With the default of 8 hardware work queues two of those streams can share a queue, and a wait that
+// blocks one then holds the other one's launches back (false dependency). Ask for 32 queues unless the caller has chosen;
+// this runs when the library is loaded, i.e. before the process creates its CUDA context through it.
+__attribute__((constructor)) static void mfsgd_process_defaults() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // ------------------------------------------------------------------------------------------------
 // NCCL, loaded lazily (only a multi-process ring needs it; libmfsgd.so has no link-time dependency)
 // ------------------------------------------------------------------------------------------------
@@ -169,6 +176,23 @@ struct Member {              // one ring member ("GPU g")
     cudaStream_t stream = nullptr, copy_stream = nullptr, hot_stream = nullptr, shuffle_stream = nullptr;
     std::vector<cudaEvent_t> ev_part_done, ev_part_recv;   // pipelined rotation: per item sub-shard of the held group
     std::vector<char> part_recv_pending;
+    // Ring window (one process per GPU, one node; see "ring window" below): Q[0], Q[1], BQ[0], BQ[1] and the sequence flags of
+    // this member live in ONE allocation that the two ring neighbours map through CUDA IPC. The rotation then is a copy-engine
+    // write into the neighbour's window over NVLink plus a flag, with no kernel and no SM involved on either side.
+    struct Window {
+        void* base = nullptr;
+        size_t bytes = 0;
+        int64_t cap_rows = 0;
+        int k = 0;
+        bool biases = false, active = false;
+        size_t off_q[2] = {0, 0}, off_bq[2] = {0, 0};
+        char* to_base = nullptr;      // window of member g - 1 (we write its Q buffers and its arrival flags)
+        char* from_base = nullptr;    // window of member g + 1 (we write its credit flags)
+        uint32_t* d_seq = nullptr;    // d_seq[j] = seq_base + j: the source of the 4-byte flag writes
+        uint32_t seq_base = 0;
+        int seq_n = 0;
+        std::vector<uint32_t> sent;   // per item sub-shard: sequence number of the last hand-over
+    } win;
     int ahead_epoch = -1;    // epoch whose layout the background reshuffle has written (is writing) into recs[rcur ^ 1]
     int32_t u_lo = 0, u_hi = 0;      // owned P rows
     float* P = nullptr;
@@ -251,6 +275,10 @@ struct mfsgd_handle {
     ncclComm_t comm = nullptr;
     bool multi_process = false;
     int min_windows = 128;   // MFSGD_MIN_WINDOWS overrides (tuning aid)
+    int ring_transport = 1;  // pipelined rotation of a multi-process ring: 1 = ring window (peer writes + flags), 0 = ncclSend/ncclRecv
+                             // (MFSGD_RING_TRANSPORT = window | nccl; falls back to NCCL when the window cannot be mapped)
+    int ring_wait_kernel = 0;   // MFSGD_RING_WAIT = kernel: poll the flags with a one-thread kernel instead of cuStreamWaitValue32
+    int ring_signal_write = 0;  // MFSGD_RING_SIGNAL = write: set the flags with cuStreamWriteValue32 instead of a 4-byte copy
     int reserve_sms = 0;     // multi-process ring: SMs the run kernel leaves to the rotation's NCCL kernels (MFSGD_RESERVE_SMS)
     int n_lanes = 2;         // stream lanes of the pipelined rotation (MFSGD_LANES = 1 | 2)
     int sub_warp_div = 4;    // run kernel: at most (users of a P sub-stripe) / sub_warp_div runs in flight; MFSGD_SUBWARP_DIV overrides
@@ -366,16 +394,25 @@ static void free_eval(EvalSet& e) {
     e.group_off.clear();
 }
 
+// Q and the item biases either live in the member's ring window (which outlives a reload) or are blocks of their own
+static void release_q(Member& m) {
+    if (m.win.active) {
+        m.Q[0] = m.Q[1] = m.BQ[0] = m.BQ[1] = nullptr;
+        return;
+    }
+    dev_free(m.Q[0]);
+    dev_free(m.Q[1]);
+    dev_free(m.BQ[0]);
+    dev_free(m.BQ[1]);
+}
+
 static void free_member_data(Member& m) {
     cudaSetDevice(m.device);
     if (m.shuffle_stream) cudaStreamSynchronize(m.shuffle_stream);
     m.ahead_epoch = -1;
     dev_free(m.P);
-    dev_free(m.Q[0]);
-    dev_free(m.Q[1]);
+    release_q(m);
     dev_free(m.BU);
-    dev_free(m.BQ[0]);
-    dev_free(m.BQ[1]);
     dev_free(m.recs[0]);
     dev_free(m.recs[1]);
     dev_free(m.d_block_off);
@@ -520,6 +557,223 @@ static int validate_config(const mfsgd_config* c) {
     return MFSGD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ring window: the Q rotation of a one-process-per-GPU ring over NVLink peer memory
+// ------------------------------------------------------------------------------------------------
+// Round 2 moved the pipelined rotation off ncclSend/ncclRecv: their kernels need SM slots, and the run kernel's CTAs are
+// persistent, so with two stream lanes keeping the machine full a slice only left when the OTHER lane's launch drained -- the
+// pipeline serialised and 8 GPUs ran at 3.9x one (profiles/r02_experiments.md section 11). Here every member keeps both Q
+// buffers, the item biases and a page of flags in one allocation, its ring neighbours map that allocation (CUDA IPC; NVLink /
+// NVSwitch peer access), and a hand-over of item sub-shard `part` is, on the sender's copy stream:
+//     wait   credit[part]  >= n - 1      (own window: the receiver's own send out of the destination buffer is done)
+//     copy   slice  -> the receiver's other Q buffer            (copy engine, peer write)
+//     write  arrival[part] = n           into the receiver's window (after the slice: same stream, same engine order)
+//     write  credit[part]  = n           into the window of the member that sends to us (our buffer is free again)
+// and on the receiver's lane:  wait arrival[part] >= n  before the sub-shard's next launches. n counts the hand-overs of a
+// part since the window was built; it is the same number on every rank. Waits are stream memory operations
+// (cuStreamWaitValue32; MFSGD_RING_WAIT=kernel polls with one thread instead), flag writes are 4-byte copies out of a table
+// of sequence numbers (MFSGD_RING_SIGNAL=write: cuStreamWriteValue32). No SM, no kernel, no host thread on the data path.
+static const int RING_FLAG_STRIDE = 128;      // one flag per 128-byte line
+static const int RING_MAX_PARTS = 64;         // = the largest shards_per_gpu validate_config accepts
+static const size_t RING_FLAGS_BYTES = (size_t)2 * RING_MAX_PARTS * RING_FLAG_STRIDE;
+static inline size_t ring_arrival_off(int part) { return (size_t)part * RING_FLAG_STRIDE; }
+static inline size_t ring_credit_off(int part) { return (size_t)(RING_MAX_PARTS + part) * RING_FLAG_STRIDE; }
+
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamValue32Fn g_wait_value32 = nullptr, g_write_value32 = nullptr;
+static void stream_mem_ops_load() {
+    static bool tried = false;
+    if (tried) return;
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+        g_wait_value32 = (StreamValue32Fn)fn;
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+        g_write_value32 = (StreamValue32Fn)fn;
+    cudaGetLastError();
+}
+
+// stream waits until the flag (own window) has reached `value`
+static int ring_wait(mfsgd_handle* h, Member& m, cudaStream_t stream, size_t flag_off, uint32_t value) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(static_cast<char*>(m.win.base) + flag_off);
+    if (!h->ring_wait_kernel && g_wait_value32) {
+        CUresult r = g_wait_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return fail(MFSGD_E_CUDA, "cuStreamWaitValue32 failed (%d); set MFSGD_RING_WAIT=kernel or MFSGD_RING_TRANSPORT=nccl", (int)r);
+        return MFSGD_OK;
+    }
+    CK(launch_ring_wait_flag(flag, value, stream, &m.launches));
+    return MFSGD_OK;
+}
+
+// stream sets a flag in a neighbour's window to `value`, after everything enqueued on it so far
+static int ring_signal(mfsgd_handle* h, Member& m, cudaStream_t stream, char* peer_base, size_t flag_off, uint32_t value) {
+    if (h->ring_signal_write && g_write_value32) {
+        CUresult r = g_write_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)(peer_base + flag_off), value, 0);
+        if (r != CUDA_SUCCESS) return fail(MFSGD_E_CUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
+        return MFSGD_OK;
+    }
+    if (value < m.win.seq_base || value >= m.win.seq_base + (uint32_t)m.win.seq_n) return fail(MFSGD_E_STATE, "ring window: sequence table does not cover %u", value);
+    CK(cudaMemcpyAsync(peer_base + flag_off, m.win.d_seq + (value - m.win.seq_base), 4, cudaMemcpyDefault, stream));
+    return MFSGD_OK;
+}
+
+// the table of sequence numbers covers [first, first + count) (grown between train calls, never while the copy stream reads it)
+static int ring_seq_table(Member& m, uint32_t first, uint32_t count) {
+    Member::Window& w = m.win;
+    if (w.d_seq && first >= w.seq_base && first + count <= w.seq_base + (uint32_t)w.seq_n) return MFSGD_OK;
+    CK(cudaStreamSynchronize(m.copy_stream));
+    const uint32_t n = std::max<uint32_t>(count, 1u << 16);
+    if ((int)n > w.seq_n) {
+        if (w.d_seq) cudaFree(w.d_seq);
+        w.d_seq = nullptr;
+        w.seq_n = 0;
+        CK(cudaMalloc((void**)&w.d_seq, (size_t)n * 4));
+        w.seq_n = (int)n;
+    }
+    std::vector<uint32_t> host((size_t)w.seq_n);
+    for (int j = 0; j < w.seq_n; j++) host[(size_t)j] = first + (uint32_t)j;
+    CK(cudaMemcpy(w.d_seq, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+    w.seq_base = first;
+    return MFSGD_OK;
+}
+
+static void window_close_peers(Member& m) {
+    Member::Window& w = m.win;
+    if (w.to_base) cudaIpcCloseMemHandle(w.to_base);
+    if (w.from_base && w.from_base != w.to_base) cudaIpcCloseMemHandle(w.from_base);
+    w.to_base = w.from_base = nullptr;
+    cudaGetLastError();
+}
+
+// destroy: no barrier here -- every write into this window has landed before the last train call returned (it waits for
+// its arrivals AND its credits), and a neighbour that still maps the window only ever writes to it inside a train call
+static void window_release(Member& m) {
+    window_close_peers(m);
+    if (m.win.active) m.Q[0] = m.Q[1] = m.BQ[0] = m.BQ[1] = nullptr;
+    if (m.win.base) cudaFree(m.win.base);
+    if (m.win.d_seq) cudaFree(m.win.d_seq);
+    m.win = Member::Window();
+}
+
+// all ranks agree on a flag: min over the ring (also a barrier)
+static int ring_all_min(mfsgd_handle* h, Member& m, int* flag) {
+    uint32_t* d = nullptr;
+    CK(dev_alloc(&d, 1));
+    uint32_t v = (uint32_t)(*flag != 0);
+    cudaError_t e = cudaMemcpyAsync(d, &v, 4, cudaMemcpyHostToDevice, m.stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess) r = g_nccl.AllReduce(d, d, 1, ncclUint32, ncclMin, h->comm, m.stream);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(&v, d, 4, cudaMemcpyDeviceToHost, m.stream);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(m.stream);
+    dev_free(d);
+    if (r != ncclSuccess) return fail(MFSGD_E_NCCL, "ring window agreement: %s", g_nccl.GetErrorString(r));
+    CK(e);
+    *flag = (int)v;
+    return MFSGD_OK;
+}
+
+// Build (or keep) the member's window for `cap` rows per Q buffer and map the neighbours'. Collective over the ring: cap, k
+// and the model are the same on every rank, so every rank takes the same branch. On success m.Q / m.BQ point into the
+// window; when the window cannot be set up on ANY rank, every rank falls back to separate buffers + NCCL (win.active false).
+static int window_setup(mfsgd_handle* h, Member& m, int64_t cap) {
+    Member::Window& w = m.win;
+    const int k = h->cfg.k, G = h->G;
+    const bool want = h->multi_process && G > 1 && h->ring_transport == 1 && h->cfg.mode != MFSGD_MODE_DETERMINISTIC;
+    if (!want) {
+        if (w.base) window_release(m);
+        return MFSGD_OK;
+    }
+    auto point_into = [&]() {
+        char* b = static_cast<char*>(w.base);
+        m.Q[0] = reinterpret_cast<float*>(b + w.off_q[0]);
+        m.Q[1] = reinterpret_cast<float*>(b + w.off_q[1]);
+        m.BQ[0] = h->biases ? reinterpret_cast<float*>(b + w.off_bq[0]) : nullptr;
+        m.BQ[1] = h->biases ? reinterpret_cast<float*>(b + w.off_bq[1]) : nullptr;
+    };
+    if (w.active && w.cap_rows >= cap && w.k == k && w.biases == h->biases) {     // reload with the same shape: keep everything
+        point_into();
+        return MFSGD_OK;
+    }
+    stream_mem_ops_load();
+    int ok = 1;
+    if (w.base) {                        // rebuild: nobody may still map the old window when it is freed
+        window_close_peers(m);
+        CKRC(ring_all_min(h, m, &ok));
+        cudaFree(w.base);
+        w.base = nullptr;                // (the table of sequence numbers stays)
+        w.active = false;
+        w.sent.clear();
+        m.Q[0] = m.Q[1] = m.BQ[0] = m.BQ[1] = nullptr;
+    }
+    auto up = [](size_t v) { return (v + 511) & ~(size_t)511; };
+    w.cap_rows = cap;
+    w.k = k;
+    w.biases = h->biases;
+    w.off_q[0] = up(RING_FLAGS_BYTES);
+    w.off_q[1] = w.off_q[0] + up((size_t)cap * k * 4);
+    w.off_bq[0] = w.off_q[1] + up((size_t)cap * k * 4);
+    w.off_bq[1] = w.off_bq[0] + up(h->biases ? (size_t)cap * 4 : 0);
+    w.bytes = w.off_bq[1] + up(h->biases ? (size_t)cap * 4 : 0);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    ok = ok && (h->ring_wait_kernel || g_wait_value32 != nullptr);
+    if (cudaMalloc(&w.base, w.bytes) != cudaSuccess) {      // a plain allocation of its own: an IPC handle names a whole cudaMalloc block
+        cudaGetLastError();
+        w.base = nullptr;
+        ok = 0;
+    }
+    if (w.base && (cudaMemset(w.base, 0, RING_FLAGS_BYTES) != cudaSuccess || cudaIpcGetMemHandle(&mine, w.base) != cudaSuccess)) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    // every rank's handle to every rank (in place all-gather of 64 bytes per rank)
+    std::vector<cudaIpcMemHandle_t> all((size_t)G);
+    {
+        uint8_t* d = nullptr;
+        CK(dev_alloc(&d, (size_t)G * 64));
+        cudaError_t e = cudaMemcpyAsync(d + (size_t)m.g * 64, &mine, 64, cudaMemcpyHostToDevice, m.stream);
+        ncclResult_t r = ncclSuccess;
+        if (e == cudaSuccess) r = g_nccl.AllGather(d + (size_t)m.g * 64, d, 64, ncclUint8, h->comm, m.stream);
+        if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(all.data(), d, (size_t)G * 64, cudaMemcpyDeviceToHost, m.stream);
+        if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(m.stream);
+        dev_free(d);
+        if (r != ncclSuccess) return fail(MFSGD_E_NCCL, "ring window handles: %s", g_nccl.GetErrorString(r));
+        CK(e);
+    }
+    const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
+    if (ok) {
+        void* pt = nullptr;
+        if (cudaIpcOpenMemHandle(&pt, all[(size_t)to], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        }
+        w.to_base = static_cast<char*>(pt);
+        if (ok && from == to) w.from_base = w.to_base;
+        else if (ok) {
+            void* pf = nullptr;
+            if (cudaIpcOpenMemHandle(&pf, all[(size_t)from], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            }
+            w.from_base = static_cast<char*>(pf);
+        }
+    }
+    CKRC(ring_all_min(h, m, &ok));       // also: every flag page is zeroed before anybody writes to one
+    if (!ok) {                           // some rank could not: everybody uses separate buffers + NCCL from here on
+        if (trace_on()) fprintf(stderr, "[mfsgd] ring window unavailable, rotation falls back to ncclSend/ncclRecv\n");
+        window_release(m);
+        h->ring_transport = 0;
+        return MFSGD_OK;
+    }
+    w.active = true;
+    w.sent.assign((size_t)RING_MAX_PARTS, 0u);
+    point_into();
+    return MFSGD_OK;
+}
+
 // Run kernel: p_u updated in memory by red.global.add (MFSGD_SCATTER_ATOMIC_P / MFSGD_SCATTER_ATOMIC) or stored (last writer wins)
 static inline bool run_p_red(const mfsgd_config& c) { return c.scatter == MFSGD_SCATTER_ATOMIC_P || c.scatter == MFSGD_SCATTER_ATOMIC; }
 
@@ -582,6 +836,8 @@ extern "C" void mfsgd_destroy(mfsgd_handle* h) {
         dev_free(h->d_allreduce);
     }
     for (Member& m : h->members) {
+        cudaSetDevice(m.device);
+        window_release(m);
         free_member_data(m);
         dev_free(m.d_scratch);
         for (cudaEvent_t e : m.evpool) cudaEventDestroy(e);
@@ -628,6 +884,9 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     if (const char* sd = getenv("MFSGD_SUBWARP_DIV")) h->sub_warp_div = std::max(1, atoi(sd));
     if (const char* rs = getenv("MFSGD_RESERVE_SMS")) h->reserve_sms = std::max(0, std::min(32, atoi(rs)));
     if (const char* nl = getenv("MFSGD_LANES")) h->n_lanes = atoi(nl) == 1 ? 1 : 2;
+    if (const char* rt = getenv("MFSGD_RING_TRANSPORT")) h->ring_transport = strcmp(rt, "nccl") == 0 ? 0 : 1;
+    if (const char* rw = getenv("MFSGD_RING_WAIT")) h->ring_wait_kernel = strcmp(rw, "kernel") == 0 ? 1 : 0;
+    if (const char* rs2 = getenv("MFSGD_RING_SIGNAL")) h->ring_signal_write = strcmp(rs2, "write") == 0 ? 1 : 0;
     h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
     h->biases = (cfg->model & MFSGD_MODEL_BIASES) != 0;
     h->p_half = cfg->p_storage == MFSGD_STORAGE_F16;
@@ -908,15 +1167,20 @@ static int member_alloc_factors(mfsgd_handle* h, Member& m) {
     int64_t cap = 0;
     for (int grp = 0; grp < h->G; grp++) cap = std::max<int64_t>(cap, group_hi(h, grp) - group_lo(h, grp));
     m.q_cap_rows = cap;
-    dev_free(m.P); dev_free(m.Q[0]); dev_free(m.Q[1]); dev_free(m.d_owner_u); dev_free(m.d_owner_i);
+    dev_free(m.P); release_q(m); dev_free(m.d_owner_u); dev_free(m.d_owner_i);
     CK(dev_alloc(&m.P, h->p_half ? ((size_t)(m.u_hi - m.u_lo) * c.k + 1) / 2 : (size_t)(m.u_hi - m.u_lo) * c.k));   // binary16 rows: half the bytes
-    CK(dev_alloc(&m.Q[0], (size_t)cap * c.k));
-    if (h->G > 1) CK(dev_alloc(&m.Q[1], (size_t)cap * c.k));
-    dev_free(m.BU); dev_free(m.BQ[0]); dev_free(m.BQ[1]);
+    CKRC(window_setup(h, m, cap));           // one process per GPU: Q and the item biases live in the member's ring window
+    if (!m.win.active) {
+        CK(dev_alloc(&m.Q[0], (size_t)cap * c.k));
+        if (h->G > 1) CK(dev_alloc(&m.Q[1], (size_t)cap * c.k));
+    }
+    dev_free(m.BU);
     if (h->biases) {
         CK(dev_alloc(&m.BU, (size_t)(m.u_hi - m.u_lo)));
-        CK(dev_alloc(&m.BQ[0], (size_t)cap));
-        if (h->G > 1) CK(dev_alloc(&m.BQ[1], (size_t)cap));
+        if (!m.win.active) {
+            CK(dev_alloc(&m.BQ[0], (size_t)cap));
+            if (h->G > 1) CK(dev_alloc(&m.BQ[1], (size_t)cap));
+        }
     }
     m.cur = 0;
     m.held_group = m.g;
@@ -1484,6 +1748,13 @@ static int ensure_part_events(mfsgd_handle* h, Member& m) {
     return MFSGD_OK;
 }
 
+// `stream` waits for the slice of the held group that item sub-shard `part` trains next
+static int wait_part(mfsgd_handle* h, Member& m, int part, cudaStream_t stream) {
+    if (m.win.active) return ring_wait(h, m, stream, ring_arrival_off(part), m.win.sent[(size_t)part]);
+    CK(cudaStreamWaitEvent(stream, m.ev_part_recv[(size_t)part], 0));
+    return MFSGD_OK;
+}
+
 static int rotate_part(mfsgd_handle* h, Member& m, int part, cudaStream_t after) {
     const int G = h->G, k = h->cfg.k;
     const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
@@ -1494,6 +1765,20 @@ static int rotate_part(mfsgd_handle* h, Member& m, int part, cudaStream_t after)
     float* rptr = m.Q[m.cur ^ 1] + (size_t)(r_lo - group_lo(h, recv_grp)) * k;
     CK(cudaEventRecord(m.ev_part_done[(size_t)part], after));
     CK(cudaStreamWaitEvent(m.copy_stream, m.ev_part_done[(size_t)part], 0));
+    if (m.win.active) {          // ring window: peer write + flags (see "ring window" above); every rank flips cur in step
+        Member::Window& w = m.win;
+        const uint32_t n = ++w.sent[(size_t)part];
+        const size_t row0 = (size_t)(s_lo - group_lo(h, send_grp));
+        if (n > 1) CKRC(ring_wait(h, m, m.copy_stream, ring_credit_off(part), n - 1));
+        CK(cudaMemcpyAsync(w.to_base + w.off_q[m.cur ^ 1] + row0 * k * 4, sptr, (size_t)(s_hi - s_lo) * k * 4, cudaMemcpyDefault, m.copy_stream));
+        if (h->biases)
+            CK(cudaMemcpyAsync(w.to_base + w.off_bq[m.cur ^ 1] + row0 * 4, m.BQ[m.cur] + row0, (size_t)(s_hi - s_lo) * 4, cudaMemcpyDefault, m.copy_stream));
+        CKRC(ring_signal(h, m, m.copy_stream, w.to_base, ring_arrival_off(part), n));
+        CKRC(ring_signal(h, m, m.copy_stream, w.from_base, ring_credit_off(part), n));
+        m.part_recv_pending[(size_t)part] = 1;
+        (void)rptr;
+        return MFSGD_OK;
+    }
     CKN(g_nccl.GroupStart());
     CKN(g_nccl.Send(sptr, (size_t)(s_hi - s_lo) * k, ncclFloat, to, h->comm, m.copy_stream));
     CKN(g_nccl.Recv(rptr, (size_t)(r_hi - r_lo) * k, ncclFloat, from, h->comm, m.copy_stream));
@@ -1517,7 +1802,7 @@ static int rotate_q(mfsgd_handle* h) {
         Member& m = h->members[0];
         for (size_t part = 0; part < m.part_recv_pending.size(); part++)
             if (m.part_recv_pending[part]) {
-                CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[part], 0));
+                CKRC(wait_part(h, m, (int)part, m.stream));
                 m.part_recv_pending[part] = 0;
             }
         const int to = (m.g - 1 + G) % G, from = (m.g + 1) % G;
@@ -1785,6 +2070,12 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
     const int parts = (pipelined || (c.flags & MFSGD_FLAG_SPLIT_SHARDS)) ? h->mi : 1;
     const int blocks_per_part = h->mi / parts;
     const bool lane_mode = parts > 1 && c.mode != MFSGD_MODE_DETERMINISTIC;
+    if (pipelined && h->members[0].win.active && epochs > 0) {      // the flag values this call will write: one per sub-epoch
+        Member& m0 = h->members[0];
+        CK(cudaSetDevice(m0.device));
+        if ((uint64_t)m0.win.sent[0] + (uint64_t)h->G * (uint64_t)epochs >= 0x7fffffffULL) return fail(MFSGD_E_STATE, "ring window: sequence numbers exhausted");
+        CKRC(ring_seq_table(m0, m0.win.sent[0] + 1, (uint32_t)h->G * (uint32_t)epochs));
+    }
     int resolved = 0;   // epochs of this call whose stats are final
     // Epochs are enqueued back to back (no host sync in between) unless per-epoch evaluation is on;
     // their event records are resolved after the next synchronisation point.
@@ -1922,7 +2213,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     for (int part = 0; part < parts; part++) {
                         Lane& l = m.lanes[(size_t)(part % h->n_lanes)];
                         if (pipelined && m.part_recv_pending[(size_t)part]) {      // this slice of the group has to have arrived
-                            CK(cudaStreamWaitEvent(l.cold, m.ev_part_recv[(size_t)part], 0));
+                            CKRC(wait_part(h, m, part, l.cold));
                             m.part_recv_pending[(size_t)part] = 0;
                         }
                         const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
@@ -1983,9 +2274,17 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
             const bool drain = (ep + 1 == epochs) || want_eval;
             for (size_t part = 0; drain && part < m.part_recv_pending.size(); part++)
                 if (m.part_recv_pending[part]) {
-                    CK(cudaStreamWaitEvent(m.stream, m.ev_part_recv[part], 0));
+                    CKRC(wait_part(h, m, (int)part, m.stream));
                     m.part_recv_pending[part] = 0;
                 }
+            if (drain && pipelined && m.win.active) {
+                // ring window: the call may only return (and the buffers be reused by anything else) once our own hand-overs
+                // have left and every write a neighbour addresses to this window has landed -- the arrivals above and the credits
+                CK(cudaEventRecord(m.ev_sent, m.copy_stream));
+                CK(cudaStreamWaitEvent(m.stream, m.ev_sent, 0));
+                for (int part = 0; part < parts; part++)
+                    if (m.win.sent[(size_t)part] > 0) CKRC(ring_wait(h, m, m.stream, ring_credit_off(part), m.win.sent[(size_t)part]));
+            }
             CK(cudaEventRecord(er.end, m.stream));
             er.kend = (int)m.kev.size();
             er.launches = m.launches;

@@ -22,10 +22,18 @@ def main():
     name = sys.argv[1]
     w = mf.WORKLOADS[name]
     epochs = int(sys.argv[2]) if len(sys.argv) > 2 else w.epochs
+    kw = {}
+    if os.environ.get("RW_SHAPE"):           # experiments: the same generator on another shape, "users,items,ratings" (no oracle curve then)
+        nu_, ni_, nr_ = (int(x) for x in os.environ["RW_SHAPE"].split(","))
+        w = w._replace(name=w.name + "@%dx%dx%d" % (nu_, ni_, nr_), n_users=nu_, n_items=ni_, n_ratings=nr_)
+        name = "none"
+    for env, key in (("RW_STRIPES", "stripes_per_gpu"), ("RW_ROUNDS", "rounds"), ("RW_SHARDS", "shards_per_gpu"), ("RW_HOT_CHUNK", "hot_chunk")):
+        if os.environ.get(env):
+            kw[key] = int(os.environ[env])
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     eng = ring.create_rank_engine(dist, rank, world, local, n_users=w.n_users, n_items=w.n_items, k=w.k, lr=w.lr, lambda_=w.lambda_,
-                                  seed=mf.SEED, flags=capi.FLAG_TIME_KERNELS)
+                                  seed=mf.SEED, flags=capi.FLAG_TIME_KERNELS, **kw)
     t0 = time.time()
     nt, nh = eng.generate_synthetic(mf.synth_params_of(w))
     setup_s = time.time() - t0
