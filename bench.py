@@ -202,7 +202,8 @@ def run_ours(args):
     flags = capi.FLAG_TIME_KERNELS
     common = dict(n_users=w.n_users, n_items=w.n_items, k=w.k, lr=w.lr, lambda_=w.lambda_, seed=mf.SEED,
                   stripes_per_gpu=args.stripes, shards_per_gpu=args.shards, scatter=args.scatter, flags=flags,
-                  ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share, hot_chunk=args.hot_chunk)
+                  ctas_per_sm=args.ctas_per_sm, rounds=args.rounds, hot_share=args.hot_share, hot_chunk=args.hot_chunk,
+                  p_storage=capi.STORAGE_F16 if args.p_storage == "f16" else capi.STORAGE_F32)
     if world > 1:
         with stdout_to_stderr():
             eng = ring.create_rank_engine(dist, rank, world, local_rank, **common)
@@ -246,7 +247,8 @@ def run_ours(args):
     # one CUDA-event span per sub-epoch on the launching stream, fork to join. Algorithmic bytes = 12 + 16k per
     # update x the updates in the span.
     peak, peak_src = peaks()
-    bpu = mf.bytes_per_update(w.k)
+    half_p = args.p_storage == "f16"
+    bpu = mf.bytes_per_update(w.k) - (4 * w.k if half_p else 0)      # binary16 P rows: 2k B read + 2k B written instead of 4k + 4k
     rank_updates = float(sum(s.updates for s in stats))
     achieved = rank_updates * bpu / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -276,7 +278,7 @@ def run_ours(args):
         # random 512-B row gather + scatter inside an L2-resident buffer the size of one P sub-stripe, no arithmetic.
         ceil = mf.measure_ceilings(local_rank, 61.0)
         # what an update of the run kernel moves through L2: p_u read + written (2 x 4k B) and its record (12 B, whole sectors shared by a tile)
-        l2_bytes = 8 * w.k + 12
+        l2_bytes = (4 if half_p else 8) * w.k + 12
         l2_achieved = rank_updates * l2_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
         roofline["l2_bound"] = {"achieved": l2_achieved, "peak": ceil["row_gather_scatter_gbs"], "unit": "GB/s",
                                 "frac": l2_achieved / ceil["row_gather_scatter_gbs"], "l2_bytes_per_update": l2_bytes,
@@ -354,7 +356,7 @@ def run_ours(args):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
+               "dtype": "f32" if not half_p else "f32 arithmetic, P rows stored as binary16 (stochastic rounding), Q binary32", "data": "synthetic",
                "config": {"workload": "%s: %d users x %d items, %d ratings (%d train), k=%d, lr=%g, lambda=%g" % (
                               w.name, w.n_users, w.n_items, w.n_ratings, int(info.n_train_total), w.k, w.lr, w.lambda_),
                           "parallelism": "hogwild-1gpu" if world == 1 else "dsgd-ring%d" % world,
@@ -506,6 +508,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=0)
     ap.add_argument("--hot-share", type=float, default=0.0)
     ap.add_argument("--hot-chunk", type=int, default=0, help="longest run of the run kernel (0 = planned from the launch size)")
+    ap.add_argument("--p-storage", default="f32", choices=["f32", "f16"],
+                    help="f16: rows of P kept as binary16 with stochastic rounding (SURVEY.md 8f.3) -- a separate line, never the headline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=12_000_000)

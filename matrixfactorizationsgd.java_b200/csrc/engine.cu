@@ -185,6 +185,7 @@ struct Member {              // one ring member ("GPU g")
         int64_t cap_rows = 0;
         int k = 0;
         bool biases = false, active = false;
+        bool can_flush = false;       // the device can flush outstanding remote writes behind a flag wait (CU_STREAM_WAIT_VALUE_FLUSH)
         size_t off_q[2] = {0, 0}, off_bq[2] = {0, 0};
         char* to_base = nullptr;      // window of member g - 1 (we write its Q buffers and its arrival flags)
         char* from_base = nullptr;    // window of member g + 1 (we write its credit flags)
@@ -278,7 +279,7 @@ struct mfsgd_handle {
     int ring_transport = 1;  // pipelined rotation of a multi-process ring: 1 = ring window (peer writes + flags), 0 = ncclSend/ncclRecv
                              // (MFSGD_RING_TRANSPORT = window | nccl; falls back to NCCL when the window cannot be mapped)
     int ring_wait_kernel = 0;   // MFSGD_RING_WAIT = kernel: poll the flags with a one-thread kernel instead of cuStreamWaitValue32
-    int ring_signal_write = 0;  // MFSGD_RING_SIGNAL = write: set the flags with cuStreamWriteValue32 instead of a 4-byte copy
+    int ring_signal_copy = 0;   // MFSGD_RING_SIGNAL = copy: set the flags with a 4-byte copy instead of cuStreamWriteValue32 (experiment only)
     int reserve_sms = 0;     // multi-process ring: SMs the run kernel leaves to the rotation's NCCL kernels (MFSGD_RESERVE_SMS)
     int n_lanes = 2;         // stream lanes of the pipelined rotation (MFSGD_LANES = 1 | 2)
     int sub_warp_div = 4;    // run kernel: at most (users of a P sub-stripe) / sub_warp_div runs in flight; MFSGD_SUBWARP_DIV overrides
@@ -571,8 +572,11 @@ static int validate_config(const mfsgd_config* c) {
 //     write  credit[part]  = n           into the window of the member that sends to us (our buffer is free again)
 // and on the receiver's lane:  wait arrival[part] >= n  before the sub-shard's next launches. n counts the hand-overs of a
 // part since the window was built; it is the same number on every rank. Waits are stream memory operations
-// (cuStreamWaitValue32; MFSGD_RING_WAIT=kernel polls with one thread instead), flag writes are 4-byte copies out of a table
-// of sequence numbers (MFSGD_RING_SIGNAL=write: cuStreamWriteValue32). No SM, no kernel, no host thread on the data path.
+// (cuStreamWaitValue32, with the remote-write flush where the device offers it; MFSGD_RING_WAIT=kernel polls with one thread
+// instead), flag writes are cuStreamWriteValue32 with its default memory fence, which orders the flag behind the slice the
+// same stream copied before it. (MFSGD_RING_SIGNAL=copy writes the flag as a 4-byte copy out of a table of sequence numbers
+// instead: no fence between two copies -- the one bit-exactness failure seen on 8 GPUs was measured with that variant.)
+// No SM, no kernel, no host thread on the data path.
 static const int RING_FLAG_STRIDE = 128;      // one flag per 128-byte line
 static const int RING_MAX_PARTS = 64;         // = the largest shards_per_gpu validate_config accepts
 static const size_t RING_FLAGS_BYTES = (size_t)2 * RING_MAX_PARTS * RING_FLAG_STRIDE;
@@ -599,7 +603,8 @@ static void stream_mem_ops_load() {
 static int ring_wait(mfsgd_handle* h, Member& m, cudaStream_t stream, size_t flag_off, uint32_t value) {
     const uint32_t* flag = reinterpret_cast<const uint32_t*>(static_cast<char*>(m.win.base) + flag_off);
     if (!h->ring_wait_kernel && g_wait_value32) {
-        CUresult r = g_wait_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+        CUresult r = g_wait_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value,
+                                    CU_STREAM_WAIT_VALUE_GEQ | (m.win.can_flush ? CU_STREAM_WAIT_VALUE_FLUSH : 0u));
         if (r != CUDA_SUCCESS) return fail(MFSGD_E_CUDA, "cuStreamWaitValue32 failed (%d); set MFSGD_RING_WAIT=kernel or MFSGD_RING_TRANSPORT=nccl", (int)r);
         return MFSGD_OK;
     }
@@ -609,9 +614,11 @@ static int ring_wait(mfsgd_handle* h, Member& m, cudaStream_t stream, size_t fla
 
 // stream sets a flag in a neighbour's window to `value`, after everything enqueued on it so far
 static int ring_signal(mfsgd_handle* h, Member& m, cudaStream_t stream, char* peer_base, size_t flag_off, uint32_t value) {
-    if (h->ring_signal_write && g_write_value32) {
-        CUresult r = g_write_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)(peer_base + flag_off), value, 0);
-        if (r != CUDA_SUCCESS) return fail(MFSGD_E_CUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
+    if (!h->ring_signal_copy) {
+        // default flags: the write is preceded by a system-scope memory fence over everything the stream has done before it, so
+        // the slice (copied by the operation before this one) is in the neighbour's memory when the flag becomes visible there.
+        CUresult r = g_write_value32((CUstream)stream, (CUdeviceptr)(uintptr_t)(peer_base + flag_off), value, CU_STREAM_WRITE_VALUE_DEFAULT);
+        if (r != CUDA_SUCCESS) return fail(MFSGD_E_CUDA, "cuStreamWriteValue32 failed (%d); set MFSGD_RING_TRANSPORT=nccl", (int)r);
         return MFSGD_OK;
     }
     if (value < m.win.seq_base || value >= m.win.seq_base + (uint32_t)m.win.seq_n) return fail(MFSGD_E_STATE, "ring window: sequence table does not cover %u", value);
@@ -719,13 +726,19 @@ static int window_setup(mfsgd_handle* h, Member& m, int64_t cap) {
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    ok = ok && (h->ring_wait_kernel || g_wait_value32 != nullptr);
+    ok = ok && (h->ring_wait_kernel || g_wait_value32 != nullptr) && g_write_value32 != nullptr;
+    {
+        int flush = 0;
+        if (cudaDeviceGetAttribute(&flush, cudaDevAttrCanFlushRemoteWrites, m.device) != cudaSuccess) cudaGetLastError();
+        w.can_flush = flush != 0;
+    }
     if (cudaMalloc(&w.base, w.bytes) != cudaSuccess) {      // a plain allocation of its own: an IPC handle names a whole cudaMalloc block
         cudaGetLastError();
         w.base = nullptr;
         ok = 0;
     }
-    if (w.base && (cudaMemset(w.base, 0, RING_FLAGS_BYTES) != cudaSuccess || cudaIpcGetMemHandle(&mine, w.base) != cudaSuccess)) {
+    if (w.base && (cudaMemsetAsync(w.base, 0, RING_FLAGS_BYTES, m.stream) != cudaSuccess || cudaStreamSynchronize(m.stream) != cudaSuccess ||
+                   cudaIpcGetMemHandle(&mine, w.base) != cudaSuccess)) {
         cudaGetLastError();
         ok = 0;
     }
@@ -886,7 +899,7 @@ static int mfsgd_create_body(const mfsgd_config* cfg, mfsgd_handle** out) {
     if (const char* nl = getenv("MFSGD_LANES")) h->n_lanes = atoi(nl) == 1 ? 1 : 2;
     if (const char* rt = getenv("MFSGD_RING_TRANSPORT")) h->ring_transport = strcmp(rt, "nccl") == 0 ? 0 : 1;
     if (const char* rw = getenv("MFSGD_RING_WAIT")) h->ring_wait_kernel = strcmp(rw, "kernel") == 0 ? 1 : 0;
-    if (const char* rs2 = getenv("MFSGD_RING_SIGNAL")) h->ring_signal_write = strcmp(rs2, "write") == 0 ? 1 : 0;
+    if (const char* rs2 = getenv("MFSGD_RING_SIGNAL")) h->ring_signal_copy = strcmp(rs2, "copy") == 0 ? 1 : 0;
     h->scale = cfg->init_scale > 0.f ? cfg->init_scale : (float)(1.0 / std::sqrt((double)cfg->k));
     h->biases = (cfg->model & MFSGD_MODEL_BIASES) != 0;
     h->p_half = cfg->p_storage == MFSGD_STORAGE_F16;
@@ -1943,7 +1956,12 @@ static int join_lanes(Member& m) {
 
 // The update launches of item blocks [ib_lo, ib_hi) of sub-epoch s: every (sub-stripe, round) visit's cold records on
 // `cold_s` (full-grid Hogwild kernel) and its runs on `hot_s` (run kernel); hot_s forks from cold_s before and joins after.
-static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_t ib_lo, size_t ib_hi, bool fast_arith,
+// chain_overlap: consecutive run launches of this chain may overlap at their tails (programmatic dependent launch). Never for a
+// lane: the dependent launch takes whatever SM slots come free, and with a second lane's CTAs retiring all the time that is not
+// the predecessor's tail any more -- two visits of the SAME items run side by side, both add their increments from one base, and
+// the factors diverge (Yahoo-shaped on 8 real GPUs: NaN in the second epoch, on either transport; with plain stream order inside
+// a lane -0.17 / -0.23 / -0.10 % of the oracle and 14 % faster, since the other lane fills the tails anyway).
+static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_t ib_lo, size_t ib_hi, bool fast_arith, bool chain_overlap,
                           cudaStream_t cold_s, cudaStream_t hot_s, cudaEvent_t ev_fork, cudaEvent_t ev_join, cudaEvent_t mark_cold,
                           cudaEvent_t mark_hot, bool* any_cold, bool* any_hot) {
     const mfsgd_config& c = h->cfg;
@@ -1991,7 +2009,7 @@ static int enqueue_visits(mfsgd_handle* h, Member& m, UpdateArgs a, int s, size_
             if (m.counter_next >= m.n_counters * COUNTER_EPOCHS) return fail(MFSGD_E_STATE, "run launch counters exhausted");
             const int sub_warp_cap = (int)std::min<int64_t>(1 << 30, (int64_t)(m.u_hi - m.u_lo) / ((int64_t)h->sub_warp_div * h->mu));   // a fraction of the sub-stripe's users
             auto overlaps = [&](const Visit& w) {
-                return hot_launch_overlaps(c.k, w.unit_hi - w.unit_lo, m.unit_recs_cum[(size_t)w.unit_hi] - m.unit_recs_cum[(size_t)w.unit_lo],
+                return chain_overlap && hot_launch_overlaps(c.k, w.unit_hi - w.unit_lo, m.unit_recs_cum[(size_t)w.unit_hi] - m.unit_recs_cum[(size_t)w.unit_lo],
                                            m.run_chunk, m.hot_grid, sub_warp_cap);
             };
             bool next_overlaps = false;    // will the next run launch of this chain overlap this one's tail?
@@ -2074,7 +2092,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
         Member& m0 = h->members[0];
         CK(cudaSetDevice(m0.device));
         if ((uint64_t)m0.win.sent[0] + (uint64_t)h->G * (uint64_t)epochs >= 0x7fffffffULL) return fail(MFSGD_E_STATE, "ring window: sequence numbers exhausted");
-        CKRC(ring_seq_table(m0, m0.win.sent[0] + 1, (uint32_t)h->G * (uint32_t)epochs));
+        if (h->ring_signal_copy) CKRC(ring_seq_table(m0, m0.win.sent[0] + 1, (uint32_t)h->G * (uint32_t)epochs));
     }
     int resolved = 0;   // epochs of this call whose stats are final
     // Epochs are enqueued back to back (no host sync in between) unless per-epoch evaluation is on;
@@ -2206,7 +2224,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                     const size_t ib_lo = (size_t)grp * h->mi, ib_hi = ib_lo + (size_t)h->mi;
                     // (the time marks are recorded on the two streams before they join: cold = last Hogwild launch done,
                     // hot = last run launch done, both measured from the sub-epoch's start)
-                    CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, m.stream, m.hot_stream, m.ev_fork, m.ev_join, e_cold, e_hot,
+                    CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, true, m.stream, m.hot_stream, m.ev_fork, m.ev_join, e_cold, e_hot,
                                         &any_cold, &any_hot));
                 } else {
                     if (pipelined) CKRC(ensure_part_events(h, m));
@@ -2217,7 +2235,7 @@ static int train_impl(mfsgd_handle* h, int32_t epochs, mfsgd_epoch_stats* stats,
                             m.part_recv_pending[(size_t)part] = 0;
                         }
                         const size_t ib_lo = (size_t)grp * h->mi + (size_t)part * blocks_per_part, ib_hi = ib_lo + blocks_per_part;
-                        CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, l.cold, l.hot, l.fork, l.join, nullptr, nullptr, &any_cold,
+                        CKRC(enqueue_visits(h, m, a, s, ib_lo, ib_hi, fast_arith, false, l.cold, l.hot, l.fork, l.join, nullptr, nullptr, &any_cold,
                                             &any_hot));
                         l.used = true;
                         if (pipelined) CKRC(rotate_part(h, m, part, l.cold));

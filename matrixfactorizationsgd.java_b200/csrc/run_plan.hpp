@@ -78,15 +78,23 @@ inline int plan_rounds(int rounds_cfg, int mode, int G, int mu, int64_t member_r
 // (summing, direction-split weights, exchanging q_i inside the run) diverges on the stiff common direction that plain
 // matrix factorisation without biases has. So runs are as long as the launch can balance: the launch hands its runs out
 // longest first, so it lasts about max(records / resident sub-warps, longest run) -- the longest run may be about the
-// per-sub-warp share of the launch (two launches' worth where two stream lanes overlap them, `lanes` = 2).
-// 256 <= run <= 1024, multiple of 32: small launches leave sub-warps idle rather than cut their items into pieces
+// per-sub-warp share of the launch.
+// 256 <= run <= 1024 (from 128 for laned launches), multiple of 32: small launches leave sub-warps idle rather than cut their items into pieces
 // (they are latency-bound anyway: an ML-100K-shaped epoch takes 0.35 ms either way).
 inline int plan_run_length(int hot_chunk_cfg, int lanes, int mu, int rounds, int IB, int64_t run_records, int resident_ctas,
                            int runs_per_warp) {
     if (hot_chunk_cfg > 0) return hot_chunk_cfg;
-    const double per_launch = (double)run_records / ((double)mu * rounds * IB) * (lanes > 1 ? lanes : 1);
-    const double want = per_launch / (1.25 * resident_ctas * 8.0 * runs_per_warp);
-    return (int)std::min(1024.0, std::max(256.0, std::ceil(want / 32.0) * 32.0));
+    // Laned launches (the item sub-shards of a one-process-per-GPU ring on two stream lanes) share the machine, so a lane's launch
+    // lasts about twice its per-sub-warp share and a run may be that long (`lanes` launches' worth) -- as long as that still gives
+    // runs above the floor of 256. Below it the launches are too small for that: measured on 8 B200s (Netflix-shaped, 0.7 M ratings
+    // per launch) runs of 256 / 192 / 128 take 1.50 / 1.32 / 1.16 ms per epoch = 5.5x / 6.3x / 7.2x one GPU, because at 256 a launch
+    // offers too few runs to fill its half of the machine twice over (profiles/r02_experiments.md section 11). Such launches get
+    // runs of ONE share, down to 128.
+    const double per_launch = (double)run_records / ((double)mu * rounds * IB);
+    const double share = per_launch / (1.25 * resident_ctas * 8.0 * runs_per_warp);
+    const double laned_want = share * (lanes > 1 ? lanes : 1);
+    if (lanes > 1 && laned_want <= 256.0) return (int)std::max(128.0, std::ceil(share / 32.0) * 32.0);
+    return (int)std::min(1024.0, std::max(256.0, std::ceil(laned_want / 32.0) * 32.0));
 }
 
 // Merge weight of a run whose slice of its item's bucket was cut into `pieces` runs for one launch: min(1, boost / pieces).
