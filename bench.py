@@ -469,25 +469,46 @@ def run_reference(args):
     del us, is_, rs
     P = orc.init_factors(w.n_users, w.k, seed, 0)
     Q = orc.init_factors(w.n_items, w.k, seed, 1)
-    for s in range(args.warmup):
-        orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, seed, threads, shuffled=True)
-    wall = loops = 0.0
-    for s in range(args.warmup, args.warmup + args.steps):
+    # Bounded run: every step covers the whole workload unless this host is too slow for --warmup + --steps of them to end
+    # within --ref-budget-s; then the remaining steps cover a prefix of the records (said in `sample`, and
+    # same_workload_as_product_arm turns false). value = records of the timed steps / their wall time either way.
+    n_train = len(r)
+    wall = loops = spent = 0.0
+    done = 0
+    per_step = []
+    for s in range(args.warmup + args.steps):
         t0 = time.time()
-        loops += orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, seed, threads, shuffled=True)
-        wall += time.time() - t0
-    value = len(r) * args.steps / wall
-    full = n == w.n_ratings
-    sample = "each step = 1 Hogwild epoch (per-epoch shuffle + update loops), %d host threads, over %s records (%d train) of %s, full-size P/Q" % (
-        threads, "ALL %d" % n if full else "the first %d" % n, len(r), w.name)
+        lp = orc.train_hogwild(u, i, r, P, Q, w.lr, w.lambda_, s, s + 1, seed, threads, shuffled=True)
+        dt = time.time() - t0
+        spent += dt
+        if s >= args.warmup:
+            wall += dt
+            loops += lp
+            done += len(r)
+            per_step.append(len(r))
+        left = args.warmup + args.steps - (s + 1)
+        room = max(args.ref_budget_s - spent, 1.0)
+        if args.ref_budget_s > 0 and left > 0 and dt * left > room:
+            keep = max(1_000_000, int(len(r) * room / (dt * left)))
+            if keep < len(r):
+                u, i, r = u[:keep].copy(), i[:keep].copy(), r[:keep].copy()
+    value = done / wall
+    full = n == w.n_ratings and all(c == n_train for c in per_step)
+    if all(c == n_train for c in per_step):
+        covered = "ALL %d records (%d train)" % (n, n_train) if n == w.n_ratings else "the first %d records (%d train)" % (n, n_train)
+    else:
+        covered = "a prefix of the %d training records (%d..%d per timed step: the %g s budget of the whole run required the cut)" % (
+            n_train, min(per_step), max(per_step), args.ref_budget_s)
+    sample = "each step = 1 Hogwild epoch (per-epoch shuffle + update loops), %d host threads, over %s of %s, full-size P/Q" % (
+        threads, covered, w.name)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s: %d users x %d items, %d ratings (%d train), k=%d, lr=%g, lambda=%g" % (
-               w.name, w.n_users, w.n_items, n, len(r), w.k, w.lr, w.lambda_), "parallelism": "cpu-hogwild-%dthreads" % threads,
+               w.name, w.n_users, w.n_items, n, n_train, w.k, w.lr, w.lambda_), "parallelism": "cpu-hogwild-%dthreads" % threads,
                "same_workload_as_product_arm": full, "shuffled_every_epoch": True},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                            "update_loops_only": len(r) * args.steps / loops},
+                            "update_loops_only": done / loops},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "reference = C++ oracle port of the Java stand-in's factorizeThreaded (no JDK in the image; /root/reference has no "
                    "source); the per-epoch order is the stand-in's (same permutation), produced with all host threads"}
@@ -514,6 +535,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=12_000_000)
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: records per step, 0 = the whole workload")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0,
+                    help="reference arm: wall-clock budget of the whole run; later steps shrink to a prefix of the records if needed (0 = never)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side run that measures roofline.traffic")
     ap.add_argument("--no-ceilings", action="store_true")
     ap.add_argument("--trace-e2e", action="store_true", help="MFSGD_TRACE=1 during the end-to-end calls (phase timings on stderr)")

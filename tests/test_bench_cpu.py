@@ -25,6 +25,17 @@ def test_reference_arm_json_contract():
     assert "netflix-shaped" in d["config"]["workload"] and "k=128" in d["config"]["workload"]
 
 
+def test_reference_arm_keeps_to_its_time_budget():
+    """A host too slow for the whole run shrinks the LATER steps to a prefix of the records and says so; value stays records / time."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                          "--ref-sample", "4000000", "--ref-budget-s", "0.5"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+    assert d["config"]["same_workload_as_product_arm"] is False
+    assert "budget" in d["cpu_baseline"]["sample"] and "prefix" in d["cpu_baseline"]["sample"]
+    assert d["value"] > 0 and d["cpu_baseline"]["update_loops_only"] >= d["value"]
+
+
 def test_product_arm_fails_loudly_without_a_gpu():
     if mf.device_count() > 0:
         import pytest
