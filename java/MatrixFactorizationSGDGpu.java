@@ -76,6 +76,21 @@ public final class MatrixFactorizationSGDGpu {
     private static final MethodHandle GET_FACTORS = down("mfsgd_get_factors", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle RMSE = down("mfsgd_rmse", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
 
+    /* model extension / schedule / mixed storage (SURVEY.md 8f.3, 8f.4): the calls the handle API adds for them */
+    private static final MethodHandle SET_FACTORS = down("mfsgd_set_factors", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle LOAD_HELDOUT = down("mfsgd_load_heldout", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
+    private static final MethodHandle GET_MODEL = down("mfsgd_get_model", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_BIASES = down("mfsgd_set_biases", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle GET_PROGRESS = down("mfsgd_get_progress", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_EVAL_EVERY_EPOCH = down("mfsgd_set_eval_every_epoch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+
+    /* mfsgd_config members the extension rows set (offsets: CONFIG above; tests/test_java_cpu.py checks them against the C struct) */
+    static final long OFF_MODEL = 216, OFF_LR_DECAY = 224, OFF_ES_PATIENCE = 228, OFF_ES_MIN_DELTA = 232, OFF_P_STORAGE = 236;
+    public static final int MODEL_GLOBAL_MEAN = 1, MODEL_BIASES = 2;       /* mfsgd_config.model bits */
+    public static final int STORAGE_F32 = 0, STORAGE_F16 = 1;               /* mfsgd_config.p_storage */
+    /* struct mfsgd_epoch_stats (include/mfsgd.h): 72 bytes, heldout_rmse (double) at offset 40 */
+    static final long EPOCH_STATS_BYTES = 72, OFF_STATS_HELDOUT_RMSE = 40;
+
     private static final MethodHandle READ_RATINGS = down("mfsgd_read_ratings", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
     private static final MethodHandle FREE_RATINGS = down("mfsgd_free_ratings", FunctionDescriptor.ofVoid(ADDRESS));
 
@@ -186,11 +201,148 @@ public final class MatrixFactorizationSGDGpu {
             MemorySegment h = hp.get(ADDRESS, 0);
             try {
                 check((int) LOAD_RATINGS.invokeExact(h, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, 0L));
-                MethodHandle setFactors = down("mfsgd_set_factors", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
-                check((int) setFactors.invokeExact(h, arena.allocateFrom(JAVA_FLOAT, P), arena.allocateFrom(JAVA_FLOAT, Q)));
+                check((int) SET_FACTORS.invokeExact(h, arena.allocateFrom(JAVA_FLOAT, P), arena.allocateFrom(JAVA_FLOAT, Q)));
                 MemorySegment out = arena.allocate(ValueLayout.JAVA_DOUBLE);
                 check((int) RMSE.invokeExact(h, arena.allocateFrom(JAVA_INT, users), arena.allocateFrom(JAVA_INT, items),
                         arena.allocateFrom(JAVA_FLOAT, ratings), (long) ratings.length, out));
+                return out.get(ValueLayout.JAVA_DOUBLE, 0);
+            } finally {
+                DESTROY.invokeExact(h);
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /**
+     * Stand-in factorizeMixed (:439): the rows of P are KEPT as binary16 on the device (narrowed with stochastic rounding from a
+     * counter hash), every operation of the rule stays binary32; P comes back widened exactly. One GPU, Hogwild.
+     */
+    public static MatrixFactorizationSGD.Factors factorizeMixed(int[] users, int[] items, float[] ratings, int nUsers, int nItems, int k,
+                                                               float lr, float lambda, int epochs, long seed) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || k % 4 != 0 || nUsers <= 0 || nItems <= 0 || epochs < 0) throw new IllegalArgumentException("bad shape");
+        try (Arena arena = Arena.ofConfined()) {
+            MemorySegment p = arena.allocate(JAVA_FLOAT, (long) nUsers * k);
+            MemorySegment q = arena.allocate(JAVA_FLOAT, (long) nItems * k);
+            MemorySegment cfg = config(arena, nUsers, nItems, k, lr, lambda, seed, MODE_HOGWILD, 1);
+            cfg.set(JAVA_INT, OFF_P_STORAGE, STORAGE_F16);
+            check((int) FACTORIZE.invokeExact(arena.allocateFrom(JAVA_INT, users), arena.allocateFrom(JAVA_INT, items),
+                    arena.allocateFrom(JAVA_FLOAT, ratings), (long) ratings.length, cfg, epochs, p, q));
+            return newFactors(p.toArray(JAVA_FLOAT), q.toArray(JAVA_FLOAT), nUsers, nItems, k);
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /**
+     * Stand-in factorizeModel (:305): r ~ mu + b_u + b_i + p_u . q_i. The mean is taken on the device while the ratings are
+     * counted, ratings are stored centred, the biases ride through the update kernels beside their rows.
+     */
+    public static MatrixFactorizationSGD.Model factorizeModel(int[] users, int[] items, float[] ratings, int nUsers, int nItems, int k,
+                                                             float lr, float lambda, int epochs, long seed,
+                                                             boolean useGlobalMean, boolean useBiases) {
+        return trainModel(users, items, ratings, null, null, null, nUsers, nItems, k, lr, lambda, epochs, seed,
+                useGlobalMean, useBiases, 1.0f, 0, 0.0f).model;
+    }
+
+    /**
+     * Stand-in factorizeEarlyStop (:350): the schedule lr_(e+1) = lr_e * lrDecay and the early-stopping rule on the validation
+     * RMSE, both evaluated inside mfsgd_train (the validation triplets live on the device).
+     */
+    public static MatrixFactorizationSGD.EarlyStopResult factorizeEarlyStop(int[] users, int[] items, float[] ratings,
+                                                                           int[] vUsers, int[] vItems, float[] vRatings,
+                                                                           int nUsers, int nItems, int k, float lr, float lambda, int maxEpochs, long seed,
+                                                                           boolean useGlobalMean, boolean useBiases,
+                                                                           float lrDecay, int patience, float minDelta) {
+        if (!(lrDecay > 0.0f) || lrDecay > 1.0f || patience < 0 || !(minDelta >= 0.0f) || minDelta >= 1.0f)
+            throw new IllegalArgumentException("bad schedule");
+        if (vUsers.length != vItems.length || vUsers.length != vRatings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        return trainModel(users, items, ratings, vUsers, vItems, vRatings, nUsers, nItems, k, lr, lambda, maxEpochs, seed,
+                useGlobalMean, useBiases, lrDecay, patience, minDelta);
+    }
+
+    private static MatrixFactorizationSGD.EarlyStopResult trainModel(int[] users, int[] items, float[] ratings,
+                                                                    int[] vUsers, int[] vItems, float[] vRatings,
+                                                                    int nUsers, int nItems, int k, float lr, float lambda, int epochs, long seed,
+                                                                    boolean useGlobalMean, boolean useBiases,
+                                                                    float lrDecay, int patience, float minDelta) {
+        if (users.length != items.length || users.length != ratings.length)
+            throw new IllegalArgumentException("triplet arrays differ in length");
+        if (k <= 0 || nUsers <= 0 || nItems <= 0 || epochs < 0) throw new IllegalArgumentException("bad shape");
+        final boolean validated = vRatings != null;
+        try (Arena arena = Arena.ofConfined()) {
+            MemorySegment cfg = config(arena, nUsers, nItems, k, lr, lambda, seed, MODE_HOGWILD, 1);
+            cfg.set(JAVA_INT, OFF_MODEL, (useGlobalMean ? MODEL_GLOBAL_MEAN : 0) | (useBiases ? MODEL_BIASES : 0));
+            cfg.set(JAVA_FLOAT, OFF_LR_DECAY, lrDecay);
+            cfg.set(JAVA_INT, OFF_ES_PATIENCE, patience);
+            cfg.set(JAVA_FLOAT, OFF_ES_MIN_DELTA, minDelta);
+            MemorySegment hp = arena.allocate(ADDRESS);
+            check((int) CREATE.invokeExact(cfg, hp));
+            MemorySegment h = hp.get(ADDRESS, 0);
+            try {
+                check((int) LOAD_RATINGS.invokeExact(h, arena.allocateFrom(JAVA_INT, users), arena.allocateFrom(JAVA_INT, items),
+                        arena.allocateFrom(JAVA_FLOAT, ratings), (long) ratings.length));
+                if (validated) {
+                    check((int) LOAD_HELDOUT.invokeExact(h, arena.allocateFrom(JAVA_INT, vUsers), arena.allocateFrom(JAVA_INT, vItems),
+                            arena.allocateFrom(JAVA_FLOAT, vRatings), (long) vRatings.length));
+                    check((int) SET_EVAL_EVERY_EPOCH.invokeExact(h, 1));
+                }
+                check((int) INIT_FACTORS.invokeExact(h));
+                MemorySegment stats = validated && epochs > 0 ? arena.allocate(EPOCH_STATS_BYTES * epochs, 8) : MemorySegment.NULL;
+                if (epochs > 0) check((int) TRAIN.invokeExact(h, epochs, stats));
+                MemorySegment ran = arena.allocate(JAVA_INT);
+                check((int) GET_PROGRESS.invokeExact(h, ran, MemorySegment.NULL, MemorySegment.NULL));
+                final int epochsRun = ran.get(JAVA_INT, 0);
+                MemorySegment p = arena.allocate(JAVA_FLOAT, (long) nUsers * k);
+                MemorySegment q = arena.allocate(JAVA_FLOAT, (long) nItems * k);
+                check((int) GET_FACTORS.invokeExact(h, p, q));
+                MemorySegment mu = arena.allocate(JAVA_FLOAT);
+                MemorySegment bu = useBiases ? arena.allocate(JAVA_FLOAT, (long) nUsers) : MemorySegment.NULL;
+                MemorySegment bi = useBiases ? arena.allocate(JAVA_FLOAT, (long) nItems) : MemorySegment.NULL;
+                check((int) GET_MODEL.invokeExact(h, mu, bu, bi));
+                double[] curve = new double[validated ? epochsRun : 0];
+                for (int e = 0; e < curve.length; e++) curve[e] = stats.get(ValueLayout.JAVA_DOUBLE, EPOCH_STATS_BYTES * e + OFF_STATS_HELDOUT_RMSE);
+                /* Model's and EarlyStopResult's constructors are package-private: both classes live in the default package. */
+                MatrixFactorizationSGD.Model m = new MatrixFactorizationSGD.Model(p.toArray(JAVA_FLOAT), q.toArray(JAVA_FLOAT),
+                        useBiases ? bu.toArray(JAVA_FLOAT) : null, useBiases ? bi.toArray(JAVA_FLOAT) : null,
+                        mu.get(JAVA_FLOAT, 0), nUsers, nItems, k);
+                return new MatrixFactorizationSGD.EarlyStopResult(m, epochsRun, curve);
+            } finally {
+                DESTROY.invokeExact(h);
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /** Stand-in rmseModel (:389): e = (r - mu) - ((p_u . q_i + b_u) + b_i), evaluated by the GPU RMSE kernel. */
+    public static double rmseModel(MatrixFactorizationSGD.Model m, int[] users, int[] items, float[] ratings) {
+        final boolean biased = m.userBias != null;
+        float[] centred = new float[ratings.length];
+        for (int t = 0; t < ratings.length; t++) centred[t] = ratings[t] - m.globalMean;      /* one binary32 subtraction, as :399 */
+        try (Arena arena = Arena.ofConfined()) {
+            MemorySegment cfg = config(arena, m.nUsers, m.nItems, m.k, 1e-3f, 0.0f, 0L, MODE_HOGWILD, 1);
+            cfg.set(JAVA_INT, OFF_MODEL, biased ? MODEL_BIASES : 0);
+            MemorySegment hp = arena.allocate(ADDRESS);
+            check((int) CREATE.invokeExact(cfg, hp));
+            MemorySegment h = hp.get(ADDRESS, 0);
+            try {
+                check((int) LOAD_RATINGS.invokeExact(h, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, 0L));
+                check((int) SET_FACTORS.invokeExact(h, arena.allocateFrom(JAVA_FLOAT, m.P), arena.allocateFrom(JAVA_FLOAT, m.Q)));
+                if (biased)
+                    check((int) SET_BIASES.invokeExact(h, arena.allocateFrom(JAVA_FLOAT, m.userBias), arena.allocateFrom(JAVA_FLOAT, m.itemBias)));
+                MemorySegment out = arena.allocate(ValueLayout.JAVA_DOUBLE);
+                check((int) RMSE.invokeExact(h, arena.allocateFrom(JAVA_INT, users), arena.allocateFrom(JAVA_INT, items),
+                        arena.allocateFrom(JAVA_FLOAT, centred), (long) centred.length, out));
                 return out.get(ValueLayout.JAVA_DOUBLE, 0);
             } finally {
                 DESTROY.invokeExact(h);

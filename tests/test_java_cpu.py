@@ -75,6 +75,17 @@ def test_java_hard_coded_offsets_and_descriptors_match_the_binding():
             assert (f.offset, f.size) == (int(m.group(2)), _JSIZE[m.group(1)]), m.group(0)
             seen += 1
     assert seen >= 6
+    # the extension rows' config members and the epoch-stats entry factorizeEarlyStop reads its validation curve from
+    consts = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(OFF_\w+|EPOCH_STATS_BYTES)\s*=\s*(\d+)", src))
+    for jname, cname in (("OFF_MODEL", "model"), ("OFF_LR_DECAY", "lr_decay"), ("OFF_ES_PATIENCE", "early_stop_patience"),
+                         ("OFF_ES_MIN_DELTA", "early_stop_min_delta"), ("OFF_P_STORAGE", "p_storage")):
+        assert consts[jname] == getattr(capi.Config, cname).offset, jname
+    assert consts["EPOCH_STATS_BYTES"] == C.sizeof(capi.EpochStats)
+    assert consts["OFF_STATS_HELDOUT_RMSE"] == capi.EpochStats.heldout_rmse.offset
+    assert (capi.MODEL_GLOBAL_MEAN, capi.MODEL_BIASES, capi.STORAGE_F16) == (1, 2, 1) and "MODEL_GLOBAL_MEAN = 1, MODEL_BIASES = 2" in src
+    # the host mirrors the stand-in's public entry points for every built row of SURVEY.md section 8
+    for method in ("factorize", "factorizeMixed", "factorizeModel", "factorizeEarlyStop", "rmse", "rmseModel", "readRatings"):
+        assert re.search(r"public static [\w.]+ %s\(" % method, src), method
     # struct mfsgd_ratings as readRatings reads it
     for name, offset in (("users", 0), ("items", 8), ("ratings", 16), ("n", 24), ("n_users", 32), ("n_items", 36), ("user_ids", 40), ("item_ids", 48)):
         assert getattr(capi.Ratings, name).offset == offset
@@ -104,4 +115,4 @@ def test_java_hard_coded_offsets_and_descriptors_match_the_binding():
             assert res is None, name
         assert [klass(t) for t in argtypes] == args, (name, [klass(t) for t in argtypes], args)
         n += 1
-    assert n >= 12
+    assert n >= 18
