@@ -125,3 +125,17 @@ def test_workloads_match_baseline_json():
     assert "700M ratings" in cfgs[3] and w["yahoo"].n_ratings == 700_000_000
     assert "k=64" in cfgs[4] and w["powerlaw"].k == 64 and w["powerlaw"].n_ratings == 2_000_000_000
     assert mf.bytes_per_update(128) == 2060 and mf.bytes_per_update(64) == 1036 and mf.bytes_per_update(32) == 524
+
+
+def test_cpp_host_rejects_bad_arguments_before_any_gpu_work():
+    """host/factorize_demo (C++ twin of the Java host): the stand-in's argument errors (bad shape :114, k % 4 :443, bad schedule :356)
+    are raised by the host itself; without a GPU the first real call then fails loudly (exit 3) -- there is no CPU fallback."""
+    exe = os.path.join(ROOT, "host", "factorize_demo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "host"])
+    out = subprocess.run([exe, capi.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert "was not rejected" not in out.stderr
+    if mf.device_count() > 0:
+        assert out.returncode == 0, (out.stdout, out.stderr)
+    else:
+        assert out.returncode == 3 and "GPU path unavailable" in out.stderr and "no CPU fallback" in out.stderr

@@ -689,3 +689,14 @@ def test_c_harness_gpu_one_shot():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.check_output([os.path.join(root, "tests", "c", "abi_harness"), capi.LIB_PATH, "gpu"], text=True)
     assert "GPU one-shot factorize" in out
+
+
+def test_cpp_host_mirror_runs_every_entry_point():
+    """host/factorize_demo: the C++ twin of the Java host through factorize, factorizeMixed, factorizeModel, factorizeEarlyStop,
+    rmse and rmseModel (stand-in :109, :439, :305, :350, :169, :389) over dlopen/dlsym -- exit 0 only if every one trains."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([os.path.join(root, "host", "factorize_demo"), capi.LIB_PATH], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "early stopping:" in out.stdout and "extended model:" in out.stdout and "binary16 rows of P:" in out.stdout
