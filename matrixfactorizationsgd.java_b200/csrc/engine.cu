@@ -1374,6 +1374,15 @@ static inline void slice_of(const Member& m, size_t blk_lo, size_t blk_hi, int r
     *hi = blo + (bhi - blo) * (rnd + 1) / rounds;
 }
 
+// host threads of the run planner: 0 = its own choice (one for small plans, up to 8 for large ones); MFSGD_PLAN_THREADS overrides
+// (tests force 1, 3 and 8 and compare the plans bit for bit)
+static int plan_threads_env() {
+    const char* e = getenv("MFSGD_PLAN_THREADS");
+    if (!e || !*e) return 0;
+    const int t = atoi(e);
+    return t < 0 ? 0 : std::min(t, 64);
+}
+
 // Hot-item units of every visit (sa, grp, rnd): the round's slice of each (sa, hot item) bucket, cut into
 // runs of <= hot_chunk records. Bucket sizes never change, so this is built once per load.
 static int build_hot_units(mfsgd_handle* h, Member& m) {
@@ -1396,7 +1405,7 @@ static int build_hot_units(mfsgd_handle* h, Member& m) {
     pa.boost = h->cfg.merge_boost > 0.f ? h->cfg.merge_boost : DEFAULT_MERGE_BOOST;
     pa.hot_block_lo = h->hot_block_lo.data();
     pa.hot_items = h->hot_items.data();
-    plan_runs(pa, units, m.visit_units);
+    plan_runs(pa, units, m.visit_units, plan_threads_env());
     m.run_chunk = chunk;
     m.unit_recs_cum.assign(units.size() + 1, 0);
     for (size_t j = 0; j < units.size(); j++) m.unit_recs_cum[j + 1] = m.unit_recs_cum[j] + units[j].count;
@@ -2590,7 +2599,7 @@ static int mfsgd_plan_runs_body(const int64_t* block_off, int32_t stripes, int32
     pa.hot_items = hot_items;
     std::vector<HotUnit> units;
     std::vector<int> visits;
-    plan_runs(pa, units, visits);
+    plan_runs(pa, units, visits, plan_threads_env());
     const int64_t cap = *n_units;
     *n_units = (int64_t)units.size();
     for (size_t v = 0; v < visits.size(); v++) visit_units[v] = visits[v];

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/mfsgd.h"
@@ -121,56 +123,100 @@ struct RunPlanArgs {
 };
 
 // units: all runs, visit after visit; visit_units[(sa * rounds + rnd) * IB + ib] = first run of that visit (+1 entry: total)
-inline void plan_runs(const RunPlanArgs& a, std::vector<HotUnit>& units, std::vector<int>& visit_units) {
+// The plan is on the critical path of every load (16-27 ms of a 226 ms end-to-end factorize call on the Netflix-shaped set:
+// 71 K buckets, 224 K runs), so it is a two-pass counting sort with no intermediate lists, cut over host threads when it is
+// large: thread t takes the t-th range of run items (every sub-stripe), pass 1 counts its runs per (visit, run length), a
+// prefix sum in (visit, longest first, thread) order gives every thread its slots, pass 2 enumerates the same runs again and
+// writes each into its slot. Thread order is item order, so the result is the serial stable sort, bit for bit, whatever the
+// thread count (tests/test_run_plan_cpu.py).
+inline void plan_runs(const RunPlanArgs& a, std::vector<HotUnit>& units, std::vector<int>& visit_units, int threads = 0) {
     units.clear();
-    visit_units.assign((size_t)a.mu * a.rounds * a.IB + 1, 0);
+    const size_t n_visits = (size_t)a.mu * a.rounds * a.IB;
+    visit_units.assign(n_visits + 1, 0);
+    if (a.H <= 0 || a.chunk <= 0 || a.mu <= 0 || a.rounds <= 0 || a.IB <= 0) return;
     const size_t hot_base = (size_t)a.mu * a.IB;
-    if (a.H > 0 && a.chunk > 0)
-        units.reserve((size_t)((a.block_off[a.n_blocks] - a.block_off[hot_base]) / a.chunk) + (size_t)a.mu * a.H + 16);
-    std::vector<std::vector<HotUnit>> seg((size_t)a.rounds * a.IB);       // the (round, item block) segments of one sub-stripe
-    std::vector<size_t> place;
-    for (int sa = 0; sa < a.mu; sa++) {
-        for (auto& v : seg) v.clear();
-        for (int ib = 0; ib < a.IB; ib++)
-            for (int hx = a.hot_block_lo[ib]; hx < a.hot_block_lo[ib + 1]; hx++) {
-                const size_t blk = hot_base + (size_t)sa * a.H + (size_t)hx;
-                const int64_t bn = a.block_off[blk + 1] - a.block_off[blk];
-                if (bn <= 0) continue;
-                const int spread = (int)std::min<int64_t>(a.rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
-                const int first = (int)(hash64(a.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)a.hot_items[hx]) % (uint64_t)a.rounds);
-                for (int sl = 0; sl < spread; sl++) {
-                    const int rnd = (first + sl * a.rounds / spread) % a.rounds;     // distinct for distinct sl (spread <= rounds)
-                    const int64_t lo = a.block_off[blk] + bn * sl / spread, hi = a.block_off[blk] + bn * (sl + 1) / spread;
-                    const int64_t n = hi - lo;
-                    if (n <= 0) continue;
-                    const int64_t pieces = (n + a.chunk - 1) / a.chunk;
-                    std::vector<HotUnit>& out = seg[(size_t)rnd * a.IB + ib];
-                    for (int64_t pc = 0; pc < pieces; pc++) {
-                        HotUnit u{};
-                        u.bstart = a.block_off[blk];
-                        u.bn = (int32_t)bn;
-                        u.bid = (uint32_t)((size_t)a.member * a.n_blocks + blk);
-                        u.start = lo + n * pc / pieces;
-                        u.count = (int32_t)(lo + n * (pc + 1) / pieces - u.start);
-                        u.item = a.hot_items[hx];
-                        u.weight = merge_weight(pieces, a.boost);
-                        out.push_back(u);
+    const size_t keys = (size_t)a.chunk + 1;                 // key = chunk - run length: 0 = longest
+    int T = threads;
+    if (T <= 0) {
+        T = 1;
+        if ((size_t)a.mu * (size_t)a.H >= 16384) T = (int)std::min<unsigned>(8u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    }
+    T = std::max(1, std::min(T, a.H));
+    while (T > 1 && (size_t)T * n_visits * keys > ((size_t)1 << 24)) T--;      // slot tables: at most 128 MB
+    std::vector<uint64_t> slot((size_t)T * n_visits * keys, 0);               // pass 1: counts; after the prefix sum: next free slot
+
+    // the runs of run items [H t / T, H (t + 1) / T), every sub-stripe, in the order (sub-stripe, item block, item, slice, piece)
+    auto enumerate = [&](int t, auto&& emit) {
+        const int hx_lo = (int)((int64_t)a.H * t / T), hx_hi = (int)((int64_t)a.H * (t + 1) / T);
+        for (int sa = 0; sa < a.mu; sa++)
+            for (int ib = 0; ib < a.IB; ib++) {
+                const int lo_x = std::max(hx_lo, (int)a.hot_block_lo[ib]), hi_x = std::min(hx_hi, (int)a.hot_block_lo[ib + 1]);
+                for (int hx = lo_x; hx < hi_x; hx++) {
+                    const size_t blk = hot_base + (size_t)sa * a.H + (size_t)hx;
+                    const int64_t bn = a.block_off[blk + 1] - a.block_off[blk];
+                    if (bn <= 0) continue;
+                    const int spread = (int)std::min<int64_t>(a.rounds, std::max<int64_t>(1, bn / (2 * MIN_RUN)));
+                    const int first = (int)(hash64(a.seed, 11, ((uint64_t)sa << 32) | (uint64_t)(uint32_t)a.hot_items[hx]) % (uint64_t)a.rounds);
+                    for (int sl = 0; sl < spread; sl++) {
+                        const int rnd = (first + sl * a.rounds / spread) % a.rounds;     // distinct for distinct sl (spread <= rounds)
+                        const int64_t lo = a.block_off[blk] + bn * sl / spread, hi = a.block_off[blk] + bn * (sl + 1) / spread;
+                        const int64_t n = hi - lo;
+                        if (n <= 0) continue;
+                        const int64_t pieces = (n + a.chunk - 1) / a.chunk;
+                        const size_t visit = ((size_t)sa * a.rounds + rnd) * a.IB + ib;
+                        const float w = merge_weight(pieces, a.boost);
+                        int64_t at = lo;
+                        for (int64_t pc = 0; pc < pieces; pc++) {
+                            const int64_t next = lo + n * (pc + 1) / pieces;
+                            emit(visit, blk, bn, hx, at, (int32_t)(next - at), w);
+                            at = next;
+                        }
                     }
                 }
             }
-        for (int rnd = 0; rnd < a.rounds; rnd++)
-            for (int ib = 0; ib < a.IB; ib++) {
-                const std::vector<HotUnit>& v = seg[(size_t)rnd * a.IB + ib];
-                visit_units[((size_t)sa * a.rounds + rnd) * a.IB + ib] = (int)units.size();
-                const size_t base = units.size();
-                units.resize(base + v.size());
-                place.assign((size_t)a.chunk + 2, 0);                    // stable counting sort, key 0 = longest run
-                for (const HotUnit& u : v) place[(size_t)(a.chunk - u.count) + 1]++;
-                for (size_t c = 1; c < place.size(); c++) place[c] += place[c - 1];
-                for (const HotUnit& u : v) units[base + place[(size_t)(a.chunk - u.count)]++] = u;
+    };
+    auto fan_out = [&](auto&& job) {     // job(t) for t in [0, T) on T threads (the caller's is one of them)
+        std::vector<std::thread> pool;
+        try {
+            for (int t = 1; t < T; t++) pool.emplace_back(job, t);
+        } catch (...) {                  // no thread to be had: the caller does the rest itself
+        }
+        const int started = (int)pool.size() + 1;
+        job(0);
+        for (std::thread& th : pool) th.join();
+        for (int t = started; t < T; t++) job(t);
+    };
+    fan_out([&](int t) {
+        uint64_t* mine = slot.data() + (size_t)t * n_visits * keys;
+        enumerate(t, [&](size_t visit, size_t, int64_t, int, int64_t, int32_t count, float) { mine[visit * keys + (size_t)(a.chunk - count)]++; });
+    });
+    uint64_t run = 0;
+    for (size_t v = 0; v < n_visits; v++) {
+        visit_units[v] = (int)run;
+        for (size_t key = 0; key < keys; key++)
+            for (int t = 0; t < T; t++) {
+                uint64_t& c = slot[((size_t)t * n_visits + v) * keys + key];
+                const uint64_t cnt = c;
+                c = run;
+                run += cnt;
             }
     }
-    visit_units.back() = (int)units.size();
+    visit_units[n_visits] = (int)run;
+    units.resize((size_t)run);
+    fan_out([&](int t) {
+        uint64_t* mine = slot.data() + (size_t)t * n_visits * keys;
+        enumerate(t, [&](size_t visit, size_t blk, int64_t bn, int hx, int64_t start, int32_t count, float w) {
+            HotUnit u{};
+            u.bstart = a.block_off[blk];
+            u.bn = (int32_t)bn;
+            u.bid = (uint32_t)((size_t)a.member * a.n_blocks + blk);
+            u.start = start;
+            u.count = count;
+            u.item = a.hot_items[hx];
+            u.weight = w;
+            units[(size_t)mine[visit * keys + (size_t)(a.chunk - count)]++] = u;
+        });
+    });
 }
 
 }  // namespace mfsgd

@@ -74,6 +74,67 @@ def test_small_buckets_spread_evenly_over_the_rounds():
     assert per_round.sum() == H and per_round.min() > 0.8 * H / rounds and per_round.max() < 1.2 * H / rounds
 
 
+def _plan_restated(off, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed, member, boost):
+    """The plan as run_plan.hpp's header comment states it, in plain Python (one thread, Python integers): slices of every
+    bucket hashed over the rounds, cut into equal pieces, every visit's runs longest first (stable)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from np_restatement import hash64
+    hot_base = mu * IB
+    n_blocks = mu * (IB + H)
+    visits = {}
+    for sa in range(mu):
+        for ib in range(IB):
+            for hx in range(hot_block_lo[ib], hot_block_lo[ib + 1]):
+                blk = hot_base + sa * H + hx
+                bn = int(off[blk + 1] - off[blk])
+                if bn <= 0:
+                    continue
+                spread = min(rounds, max(1, bn // (2 * MIN_RUN)))
+                first = int(hash64(seed, 11, (sa << 32) | int(hot_items[hx]))) % rounds
+                for sl in range(spread):
+                    rnd = (first + sl * rounds // spread) % rounds
+                    lo, hi = int(off[blk]) + bn * sl // spread, int(off[blk]) + bn * (sl + 1) // spread
+                    n = hi - lo
+                    if n <= 0:
+                        continue
+                    pieces = -(-n // chunk)
+                    w = 1.0 if pieces <= 1 else min(1.0, float(np.float32(np.float32(max(boost, 1.0)) / np.float32(pieces))))
+                    for pc in range(pieces):
+                        st = lo + n * pc // pieces
+                        visits.setdefault((sa * rounds + rnd) * IB + ib, []).append((st, lo + n * (pc + 1) // pieces - st, int(hot_items[hx]), w))
+    out, first_of = [], [0]
+    for v in range(mu * rounds * IB):
+        runs = sorted(visits.get(v, []), key=lambda r: -r[1])          # Python's sort is stable
+        out += runs
+        first_of.append(len(out))
+    return out, first_of
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8", ""])
+def test_threaded_plan_is_the_serial_plan_bit_for_bit(threads, monkeypatch):
+    """Large plans are cut by several host threads (two-pass counting sort); whatever their number, the runs, their order inside
+    every visit and the visit offsets are those of the one-thread restatement. 20 000 buckets: above the planner's own threshold
+    for going parallel, so the empty setting exercises its automatic choice."""
+    if threads:
+        monkeypatch.setenv("MFSGD_PLAN_THREADS", threads)
+    else:
+        monkeypatch.delenv("MFSGD_PLAN_THREADS", raising=False)
+    rng = np.random.default_rng(5)
+    mu, IB, rounds, chunk, H = 4, 3, 4, 96, 5000
+    hot_items = np.sort(rng.choice(60_000, H, replace=False)).astype(np.int32)
+    hot_block_lo = np.concatenate([[0], np.sort(rng.choice(np.arange(1, H), IB - 1, replace=False)), [H]]).astype(np.int32)
+    sizes_cold = rng.integers(0, 50, (mu, IB))
+    sizes_hot = rng.choice([0, 1, 16, 31, 32, 64, 65, 95, 96, 97, 200, 500, 1000, 4000], (mu, H))
+    off, start, count, item, weight, visits = plan(sizes_cold, sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed=99, member=2, boost=1.25)
+    want, first_of = _plan_restated(off, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, 99, 2, 1.25)
+    assert list(visits) == first_of and len(start) == len(want)
+    assert np.array_equal(start, np.array([r[0] for r in want], np.int64))
+    assert np.array_equal(count, np.array([r[1] for r in want], np.int32))
+    assert np.array_equal(item, np.array([r[2] for r in want], np.int32))
+    assert np.array_equal(weight, np.array([r[3] for r in want], np.float32))
+
+
 def test_plan_arguments_are_checked():
     n = C.c_int64(0)
     v = np.zeros(2, np.int32)
