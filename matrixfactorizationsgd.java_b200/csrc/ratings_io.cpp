@@ -3,10 +3,12 @@
 // sparse ids of the files compacted to dense row numbers (ascending original id). Host-only code, no CUDA.
 //   MFSGD_FORMAT_TRIPLETS      "user <sep> item <sep> rating [<sep> anything]" per line, <sep> any run of tab, blank, ',',
 //                              ';', ':' or '|': MovieLens u.data (tab), ratings.csv (comma, header line), ratings.dat ("::");
-//                              lines that do not start with a digit (headers, comments, blank lines) are skipped
+//                              fields may be quoted ("1","31","2.5"), a UTF-8 BOM is skipped; lines that do not start with a
+//                              digit (headers, comments, blank lines) are skipped -- except a signed number, which is a data
+//                              line with an id this interface cannot hold and is reported, not dropped
 //   MFSGD_FORMAT_NETFLIX_PRIZE "movie:" lines, each followed by that movie's "customer,rating[,date]" lines
 //                              (combined_data_*.txt / mv_*.txt of the Netflix Prize set)
-//   MFSGD_FORMAT_AUTO          NETFLIX_PRIZE if the first line that starts with a digit is "<digits>:", else TRIPLETS
+//   MFSGD_FORMAT_AUTO          NETFLIX_PRIZE if the first line that starts with a digit (after a BOM, blanks, quotes) is "<digits>:", else TRIPLETS
 // The file is mmapped and parsed by up to 16 threads (one slice of lines each), ids are ranked through a presence table:
 // 45 M ratings/s (1.2 GB/s) on 8 cores for a 10 M-line ratings.csv, 17 M ratings/s single-threaded.
 #include <fcntl.h>
@@ -45,7 +47,9 @@ struct Mapped {
     }
 };
 
-inline bool is_sep(char c) { return c == '\t' || c == ' ' || c == ',' || c == ';' || c == ':' || c == '|' || c == '\r'; }
+inline bool is_quote(char c) { return c == '"' || c == '\''; }
+// field separators; quotes count as separators so that a quoted CSV ("1","31","2.5") reads like a plain one
+inline bool is_sep(char c) { return c == '\t' || c == ' ' || c == ',' || c == ';' || c == ':' || c == '|' || c == '\r' || is_quote(c); }
 inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
 
 // unsigned decimal integer at s (< end); returns false if none / overflow
@@ -139,7 +143,13 @@ void parse_slice(const char* base, const char* begin, const char* end, int forma
     while (s < end) {
         const char* const line = s;
         const char* nl = next_line(s, end);
-        while (s < nl && (*s == ' ' || *s == '\t')) s++;
+        if (line == base && nl - s >= 3 && (unsigned char)s[0] == 0xEF && (unsigned char)s[1] == 0xBB && (unsigned char)s[2] == 0xBF) s += 3;   // UTF-8 BOM
+        while (s < nl && (*s == ' ' || *s == '\t' || is_quote(*s))) s++;
+        if (s < nl && (*s == '-' || *s == '+') && s + 1 < nl && is_digit(s[1])) {     // a data line, not a header: say so instead of dropping it
+            out.error = "signed id (ids are non-negative integers)";
+            out.error_at = line;
+            return;
+        }
         if (s >= nl || !is_digit(*s)) { s = nl; continue; }            // header, comment, blank line
         int64_t a = 0, b = 0;
         float r = 0.f;
@@ -286,7 +296,8 @@ static int read_ratings_body(const char* path, int32_t format, mfsgd_ratings* ou
         format = MFSGD_FORMAT_TRIPLETS;
         for (const char* t = s; t < end; t = next_line(t, end)) {
             const char* c = t;
-            while (c < end && (*c == ' ' || *c == '\t')) c++;
+            if (t == s && end - c >= 3 && (unsigned char)c[0] == 0xEF && (unsigned char)c[1] == 0xBB && (unsigned char)c[2] == 0xBF) c += 3;   // UTF-8 BOM
+            while (c < end && (*c == ' ' || *c == '\t' || is_quote(*c))) c++;
             if (c < end && is_digit(*c)) {
                 while (c < end && is_digit(*c)) c++;
                 const char* d = c;

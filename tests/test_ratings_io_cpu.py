@@ -95,3 +95,68 @@ def test_large_sparse_ids_take_the_sort_path(tmp_path):
     rf = mf.read_ratings(path)
     assert rf.userIds.tolist() == [7, 9000000000] and rf.itemIds.tolist() == [5, 6000000000]
     assert rf.users.tolist() == [1, 0, 1] and rf.items.tolist() == [0, 1, 1]
+
+
+def test_quoted_fields_bom_and_signed_ids(tmp_path):
+    """Exports of spreadsheet tools quote every field and start with a byte-order mark; both used to be read as an empty set
+    (every line 'does not start with a digit'), and so was a line with a negative id. Quotes are separators now, the BOM is
+    skipped, and a signed id is an error with its line number."""
+    q = tmp_path / "quoted.csv"
+    q.write_bytes(b'\xef\xbb\xbf"userId","movieId","rating","timestamp"\r\n"7","31","2.5","1260759144"\r\n"3","31","4.0","1260759179"\r\n')
+    rf = mf.read_ratings(q)
+    assert rf.format == capi.FORMAT_TRIPLETS and rf.userIds.tolist() == [3, 7] and rf.itemIds.tolist() == [31]
+    assert rf.users.tolist() == [1, 0] and rf.ratings.tolist() == [2.5, 4.0]
+    b = tmp_path / "bom_then_data.txt"
+    b.write_bytes(b"\xef\xbb\xbf5 6 1.5\n8 6 3\n")
+    rf = mf.read_ratings(b)
+    assert rf.userIds.tolist() == [5, 8] and rf.ratings.tolist() == [1.5, 3.0]
+    nb = tmp_path / "bom_netflix.txt"
+    nb.write_bytes(b"\xef\xbb\xbf12:\n5,3,2005-01-01\n")
+    rf = mf.read_ratings(nb)
+    assert rf.format == capi.FORMAT_NETFLIX_PRIZE and rf.itemIds.tolist() == [12] and rf.userIds.tolist() == [5]
+    for text in ("1 2 3\n-4 2 5\n", "1 2 3\n+4 2 5\n"):
+        s = tmp_path / "signed.txt"
+        s.write_text(text)
+        with pytest.raises(mf.MfsgdError) as ei:
+            mf.read_ratings(s)
+        assert ei.value.code == capi.E_INVALID_ARG and "signed.txt:2" in str(ei.value) and "signed id" in str(ei.value)
+    # a negative RATING is a value, not an id: kept
+    n = tmp_path / "negrating.txt"
+    n.write_text("1 2 -0.5\n")
+    assert mf.read_ratings(n).ratings.tolist() == [-0.5]
+
+
+@pytest.mark.parametrize("threads", [2, 3, 7, 16, 64, 200])
+def test_netflix_prize_slices_find_their_movie(tmp_path, monkeypatch, threads):
+    """Slice-parallel parsing: a slice that starts in the middle of a movie's block (or on an empty movie, or on a header line)
+    looks backwards for the header it continues. MFSGD_IO_THREADS forces many slices on a small file."""
+    rng = np.random.default_rng(threads)
+    lines, want = [], []
+    for m in range(1, 80):
+        lines.append("%d:" % m)
+        for _ in range(int(rng.integers(0, 25))):          # some movies have no ratings at all
+            u, r = int(rng.integers(1, 1000)), int(rng.integers(1, 6))
+            lines.append("%d,%d,2005-01-01" % (u, r))
+            want.append((u, m, r))
+    path = tmp_path / "combined.txt"
+    path.write_text("\n".join(lines) + "\n")
+    monkeypatch.setenv("MFSGD_IO_THREADS", str(threads))
+    rf = mf.read_ratings(path)
+    got = list(zip(rf.userIds[rf.users].tolist(), rf.itemIds[rf.items].tolist(), [int(x) for x in rf.ratings]))
+    assert rf.format == capi.FORMAT_NETFLIX_PRIZE and got == want
+
+
+@pytest.mark.parametrize("threads", [3, 16])
+def test_triplet_slices_and_first_error_in_file_order(tmp_path, monkeypatch, threads):
+    users, items, ratings = synth(3000, seed=11)
+    path = tmp_path / "many.tsv"
+    rows = ["%d\t%d\t%g" % (a, b, c) for a, b, c in zip(users, items, ratings)]
+    path.write_text("\n".join(rows) + "\n")
+    monkeypatch.setenv("MFSGD_IO_THREADS", str(threads))
+    check(mf.read_ratings(path), users, items, ratings, capi.FORMAT_TRIPLETS)
+    rows[2500] = "7\tx\t3"            # two bad lines in different slices: the first one in the file is reported
+    rows[700] = "7\t\t"
+    path.write_text("\n".join(rows) + "\n")
+    with pytest.raises(mf.MfsgdError) as ei:
+        mf.read_ratings(path)
+    assert "many.tsv:701" in str(ei.value)
