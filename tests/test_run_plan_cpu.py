@@ -135,6 +135,30 @@ def test_threaded_plan_is_the_serial_plan_bit_for_bit(threads, monkeypatch):
     assert np.array_equal(weight, np.array([r[3] for r in want], np.float32))
 
 
+def test_random_plans_match_the_restatement(monkeypatch):
+    """60 random shapes (sub-stripes, item blocks, rounds, run lengths from 1 to 4096, empty and huge buckets, every merge
+    boost) under random thread counts, each compared with the plain-Python restatement."""
+    rng = np.random.default_rng(2)
+    for _ in range(60):
+        mu, IB = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+        rounds, chunk = int(rng.choice([1, 2, 3, 4, 8, 16])), int(rng.choice([1, 2, 16, 31, 32, 96, 256, 1024, 4096]))
+        H = int(rng.integers(max(IB, 2), 60))
+        hot_items = np.sort(rng.choice(100_000, H, replace=False)).astype(np.int32)
+        cuts = np.sort(rng.choice(np.arange(1, H), IB - 1, replace=False)) if IB > 1 else np.array([], int)
+        hot_block_lo = np.concatenate([[0], cuts, [H]]).astype(np.int32)
+        sizes_hot = rng.choice([0, 1, 2, 15, 16, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 5000], (mu, H))
+        if chunk < 16:
+            sizes_hot = np.minimum(sizes_hot, 200)
+        boost, seed, member = float(rng.choice([1.0, 1.25, 1.9])), int(rng.integers(0, 2 ** 40)), int(rng.integers(0, 8))
+        monkeypatch.setenv("MFSGD_PLAN_THREADS", str(int(rng.choice([1, 2, 5, 8]))))
+        off, start, count, item, weight, visits = plan(rng.integers(0, 20, (mu, IB)), sizes_hot, mu, H, IB, hot_block_lo, hot_items, rounds,
+                                                       chunk, seed=seed, member=member, boost=boost)
+        want, first_of = _plan_restated(off, mu, H, IB, hot_block_lo, hot_items, rounds, chunk, seed, member, boost)
+        assert list(visits) == first_of and len(start) == len(want), (mu, IB, rounds, chunk, H)
+        assert np.array_equal(start, np.array([r[0] for r in want], np.int64)) and np.array_equal(count, np.array([r[1] for r in want], np.int32))
+        assert np.array_equal(item, np.array([r[2] for r in want], np.int32)) and np.array_equal(weight, np.array([r[3] for r in want], np.float32))
+
+
 def test_plan_arguments_are_checked():
     n = C.c_int64(0)
     v = np.zeros(2, np.int32)
