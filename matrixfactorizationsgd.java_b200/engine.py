@@ -175,6 +175,8 @@ class Engine:
 
     def rmse(self, users, items, ratings):
         u, i, r = as_i32(users), as_i32(items), as_f32(ratings)
+        if not (len(u) == len(i) == len(r)):
+            raise ValueError("triplet arrays differ in length")
         out = C.c_double(0.0)
         check(lib.mfsgd_rmse(self._h, ptr(u), ptr(i), ptr(r), len(r), C.byref(out)))
         return out.value

@@ -100,6 +100,8 @@ class MatrixFactorizationSGD:
         MatrixFactorizationSGD._check(users, items, ratings, nUsers, nItems, k, maxEpochs)
         if not (0.0 < lrDecay <= 1.0) or patience < 0 or not (0.0 <= minDelta < 1.0):
             raise ValueError("bad schedule")                                  # stand-in line 356-357
+        if not (len(vUsers) == len(vItems) == len(vRatings)):
+            raise ValueError("triplet arrays differ in length")               # before any GPU work, like the training triplets
         bits = (capi.MODEL_GLOBAL_MEAN if useGlobalMean else 0) | (capi.MODEL_BIASES if useBiases else 0)
         cfg = make_config(nUsers, nItems, k, lr, lambda_, seed=seed, mode=mode, n_gpus=n_gpus, device=device, model=bits,
                           lr_decay=lrDecay, early_stop_patience=patience, early_stop_min_delta=minDelta, **cfg_kw)

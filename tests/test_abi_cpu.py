@@ -101,6 +101,19 @@ def test_host_mirror_argument_checks_match_stand_in():
         mf.MatrixFactorizationSGD.factorize(z, z, np.ones(2, np.float32), 3, 3, 0, 0.1, 0.1, 1, 1)
     with pytest.raises(ValueError):
         mf.MatrixFactorizationSGD.factorize(z, z, np.ones(2, np.float32), 3, 3, 8, 0.1, 0.1, -1, 1)
+    # the extension entry points (stand-in :305, :350, :439) reject what the stand-in rejects, before any GPU work
+    M, r = mf.MatrixFactorizationSGD, np.ones(2, np.float32)
+    with pytest.raises(ValueError, match="bad shape"):
+        M.factorizeMixed(z, z, r, 3, 3, 6, 0.1, 0.1, 1, 1)                      # binary16 rows: k % 4 == 0 (:443)
+    with pytest.raises(ValueError, match="differ in length"):
+        M.factorizeModel(z, z, r[:1], 3, 3, 8, 0.1, 0.1, 1, 1, True, True)
+    for decay, patience, delta in ((1.5, 1, 0.0), (0.0, 1, 0.0), (0.9, -1, 0.0), (0.9, 1, 1.0), (0.9, 1, -0.1)):
+        with pytest.raises(ValueError, match="bad schedule"):                   # :356-357
+            M.factorizeEarlyStop(z, z, r, z, z, r, 3, 3, 8, 0.1, 0.1, 1, 1, True, True, decay, patience, delta)
+    with pytest.raises(ValueError, match="differ in length"):
+        M.factorizeEarlyStop(z, z, r, z, z, r[:1], 3, 3, 8, 0.1, 0.1, 1, 1, True, True, 0.9, 1, 0.0)
+    with pytest.raises(ValueError):
+        M.rmse(np.zeros((3, 8), np.float32), np.zeros((3, 4), np.float32), 8, z, z, r)
 
 
 def test_product_does_not_touch_the_oracle():
