@@ -66,3 +66,19 @@ def test_cpu_baseline_ml100k_runs_the_oracle_cli():
     assert ("seq", 1) in modes and any(m == "threads" for m, _ in modes)
     seq = [r for r in d["runs"] if r.get("mode") == "seq"][0]
     assert abs(seq["heldout_rmse"] - 0.393763) < 1e-5          # tests/golden/oracle_rmse_ml100k.json, last epoch
+
+
+def test_oracle_curve_covers_the_bench_runs_epoch_counts():
+    """bench.py prints rmse_vs_oracle only when the committed sequential-oracle curve reaches warm-up + steps epochs: the
+    Netflix-shaped fixture (the bench workload) covers the default 3 + 30 and the driver's shorter runs, for one GPU and
+    for rings of 2, 4 and 8 (the DSGD-ordered sequential curves)."""
+    import pytest
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_rmse_netflix.json")))
+    if len(fx["heldout_rmse_per_epoch"]) <= 10:
+        pytest.skip("the fixture holds the 10-epoch curves only (tools/oracle_reference_rmse.py netflix 35 --dsgd 2,4,8 extends them)")
+    assert len(fx["heldout_rmse_per_epoch"]) >= 33
+    for G in (2, 4, 8):
+        assert len(fx["dsgd%d" % G]["heldout_rmse_per_epoch"]) >= 33
+    curve = fx["heldout_rmse_per_epoch"]
+    assert abs(curve[9] - 0.389229263310776) < 1e-12          # the first ten epochs are the values round 1 committed
+    assert all(0.38 < v < 0.41 for v in curve) and curve[-1] < curve[9]
