@@ -648,3 +648,21 @@ def test_mixed_storage_tracks_binary32_training():
         orc.train_mixed(*tr, P16, Qm, lr, lam, 0, ep, SEED)
         got = orc.rmse(orc.widen(P16), Qm, *ho)
         assert abs(got / base - 1.0) < 3e-3, (got, base)
+
+
+def test_order_spread_of_the_full_size_sets_is_recorded_consistently():
+    """tests/golden/order_spread_large.json (tools/order_spread_large.py): sequential executions of the rule on the Netflix-shaped
+    sets that differ only in the visiting order. Order 0 is the committed oracle curve itself; the spread at the last epoch is the
+    scale against which the 0.5 % parity bar has to be read on these sets."""
+    import json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "tests", "golden", "order_spread_large.json")))["workloads"]
+    for name in ("netflix", "netflix_signal"):
+        w = d[name]
+        fx = json.load(open(os.path.join(root, "tests", "golden", "oracle_rmse_%s.json" % name)))
+        assert w["heldout_rmse_per_epoch_per_order"]["0"] == fx["heldout_rmse_per_epoch"][:w["epochs"]]
+        assert len(w["heldout_rmse_per_epoch_per_order"]) >= 4 and w["epochs"] == 10
+        finals = [c[-1] for c in w["heldout_rmse_per_epoch_per_order"].values()]
+        assert abs((max(finals) - min(finals)) / np.mean(finals) - w["final_spread_rel"]) < 1e-12
+    assert d["netflix"]["final_spread_rel"] < 0.002          # noise-dominant: the order hardly matters (< 0.2 %)
+    assert 0.001 < d["netflix_signal"]["final_spread_rel"] < 0.006      # signal-dominant: a few tenths of a per cent
